@@ -1,0 +1,86 @@
+"""Synthetic DPD-fluid inputs shaped like the reference's example/simple/*.data.
+
+Structure verified on the reference's 25.data: rho uniformly random
+points per unit cell, cells enumerated x-fastest then y then z, ids 1..N in that
+order, one atom type of mass 1.  48.data/64.data are absent from the reference
+tree, so every size other than 25 comes from here (PCG64, seed recorded below).
+"""
+import numpy as np
+
+DEFAULT_SEED = 20140901
+
+
+def dpd_fluid(L, rho=4, seed=DEFAULT_SEED, dtype=np.float64):
+    """Positions (N,3) of a rho-per-unit-cell random fluid in [0,L)^3; L may be a 3-tuple."""
+    Lx, Ly, Lz = (L, L, L) if np.isscalar(L) else L
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ncell = Lx * Ly * Lz
+    frac = rng.random((ncell, rho, 3))
+    c = np.arange(ncell)
+    origin = np.stack([c % Lx, (c // Lx) % Ly, c // (Lx * Ly)], axis=1).astype(np.float64)
+    x = (origin[:, None, :] + frac).reshape(-1, 3)
+    # same text round-trip as a %.9e data file, so file-based and in-memory runs agree
+    return np.ascontiguousarray(np.round(x, 9), dtype=dtype)
+
+
+def maxwell_velocities(n, temperature=1.0, seed=788662042, mass=1.0):
+    """Gaussian velocities with zero net momentum, scaled to exactly `temperature`
+    under LAMMPS' dof = 3N-3 (what `velocity all create T seed` guarantees)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    v = rng.standard_normal((n, 3))
+    v -= v.mean(axis=0)
+    t = mass * (v * v).sum() / (3.0 * n - 3.0)
+    v *= np.sqrt(temperature / t)
+    return np.ascontiguousarray(v)
+
+
+def write_data(path, x, L, types=None, ntypes=1, masses=None):
+    """LAMMPS data file, atom_style atomic, identical layout to example/simple/25.data."""
+    Lx, Ly, Lz = (L, L, L) if np.isscalar(L) else L
+    n = len(x)
+    types = np.ones(n, dtype=int) if types is None else types
+    masses = [1.0] * ntypes if masses is None else masses
+    with open(path, "w") as f:
+        f.write("LAMMPS\n\n%d atoms\n\n%d atom types\n\n" % (n, ntypes))
+        f.write("0 %g xlo xhi\n0 %g ylo yhi\n0 %g zlo zhi\n\nMasses\n\n" % (Lx, Ly, Lz))
+        for t, m in enumerate(masses):
+            f.write("%d %f\n" % (t + 1, m))
+        f.write("\nAtoms\n\n")
+        for i in range(n):
+            f.write("%d %d %.9e %.9e %.9e\n" % (i + 1, types[i], x[i, 0], x[i, 1], x[i, 2]))
+
+
+def read_data(path):
+    """Minimal reader for the files above: returns (x, tag, type, boxlo, boxhi, masses)."""
+    with open(path) as f:
+        lines = f.read().split("\n")
+    n = ntypes = 0
+    lo, hi = [0.0] * 3, [0.0] * 3
+    i = 0
+    masses = {}
+    while i < len(lines):
+        s = lines[i].strip()
+        if s.endswith("atoms"):
+            n = int(s.split()[0])
+        elif s.endswith("atom types"):
+            ntypes = int(s.split()[0])
+        elif s.endswith("xlo xhi"):
+            lo[0], hi[0] = map(float, s.split()[:2])
+        elif s.endswith("ylo yhi"):
+            lo[1], hi[1] = map(float, s.split()[:2])
+        elif s.endswith("zlo zhi"):
+            lo[2], hi[2] = map(float, s.split()[:2])
+        elif s == "Masses":
+            for k in range(ntypes):
+                t, m = lines[i + 2 + k].split()[:2]
+                masses[int(t)] = float(m)
+            i += 1 + ntypes
+        elif s == "Atoms":
+            body = np.loadtxt(lines[i + 2:i + 2 + n])
+            order = np.argsort(body[:, 0], kind="stable")
+            body = body  # keep file order: LAMMPS stores atoms in file order
+            x = np.ascontiguousarray(body[:, 2:5])
+            return x, body[:, 0].astype(np.int32), body[:, 1].astype(np.int32), lo, hi, \
+                [0.0] + [masses.get(t, 1.0) for t in range(1, ntypes + 1)]
+        i += 1
+    raise ValueError("no Atoms section in %s" % path)
