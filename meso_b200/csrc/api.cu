@@ -1,0 +1,776 @@
+// api.cu -- the extern "C" boundary (include/meso_b200.h) and the step orchestration.
+//
+// Orchestration follows ModifiedVerlet::setup / ::run (UM/mvv_meso.cu:139-219, 243-425) but
+// never leaves the device: the reference's transfer_pre_exchange / pre_sort / pre_border /
+// post_border / pre_comm / post_comm PCIe round trips (UM/atom_meso.cu:152-266) have no
+// counterpart here; the host only enqueues kernels.
+#include "internal.h"
+#include "device_math.cuh"
+#include <cuda_profiler_api.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace meso;
+
+namespace meso {
+int launch_deinterleave3(meso_ctx *ctx, const double *aos, DevBuf<double> *dst, int n);
+int launch_interleave3(meso_ctx *ctx, DevBuf<double> *src, double *aos, int n);
+int launch_fill_defaults(meso_ctx *ctx, int n, int st, int sy, int sm, int si);
+int launch_zero3(meso_ctx *ctx, DevBuf<double> *a, int n);
+int eval_gaussian(meso_ctx *ctx, int n, const uint32_t *si, const uint32_t *sj, float *osp, double *odp);
+int eval_math(meso_ctx *ctx, int fn, int n, const double *a, const double *b, double *out);
+int eval_log2u(meso_ctx *ctx, int n, const uint32_t *a, double *out);
+int comm_init(meso_ctx *ctx, const void *nccl_id);
+void comm_destroy(meso_ctx *ctx);
+int comm_allreduce_sum(meso_ctx *ctx, double *host_vals, int n);
+}
+
+static std::string g_create_err;
+
+#define CHECK_CTX() do { if (!ctx) return MESO_EINVAL; } while (0)
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+#define TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+
+// ---------------------------------------------------------------- timers
+namespace {
+struct PhaseTimer {
+    meso_ctx *ctx; int id; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(meso_ctx *ctx)
+    {
+        if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    PhaseTimer(meso_ctx *c, int i) : ctx(c), id(i)
+    {
+        if (!ctx->timers_on) return;
+        a = get(ctx); b = get(ctx);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~PhaseTimer()
+    {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->t_pending.push_back({id, {a, b}});
+    }
+};
+void drain_timers(meso_ctx *ctx)
+{
+    for (auto &p : ctx->t_pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(p.second.second);
+        cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+        ctx->t_ms[p.first] += ms; ctx->t_calls[p.first]++;
+        ctx->ev_pool.push_back(p.second.first); ctx->ev_pool.push_back(p.second.second);
+    }
+    ctx->t_pending.clear();
+}
+}  // namespace
+
+// ---------------------------------------------------------------- device runtime
+extern "C" int meso_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int meso_create(meso_ctx **out, int device)
+{
+    if (!out) return MESO_EINVAL;
+    *out = nullptr;
+    int n = meso_device_count();
+    if (n <= 0) { g_create_err = "no CUDA device visible: this library has no CPU fallback"; return MESO_ENODEV; }
+    if (device < 0) device = 0;
+    device %= n;                                        // local_rank % dev_count, src/lammps.cpp:451
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_create_err = "cudaGetDeviceProperties failed"; return MESO_ECUDA; }
+    if (prop.major < 10) { g_create_err = std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only"; return MESO_ENODEV; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_err = "cudaSetDevice failed"; return MESO_ECUDA; }
+    meso_ctx *ctx = new meso_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counts, sizeof(Counts)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_counts, sizeof(Counts)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_result, 16 * sizeof(double)) != cudaSuccess) {
+        g_create_err = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return MESO_ECUDA;
+    }
+    cudaMemsetAsync(ctx->d_counts, 0, sizeof(Counts), ctx->stream);
+    memset(ctx->h_counts, 0, sizeof(Counts));
+    *out = ctx;
+    return MESO_OK;
+}
+
+extern "C" void meso_destroy(meso_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    comm_destroy(ctx);
+    drain_timers(ctx);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    delete ctx;
+}
+
+extern "C" const char *meso_last_error(meso_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+static int check_device_flags(meso_ctx *ctx)
+{
+    int e = ctx->h_counts->err;
+    if (!e) return MESO_OK;
+    ctx->err = "device-side capacity error:";
+    if (e & 1) ctx->err += " ghost capacity exceeded;";
+    if (e & 2) ctx->err += " pair table overflow (local density too high for n_col);";
+    if (e & 8) ctx->err += " atom lost in migration;";
+    return MESO_ECAPACITY;
+}
+
+static int refresh_counts(meso_ctx *ctx)
+{
+    MESO_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(Counts), cudaMemcpyDeviceToHost, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return check_device_flags(ctx);
+}
+
+extern "C" int meso_sync(meso_ctx *ctx)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    drain_timers(ctx);
+    return MESO_OK;
+}
+
+extern "C" void *meso_stream(meso_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int meso_profiler(meso_ctx *ctx, int start)
+{
+    CHECK_CTX();
+    if (start) cudaProfilerStart(); else cudaProfilerStop();
+    return MESO_OK;
+}
+
+extern "C" int meso_memory_usage(meso_ctx *ctx, uint64_t *bytes)
+{
+    CHECK_CTX();
+    uint64_t b = 0;
+    for (int d = 0; d < 3; d++) b += ctx->x[d].bytes() + ctx->v[d].bytes() + ctx->f[d].bytes() + ctx->xa[d].bytes() + ctx->va[d].bytes();
+    b += ctx->tag.bytes() + ctx->type.bytes() + ctx->mask.bytes() + ctx->image.bytes() + ctx->taga.bytes() + ctx->typea.bytes() +
+         ctx->maska.bytes() + ctx->imagea.bytes() + ctx->coord4.bytes() + ctx->veloc4.bytes() + ctx->virial.bytes() + ctx->e_pair.bytes() +
+         ctx->staging.bytes() + ctx->istaging.bytes() + ctx->key.bytes() + ctx->perm_from.bytes() + ctx->sort.key_alt.bytes() +
+         ctx->sort.val_alt.bytes() + ctx->sort.hist.bytes() + ctx->ghost_root.bytes() + ctx->ghost_shift.bytes() + ctx->tile_counts.bytes() +
+         ctx->cell_key.bytes() + ctx->cell_of.bytes() + ctx->cell_atoms.bytes() + ctx->cell_start.bytes() + ctx->stencil.bytes() +
+         ctx->pair_count.bytes() + ctx->pair_table.bytes() + ctx->partial.bytes();
+    *bytes = b;
+    return MESO_OK;
+}
+
+// ---------------------------------------------------------------- domain
+static void update_subbox(meso_ctx *ctx)
+{
+    Box &b = ctx->box;
+    // Domain::set_local_box (uniform split): sublo = boxlo + prd * (loc/p)
+    for (int d = 0; d < 3; d++) {
+        int p = ctx->procgrid[d], me = ctx->myloc[d];
+        double inv = 1.0 / p;
+        b.sublo[d] = b.boxlo[d] + b.prd[d] * (me * inv);
+        b.subhi[d] = (me < p - 1) ? b.boxlo[d] + b.prd[d] * ((me + 1) * inv) : b.boxhi[d];
+        b.centre[d] = 0.5 * (b.subhi[d] + b.sublo[d]);           // UM/atom_vec_meso.cu:172-176
+    }
+    ctx->bins_ready = false;
+}
+
+extern "C" int meso_set_box(meso_ctx *ctx, const double boxlo[3], const double boxhi[3], const int periodic[3])
+{
+    CHECK_CTX();
+    for (int d = 0; d < 3; d++) {
+        if (!(boxhi[d] > boxlo[d])) FAIL(MESO_EINVAL, "meso_set_box: boxhi must exceed boxlo");
+        ctx->box.boxlo[d] = boxlo[d]; ctx->box.boxhi[d] = boxhi[d]; ctx->box.prd[d] = boxhi[d] - boxlo[d];
+        ctx->box.periodic[d] = periodic[d] ? 1 : 0;
+    }
+    ctx->box_set = true;
+    update_subbox(ctx);
+    return MESO_OK;
+}
+
+extern "C" int meso_set_decomposition(meso_ctx *ctx, int rank, const int procgrid[3], const void *nccl_id)
+{
+    CHECK_CTX();
+    int n = procgrid[0] * procgrid[1] * procgrid[2];
+    if (n < 1 || rank < 0 || rank >= n) FAIL(MESO_EINVAL, "meso_set_decomposition: bad rank/procgrid");
+    ctx->rank = rank; ctx->nranks = n;
+    for (int d = 0; d < 3; d++) ctx->procgrid[d] = procgrid[d];
+    ctx->myloc[0] = rank / (procgrid[1] * procgrid[2]);
+    ctx->myloc[1] = (rank / procgrid[2]) % procgrid[1];
+    ctx->myloc[2] = rank % procgrid[2];
+    for (int d = 0; d < 3; d++) {
+        int l[3] = {ctx->myloc[0], ctx->myloc[1], ctx->myloc[2]}, u[3] = {ctx->myloc[0], ctx->myloc[1], ctx->myloc[2]};
+        l[d] = (ctx->myloc[d] - 1 + procgrid[d]) % procgrid[d];
+        u[d] = (ctx->myloc[d] + 1) % procgrid[d];
+        ctx->procneigh[d][0] = (l[0] * procgrid[1] + l[1]) * procgrid[2] + l[2];
+        ctx->procneigh[d][1] = (u[0] * procgrid[1] + u[1]) * procgrid[2] + u[2];
+    }
+    if (ctx->box_set) update_subbox(ctx);
+    if (n > 1) {
+        if (!nccl_id) FAIL(MESO_EINVAL, "meso_set_decomposition: nranks > 1 needs an ncclUniqueId");
+        TRY(comm_init(ctx, nccl_id));
+    }
+    return MESO_OK;
+}
+
+// Comm::setup (src/comm.cpp:393-640) for style SINGLE, uniform bricks, maxneed <= 1
+static int comm_setup(meso_ctx *ctx)
+{
+    Box &b = ctx->box;
+    const double cutghost = ctx->cutneighmax;
+    for (int d = 0; d < 3; d++) {
+        int p = ctx->procgrid[d], me = ctx->myloc[d];
+        int maxneed = (int)(cutghost * p / b.prd[d]) + 1;
+        if (!b.periodic[d]) maxneed = std::min(maxneed, p - 1);
+        if (maxneed > 1) FAIL(MESO_EINVAL, "sub-domain thinner than the ghost cutoff (maxneed > 1) is not supported");
+        int sendneed[2];
+        if (!b.periodic[d]) {
+            int left = me - 1; if (left < 0) left = p - 1;
+            sendneed[0] = std::min(maxneed, p - left - 1);
+            int right = me + 1; if (right == p) right = 0;
+            sendneed[1] = std::min(maxneed, right);
+        } else sendneed[0] = sendneed[1] = maxneed;
+        b.sendflag[2 * d] = (maxneed > 0 && sendneed[0] > 0) ? 1 : 0;
+        b.sendflag[2 * d + 1] = (maxneed > 0 && sendneed[1] > 0) ? 1 : 0;
+        b.slab_lo_hi[d] = b.sublo[d] + cutghost;
+        b.slab_hi_lo[d] = b.subhi[d] - cutghost;
+        b.pbc[2 * d] = (me == 0) ? 1 : 0;
+        b.pbc[2 * d + 1] = (me == p - 1) ? -1 : 0;
+    }
+    return MESO_OK;
+}
+
+// ---------------------------------------------------------------- settings
+extern "C" int meso_set_neighbor(meso_ctx *ctx, double skin, int every)
+{
+    CHECK_CTX();
+    if (skin < 0 || every < 1) FAIL(MESO_EINVAL, "meso_set_neighbor: skin >= 0 and every >= 1 required");
+    ctx->skin = skin; ctx->every = every;
+    ctx->cutneighmax = ctx->cut_global + skin;
+    ctx->bins_ready = false;
+    return MESO_OK;
+}
+
+extern "C" int meso_set_types(meso_ctx *ctx, int ntypes, const double *mass)
+{
+    CHECK_CTX();
+    if (ntypes < 1 || !mass) FAIL(MESO_EINVAL, "meso_set_types: ntypes >= 1 and mass[ntypes+1] required");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    ctx->ntypes = ntypes;
+    ctx->mass.assign(mass, mass + ntypes + 1);
+    if (!ctx->mass_dev.reserve(ntypes + 1)) FAIL(MESO_ECUDA, "out of device memory");
+    MESO_CUDA(cudaMemcpyAsync(ctx->mass_dev.p, ctx->mass.data(), sizeof(double) * (ntypes + 1), cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->coeff_ready = false;
+    return MESO_OK;
+}
+
+extern "C" int meso_pair_dpd_settings(meso_ctx *ctx, int precision, double cut_global, int seed)
+{
+    CHECK_CTX();
+    if (precision != MESO_SP && precision != MESO_DP) FAIL(MESO_EINVAL, "Illegal pair_style command");
+    ctx->precision = precision; ctx->cut_global = cut_global; ctx->seed = seed;
+    ctx->cutneighmax = cut_global + ctx->skin;
+    ctx->bins_ready = false;
+    return MESO_OK;
+}
+
+extern "C" int meso_pair_dpd_coeff(meso_ctx *ctx, const double *coeff7)
+{
+    CHECK_CTX();
+    if (ctx->ntypes < 1) FAIL(MESO_EINVAL, "meso_pair_dpd_coeff: call meso_set_types first");
+    if (!coeff7) FAIL(MESO_EINVAL, "All pair coeffs are not set");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    const int n = ctx->ntypes * ctx->ntypes * NCOEFF;
+    ctx->coeff.assign(coeff7, coeff7 + n);
+    double cmax = 0;
+    for (int t = 0; t < ctx->ntypes * ctx->ntypes; t++) cmax = std::max(cmax, coeff7[t * NCOEFF + P_CUT]);
+    // Neighbor::init: cutneighmax = max pair cutoff + skin
+    ctx->cutneighmax = std::max(cmax, 0.0) + ctx->skin;
+    std::vector<float> sp(n);
+    for (int i = 0; i < n; i++) sp[i] = (float)coeff7[i];
+    if (!ctx->coeff_sp.reserve(n) || !ctx->coeff_dp.reserve(n)) FAIL(MESO_ECUDA, "out of device memory");
+    MESO_CUDA(cudaMemcpyAsync(ctx->coeff_sp.p, sp.data(), sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaMemcpyAsync(ctx->coeff_dp.p, ctx->coeff.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->coeff_ready = true;
+    ctx->bins_ready = false;
+    return MESO_OK;
+}
+
+extern "C" int meso_set_timestep_size(meso_ctx *ctx, double dt)
+{
+    CHECK_CTX();
+    if (!(dt > 0)) FAIL(MESO_EINVAL, "timestep must be positive");
+    ctx->dt = dt;
+    return MESO_OK;
+}
+extern "C" int meso_set_ntimestep(meso_ctx *ctx, int64_t t) { CHECK_CTX(); ctx->ntimestep = t; return MESO_OK; }
+extern "C" int64_t meso_get_ntimestep(meso_ctx *ctx) { return ctx ? ctx->ntimestep : -1; }
+
+// ---------------------------------------------------------------- atom store
+static int ensure_capacity(meso_ctx *ctx, size_t nlocal)
+{
+    // ghosts: shell of width cutghost around the brick at the brick's density, with head room
+    const Box &b = ctx->box;
+    double vin = 1, vout = 1;
+    for (int d = 0; d < 3; d++) { double w = b.subhi[d] - b.sublo[d]; vin *= w; vout *= w + 2.0 * ctx->cutneighmax; }
+    size_t nghost = (size_t)((double)nlocal * (vout / vin - 1.0) * 1.25) + 4096;
+    size_t nloc_cap = (ctx->nranks > 1) ? nlocal + nlocal / 8 + 1024 : nlocal;
+    size_t cap = nloc_cap + nghost;
+    if (cap <= ctx->cap) return MESO_OK;
+    bool ok = true;
+    for (int d = 0; d < 3; d++)
+        ok = ok && ctx->x[d].reserve(cap) && ctx->v[d].reserve(cap) && ctx->f[d].reserve(cap) && ctx->xa[d].reserve(cap) && ctx->va[d].reserve(cap);
+    ok = ok && ctx->tag.reserve(cap) && ctx->type.reserve(cap) && ctx->mask.reserve(cap) && ctx->image.reserve(cap) &&
+         ctx->taga.reserve(cap) && ctx->typea.reserve(cap) && ctx->maska.reserve(cap) && ctx->imagea.reserve(cap) &&
+         ctx->coord4.reserve(cap) && ctx->veloc4.reserve(cap) && ctx->key.reserve(cap) && ctx->perm_from.reserve(cap) &&
+         ctx->ghost_root.reserve(cap) && ctx->ghost_shift.reserve(cap) && ctx->cell_key.reserve(cap) && ctx->cell_of.reserve(cap) &&
+         ctx->cell_atoms.reserve(cap) && ctx->e_pair.reserve(cap) && ctx->pair_count.reserve(cap);
+    if (!ok) FAIL(MESO_ECUDA, "out of device memory growing the atom store");
+    ctx->cap = cap;
+    if (!ctx->virial.reserve(6 * ctx->cap)) FAIL(MESO_ECUDA, "out of device memory (virial)");
+    ctx->table_rows = ((nloc_cap + 31) / 32) * 32;
+    return MESO_OK;
+}
+
+extern "C" int meso_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, const double *v, const int *tag, const int *type,
+                                 const int *mask, const int *image)
+{
+    CHECK_CTX();
+    if (!ctx->box_set) FAIL(MESO_EINVAL, "meso_atoms_upload: call meso_set_box first");
+    if (nlocal < 0 || (nlocal > 0 && !x)) FAIL(MESO_EINVAL, "meso_atoms_upload: bad arguments");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(ensure_capacity(ctx, (size_t)nlocal));
+    const size_t n = (size_t)nlocal;
+    if (!ctx->staging.reserve(3 * n + 8)) FAIL(MESO_ECUDA, "out of device memory (staging)");
+    MESO_CUDA(cudaMemcpyAsync(ctx->staging.p, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(launch_deinterleave3(ctx, ctx->staging.p, ctx->x, nlocal));
+    if (v) {
+        MESO_CUDA(cudaMemcpyAsync(ctx->staging.p, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(launch_deinterleave3(ctx, ctx->staging.p, ctx->v, nlocal));
+    } else TRY(launch_zero3(ctx, ctx->v, nlocal));
+    TRY(launch_zero3(ctx, ctx->f, nlocal));
+    if (tag) MESO_CUDA(cudaMemcpyAsync(ctx->tag.p, tag, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (type) MESO_CUDA(cudaMemcpyAsync(ctx->type.p, type, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (mask) MESO_CUDA(cudaMemcpyAsync(ctx->mask.p, mask, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (image) MESO_CUDA(cudaMemcpyAsync(ctx->image.p, image, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(launch_fill_defaults(ctx, nlocal, !tag, !type, !mask, !image));
+    Counts c;
+    memset(&c, 0, sizeof c);
+    c.nlocal = nlocal; c.n_bulk = nlocal; c.nall = nlocal;
+    for (int s = 0; s < 6; s++) c.swap_first[s] = nlocal;
+    *ctx->h_counts = c;
+    MESO_CUDA(cudaMemcpyAsync(ctx->d_counts, ctx->h_counts, sizeof(Counts), cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->nlocal_host = nlocal;
+    double tot = nlocal;
+    if (ctx->nranks > 1) TRY(comm_allreduce_sum(ctx, &tot, 1));
+    ctx->natoms_global = (int64_t)(tot + 0.5);
+    ctx->bins_ready = false;
+    ctx->setup_done = false;
+    ctx->f_cleared = true;
+    return MESO_OK;
+}
+
+extern "C" int meso_atoms_download(meso_ctx *ctx, int nmax, double *x, double *v, double *f, int *tag, int *type, int *mask, int *image)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    const int n = ctx->h_counts->nlocal;
+    if (nmax < n) FAIL(MESO_EINVAL, "meso_atoms_download: buffer smaller than nlocal");
+    if (!ctx->staging.reserve(3 * (size_t)n + 8)) FAIL(MESO_ECUDA, "out of device memory (staging)");
+    DevBuf<double> *src[3] = {ctx->x, ctx->v, ctx->f};
+    double *dst[3] = {x, v, f};
+    for (int a = 0; a < 3; a++) {
+        if (!dst[a]) continue;
+        TRY(launch_interleave3(ctx, src[a], ctx->staging.p, n));
+        MESO_CUDA(cudaMemcpyAsync(dst[a], ctx->staging.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (tag) MESO_CUDA(cudaMemcpyAsync(tag, ctx->tag.p, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (type) MESO_CUDA(cudaMemcpyAsync(type, ctx->type.p, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask) MESO_CUDA(cudaMemcpyAsync(mask, ctx->mask.p, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (image) MESO_CUDA(cudaMemcpyAsync(image, ctx->image.p, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MESO_OK;
+}
+
+extern "C" int meso_counts(meso_ctx *ctx, int *nlocal, int *nghost, int *n_bulk, int *n_border)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    if (nlocal) *nlocal = ctx->h_counts->nlocal;
+    if (nghost) *nghost = ctx->h_counts->nghost;
+    if (n_bulk) *n_bulk = ctx->h_counts->n_bulk;
+    if (n_border) *n_border = ctx->h_counts->n_border;
+    return MESO_OK;
+}
+
+extern "C" int64_t meso_natoms_global(meso_ctx *ctx) { return ctx ? ctx->natoms_global : -1; }
+
+// ---------------------------------------------------------------- phases
+static int ready(meso_ctx *ctx)
+{
+    if (!ctx->box_set) FAIL(MESO_EINVAL, "box not set");
+    if (!ctx->coeff_ready) FAIL(MESO_EINVAL, "All pair coeffs are not set");
+    if (ctx->ntypes < 1) FAIL(MESO_EINVAL, "atom types not set");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    return MESO_OK;
+}
+
+extern "C" int meso_initial_integrate(meso_ctx *ctx, int groupbit)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    PhaseTimer t(ctx, MESO_T_INTEGRATE);
+    return launch_initial_integrate(ctx, groupbit, false);
+}
+
+extern "C" int meso_final_integrate(meso_ctx *ctx, int groupbit)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    PhaseTimer t(ctx, MESO_T_INTEGRATE);
+    return launch_final_integrate(ctx, groupbit);
+}
+
+extern "C" int meso_neighbor_decide(meso_ctx *ctx)
+{
+    CHECK_CTX();
+    ctx->ago++;                                            // Neighbor::decide, src/neighbor.cpp:1216-1231 (delay 0, check no)
+    return (ctx->ago % ctx->every == 0) ? 1 : 0;
+}
+
+static int rebuild_impl(meso_ctx *ctx)
+{
+    if (!ctx->bins_ready) {
+        TRY(comm_setup(ctx));
+        TRY(launch_setup_bins(ctx));
+        size_t need = ctx->table_rows * (size_t)ctx->n_col;
+        if (!ctx->pair_table.reserve(need)) FAIL(MESO_ECUDA, "out of device memory (pair table)");
+    }
+    if (ctx->nranks > 1) FAIL(MESO_EINVAL, "multi-rank rebuild is not available in this build");
+    {
+        PhaseTimer t(ctx, MESO_T_REBUILD);
+        TRY(launch_reorder(ctx));
+        TRY(launch_borders(ctx));
+    }
+    {
+        PhaseTimer t(ctx, MESO_T_NEIGH);
+        TRY(launch_neighbor_build(ctx));
+    }
+    MESO_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(Counts), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->ago = 0;
+    return MESO_OK;
+}
+
+extern "C" int meso_rebuild(meso_ctx *ctx)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    return rebuild_impl(ctx);
+}
+
+extern "C" int meso_forward_comm(meso_ctx *ctx)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    PhaseTimer t(ctx, MESO_T_FORWARD);
+    // phase API keeps the reference's order: ghosts' fp64 x,v are refreshed, packing happens in meso_pair_compute
+    return launch_forward(ctx, true);
+}
+
+extern "C" int meso_force_clear(meso_ctx *ctx, int range, int vflag)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    return launch_clear(ctx, range, vflag);
+}
+
+extern "C" int meso_pair_compute(meso_ctx *ctx, int range, int eflag, int vflag)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    PhaseTimer t(ctx, MESO_T_PAIR);
+    // compute_bulk packs LOCAL, compute_border packs GHOST, compute packs ALL (UM/pair_dpd_meso.cu:241-266)
+    int pack_range = (range == MESO_BULK) ? MESO_LOCAL : (range == MESO_BORDER ? MESO_GHOST : MESO_ALL);
+    TRY(launch_pack(ctx, pack_range));
+    return launch_pair(ctx, range, eflag || vflag, true, false, 0);
+}
+
+extern "C" int meso_compute_ke(meso_ctx *ctx, int groupbit, double *mv2_sum, double *count)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    double vals[2];
+    TRY(launch_ke(ctx, groupbit, &vals[0], &vals[1]));
+    if (ctx->nranks > 1) TRY(comm_allreduce_sum(ctx, vals, 2));
+    if (mv2_sum) *mv2_sum = vals[0];
+    if (count) *count = vals[1];
+    return MESO_OK;
+}
+
+extern "C" int meso_compute_virial(meso_ctx *ctx, double virial6[6], double *e_pair)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    double out[7];
+    TRY(launch_virial_sum(ctx, out));
+    if (ctx->nranks > 1) TRY(comm_allreduce_sum(ctx, out, 7));
+    if (virial6) memcpy(virial6, out, 6 * sizeof(double));
+    if (e_pair) *e_pair = out[6];
+    return MESO_OK;
+}
+
+// ---------------------------------------------------------------- whole-run drivers
+extern "C" int meso_setup(meso_ctx *ctx, int eflag, int vflag)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    ctx->bins_ready = false;
+    TRY(rebuild_impl(ctx));                                  // pbc, sort_local, borders, neighbor build (UM/mvv_meso.cu:150-185)
+    {
+        PhaseTimer t(ctx, MESO_T_PAIR);                      // force_clear + pair->compute (UM/mvv_meso.cu:191-197)
+        TRY(launch_pair(ctx, MESO_LOCAL, eflag || vflag, false, false, 0));
+    }
+    ctx->setup_done = true;
+    return refresh_counts(ctx);
+}
+
+extern "C" int meso_run(meso_ctx *ctx, int nsteps, int groupbit)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    if (!ctx->setup_done) FAIL(MESO_EINVAL, "meso_run: call meso_setup first");
+    for (int s = 0; s < nsteps; s++) {
+        ctx->ntimestep++;                                    // UM/mvv_meso.cu:256
+        const bool rebuild = meso_neighbor_decide(ctx) != 0;
+        {
+            PhaseTimer t(ctx, MESO_T_INTEGRATE);
+            TRY(launch_initial_integrate(ctx, groupbit, !rebuild));
+        }
+        if (rebuild) TRY(rebuild_impl(ctx));                 // gather + ghost kernels emit this step's packed views
+        else {
+            PhaseTimer t(ctx, MESO_T_FORWARD);
+            TRY(launch_forward(ctx, false));
+        }
+        PhaseTimer t(ctx, MESO_T_PAIR);                      // fused: clear + bulk + border + final_integrate
+        TRY(launch_pair(ctx, MESO_LOCAL, 0, false, true, groupbit));
+    }
+    return MESO_OK;
+}
+
+// ---------------------------------------------------------------- exports
+extern "C" int meso_export_bins(meso_ctx *ctx, int m[3], double binsize[3], double bininv[3], int *n_col)
+{
+    CHECK_CTX();
+    if (!ctx->bins_ready) FAIL(MESO_EINVAL, "bins not set up");
+    for (int d = 0; d < 3; d++) { m[d] = ctx->box.m[d]; binsize[d] = ctx->box.binsize[d]; bininv[d] = ctx->box.bininv[d]; }
+    if (n_col) *n_col = ctx->n_col;
+    return MESO_OK;
+}
+
+template <typename T>
+static int d2h(meso_ctx *ctx, T *dst, const T *src, size_t n)
+{
+    MESO_CUDA(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MESO_OK;
+}
+
+extern "C" int meso_export_reorder(meso_ctx *ctx, int nmax, uint64_t *key_sorted, int *permute_from)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    int n = ctx->h_counts->nlocal;
+    if (nmax < n) FAIL(MESO_EINVAL, "buffer too small");
+    if (key_sorted) TRY(d2h(ctx, key_sorted, ctx->key.p, n));
+    if (permute_from) TRY(d2h(ctx, permute_from, ctx->perm_from.p, n));
+    return MESO_OK;
+}
+
+extern "C" int meso_export_packed(meso_ctx *ctx, int nmax, float *coord4, float *veloc4)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    int n = ctx->h_counts->nlocal + ctx->h_counts->nghost;
+    if (nmax < n) FAIL(MESO_EINVAL, "buffer too small");
+    if (coord4) TRY(d2h(ctx, reinterpret_cast<float4 *>(coord4), ctx->coord4.p, n));
+    if (veloc4) TRY(d2h(ctx, reinterpret_cast<float4 *>(veloc4), ctx->veloc4.p, n));
+    return MESO_OK;
+}
+
+extern "C" int meso_export_ghosts(meso_ctx *ctx, int nmax, double *x, double *v, int *tag, int *type)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    const int nl = ctx->h_counts->nlocal, ng = ctx->h_counts->nghost;
+    if (nmax < ng) FAIL(MESO_EINVAL, "buffer too small");
+    std::vector<double> tmp(ng > 0 ? ng : 1);
+    for (int d = 0; d < 3; d++) {
+        if (x) { TRY(d2h(ctx, tmp.data(), ctx->x[d].p + nl, ng)); for (int i = 0; i < ng; i++) x[3 * (size_t)i + d] = tmp[i]; }
+        if (v) { TRY(d2h(ctx, tmp.data(), ctx->v[d].p + nl, ng)); for (int i = 0; i < ng; i++) v[3 * (size_t)i + d] = tmp[i]; }
+    }
+    if (tag) TRY(d2h(ctx, tag, ctx->tag.p + nl, ng));
+    if (type) TRY(d2h(ctx, type, ctx->type.p + nl, ng));
+    return MESO_OK;
+}
+
+extern "C" int meso_export_cells(meso_ctx *ctx, int ncell_plus1, int *cell_start, int nmax, int *cell_atoms)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    int n = ctx->h_counts->nlocal + ctx->h_counts->nghost;
+    if (cell_start) {
+        if (ncell_plus1 < ctx->box.ncell + 1) FAIL(MESO_EINVAL, "buffer too small");
+        TRY(d2h(ctx, cell_start, ctx->cell_start.p, ctx->box.ncell + 1));
+    }
+    if (cell_atoms) {
+        if (nmax < n) FAIL(MESO_EINVAL, "buffer too small");
+        TRY(d2h(ctx, cell_atoms, ctx->cell_atoms.p, n));
+    }
+    return MESO_OK;
+}
+
+extern "C" int meso_export_stencil(meso_ctx *ctx, int cell, int out27[27])
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->bins_ready || cell < 0 || cell >= ctx->box.ncell) FAIL(MESO_EINVAL, "bad cell");
+    unsigned char row[32];
+    TRY(d2h(ctx, row, ctx->stencil.p + (size_t)cell * 32, 32));
+    const Box &b = ctx->box;
+    int n = row[31];
+    for (int s = 0; s < n; s++) {
+        int code = row[s];
+        out27[s] = cell + (code % 3 - 1) + b.m[0] * ((code / 3) % 3 - 1 + b.m[1] * (code / 9 - 1));
+    }
+    return n;
+}
+
+extern "C" int meso_export_pair_count(meso_ctx *ctx, int nmax, int *pair_count)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    int n = ctx->h_counts->nlocal;
+    if (nmax < n) FAIL(MESO_EINVAL, "buffer too small");
+    return d2h(ctx, pair_count, ctx->pair_count.p, n);
+}
+
+extern "C" int meso_export_pair_table(meso_ctx *ctx, int64_t nmax, int *pair_table)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    size_t rows = ((size_t)ctx->h_counts->nlocal + 31) / 32 * 32;
+    size_t n = rows * (size_t)ctx->n_col;
+    if ((size_t)nmax < n) FAIL(MESO_EINVAL, "buffer too small");
+    return d2h(ctx, pair_table, ctx->pair_table.p, n);
+}
+
+extern "C" int meso_export_virial(meso_ctx *ctx, int nmax, double *virial6, double *e_pair)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    const int n = ctx->h_counts->nlocal;
+    if (nmax < n) FAIL(MESO_EINVAL, "buffer too small");
+    if (virial6) {
+        std::vector<double> tmp(n > 0 ? n : 1);
+        for (int q = 0; q < 6; q++) {
+            TRY(d2h(ctx, tmp.data(), ctx->virial.p + (size_t)q * ctx->cap, n));
+            for (int i = 0; i < n; i++) virial6[6 * (size_t)i + q] = tmp[i];
+        }
+    }
+    if (e_pair) TRY(d2h(ctx, e_pair, ctx->e_pair.p, n));
+    return MESO_OK;
+}
+
+template <typename T>
+struct Tmp {
+    T *p = nullptr;
+    ~Tmp() { if (p) cudaFree(p); }
+    bool alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)) == cudaSuccess; }
+};
+
+extern "C" int meso_eval_gaussian(meso_ctx *ctx, int n, const uint32_t *sig_i, const uint32_t *sig_j, float *out_sp, double *out_dp)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    Tmp<uint32_t> a, b; Tmp<float> s; Tmp<double> d;
+    if (!a.alloc(n) || !b.alloc(n) || !s.alloc(n) || !d.alloc(n)) FAIL(MESO_ECUDA, "out of device memory");
+    MESO_CUDA(cudaMemcpyAsync(a.p, sig_i, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaMemcpyAsync(b.p, sig_j, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(eval_gaussian(ctx, n, a.p, b.p, out_sp ? s.p : nullptr, out_dp ? d.p : nullptr));
+    if (out_sp) TRY(d2h(ctx, out_sp, s.p, n));
+    if (out_dp) TRY(d2h(ctx, out_dp, d.p, n));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MESO_OK;
+}
+
+extern "C" int meso_eval_math(meso_ctx *ctx, int fn, int n, const double *a, const double *b, double *out)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    if (fn < 0 || fn > 7 || (fn == 7 && !b)) FAIL(MESO_EINVAL, "meso_eval_math: bad function id");
+    Tmp<double> da, db, dout;
+    if (!da.alloc(n) || !db.alloc(n) || !dout.alloc(n)) FAIL(MESO_ECUDA, "out of device memory");
+    MESO_CUDA(cudaMemcpyAsync(da.p, a, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) MESO_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(eval_math(ctx, fn, n, da.p, db.p, dout.p));
+    return d2h(ctx, out, dout.p, n);
+}
+
+extern "C" int meso_eval_log2u(meso_ctx *ctx, int n, const uint32_t *a, double *out)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    Tmp<uint32_t> da; Tmp<double> dout;
+    if (!da.alloc(n) || !dout.alloc(n)) FAIL(MESO_ECUDA, "out of device memory");
+    MESO_CUDA(cudaMemcpyAsync(da.p, a, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(eval_log2u(ctx, n, da.p, dout.p));
+    return d2h(ctx, out, dout.p, n);
+}
+
+// ---------------------------------------------------------------- timers
+extern "C" int meso_timers_enable(meso_ctx *ctx, int on)
+{
+    CHECK_CTX();
+    ctx->timers_on = on != 0;
+    return MESO_OK;
+}
+
+extern "C" int meso_timers_read(meso_ctx *ctx, double ms[MESO_T_COUNT], int64_t calls[MESO_T_COUNT], int reset)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    drain_timers(ctx);
+    for (int i = 0; i < MESO_T_COUNT; i++) {
+        if (ms) ms[i] = ctx->t_ms[i];
+        if (calls) calls[i] = ctx->t_calls[i];
+        if (reset) { ctx->t_ms[i] = 0; ctx->t_calls[i] = 0; }
+    }
+    return MESO_OK;
+}

@@ -1,0 +1,178 @@
+// internal.h -- context and device-side layout shared by the kernels.
+//
+// HBM layout (one context = one GPU = one rank):
+//   x[3], v[3]  fp64 SoA, capacity = locals + ghosts   (A1: MesoAtomVec fields, UM/atom_vec_meso.h:133-163)
+//   f[3]        fp64 SoA, locals
+//   tag,type,mask,image int32
+//   coord4      float4 {x-cx, y-cy, z-cz, bits(type-1)}  \ the per-step packed view the
+//   veloc4      float4 {vx, vy, vz, bits(signature)}     / force kernel gathers from (A7)
+//   pair_table  int32, tile-transposed [ceil32(n)][n_col] (A6, UM/neigh_list_meso.cu:97-102)
+// All per-rebuild counts live in a device-side Counts struct so the step loop never
+// needs a host round trip; a pinned mirror is refreshed after each rebuild.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/meso_b200.h"
+
+namespace meso {
+
+struct Counts {
+    int nlocal, nghost, n_bulk, n_border;
+    int swap_first[6], swap_n[6];   // ghost index range created by each of the 6 border swaps
+    int err;                        // bit 0: ghost capacity, 1: pair table overflow, 2: join overlap, 3: lost atom
+    int max_pair;
+    int nall;                       // nlocal + nghost
+    int pad[1];
+};
+
+struct Box {
+    double boxlo[3], boxhi[3], prd[3];
+    double sublo[3], subhi[3], centre[3];
+    int periodic[3];
+    int m[3];                       // cells per dim incl. ghost layer (mbinx..)
+    double binsize[3], bininv[3];
+    double slab_lo_hi[3];           // send slab: x <= sublo + cutghost   (swap 2d)
+    double slab_hi_lo[3];           // send slab: x >= subhi - cutghost   (swap 2d+1)
+    int sendflag[6];
+    int pbc[6];                     // -1/0/+1 shift of swap s along its own dim
+    int ncell;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    // returns false on allocation failure; contents are NOT preserved unless keep
+    bool reserve(size_t n, bool keep = false, cudaStream_t s = 0)
+    {
+        if (n <= cap) return true;
+        size_t ncap = n + n / 4 + 256;
+        T *q = nullptr;
+        if (cudaMalloc(&q, ncap * sizeof(T)) != cudaSuccess) return false;
+        if (keep && p && cap) { cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s); cudaStreamSynchronize(s); }
+        if (p) cudaFree(p);
+        p = q; cap = ncap;
+        return true;
+    }
+    size_t bytes() const { return cap * sizeof(T); }
+};
+
+struct SortScratch {
+    DevBuf<uint64_t> key_alt;
+    DevBuf<int> val_alt;
+    DevBuf<uint32_t> hist;     // [256][ntiles]
+};
+
+enum { NCOEFF = 7, P_CUT = 0, P_CUTSQ, P_CUTINV, P_EXPW, P_A0, P_GAMMA, P_SIGMA };
+
+}  // namespace meso
+
+struct meso_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;
+    std::string err;
+
+    // domain / decomposition
+    meso::Box box{};
+    bool box_set = false, bins_ready = false;
+    int rank = 0, nranks = 1, procgrid[3] = {1, 1, 1}, myloc[3] = {0, 0, 0}, procneigh[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    void *nccl = nullptr;          // ncclComm_t
+
+    // settings
+    double skin = 0.3, cut_global = 1.0, cutneighmax = 1.3, dt = 0.005;
+    int every = 5, ago = 0;
+    int64_t ntimestep = 0;
+    int ntypes = 0;
+    std::vector<double> mass, coeff;
+    int precision = MESO_SP;
+    int seed = 0;
+    bool coeff_ready = false;
+    int n_col = 0;
+    double expected_neigh_count = 0;
+
+    // atom store
+    int nlocal_host = 0;           // host knowledge of nlocal (exact on 1 rank; refreshed after migration)
+    int64_t natoms_global = 0;
+    size_t cap = 0;                // capacity of per-atom arrays (locals + ghosts)
+    meso::DevBuf<double> x[3], v[3], f[3], xa[3], va[3];
+    meso::DevBuf<int> tag, type, mask, image, taga, typea, maska, imagea;
+    meso::DevBuf<float4> coord4, veloc4;
+    meso::DevBuf<double> virial, e_pair;      // [6][cap] SoA, [cap]
+    meso::DevBuf<double> mass_dev;            // [ntypes+1]
+    meso::DevBuf<float> coeff_sp;
+    meso::DevBuf<double> coeff_dp;
+    meso::DevBuf<double> staging;             // upload/download AoS staging
+    meso::DevBuf<int> istaging;
+
+    // reorder
+    meso::DevBuf<uint64_t> key;
+    meso::DevBuf<int> perm_from;
+    meso::SortScratch sort;
+    // ghosts
+    meso::DevBuf<int> ghost_root;             // per ghost g: local source index
+    meso::DevBuf<int> ghost_shift;            // per ghost g: packed shift code (2 bits per dim)
+    meso::DevBuf<int> tile_counts;            // compaction scratch
+    // cells
+    meso::DevBuf<uint64_t> cell_key;          // sort key (cell id) per atom
+    meso::DevBuf<int> cell_of, cell_atoms, cell_start;
+    meso::DevBuf<unsigned char> stencil;      // [ncell][32]
+    // neighbor list
+    meso::DevBuf<int> pair_count, pair_table;
+    size_t table_rows = 0;
+
+    // reductions
+    meso::DevBuf<double> partial;
+    double *h_result = nullptr;               // pinned, 16 doubles
+    meso::Counts *d_counts = nullptr;
+    meso::Counts *h_counts = nullptr;         // pinned mirror
+    bool f_cleared = true, v_cleared = true;
+    bool setup_done = false;
+
+    // timers
+    bool timers_on = false;
+    double t_ms[MESO_T_COUNT] = {0};
+    int64_t t_calls[MESO_T_COUNT] = {0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> t_pending;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace meso {
+
+#define MESO_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            return MESO_ECUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+// kernels are persistent grid-stride: one launch shape for any n (counts are device-side)
+inline int grid_for(const meso_ctx *ctx, int blocks_per_sm) { return ctx->sm_count * blocks_per_sm; }
+
+// ---- sort.cu
+// ---- reorder.cu
+int launch_reorder(meso_ctx *ctx);     // pbc + key + sort + gather(+pack)
+int launch_borders(meso_ctx *ctx);     // ghost creation (single rank: periodic images)
+int launch_forward(meso_ctx *ctx, bool full);     // per-step ghost refresh
+// ---- neighbor.cu
+int launch_setup_bins(meso_ctx *ctx);
+int launch_neighbor_build(meso_ctx *ctx);
+// ---- pair.cu
+int launch_pack(meso_ctx *ctx, int range);
+int launch_pair(meso_ctx *ctx, int range, int evflag, bool accumulate, bool fuse_final, int groupbit);
+// ---- integrate.cu
+int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack);
+int launch_final_integrate(meso_ctx *ctx, int groupbit);
+int launch_ke(meso_ctx *ctx, int groupbit, double *mv2, double *count);
+int launch_virial_sum(meso_ctx *ctx, double out7[7]);
+int launch_clear(meso_ctx *ctx, int range, int vflag);
+
+uint32_t seed_now(const meso_ctx *ctx);
+
+}  // namespace meso

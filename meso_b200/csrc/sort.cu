@@ -1,0 +1,176 @@
+// sort.cu -- stable LSD radix sort of (key, value) pairs with a DEVICE-SIDE element count.
+//
+// Replaces SortPlan<16,K,V> (UM/sort_meso.h:21-112, 350-429: 4-bit digits, 16 ballots per
+// element, 16 single-block scans, 3 launches per 4 bits).  Blackwell version: 8-bit digits,
+// warp-level MATCH.ANY ranking (one instruction instead of 16 ballots), each CTA owns a
+// contiguous span of the input so the digit histogram is [256][#CTAs] with #CTAs a multiple
+// of the SM count, and n is read from device memory so the caller never synchronises.
+// Stability (needed for "ascending atom index inside a cell", UM/neighbor_meso.cu:588, and
+// for tie order in MesoAtom::sort_local) comes from the warp-blocked element order.
+#include "internal.h"
+
+namespace meso {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 8;                              // per thread per chunk
+constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;      // 2048
+
+__device__ __forceinline__ void block_span(int n, int &beg, int &end)
+{
+    // contiguous span of whole chunks per CTA
+    int nchunks = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+    int per = (nchunks + gridDim.x - 1) / gridDim.x;
+    beg = min((int)blockIdx.x * per, nchunks) * SORT_CHUNK;
+    end = min(min(((int)blockIdx.x + 1) * per, nchunks) * SORT_CHUNK, n);
+    if (beg > n) beg = n;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const K *__restrict__ key, const int *__restrict__ d_n,
+                                                             uint32_t *__restrict__ hist, int shift)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int beg, end;
+    block_span(*d_n, beg, end);
+    for (int i = beg + threadIdx.x; i < end; i += SORT_THREADS) atomicAdd(&h[(uint32_t)(key[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    hist[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of m entries by one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan_exclusive(uint32_t *__restrict__ a, int m)
+{
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    // strip-mined so that loads stay coalesced: 1024 consecutive entries per iteration
+    for (int base = 0; base < m; base += 1024) {
+        int i = base + t;
+        uint32_t v = i < m ? a[i] : 0u, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t s = warp_sum[lane], z = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+                if (lane >= o) z += y;
+            }
+            warp_sum[lane] = z - s;   // exclusive
+        }
+        __syncthreads();
+        uint32_t carry = carry_s;
+        uint32_t excl = carry + warp_sum[w] + x - v;
+        if (i < m) a[i] = excl;
+        __syncthreads();
+        if (t == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const K *__restrict__ key_in, const int *__restrict__ val_in,
+                                                                K *__restrict__ key_out, int *__restrict__ val_out,
+                                                                const int *__restrict__ d_n, const uint32_t *__restrict__ hist,
+                                                                int shift)
+{
+    __shared__ uint32_t warp_hist[SORT_WARPS][256];
+    __shared__ uint32_t gbase[256], cur_base[256];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    gbase[t] = hist[t * gridDim.x + blockIdx.x];
+    int beg, end;
+    block_span(*d_n, beg, end);
+    for (int chunk = beg; chunk < end; chunk += SORT_CHUNK) {
+#pragma unroll
+        for (int ww = 0; ww < SORT_WARPS; ww++) warp_hist[ww][t] = 0;
+        __syncthreads();
+        K k[SORT_ITEMS];
+        int v[SORT_ITEMS];
+        uint32_t rank[SORT_ITEMS], dig[SORT_ITEMS];
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; r++) {
+            int i = chunk + w * (32 * SORT_ITEMS) + r * 32 + lane;     // warp-blocked: order = (warp, round, lane)
+            bool ok = i < end;
+            k[r] = ok ? key_in[i] : (K)0;
+            v[r] = ok ? val_in[i] : 0;
+            dig[r] = ok ? ((uint32_t)(k[r] >> shift) & 255u) : 0xFFFFFFFFu;
+            uint32_t peers = __match_any_sync(0xffffffffu, dig[r]);
+            int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader && ok) {
+                old = warp_hist[w][dig[r]];
+                warp_hist[w][dig[r]] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[r] = old + __popc(peers & lt);
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // thread t owns digit t: exclusive prefix over warps, then advance the CTA's global base
+            uint32_t run = 0;
+#pragma unroll
+            for (int ww = 0; ww < SORT_WARPS; ww++) {
+                uint32_t c = warp_hist[ww][t];
+                warp_hist[ww][t] = run;
+                run += c;
+            }
+            cur_base[t] = gbase[t];
+            gbase[t] += run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; r++) {
+            if (dig[r] != 0xFFFFFFFFu) {
+                uint32_t dst = cur_base[dig[r]] + warp_hist[w][dig[r]] + rank[r];
+                key_out[dst] = k[r];
+                val_out[dst] = v[r];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename K>
+static int sort_impl(meso_ctx *ctx, K *&key, int *&val, K *&key_alt, int *&val_alt, const int *d_n, size_t cap, int bits)
+{
+    const int nblk = grid_for(ctx, 4);
+    if (!ctx->sort.hist.reserve((size_t)256 * nblk)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
+    (void)cap;
+    for (int shift = 0; shift < bits; shift += 8) {
+        k_radix_hist<K><<<nblk, SORT_THREADS, 0, ctx->stream>>>(key, d_n, ctx->sort.hist.p, shift);
+        k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(ctx->sort.hist.p, 256 * nblk);
+        k_radix_scatter<K><<<nblk, SORT_THREADS, 0, ctx->stream>>>(key, val, key_alt, val_alt, d_n, ctx->sort.hist.p, shift);
+        K *tk = key; key = key_alt; key_alt = tk;
+        int *tv = val; val = val_alt; val_alt = tv;
+    }
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+// Sorts in place from the caller's point of view: on return `key`/`val` hold the sorted
+// pairs (the DevBuf pointers are swapped with the scratch buffers when the pass count is odd).
+int sort_pairs_u64(meso_ctx *ctx, DevBuf<uint64_t> &key, DevBuf<int> &val, const int *d_n, size_t cap, int bits)
+{
+    if (!ctx->sort.key_alt.reserve(key.cap) || !ctx->sort.val_alt.reserve(val.cap)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
+    uint64_t *k = key.p, *ka = ctx->sort.key_alt.p;
+    int *v = val.p, *va = ctx->sort.val_alt.p;
+    int rc = sort_impl<uint64_t>(ctx, k, v, ka, va, d_n, cap, bits);
+    if (k != key.p) {   // odd number of passes: swap buffer ownership (capacities are compatible by construction)
+        std::swap(key.p, ctx->sort.key_alt.p); std::swap(key.cap, ctx->sort.key_alt.cap);
+        std::swap(val.p, ctx->sort.val_alt.p); std::swap(val.cap, ctx->sort.val_alt.cap);
+    }
+    return rc;
+}
+
+}  // namespace meso

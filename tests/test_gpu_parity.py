@@ -1,0 +1,392 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * integer work -- sort keys, permutation, ghost order, cells, neighbor lists (sets AND order),
+    packed coordinates, TEA signatures -- bit-exact;
+  * dpd/meso (fp64) forces and the fp64 Gaussian/polynomials: 1e-12 relative;
+  * dpd/fast/meso (fp32) forces: 1e-5 relative (|dF| <= 1e-5 * max(|F_i|, mean|F|)).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from meso_b200 import lib, workload
+from meso_b200.engine import Meso, MesoError
+
+pytestmark = pytest.mark.gpu
+
+SP_TOL = 1e-5
+DP_TOL = 1e-12
+
+
+def make_pair(L, precision="sp", seed=419084618, ntypes=1, periodic=(1, 1, 1), coeff=None, mass=None, types=None,
+              x=None, v=None, skin=0.3, every=5, mask=None, tag=None, gamma_sigma=True):
+    dims = (L, L, L) if np.isscalar(L) else tuple(L)
+    if x is None:
+        x = workload.dpd_fluid(L if np.isscalar(L) else tuple(int(d) for d in dims))
+    if v is None:
+        v = workload.maxwell_velocities(len(x))
+    mass = [0.0] + [1.0] * ntypes if mass is None else mass
+    m = Meso(0)
+    m.box((0.0, 0.0, 0.0), dims, periodic)
+    m.masses(mass)
+    m.neighbor(skin, "bin")
+    m.neigh_modify(delay=0, every=every, check=False)
+    m.pair_style("dpd/fast/meso" if precision == "sp" else "dpd/meso", 1.0, seed)
+    if coeff is None:
+        g, s = (4.5, 3.0) if gamma_sigma else (0.0, 0.0)
+        m.pair_coeff("*", "*", 15, g, s, 1.0, 1.0)
+    else:
+        for (i, j, args) in coeff:
+            m.pair_coeff(i, j, *args)
+    m.timestep(0.005)
+    m.upload(x, v, tag=tag, type=types, mask=mask)
+    m._push_coeff()
+    w = oracle.World((0, 0, 0), dims, periodic=periodic, ntypes=ntypes, mass=mass, coeff=m._coeff.reshape(-1, 7),
+                     cut_max=float(m._coeff[..., 0].max()), skin=skin, every=every, seed=seed, dt=0.005,
+                     precision=0 if precision == "sp" else 1)
+    w.set_atoms(x, v, tag=tag, type=types, mask=mask)
+    return m, w
+
+
+def force_err(fg, fo):
+    d = np.linalg.norm(fg - fo, axis=1)
+    mag = np.linalg.norm(fo, axis=1)
+    scale = np.maximum(mag, mag.mean() if len(mag) else 1.0)
+    return float((d / scale).max()) if len(d) else 0.0
+
+
+def assert_state_identical(m, w, check_forces=True, tol=None, precision="sp"):
+    """everything the rebuild produces, bit for bit"""
+    cg, co = m.counts(), w.counts()
+    for k in ("nlocal", "nghost", "n_bulk", "n_border"):
+        assert cg[k] == co[k], (k, cg, co)
+    mg, bsg, big, ncol = m.bins()
+    mo, bso, bio = w.bins()
+    assert mg == mo and bsg == bso and big == bio and ncol == co["n_col"]
+    kg, pg = m.reorder()
+    ko, po = w.reorder()
+    assert np.array_equal(kg, ko), "sorted reorder keys differ"
+    assert np.array_equal(pg, po), "permutation differs"
+    ag, ao = m.download(), w.atoms()
+    nl = cg["nlocal"]
+    assert np.array_equal(ag["tag"], ao["tag"][:nl])
+    assert np.array_equal(ag["x"], ao["x"][:nl]) and np.array_equal(ag["v"], ao["v"][:nl])
+    assert np.array_equal(ag["type"], ao["type"][:nl]) and np.array_equal(ag["mask"], ao["mask"][:nl])
+    assert np.array_equal(ag["image"], ao["image"])
+    gg = m.ghosts()
+    assert np.array_equal(gg["tag"], ao["tag"][nl:]) and np.array_equal(gg["type"], ao["type"][nl:])
+    assert np.array_equal(gg["x"], ao["x"][nl:]) and np.array_equal(gg["v"], ao["v"][nl:])
+    sg, cag = m.cells()
+    so, cao = w.cells()
+    assert np.array_equal(sg, so) and np.array_equal(cag, cao)
+    rng = np.random.default_rng(0)
+    ncell = mg[0] * mg[1] * mg[2]
+    for c in list(rng.integers(0, ncell, 40)) + [0, ncell - 1]:
+        assert np.array_equal(m.stencil(int(c)), w.stencil(int(c)))
+    cntg, rowsg = m.neighbors()
+    cnto, rowso = w.neighbors()
+    assert np.array_equal(cntg, cnto), "neighbor counts differ"
+    mask = np.arange(rowso.shape[1])[None, :] < cnto[:, None]
+    assert np.array_equal(rowsg[mask], rowso[mask]), "neighbor lists differ (order included)"
+    tg, _ = m.pair_table()
+    to = w.neighbors_transposed()
+    valid = to >= 0
+    assert np.array_equal(tg[valid], to[valid]), "tile-transposed table differs"
+    c4g, v4g = m.packed()
+    c4o, v4o = w.packed()
+    assert np.array_equal(c4g.view(np.uint32), c4o.view(np.uint32)), "packed coordinates differ"
+    assert np.array_equal(v4g.view(np.uint32), v4o.view(np.uint32)), "packed velocities / TEA signatures differ"
+    if check_forces:
+        e = force_err(ag["f"], ao["f"])
+        assert e <= (tol if tol is not None else (SP_TOL if precision == "sp" else DP_TOL)), e
+
+
+# ------------------------------------------------------------------ A8 / A9
+def test_device_fp64_math_and_gaussians_match_oracle():
+    m = Meso(0)
+    L = oracle.lib()
+    rng = np.random.default_rng(7)
+    x = rng.uniform(1e-3, 50.0, 4096)
+    for name, dom in (("rsqrt", x), ("rcp", x), ("sqrtd", x), ("log2d_frac", rng.uniform(1, 2, 4096)),
+                      ("exp2d_frac", rng.uniform(0, 1, 4096)), ("sinpi", rng.uniform(0, 1, 4096)), ("cospi", rng.uniform(0, 1, 4096))):
+        got = m.eval_math(name, dom)
+        ref = np.array([getattr(L, "orc_" + name)(float(t)) for t in dom])
+        assert np.array_equal(got, ref), name
+    a, b = rng.uniform(1e-6, 1, 4096), rng.choice([0.25, 0.5, 1.0, 2.0, 1.37], 4096)
+    assert np.array_equal(m.eval_math("powd", a, b), np.array([L.orc_powd(float(p), float(q)) for p, q in zip(a, b)]))
+    u = np.concatenate([rng.integers(1, 2 ** 32, 4092, dtype=np.uint64).astype(np.uint32), np.array([1, 2, 3, 2 ** 32 - 1], np.uint32)])
+    assert np.array_equal(m.eval_log2u(u), np.array([L.orc_log2u(int(t)) for t in u]))
+    si = rng.integers(0, 2 ** 32, 20000, dtype=np.uint64).astype(np.uint32)
+    sj = rng.integers(0, 2 ** 32, 20000, dtype=np.uint64).astype(np.uint32)
+    sp, dp = m.eval_gaussian(si, sj)
+    rdp = np.array([L.orc_gaussian_dp(int(p), int(q)) for p, q in zip(si, sj)])
+    rsp = np.array([L.orc_gaussian_sp(int(p), int(q)) for p, q in zip(si, sj)], dtype=np.float32)
+    assert np.array_equal(dp, rdp), "fp64 Gaussian must be bit-exact (same FMA chains)"
+    assert np.abs(sp - rsp).max() <= 4e-6, np.abs(sp - rsp).max()     # libdevice vs libm last-ulp differences
+    # degenerate inputs: v1 == 0 (log2f(0) = -inf) must clamp to +-4, never NaN
+    assert np.isfinite(sp).all() and np.abs(sp).max() <= 4.0 and np.abs(dp).max() <= 4.0
+    m.close()
+
+
+# ------------------------------------------------------------------ rebuild + forces at setup
+@pytest.mark.parametrize("precision", ["sp", "dp"])
+def test_setup_parity_small(precision):
+    m, w = make_pair(10, precision)
+    m.setup()
+    w.setup()
+    assert_state_identical(m, w, precision=precision)
+    assert abs(m.temperature() - w.temperature()) < 1e-12
+    m.close()
+
+
+@pytest.mark.parametrize("precision", ["sp", "dp"])
+def test_setup_parity_case25(precision):
+    """BASELINE.json configs[0]: the 25^3 rho=4 DPD fluid (62,500 particles)."""
+    m, w = make_pair(25, precision)
+    m.setup()
+    w.setup()
+    assert_state_identical(m, w, precision=precision)
+    c = m.counts()
+    assert c["nlocal"] == 62500 and m.bins()[0] == [21, 21, 21] and m.bins()[3] == 160
+    m.close()
+
+
+def test_conservative_only_forces():
+    """gamma = sigma = 0: the part that is also pinned against stock LAMMPS pair_style dpd (tests/golden)."""
+    for precision in ("sp", "dp"):
+        m, w = make_pair(8, precision, gamma_sigma=False)
+        m.setup(); w.setup()
+        e = force_err(m.download()["f"], w.atoms()["f"])
+        assert e <= (SP_TOL if precision == "sp" else DP_TOL), e
+        m.close()
+
+
+def test_energy_virial():
+    for precision in ("sp", "dp"):
+        m, w = make_pair(8, precision)
+        m.setup(eflag=1, vflag=1); w.setup(eflag=1, vflag=1)
+        vg, eg = m.per_atom_virial()
+        vo, eo = w.virial()
+        tol = 2e-5 if precision == "sp" else 1e-11
+        assert np.abs(vg - vo).max() <= tol * max(1.0, np.abs(vo).max())
+        assert np.abs(eg - eo).max() <= tol * max(1.0, np.abs(eo).max())
+        tot, etot = m.virial()
+        assert np.allclose(tot, vo.sum(0), rtol=1e-9, atol=1e-6) and abs(etot - eo.sum()) <= 1e-9 * abs(eo.sum()) + 1e-6
+        m.close()
+
+
+# ------------------------------------------------------------------ edge cases
+def test_two_types_masses_ragged_box_and_group_mask():
+    rng = np.random.default_rng(3)
+    L = (9, 7, 12)
+    x = workload.dpd_fluid(L, seed=5)
+    n = len(x)
+    types = rng.integers(1, 3, n).astype(np.int32)
+    mask = np.where(rng.random(n) < 0.9, 1, 2).astype(np.int32)       # 10 % of the atoms outside group bit 1
+    tag = (rng.permutation(n) * 3 + 7).astype(np.int32)               # non-contiguous, shuffled tags
+    coeff = [(1, 1, (15, 4.5, 3.0, 1.0, 1.0)), (1, 2, (20, 3.0, 2.449489742783178, 0.5, 0.9)), (2, 2, (25, 6.0, 3.4641016151377544, 2.0, 0.8))]
+    for precision in ("sp", "dp"):
+        m, w = make_pair(L, precision, ntypes=2, coeff=coeff, mass=[0.0, 1.0, 2.5], types=types, x=x, mask=mask, tag=tag)
+        m.setup(); w.setup()
+        assert_state_identical(m, w, precision=precision, tol=2e-5 if precision == "sp" else 1e-11)
+        m.close()
+
+
+def test_non_periodic_dimension_and_tiny_box():
+    x = workload.dpd_fluid((6, 5, 4), seed=9)
+    m, w = make_pair((6, 5, 4), "dp", periodic=(1, 0, 1), x=x)
+    m.setup(); w.setup()
+    assert_state_identical(m, w, precision="dp")
+    m.close()
+    # 4^3: three inner cells per dimension, every atom is a border atom, lo and hi slabs overlap
+    m, w = make_pair(4, "dp")
+    m.setup(); w.setup()
+    assert w.counts()["n_bulk"] == 0
+    assert_state_identical(m, w, precision="dp")
+    m.close()
+
+
+def test_atoms_on_cell_and_box_boundaries():
+    x = workload.dpd_fluid(6, seed=2)
+    x[:50] = np.round(x[:50])            # exactly on unit-lattice planes, including 0.0
+    x[50:60, 0] = 6.0                    # exactly boxhi: wraps to 0 with an image flag
+    x[60:70, 1] = -0.25                  # outside: wraps up
+    x[70:80, 2] = 6.0 + 1e-12
+    x[80:90] = x[90:100] + 1e-7          # near-coincident pairs (rsq ~ 1e-14 >= EPSILON_SQ) -> huge but finite forces
+    m, w = make_pair(6, "dp", x=x)
+    m.setup(); w.setup()
+    assert_state_identical(m, w, precision="dp", tol=1e-11)
+    m.close()
+
+
+def test_empty_and_single_atom():
+    for n in (0, 1):
+        x = np.full((n, 3), 2.5)
+        m, w = make_pair(5, "sp", x=x, v=np.zeros((n, 3)))
+        m.setup(); w.setup()
+        c = m.counts()
+        assert c["nlocal"] == n and c["nghost"] == w.counts()["nghost"]
+        if n:
+            assert np.array_equal(m.pair_count(), w.neighbors()[0])
+            assert np.abs(m.download()["f"]).max() == 0.0
+        m.run(3)
+        m.sync()
+        m.close()
+
+
+def test_errors():
+    m = Meso(0)
+    with pytest.raises(MesoError, match="Illegal pair_style command"):
+        m.pair_style("dpd/fast/meso", 1.0)
+    m.box((0, 0, 0), (5, 5, 5))
+    m.masses([0.0, 1.0, 1.0])
+    m.pair_style("dpd/fast/meso", 1.0, 1)
+    with pytest.raises(MesoError, match="Incorrect args for pair coefficients"):
+        m.pair_coeff(1, 1, 15, 4.5)
+    m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0)
+    m.upload(workload.dpd_fluid(5))
+    with pytest.raises(MesoError, match="All pair coeffs are not set"):
+        m.setup()
+    m.close()
+    m = Meso(0)
+    m.box((0, 0, 0), (1.2, 5, 5))
+    m.masses([0.0, 1.0])
+    m.pair_style("dpd/fast/meso", 1.0, 1)
+    m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0)
+    m.upload(np.random.default_rng(0).uniform(0, 1, (100, 3)) * np.array([1.2, 5, 5]))
+    with pytest.raises(MesoError, match="thinner than the ghost cutoff"):
+        m.setup()
+    m.close()
+
+
+# ------------------------------------------------------------------ time stepping
+def test_dp_trajectory_lockstep_12_steps():
+    """fp64 path stays locked to the oracle across two rebuilds: x, v to 1e-10, lists and signatures bit-exact."""
+    m, w = make_pair(10, "dp")
+    m.setup(); w.setup()
+    m.run(12); w.run(12)
+    assert m.ntimestep == 12 and w.ntimestep == 12
+    ag, ao = m.download(), w.atoms()
+    nl = ao["nlocal"]
+    assert np.array_equal(ag["tag"], ao["tag"][:nl])
+    assert np.abs(ag["x"] - ao["x"][:nl]).max() < 1e-10 and np.abs(ag["v"] - ao["v"][:nl]).max() < 1e-10
+    assert force_err(ag["f"], ao["f"]) < 1e-10
+    cntg, rowsg = m.neighbors()
+    cnto, rowso = w.neighbors()
+    assert np.array_equal(cntg, cnto)
+    mask = np.arange(rowso.shape[1])[None, :] < cnto[:, None]
+    assert np.array_equal(rowsg[mask], rowso[mask])
+    c4g, v4g = m.packed()
+    c4o, v4o = w.packed()
+    assert np.array_equal(v4g.view(np.uint32)[:, 3], v4o.view(np.uint32)[:, 3]), "signatures drifted"
+    assert abs(m.temperature() - w.temperature()) < 1e-10
+    m.close()
+
+
+def test_phase_api_equals_fused_run():
+    """ModifiedVerlet::run spelled phase by phase (bulk/border split, separate clears) == meso_run, bit for bit."""
+    B, O, LOC = lib.MESO_BULK, lib.MESO_BORDER, lib.MESO_LOCAL
+    for precision in ("sp", "dp"):
+        a, _ = make_pair(8, precision)
+        b, _ = make_pair(8, precision)
+        a.setup(); b.setup()
+        a.run(11)
+        for _ in range(11):
+            b.ntimestep = b.ntimestep + 1
+            b.initial_integrate()
+            if b.neighbor_decide():
+                b.rebuild()
+                b.force_clear(LOC)
+                b.pair_compute(B)
+            else:
+                b.force_clear(B)
+                b.pair_compute(B)
+                b.forward_comm()
+                b.force_clear(O)
+            b.pair_compute(O)
+            b.final_integrate()
+        da, db = a.download(), b.download()
+        for k in ("x", "v", "f", "tag", "image"):
+            assert np.array_equal(da[k], db[k]), (precision, k)
+        a.close(); b.close()
+
+
+def test_sp_run_then_oracle_force_from_device_state():
+    """fp32 trajectories cannot be locked (the RNG keys on fp32 velocity mantissa bits), so the
+    multi-step fp32 path is checked by recomputing the LAST force on the oracle from the device's own state."""
+    m, w = make_pair(10, "sp")
+    m.setup()
+    nsteps = 13
+    m.run(nsteps)
+    d = m.download()
+    dtfm = 0.5 * 0.005
+    v_half = d["v"] - dtfm * d["f"]                     # undo the fused final half-kick
+    w.set_atoms(d["x"], v_half, tag=d["tag"], image=d["image"])
+    w.ntimestep = nsteps
+    w.rebuild(); w.force_clear(); w.pair_compute()
+    ao = w.atoms()
+    fo = np.empty_like(d["f"])
+    fo[ao["tag"][:ao["nlocal"]] - 1] = ao["f"]
+    fg = np.empty_like(d["f"])
+    fg[d["tag"] - 1] = d["f"]
+    # a handful of atoms may see a different RNG draw if (float)v_half rounds differently: allow 1e-4 of them
+    derr = np.linalg.norm(fg - fo, axis=1) / np.maximum(np.linalg.norm(fo, axis=1), np.linalg.norm(fo, axis=1).mean())
+    assert (derr > SP_TOL).mean() <= 1e-4, (derr > SP_TOL).sum()
+    m.close()
+
+
+def test_thermostat_equilibrium_statistics():
+    """sigma^2 = 2 gamma kT: the device trajectory thermalises at T = 1 (stock LAMMPS: 1.000 +- 0.005)."""
+    m, _ = make_pair(16, "sp")
+    m.setup()
+    m.run(600)
+    ts = []
+    for _ in range(20):
+        m.run(20)
+        ts.append(m.temperature())
+    assert abs(np.mean(ts) - 1.0) < 0.02, np.mean(ts)
+    d = m.download(("x", "v"))
+    assert np.abs((d["v"]).sum(0)).max() < 1e-6 * len(d["v"])      # momentum conserved (pairwise antisymmetric forces)
+    assert d["x"].min() >= -1.0 and d["x"].max() <= 17.0
+    m.close()
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs[1], [2])
+@pytest.mark.parametrize("L,precision", [(64, "sp"), (48, "dp")])
+def test_full_size_properties(L, precision):
+    from meso_b200.engine import dpd_fluid_deck
+    m = dpd_fluid_deck(L, precision)
+    m.setup()
+    c = m.counts()
+    assert c["nlocal"] == 4 * L ** 3
+    k, p = m.reorder()
+    assert (np.diff(k.astype(np.int64)) >= 0).all(), "reorder keys not sorted"
+    assert np.array_equal(np.sort(p), np.arange(len(p))), "permutation is not a permutation"
+    cnt = m.pair_count()
+    assert abs(cnt.mean() - 4 * 4.0 / 3.0 * np.pi * 1.3 ** 3) < 0.5      # 36.8 stored neighbors per atom
+    d = m.download(("f", "tag"))
+    assert np.abs(d["f"].sum(0)).max() < (2e-2 if precision == "sp" else 1e-8) * np.sqrt(len(cnt))   # sum F = 0
+    s, a = m.cells()
+    assert s[-1] == c["nlocal"] + c["nghost"] and (np.diff(s) >= 0).all()
+    assert np.array_equal(np.sort(a), np.arange(len(a)))
+    # neighbor symmetry on a sample: j in N(i) <=> i in N(j) (by tag, ghosts map to their owners)
+    t, n_col = m.pair_table()
+    g = m.ghosts()
+    tags_all = np.concatenate([d["tag"], g["tag"]])
+    tag2loc = np.empty(len(d["tag"]) + 1, np.int64)
+    tag2loc[d["tag"]] = np.arange(len(d["tag"]))
+    rng = np.random.default_rng(1)
+
+    def row(i):
+        ks = np.arange(cnt[i])
+        return t[((i & ~31) + (ks & 31)).astype(np.int64) * n_col + (ks >> 5) * 32 + (i & 31)]
+
+    for i in rng.integers(0, c["nlocal"], 200):
+        for j in row(int(i))[:8]:
+            jl = tag2loc[tags_all[j]]
+            assert d["tag"][i] in tags_all[row(int(jl))]
+    m.run(10)
+    T = m.temperature()
+    assert 0.5 < T < 2.5
+    m.close()
