@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the DPD time step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...   # stock CPU LAMMPS of the reference tree
+
+A "step" is one DPD time step (velocity-Verlet halves + halo refresh + pair force; every 5th step also
+wrap + reorder + ghost rebuild + neighbor-list build) of the example/simple sp.run deck on a synthetic
+rho = 4 fluid.  N = 1: case 64 (1,048,576 particles, BASELINE configs[1]).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CASE = 64                      # box edge of the N = 1 workload
+RHO = 4
+N_BAR_FALLBACK = 35.84         # stored neighbors per particle (measured; stock LAMMPS: 17.92 half-list)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                 stdout=subprocess.PIPE, text=True)
+        except Exception:
+            return
+        self.p = p
+        for line in p.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+            if self.stop_flag:
+                break
+        p.kill()
+
+    def summary(self):
+        self.stop_flag = True
+        time.sleep(0.15)
+        try:
+            self.p.kill()
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def procgrid_for(n):
+    """LAMMPS ProcMap: the factorisation with the smallest brick surface, first found wins (cubic box)."""
+    best, bs = (1, 1, n), None
+    for px in range(1, n + 1):
+        if n % px:
+            continue
+        for py in range(1, n // px + 1):
+            if (n // px) % py:
+                continue
+            pz = n // px // py
+            s = 1.0 / (px * py) + 1.0 / (px * pz) + 1.0 / (py * pz)
+            if bs is None or s < bs - 1e-12:
+                best, bs = (px, py, pz), s
+    return best
+
+
+# ---------------------------------------------------------------------------------------- reference arm
+def reference_arm(args):
+    """Stock LAMMPS pair_style dpd + fix nve on the box's host cores: 1 core, because the image
+    has no MPI and the 2013 tree has no threading on this path."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from meso_b200 import workload
+    lmp = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
+    L = args.case
+    n = RHO * L ** 3
+    sample_steps = max(1, min(args.steps, args.ref_steps))
+    warm = max(1, min(args.warmup, 3))
+    if os.path.exists(lmp):
+        with tempfile.TemporaryDirectory() as d:
+            workload.write_data(os.path.join(d, "c.data"), workload.dpd_fluid(L), L)
+            deck = ("dimension 3\nunits lj\natom_style atomic\ncommunicate single vel yes\nneighbor 0.3 bin\n"
+                    "neigh_modify delay 0 every 5 check no\nread_data c.data\npair_style dpd 1.0 1.0 419084618\n"
+                    "pair_coeff 1 1 15 4.5 1.0\nvelocity all create 1.0 788662042 loop all\nfix 3 all nve\n"
+                    "thermo_style custom step temp press cpu spcpu\nthermo 100\ntimestep 0.005\nrun %d\nrun %d\n" % (warm, sample_steps))
+            open(os.path.join(d, "in.ref"), "w").write(deck)
+            out = subprocess.run([lmp, "-meso", "off", "-in", "in.ref", "-log", "none"], cwd=d, capture_output=True, text=True)
+            loops = [float(s.split()[3]) for s in out.stdout.split("\n") if s.startswith("Loop time of")]
+            if out.returncode != 0 or len(loops) < 2:
+                print(json.dumps({"impl": "reference", "unavailable": "stock LAMMPS run failed: " + (out.stderr or out.stdout)[-200:].replace("\n", " ")}))
+                return
+            t = loops[-1]
+        kind, what = "reference", "stock LAMMPS 30Sep2013 pair_style dpd + fix nve (oracle/_ref/lmp_serial), serial"
+    else:
+        import oracle
+        w = oracle.World((0, 0, 0), (L, L, L))
+        w.set_atoms(workload.dpd_fluid(L), workload.maxwell_velocities(n))
+        w.setup()
+        w.run(warm)
+        t0 = time.perf_counter()
+        w.run(sample_steps)
+        t = time.perf_counter() - t0
+        kind, what = "port", "oracle/meso_oracle.c (scalar C restatement of the MESO algorithm)"
+    value = n * sample_steps / t
+    line = {"impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / sample_steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "example/simple DPD fluid case=%d (%d particles, rho=4, rc=1, skin 0.3, rebuild every 5)" % (L, n),
+                       "what": what},
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": kind,
+                             "sample": "%d time steps of the case=%d box after %d warm-up steps (of --steps %d)" % (sample_steps, L, warm, args.steps)},
+            "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(L, budget_s=20.0):
+    """bounded CPU sample for the cpu_baseline key: stock LAMMPS if it travelled, else the oracle port"""
+    from meso_b200 import workload
+    lmp = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
+    n = RHO * L ** 3
+    steps = 10
+    if os.path.exists(lmp):
+        with tempfile.TemporaryDirectory() as d:
+            workload.write_data(os.path.join(d, "c.data"), workload.dpd_fluid(L), L)
+            deck = ("dimension 3\nunits lj\natom_style atomic\ncommunicate single vel yes\nneighbor 0.3 bin\n"
+                    "neigh_modify delay 0 every 5 check no\nread_data c.data\npair_style dpd 1.0 1.0 419084618\n"
+                    "pair_coeff 1 1 15 4.5 1.0\nvelocity all create 1.0 788662042 loop all\nfix 3 all nve\n"
+                    "thermo 100\ntimestep 0.005\nrun 2\nrun %d\n" % steps)
+            open(os.path.join(d, "in.ref"), "w").write(deck)
+            out = subprocess.run([lmp, "-meso", "off", "-in", "in.ref", "-log", "none"], cwd=d, capture_output=True, text=True)
+            loops = [float(s.split()[3]) for s in out.stdout.split("\n") if s.startswith("Loop time of")]
+        if len(loops) >= 2:
+            return {"value": n * steps / loops[-1], "unit": "particle-steps/s", "cores": 1, "kind": "reference",
+                    "sample": "stock LAMMPS pair_style dpd + fix nve, %d steps of the same case=%d box (after 2 warm-up steps), 1 core (no MPI in the image)" % (steps, L)}
+    import oracle
+    w = oracle.World((0, 0, 0), (L, L, L))
+    w.set_atoms(workload.dpd_fluid(L), workload.maxwell_velocities(n))
+    w.setup()
+    steps = 5
+    t0 = time.perf_counter()
+    w.run(steps)
+    t = time.perf_counter() - t0
+    return {"value": n * steps / t, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": "oracle C port, %d steps of the same case=%d box" % (steps, L)}
+
+
+# ---------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="meso_b200", choices=["meso_b200", "reference"])
+    ap.add_argument("--case", type=int, default=CASE, help="box edge per GPU brick (64 = BASELINE configs[1])")
+    ap.add_argument("--precision", default="sp", choices=["sp", "dp"])
+    ap.add_argument("--ref-steps", type=int, default=20, help="time steps the reference arm actually runs (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--thermo", type=int, default=100, help="e2e leg: thermo/output interval (deck: 100)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from meso_b200 import workload
+    from meso_b200.engine import Meso
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # weak scaling: every rank owns a case^3 brick of a (px*case, py*case, pz*case) periodic box
+    grid = procgrid_for(world)
+    L = args.case
+    dims = tuple(g * L for g in grid)
+    nloc = RHO * L ** 3
+    nglob = nloc * world
+    loc = (rank // (grid[1] * grid[2]), (rank // grid[2]) % grid[1], rank % grid[2])
+    x = workload.dpd_fluid(L, seed=workload.DEFAULT_SEED + rank) + np.array([loc[0] * L, loc[1] * L, loc[2] * L], dtype=np.float64)
+    v = workload.maxwell_velocities(nloc, seed=788662042 + rank)
+    tag = (np.arange(nloc, dtype=np.int64) + 1 + rank * nloc).astype(np.int32)
+
+    def deck():
+        m = Meso(local_rank)
+        m.box((0.0, 0.0, 0.0), dims)
+        if world > 1:
+            ids = [Meso.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            m.decomposition(rank, grid, ids[0])
+        m.masses([0.0, 1.0])
+        m.neighbor(0.3, "bin")
+        m.neigh_modify(delay=0, every=5, check=False)
+        m.pair_style("dpd/fast/meso" if args.precision == "sp" else "dpd/meso", 1.0, 419084618)
+        m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
+        m.timestep(0.005)
+        return m
+
+    xp = torch.from_numpy(x).pin_memory()
+    vp = torch.from_numpy(v).pin_memory()
+    tp = torch.from_numpy(tag).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: `value`
+    m = deck()
+    m.upload(xp.numpy(), vp.numpy(), tag=tp.numpy())
+    m.setup()
+    stream = torch.cuda.ExternalStream(m.stream())
+    m.run(max(args.warmup, 3))
+    m.sync()
+    n_bar = float(m.pair_count().mean())
+    m.timers(enable=True, reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    m.run(args.steps)
+    e1.record(stream)
+    m.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    tm = m.timers(enable=False)
+    T_end = m.temperature()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = nglob * args.steps / (ms * 1e-3)
+    rebuilds = tm["neigh"][1]
+    launches = tm["integrate"][1] + tm["forward"][1] + tm["pair"][1] + rebuilds * KERNELS_PER_REBUILD(m)
+
+    # ---- roofline of the dominant kernel (the pair-force kernel)
+    peak, peak_src = peaks()
+    pair_ms, pair_calls = tm["pair"]
+    b_force = 4.0 * n_bar + 32.0 + 24.0                        # algorithmic bytes per particle per force evaluation
+    achieved = b_force * nloc / (pair_ms / max(pair_calls, 1) * 1e-3) / 1e9
+    traffic = None
+    tp_path = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
+    if os.path.exists(tp_path):
+        traffic = json.load(open(tp_path)).get("dram_bytes_per_launch_%s" % args.precision)
+    roofline = {"bound": "hbm", "kernel": "k_dpd_%s<0> (+fused final_integrate)" % args.precision, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": b_force, "particles_per_launch": nloc,
+                "avg_launch_ms": pair_ms / max(pair_calls, 1), "share_of_step": pair_ms / ms,
+                "note": "ALU-limited by construction (SURVEY.md s7.3): ~14 lane-ops/B vs a ridge of ~4.4"}
+    phases = {k: {"ms_total": round(v[0], 3), "calls": int(v[1])} for k, v in tm.items()}
+
+    # ---- end-to-end leg through the C ABI with HOST buffers: the deck's `run K` with `thermo 100`
+    # upload of all atoms (H2D from pinned memory), setup, K steps, temp/meso + transfer_pre_output (D2H x,v,f,tag) every `thermo` steps
+    m.close()
+    m = deck()
+    out = {k: torch.empty((nloc, 3), dtype=torch.float64).pin_memory() for k in ("x", "v", "f")}
+    otag = torch.empty(nloc, dtype=torch.int32).pin_memory()
+    import ctypes as C
+    vp_ = lambda t_: C.c_void_p(t_.data_ptr())
+
+    def run_deck(nsteps):
+        m.upload(xp.numpy(), vp.numpy(), tag=tp.numpy())
+        m.ntimestep = 0
+        m.setup()
+        done, d2h, temps = 0, 0, []
+        while done < nsteps:
+            chunk = min(args.thermo, nsteps - done)
+            m.run(chunk)
+            done += chunk
+            temps.append(m.temperature())
+            m._chk(m.L.meso_atoms_download(m.h, nloc, vp_(out["x"]), vp_(out["v"]), vp_(out["f"]), vp_(otag), None, None, None))
+            d2h += nloc * (72 + 4) + 16
+        return d2h, temps
+
+    run_deck(min(args.steps, 2 * args.thermo))          # warm-up (allocations, first-touch)
+    barrier()
+    t0 = time.perf_counter()
+    d2h, temps = run_deck(args.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    h2d = nloc * (48 + 4)
+    e2e = {"value": nglob * args.steps / wall, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / args.steps,
+           "d2h_bytes_per_step": d2h / args.steps,
+           "what": "C-ABI deck run: meso_atoms_upload (pinned host AoS) + meso_setup + %d x meso_run(%d) each followed by temp/meso and "
+                   "meso_atoms_download of x,v,f,tag (transfer_pre_output), wall clock incl. all copies" % (-(-args.steps // args.thermo), args.thermo)}
+    m.close()
+
+    line = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "sp" else "f64", "data": "synthetic",
+            "config": {"workload": "example/simple %s.run case=%d per GPU: DPD fluid rho=4, %d particles/GPU, box %dx%dx%d, rc=1, skin 0.3, "
+                                   "rebuild every 5 steps, dt 0.005" % (args.precision, L, nloc, *dims),
+                       "procgrid": list(grid), "pair_style": "dpd/fast/meso" if args.precision == "sp" else "dpd/meso",
+                       "l2": "per-step working set (~0.8 GB at 1M particles) exceeds the 126 MB L2; no explicit flush",
+                       "mean_neighbors": n_bar, "temperature_end": T_end},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "phases": phases, "clocks": clocks}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(L)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def KERNELS_PER_REBUILD(m):
+    # reorder: key + 3/pass sort + gather; borders: 1 + 4/dim; neighbor: cell id + 3/pass sort + bounds + build
+    mm = m.bins()[0]
+    import math
+    l1 = 3 * int(math.floor(math.log2(max(mm) * 2.0)))
+    p1 = -(-(1 + l1 + 12) // 8)
+    ncell = mm[0] * mm[1] * mm[2]
+    p2 = -(-max(1, math.ceil(math.log2(ncell))) // 8)
+    return 2 + 3 * p1 + 1 + 12 + 3 + 3 * p2
+
+
+if __name__ == "__main__":
+    main()

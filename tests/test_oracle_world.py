@@ -1,0 +1,166 @@
+"""CPU tests of the oracle's whole-step restatement: pinned against stock LAMMPS (golden fixture made by
+tests/golden/make_lammps_golden.py with the reference tree's own pair_style dpd), and checked for the
+size-independent properties of the domain (momentum conservation, decomposition independence of the
+neighbor SETS, periodic images, tile-transposed layout)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from meso_b200 import workload
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "stock_dpd_conservative_L8.npz"))
+
+
+def world(L, precision=0, procgrid=(1, 1, 1), gamma_sigma=True, x=None, v=None, **kw):
+    x = workload.dpd_fluid(L) if x is None else x
+    v = workload.maxwell_velocities(len(x)) if v is None else v
+    g, s = (4.5, 3.0) if gamma_sigma else (0.0, 0.0)
+    dims = (L, L, L) if np.isscalar(L) else L
+    w = oracle.World((0, 0, 0), dims, procgrid=procgrid, precision=precision, coeff=oracle.default_coeff(1, 15.0, g, s), **kw)
+    w.set_atoms(x, v)
+    return w
+
+
+def by_tag(w, key="f"):
+    n = sum(w.counts(r)["nlocal"] for r in range(w.nranks))
+    out = np.zeros((n, 3))
+    for r in range(w.nranks):
+        a = w.atoms(r)
+        out[a["tag"][:a["nlocal"]] - 1] = a[key][:a["nlocal"]]
+    return out
+
+
+@pytest.mark.parametrize("precision,tol", [(1, 1e-5), (0, 1e-5)])
+def test_conservative_forces_match_stock_lammps(precision, tol):
+    """gamma = sigma = 0 against stock pair_style dpd.  Stock LAMMPS works on fp64 coordinates, the MESO
+    styles on fl32(x - centre), so even the fp64 style is limited by the packing (~1e-6)."""
+    w = world(int(GOLD["L"]), precision, gamma_sigma=False)
+    w.setup(eflag=1, vflag=1)
+    f = by_tag(w)
+    ref = GOLD["f"]
+    mag = np.linalg.norm(ref, axis=1)
+    err = (np.linalg.norm(f - ref, axis=1) / np.maximum(mag, mag.mean())).max()
+    assert err <= tol, err
+    vir, e = w.virial()
+    n = len(ref)
+    assert abs(e.sum() / n - float(GOLD["pe"])) < 1e-5 * float(GOLD["pe"])
+    # P = (N kT + sum_i tr(W_i)) / (3V); thermo `press` at run 0 with the T = 1 velocities is not stored, so
+    # check the virial part only: P_virial = sum(vxx+vyy+vzz) / (3 V)
+    L = float(GOLD["L"])
+    p_vir = vir[:, :3].sum() / (3 * L ** 3)
+    assert abs(p_vir - float(GOLD["press"])) < 1e-4 * float(GOLD["press"])   # golden run had v = 0: kinetic part is 0
+
+
+def test_momentum_conservation_and_symmetry():
+    for precision in (0, 1):
+        w = world(8, precision)
+        w.setup()
+        f = by_tag(w)
+        # pairs across a periodic face see fl32-rounded image coordinates: antisymmetry holds to ~1e-7 per pair
+        assert np.abs(f.sum(0)).max() < 5e-3
+        cnt, rows = w.neighbors()
+        a = w.atoms()
+        tags = a["tag"]
+        sets = [set(tags[rows[i, :cnt[i]]]) for i in range(a["nlocal"])]
+        loc = {int(t): i for i, t in enumerate(tags[:a["nlocal"]])}
+        for i in range(0, a["nlocal"], 7):
+            for t in sets[i]:
+                assert int(tags[i]) in sets[loc[int(t)]]
+
+
+def test_neighbor_order_core_then_reversed_skin():
+    w = world(6, 1)
+    w.setup()
+    cnt, rows = w.neighbors()
+    c4, _ = w.packed()
+    for i in range(0, len(cnt), 11):
+        j = rows[i, :cnt[i]]
+        d = c4[i, :3] - c4[j, :3]
+        r2 = d[:, 2] * d[:, 2] + (d[:, 1] * d[:, 1] + d[:, 0] * d[:, 0])
+        core = r2 <= 1.0
+        ncore = int(core.sum())
+        assert core[:ncore].all() and not core[ncore:].any()
+        assert (r2 <= np.float32(1.69) * (1 + 1e-6)).all()
+
+
+def test_transposed_layout_roundtrip():
+    w = world(6, 0)
+    w.setup()
+    cnt, rows = w.neighbors()
+    t = w.neighbors_transposed()
+    n_col = w.counts()["n_col"]
+    for i in (0, 1, 31, 32, 33, len(cnt) - 1):
+        for k in range(cnt[i]):
+            assert t[((i & ~31) + (k & 31)) * n_col + (k >> 5) * 32 + (i & 31)] == rows[i, k]
+
+
+@pytest.mark.parametrize("procgrid", [(2, 1, 1), (1, 2, 2), (2, 2, 2), (3, 1, 1)])
+def test_decomposition_independent_neighbor_sets_and_forces(procgrid):
+    """bit-exactness of the ordered list holds per decomposition (the packing centre moves); the neighbor SETS
+    by tag and the fp64 forces must not depend on the processor grid."""
+    L = 12
+    x, v = workload.dpd_fluid(L), workload.maxwell_velocities(4 * L ** 3)
+    w1 = world(L, 1, x=x, v=v)
+    wn = world(L, 1, procgrid=procgrid, x=x, v=v)
+    w1.setup(); wn.setup()
+
+    def tagsets(w):
+        out = {}
+        for r in range(w.nranks):
+            a = w.atoms(r)
+            cnt, rows = w.neighbors(r)
+            for i in range(a["nlocal"]):
+                out[int(a["tag"][i])] = frozenset(a["tag"][rows[i, :cnt[i]]].tolist())
+        return out
+
+    s1, sn = tagsets(w1), tagsets(wn)
+    diff = [t for t in s1 if s1[t] != sn[t]]
+    # membership is decided on fl32(x - centre): a pair within 1 ulp of r_n may flip with the centre
+    assert len(diff) <= 2, len(diff)
+    f1, fn = by_tag(w1), by_tag(wn)
+    mag = np.linalg.norm(f1, axis=1)
+    assert (np.linalg.norm(f1 - fn, axis=1) / np.maximum(mag, mag.mean())).max() < 5e-5
+    assert sum(wn.counts(r)["nlocal"] for r in range(wn.nranks)) == 4 * L ** 3
+    w1.run(7); wn.run(7)        # crosses a rebuild with migration
+    assert sum(wn.counts(r)["nlocal"] for r in range(wn.nranks)) == 4 * L ** 3
+    assert abs(w1.temperature() - wn.temperature()) < 0.05
+
+
+def test_ghosts_are_periodic_images():
+    L = 7
+    w = world(L, 0)
+    w.setup()
+    a = w.atoms()
+    nl = a["nlocal"]
+    pos = {int(t): a["x"][i] for i, t in enumerate(a["tag"][:nl])}
+    for g in range(nl, nl + a["nghost"], 5):
+        d = a["x"][g] - pos[int(a["tag"][g])]
+        k = np.round(d / L)
+        assert np.all(np.isin(k, (-1, 0, 1))) and np.array_equal(a["x"][g], pos[int(a["tag"][g])] + k * L)
+        assert np.any(d != 0)
+    c = w.counts()
+    assert c["n_bulk"] + c["n_border"] == nl
+    # every atom within the ghost cutoff of a face is a border atom and comes after all bulk atoms
+    xl = a["x"][:nl]
+    near = ((xl <= 1.3) | (xl >= L - 1.3)).any(1)
+    assert not near[:c["n_bulk"]].any() and near[c["n_bulk"]:].all()
+
+
+def test_nve_energy_drift_conservative():
+    """velocity-Verlet with gamma = sigma = 0 conserves KE + PE"""
+    x = workload.dpd_fluid(6, seed=11)
+    w = world(6, 1, gamma_sigma=False, x=x, v=workload.maxwell_velocities(len(x), 0.1))
+
+    def etot():
+        w.force_clear(); w.pair_compute(1, 1)
+        _, e = w.virial()
+        a = w.atoms()
+        return e.sum() + 0.5 * (a["v"][:a["nlocal"]] ** 2).sum()
+
+    w.setup(1, 1)
+    e0 = etot()
+    w.run(40, 1, 1)
+    e1 = etot()
+    assert abs(e1 - e0) < 2e-3 * abs(e0), (e0, e1)
