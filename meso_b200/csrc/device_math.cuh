@@ -194,6 +194,23 @@ __device__ __forceinline__ float gaussian_sp(uint32_t si, uint32_t sj)    // UM/
     return fmaxf(-4.0f, fminf(__fmul_rn(r, f), 4.0f));
 }
 
+// MUFU-based, non-branching fp32 variant used by the fp32 force kernel: lg2/sin/sqrt.approx replace
+// log2f/sinpif/sqrtf (sin.approx: 2^-21.4 abs on [-pi,pi]; lg2.approx: 2^-22 abs) -> |error| < ~5e-6 on a
+// value of O(1), inside the 1e-5 relative force tolerance.  Same clamp / NaN semantics as the reference.
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sin_approx(float x) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float gaussian_sp_fast(uint32_t si, uint32_t sj)
+{
+    bool pred = si > sj;
+    uint32_t v0 = pred ? si : sj, v1 = pred ? sj : si;
+    tea<4>(v0, v1);
+    const float f = sin_approx(__fmul_rn((float)(int)v0, 3.14159265358979323846f * 4.6566128730773925781E-10f));
+    const float r = sqrt_approx(__fmul_rn(-2.0f * (float)MESO_LN_2, lg2_approx(__fmul_rn((float)v1, 2.3283064365386962891E-10f))));
+    return fmaxf(-4.0f, fminf(__fmul_rn(r, f), 4.0f));
+}
+
 // saturating double -> int truncation, then clamp to [lo, hi)  (UM/math_meso.h:155-158)
 __device__ __forceinline__ int clamp_rz(double v, int lo, int hi) { return max(lo, min(__double2int_rz(v), hi - 1)); }
 

@@ -5,24 +5,29 @@
 //   gpu_dpd_fast<ev>                  UM/pair_dpd_fast_meso.cu:91-205   (A10, fp32)
 //   gpu_dpd<ev>                       UM/pair_dpd_meso.cu:91-205        (A11, fp64 on the fp32-packed inputs)
 //   compute / compute_bulk / compute_border  UM/pair_dpd_meso.cu:241-266
-// One thread owns one local particle and walks its row of the tile-transposed table
-// (coalesced 128-byte index loads across the warp); neighbor float4s are gathered
-// through L1/L2, which the Morton reorder keeps hot.  Forces are assigned (fused clear)
-// or accumulated in fp64, and velocity-Verlet's second half-kick can be fused into the
-// epilogue (saves one streaming pass over v and f per step).
+//
+// Blackwell design.  One thread owns one local particle and a warp owns one 32-wide tile of the
+// tile-transposed table, so index loads are 128-byte coalesced.  The reference evaluates the
+// expensive part (4 TEA rounds + Box-Muller + force) inside the divergent `if (rsq < cutsq)` of its
+// neighbor loop: at rho = 4 only 45 % of the stored neighbors are in range, so most issue slots of
+// the heavy code are predicated off.  Here the loop is split in two warp-uniform phases:
+//   scan : walk the row, test the distance, push in-range j's into a per-lane FIFO in shared
+//          memory (column layout [depth][32 lanes]: bank == lane, conflict-free, no atomics);
+//   drain: every lane pops its own FIFO, so the heavy code runs max_lane(hits) times instead of
+//          once per stored neighbor, in list order (same summation order as the reference).
+// Forces are assigned (fused clear) or accumulated in fp64, and velocity-Verlet's second
+// half-kick can be fused into the epilogue (one streaming pass over v and f less per step).
+// The kernel is issue-bound, not HBM-bound: the fp32 path uses MUFU-based
+// lg2/sin/rsqrt/sqrt (non-branching, ~1e-6 abs on the Gaussian, inside the 1e-5 force tolerance).
 #include "internal.h"
 #include "device_math.cuh"
+#include <algorithm>
 
 namespace meso {
 
 struct SoA3 { double *c[3]; };
 struct SoA3c { const double *c[3]; };
 struct Virial { double *c[6]; };
-
-__device__ __forceinline__ size_t slot(int i, int k, int n_col)
-{
-    return (size_t)((i & ~31) + (k & 31)) * (size_t)n_col + (size_t)((k >> 5) * 32 + (i & 31));
-}
 
 // ------------------------------------------------------------------ pack
 __global__ void __launch_bounds__(256) k_pack(SoA3c x, SoA3c v, const int *__restrict__ type, const int *__restrict__ tag,
@@ -43,136 +48,176 @@ __global__ void __launch_bounds__(256) k_pack(SoA3c x, SoA3c v, const int *__res
     }
 }
 
-// ------------------------------------------------------------------ force, fp32 (dpd/fast/meso)
+// ------------------------------------------------------------------ force
+constexpr int PAIR_THREADS = 128;
+constexpr int QDEPTH = 20;       // FIFO slots per lane (mean in-range count at rho = 4 is 16.8); overflow -> early drain
+constexpr int SCAN_CHUNK = 4;
+
+template <typename REAL> struct Acc {
+    REAL fx = 0, fy = 0, fz = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, e = 0;
+};
+
+// one in-range pair, fp32 (UM/pair_dpd_fast_meso.cu:143-173)
 template <int EV>
-__global__ void __launch_bounds__(128) k_dpd_sp(const float4 *__restrict__ coord4, const float4 *__restrict__ veloc4,
-                                                const int *__restrict__ pair_count, const int *__restrict__ pair_table, SoA3 f,
-                                                SoA3 v, Virial vir, double *__restrict__ e_pair, const int *__restrict__ mask,
-                                                const int *__restrict__ type, const double *__restrict__ mass,
-                                                const float *__restrict__ coeff, const Counts *__restrict__ cnt, int n_col,
-                                                int n_type, float dt_inv_sqrt, int range, int accumulate, int fuse_final,
-                                                double dtf, int groupbit)
+__device__ __forceinline__ void pair_sp(const float4 c1, const float4 v1, const float4 c2, const float4 v2, const float *__restrict__ kk,
+                                        float dtis, Acc<float> &a)
 {
-    extern __shared__ float cf[];
-    for (int p = threadIdx.x; p < n_type * n_type * NCOEFF; p += blockDim.x) cf[p] = coeff[p];
-    __syncthreads();
-    const int p_beg = (range & MESO_BULK) ? 0 : cnt->n_bulk;
-    const int p_end = (range & MESO_BORDER) ? cnt->nlocal : cnt->n_bulk;
-    // warp-aligned start so that lanes keep matching the 32-wide tiles of the table
-    for (int i = (p_beg & ~31) + blockIdx.x * blockDim.x + threadIdx.x; i < p_end; i += gridDim.x * blockDim.x) {
-        if (i < p_beg) continue;
-        const float4 c1 = coord4[i], v1 = veloc4[i];
-        const uint32_t t1 = __float_as_uint(c1.w), s1 = __float_as_uint(v1.w);
-        const int n_pair = pair_count[i];
-        float fx = 0.f, fy = 0.f, fz = 0.f;
-        float vr0 = 0.f, vr1 = 0.f, vr2 = 0.f, vr3 = 0.f, vr4 = 0.f, vr5 = 0.f, energy = 0.f;
-        for (int k = 0; k < n_pair; k++) {
-            const int j = __ldcs(pair_table + slot(i, k, n_col));
-            const float4 c2 = coord4[j];
-            const float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
-            const float rsq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-            const float *kk = cf + (t1 * n_type + __float_as_uint(c2.w)) * NCOEFF;
-            if (rsq < kk[P_CUTSQ] && rsq >= 1.0E-20f) {
-                const float4 v2 = veloc4[j];
-                const float rn = gaussian_sp(s1, __float_as_uint(v2.w));
-                const float rinv = rsqrtf(rsq);
-                const float r = rsq * rinv;
-                const float dvx = v1.x - v2.x, dvy = v1.y - v2.y, dvz = v1.z - v2.z;
-                const float dot = dx * dvx + dy * dvy + dz * dvz;
-                const float wc = 1.0f - r * kk[P_CUTINV];
-                const float ew = kk[P_EXPW];
-                const float wr = (ew == 1.0f) ? wc : powf(wc, ew);      // powf(x,1) == x exactly
-                float fpair = kk[P_A0] * wc - (kk[P_GAMMA] * wr * wr * dot * rinv) + (kk[P_SIGMA] * wr * rn * dt_inv_sqrt);
-                fpair *= rinv;
-                fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
-                if (EV) {
-                    vr0 += dx * dx * fpair; vr1 += dy * dy * fpair; vr2 += dz * dz * fpair;
-                    vr3 += dx * dy * fpair; vr4 += dx * dz * fpair; vr5 += dy * dz * fpair;
-                    energy += 0.5f * kk[P_A0] * kk[P_CUT] * wc * wc;
-                }
-            }
-        }
-        double Fx = fx, Fy = fy, Fz = fz;
-        if (accumulate) { Fx += f.c[0][i]; Fy += f.c[1][i]; Fz += f.c[2][i]; }
-        f.c[0][i] = Fx; f.c[1][i] = Fy; f.c[2][i] = Fz;
-        if (EV) {
-            const float h = 0.5f;
-            double w0 = vr0 * h, w1 = vr1 * h, w2 = vr2 * h, w3 = vr3 * h, w4 = vr4 * h, w5 = vr5 * h;
-            if (accumulate) { w0 += vir.c[0][i]; w1 += vir.c[1][i]; w2 += vir.c[2][i]; w3 += vir.c[3][i]; w4 += vir.c[4][i]; w5 += vir.c[5][i]; }
-            vir.c[0][i] = w0; vir.c[1][i] = w1; vir.c[2][i] = w2; vir.c[3][i] = w3; vir.c[4][i] = w4; vir.c[5][i] = w5;
-            e_pair[i] = energy * h;                                   // assigned, UM/pair_dpd_fast_meso.cu:187
-        }
-        if (fuse_final && (mask[i] & groupbit)) {                     // gpu_fix_NVE_final_integrate, UM/fix_nve_meso.cu:157-178
-            const double dtfm = __dmul_rn(dtf, rcp_nr(mass[type[i]]));
-            v.c[0][i] = __fma_rn(dtfm, Fx, v.c[0][i]);
-            v.c[1][i] = __fma_rn(dtfm, Fy, v.c[1][i]);
-            v.c[2][i] = __fma_rn(dtfm, Fz, v.c[2][i]);
-        }
+    const float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
+    const float rsq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    const float rn = gaussian_sp_fast(__float_as_uint(v1.w), __float_as_uint(v2.w));
+    const float rinv = rsqrt_approx(rsq);
+    const float r = rsq * rinv;
+    const float dvx = v1.x - v2.x, dvy = v1.y - v2.y, dvz = v1.z - v2.z;
+    const float dot = dx * dvx + dy * dvy + dz * dvz;
+    const float wc = 1.0f - r * kk[P_CUTINV];
+    const float ew = kk[P_EXPW];
+    const float wr = (ew == 1.0f) ? wc : __powf(wc, ew);           // pow(x,1) == x; other exponents via ex2(ew*lg2(wc))
+    float fpair = kk[P_A0] * wc - (kk[P_GAMMA] * wr * wr * dot * rinv) + (kk[P_SIGMA] * wr * rn * dtis);
+    fpair *= rinv;
+    a.fx += dx * fpair; a.fy += dy * fpair; a.fz += dz * fpair;
+    if (EV) {
+        a.v0 += dx * dx * fpair; a.v1 += dy * dy * fpair; a.v2 += dz * dz * fpair;
+        a.v3 += dx * dy * fpair; a.v4 += dx * dz * fpair; a.v5 += dy * dz * fpair;
+        a.e += 0.5f * kk[P_A0] * kk[P_CUT] * wc * wc;
     }
 }
 
-// ------------------------------------------------------------------ force, fp64 (dpd/meso)
+// one in-range pair, fp64 arithmetic on the fp32-packed inputs (UM/pair_dpd_meso.cu:136-173)
 template <int EV>
-__global__ void __launch_bounds__(128) k_dpd_dp(const float4 *__restrict__ coord4, const float4 *__restrict__ veloc4,
-                                                const int *__restrict__ pair_count, const int *__restrict__ pair_table, SoA3 f,
-                                                SoA3 v, Virial vir, double *__restrict__ e_pair, const int *__restrict__ mask,
-                                                const int *__restrict__ type, const double *__restrict__ mass,
-                                                const double *__restrict__ coeff, const Counts *__restrict__ cnt, int n_col,
-                                                int n_type, double dt_inv_sqrt, int range, int accumulate, int fuse_final,
-                                                double dtf, int groupbit)
+__device__ __forceinline__ void pair_dp(const float4 c1, const float4 v1, const float4 c2, const float4 v2, const double *__restrict__ kk,
+                                        double dtis, Acc<double> &a)
 {
-    extern __shared__ double cd[];
-    for (int p = threadIdx.x; p < n_type * n_type * NCOEFF; p += blockDim.x) cd[p] = coeff[p];
+    // fp32 differences widened to fp64: f3u members are r32 (UM/type_meso.h:17-31)
+    const double dx = (double)__fsub_rn(c1.x, c2.x), dy = (double)__fsub_rn(c1.y, c2.y), dz = (double)__fsub_rn(c1.z, c2.z);
+    const double rsq = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+    const double rn = gaussian_dp(__float_as_uint(v1.w), __float_as_uint(v2.w));
+    const double rinv = rsqrt(rsq);
+    const double r = rsq * rinv;
+    const double dvx = (double)__fsub_rn(v1.x, v2.x), dvy = (double)__fsub_rn(v1.y, v2.y), dvz = (double)__fsub_rn(v1.z, v2.z);
+    const double dot = __fma_rn(dz, dvz, __fma_rn(dy, dvy, __dmul_rn(dx, dvx)));
+    const double wc = 1.0 - r * kk[P_CUTINV];
+    const double wr = pow_poly(wc, kk[P_EXPW]);
+    double fpair = kk[P_A0] * wc - (kk[P_GAMMA] * wr * wr * dot * rinv) + (kk[P_SIGMA] * wr * rn * dtis);
+    fpair *= rinv;
+    a.fx += dx * fpair; a.fy += dy * fpair; a.fz += dz * fpair;
+    if (EV) {
+        a.v0 += dx * dx * fpair; a.v1 += dy * dy * fpair; a.v2 += dz * dz * fpair;
+        a.v3 += dx * dy * fpair; a.v4 += dx * dz * fpair; a.v5 += dy * dz * fpair;
+        a.e += 0.5 * kk[P_A0] * kk[P_CUT] * wc * wc;
+    }
+}
+
+template <typename REAL, int EV>
+__global__ void __launch_bounds__(PAIR_THREADS) k_dpd(const float4 *__restrict__ coord4, const float4 *__restrict__ veloc4,
+                                                      const int *__restrict__ pair_count, const int *__restrict__ pair_table, SoA3 f,
+                                                      SoA3 v, Virial vir, double *__restrict__ e_pair, const int *__restrict__ mask,
+                                                      const int *__restrict__ type, const double *__restrict__ mass,
+                                                      const REAL *__restrict__ coeff, const Counts *__restrict__ cnt, int n_col,
+                                                      int n_type, REAL dt_inv_sqrt, int range, int accumulate, int fuse_final,
+                                                      double dtf, int groupbit)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    REAL *cf = reinterpret_cast<REAL *>(smem_raw);
+    const int ncf = n_type * n_type * NCOEFF;
+    int *queue = reinterpret_cast<int *>(smem_raw + (((size_t)ncf * sizeof(REAL) + 15) & ~(size_t)15)) + (threadIdx.x >> 5) * (QDEPTH * 32) +
+                 (threadIdx.x & 31);
+    for (int p = threadIdx.x; p < ncf; p += blockDim.x) cf[p] = coeff[p];
     __syncthreads();
+    const unsigned full = 0xffffffffu;
     const int p_beg = (range & MESO_BULK) ? 0 : cnt->n_bulk;
     const int p_end = (range & MESO_BORDER) ? cnt->nlocal : cnt->n_bulk;
-    for (int i = (p_beg & ~31) + blockIdx.x * blockDim.x + threadIdx.x; i < p_end; i += gridDim.x * blockDim.x) {
-        if (i < p_beg) continue;
-        const float4 c1 = coord4[i], v1 = veloc4[i];
-        const uint32_t t1 = __float_as_uint(c1.w), s1 = __float_as_uint(v1.w);
-        const int n_pair = pair_count[i];
-        double fx = 0., fy = 0., fz = 0.;
-        double vr0 = 0., vr1 = 0., vr2 = 0., vr3 = 0., vr4 = 0., vr5 = 0., energy = 0.;
-        for (int k = 0; k < n_pair; k++) {
-            const int j = __ldcs(pair_table + slot(i, k, n_col));
-            const float4 c2 = coord4[j];
-            // fp32 differences widened to fp64: f3u members are r32 (UM/type_meso.h:17-31, UM/pair_dpd_meso.cu:136-139)
-            const double dx = (double)__fsub_rn(c1.x, c2.x), dy = (double)__fsub_rn(c1.y, c2.y), dz = (double)__fsub_rn(c1.z, c2.z);
-            const double rsq = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
-            const double *kk = cd + (t1 * n_type + __float_as_uint(c2.w)) * NCOEFF;
-            if (rsq < kk[P_CUTSQ] && rsq >= 1.0E-20) {
-                const float4 v2 = veloc4[j];
-                const double rn = gaussian_dp(s1, __float_as_uint(v2.w));
-                const double rinv = rsqrt(rsq);
-                const double r = rsq * rinv;
-                const double dvx = (double)__fsub_rn(v1.x, v2.x), dvy = (double)__fsub_rn(v1.y, v2.y), dvz = (double)__fsub_rn(v1.z, v2.z);
-                const double dot = __fma_rn(dz, dvz, __fma_rn(dy, dvy, __dmul_rn(dx, dvx)));
-                const double wc = 1.0 - r * kk[P_CUTINV];
-                const double wr = pow_poly(wc, kk[P_EXPW]);
-                double fpair = kk[P_A0] * wc - (kk[P_GAMMA] * wr * wr * dot * rinv) + (kk[P_SIGMA] * wr * rn * dt_inv_sqrt);
-                fpair *= rinv;
-                fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
-                if (EV) {
-                    vr0 += dx * dx * fpair; vr1 += dy * dy * fpair; vr2 += dz * dz * fpair;
-                    vr3 += dx * dy * fpair; vr4 += dx * dz * fpair; vr5 += dy * dz * fpair;
-                    energy += 0.5 * kk[P_A0] * kk[P_CUT] * wc * wc;
+    // warp-aligned start: lanes keep matching the 32-wide tiles of the table; whole warps iterate together
+    for (int i = (p_beg & ~31) + blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < p_end; i += gridDim.x * blockDim.x) {
+        const bool active = i >= p_beg && i < p_end;
+        float4 c1 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = c1;
+        int n_pair = 0;
+        if (active) { c1 = coord4[i]; v1 = veloc4[i]; n_pair = pair_count[i]; }
+        const uint32_t t1 = __float_as_uint(c1.w);
+        const int nmax = __reduce_max_sync(full, n_pair);
+        const int *tp = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);   // slot(i, k) = tp[(k&31)*n_col + (k>>5)*32]
+        const REAL *cf1 = cf + t1 * n_type * NCOEFF;       // coefficient rows of my type
+        const int jsafe = active ? i : 0;                   // gather target of masked-off slots
+        Acc<REAL> acc;
+        int qlen = 0;
+
+        // ---- drain: pop my FIFO; the next entry's gathers are issued before the current pair's math
+        auto drain = [&]() {
+            const int m = __reduce_max_sync(full, qlen);
+            int jn = qlen > 0 ? queue[0] : jsafe;
+            float4 c2n = coord4[jn], v2n = veloc4[jn];
+            for (int q = 0; q < m; q++) {
+                const float4 c2 = c2n, v2 = v2n;
+                jn = (q + 1 < qlen) ? queue[(q + 1) * 32] : jsafe;
+                c2n = coord4[jn]; v2n = veloc4[jn];
+                if (q < qlen) {
+                    const REAL *kk = cf1 + __float_as_uint(c2.w) * NCOEFF;
+                    if constexpr (sizeof(REAL) == 4) pair_sp<EV>(c1, v1, c2, v2, kk, dt_inv_sqrt, acc);
+                    else pair_dp<EV>(c1, v1, c2, v2, kk, dt_inv_sqrt, acc);
                 }
             }
+            qlen = 0;
+        };
+
+        // ---- scan: branch-free chunks of SCAN_CHUNK slots; the next chunk's index loads are in flight while
+        //      this chunk's float4 gathers and distance tests run.  k0 is a multiple of SCAN_CHUNK (a divisor of 32),
+        //      so a chunk never straddles a 32-slot tile: slot(k0+u) = tp[off(k0) + u*n_col].  Slots beyond a lane's
+        //      n_pair are read (in-bounds, stale data) but their j is replaced by jsafe before the gather.
+        auto load_chunk = [&](int k0, int (&jj)[SCAN_CHUNK]) {
+            const int *p = tp + (size_t)((k0 & 31) * n_col + (k0 >> 5) * 32);
+#pragma unroll
+            for (int u = 0; u < SCAN_CHUNK; u++) {
+                const int raw = __ldcs(p + (size_t)u * n_col);
+                jj[u] = (k0 + u < n_pair) ? raw : -1;
+            }
+        };
+        int jnext[SCAN_CHUNK];
+        if (nmax > 0) load_chunk(0, jnext);
+        for (int k0 = 0; k0 < nmax; k0 += SCAN_CHUNK) {
+            int jc[SCAN_CHUNK];
+#pragma unroll
+            for (int u = 0; u < SCAN_CHUNK; u++) jc[u] = jnext[u];
+            if (k0 + SCAN_CHUNK < nmax) load_chunk(k0 + SCAN_CHUNK, jnext);
+            if (__any_sync(full, qlen > QDEPTH - SCAN_CHUNK)) drain();
+            float4 c2[SCAN_CHUNK];
+#pragma unroll
+            for (int u = 0; u < SCAN_CHUNK; u++) c2[u] = coord4[jc[u] >= 0 ? jc[u] : jsafe];
+#pragma unroll
+            for (int u = 0; u < SCAN_CHUNK; u++) {
+                const REAL cutsq = cf1[__float_as_uint(c2[u].w) * NCOEFF + P_CUTSQ];
+                bool hit;
+                if constexpr (sizeof(REAL) == 4) {
+                    const float dx = c1.x - c2[u].x, dy = c1.y - c2[u].y, dz = c1.z - c2[u].z;
+                    const float rsq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                    hit = rsq < cutsq && rsq >= 1.0E-20f;            // UM/pair_dpd_fast_meso.cu:143
+                } else {
+                    const double dx = (double)__fsub_rn(c1.x, c2[u].x), dy = (double)__fsub_rn(c1.y, c2[u].y), dz = (double)__fsub_rn(c1.z, c2[u].z);
+                    const double rsq = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+                    hit = rsq < cutsq && rsq >= 1.0E-20;             // UM/pair_dpd_meso.cu:143
+                }
+                hit = hit && jc[u] >= 0;
+                if (hit) queue[qlen * 32] = jc[u];
+                qlen += hit ? 1 : 0;
+            }
         }
-        double Fx = fx, Fy = fy, Fz = fz;
-        if (accumulate) { Fx += f.c[0][i]; Fy += f.c[1][i]; Fz += f.c[2][i]; }
-        f.c[0][i] = Fx; f.c[1][i] = Fy; f.c[2][i] = Fz;
-        if (EV) {
-            double w0 = vr0 * 0.5, w1 = vr1 * 0.5, w2 = vr2 * 0.5, w3 = vr3 * 0.5, w4 = vr4 * 0.5, w5 = vr5 * 0.5;
-            if (accumulate) { w0 += vir.c[0][i]; w1 += vir.c[1][i]; w2 += vir.c[2][i]; w3 += vir.c[3][i]; w4 += vir.c[4][i]; w5 += vir.c[5][i]; }
-            vir.c[0][i] = w0; vir.c[1][i] = w1; vir.c[2][i] = w2; vir.c[3][i] = w3; vir.c[4][i] = w4; vir.c[5][i] = w5;
-            e_pair[i] = energy * 0.5;
-        }
-        if (fuse_final && (mask[i] & groupbit)) {
-            const double dtfm = __dmul_rn(dtf, rcp_nr(mass[type[i]]));
-            v.c[0][i] = __fma_rn(dtfm, Fx, v.c[0][i]);
-            v.c[1][i] = __fma_rn(dtfm, Fy, v.c[1][i]);
-            v.c[2][i] = __fma_rn(dtfm, Fz, v.c[2][i]);
+        drain();
+
+        if (active) {
+            double Fx = acc.fx, Fy = acc.fy, Fz = acc.fz;
+            if (accumulate) { Fx += f.c[0][i]; Fy += f.c[1][i]; Fz += f.c[2][i]; }
+            f.c[0][i] = Fx; f.c[1][i] = Fy; f.c[2][i] = Fz;
+            if (EV) {
+                const REAL h = (REAL)0.5;
+                double w0 = acc.v0 * h, w1 = acc.v1 * h, w2 = acc.v2 * h, w3 = acc.v3 * h, w4 = acc.v4 * h, w5 = acc.v5 * h;
+                if (accumulate) { w0 += vir.c[0][i]; w1 += vir.c[1][i]; w2 += vir.c[2][i]; w3 += vir.c[3][i]; w4 += vir.c[4][i]; w5 += vir.c[5][i]; }
+                vir.c[0][i] = w0; vir.c[1][i] = w1; vir.c[2][i] = w2; vir.c[3][i] = w3; vir.c[4][i] = w4; vir.c[5][i] = w5;
+                e_pair[i] = acc.e * h;                                    // assigned, UM/pair_dpd_fast_meso.cu:187
+            }
+            if (fuse_final && (mask[i] & groupbit)) {                     // gpu_fix_NVE_final_integrate, UM/fix_nve_meso.cu:157-178
+                const double dtfm = __dmul_rn(dtf, rcp_nr(mass[type[i]]));
+                v.c[0][i] = __fma_rn(dtfm, Fx, v.c[0][i]);
+                v.c[1][i] = __fma_rn(dtfm, Fy, v.c[1][i]);
+                v.c[2][i] = __fma_rn(dtfm, Fz, v.c[2][i]);
+            }
         }
     }
 }
@@ -182,7 +227,7 @@ __global__ void k_eval_gaussian(int n, const uint32_t *si, const uint32_t *sj, f
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (osp) osp[i] = gaussian_sp(si[i], sj[i]);
+    if (osp) osp[i] = gaussian_sp_fast(si[i], sj[i]);      // the variant the fp32 force kernel uses
     if (odp) odp[i] = gaussian_dp(si[i], sj[i]);
 }
 __global__ void k_eval_math(int fn, int n, const double *a, const double *b, double *out)
@@ -221,7 +266,8 @@ int launch_pack(meso_ctx *ctx, int range)
     return MESO_OK;
 }
 
-int launch_pair(meso_ctx *ctx, int range, int evflag, bool accumulate, bool fuse_final, int groupbit)
+template <typename REAL, int EV>
+static int launch_pair_t(meso_ctx *ctx, const REAL *coeff, REAL dtis, int range, bool accumulate, bool fuse_final, int groupbit)
 {
     SoA3 f, v;
     Virial vir;
@@ -229,32 +275,32 @@ int launch_pair(meso_ctx *ctx, int range, int evflag, bool accumulate, bool fuse
     for (int q = 0; q < 6; q++) vir.c[q] = ctx->virial.p + (size_t)q * ctx->cap;
     const int nt = ctx->ntypes;
     const double dtf = 0.5 * ctx->dt;   // ftm2v = 1 in lj units (FixNVEMeso::init, UM/fix_nve_meso.cu:42-46)
-    const int grid = grid_for(ctx, 16);
-    if (ctx->precision == MESO_SP) {
-        size_t sh = sizeof(float) * nt * nt * NCOEFF;
-        float dtis = (float)(1.0 / sqrt(ctx->dt));
-        if (evflag)
-            k_dpd_sp<1><<<grid, 128, sh, ctx->stream>>>(ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, f, v, vir,
-                                                      ctx->e_pair.p, ctx->mask.p, ctx->type.p, ctx->mass_dev.p, ctx->coeff_sp.p,
-                                                      ctx->d_counts, ctx->n_col, nt, dtis, range, accumulate, fuse_final, dtf, groupbit);
-        else
-            k_dpd_sp<0><<<grid, 128, sh, ctx->stream>>>(ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, f, v, vir,
-                                                      ctx->e_pair.p, ctx->mask.p, ctx->type.p, ctx->mass_dev.p, ctx->coeff_sp.p,
-                                                      ctx->d_counts, ctx->n_col, nt, dtis, range, accumulate, fuse_final, dtf, groupbit);
-    } else {
-        size_t sh = sizeof(double) * nt * nt * NCOEFF;
-        double dtis = 1.0 / sqrt(ctx->dt);
-        if (evflag)
-            k_dpd_dp<1><<<grid, 128, sh, ctx->stream>>>(ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, f, v, vir,
-                                                      ctx->e_pair.p, ctx->mask.p, ctx->type.p, ctx->mass_dev.p, ctx->coeff_dp.p,
-                                                      ctx->d_counts, ctx->n_col, nt, dtis, range, accumulate, fuse_final, dtf, groupbit);
-        else
-            k_dpd_dp<0><<<grid, 128, sh, ctx->stream>>>(ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, f, v, vir,
-                                                      ctx->e_pair.p, ctx->mask.p, ctx->type.p, ctx->mass_dev.p, ctx->coeff_dp.p,
-                                                      ctx->d_counts, ctx->n_col, nt, dtis, range, accumulate, fuse_final, dtf, groupbit);
+    const size_t sh = (((size_t)nt * nt * NCOEFF * sizeof(REAL) + 15) & ~(size_t)15) + (size_t)(PAIR_THREADS / 32) * QDEPTH * 32 * sizeof(int);
+    // one CTA per 128 particles (host-side upper bound of the range); the grid-stride loop covers any excess
+    int grid = (int)(((size_t)ctx->nlocal_host + PAIR_THREADS - 1) / PAIR_THREADS) + 1;
+    grid = std::max(1, std::min(grid, ctx->sm_count * 4096));
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_dpd<REAL, EV>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        attr_done = true;
     }
+    k_dpd<REAL, EV><<<grid, PAIR_THREADS, sh, ctx->stream>>>(ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, f, v, vir,
+                                                           ctx->e_pair.p, ctx->mask.p, ctx->type.p, ctx->mass_dev.p, coeff, ctx->d_counts,
+                                                           ctx->n_col, nt, dtis, range, accumulate, fuse_final, dtf, groupbit);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
+}
+
+int launch_pair(meso_ctx *ctx, int range, int evflag, bool accumulate, bool fuse_final, int groupbit)
+{
+    if (ctx->precision == MESO_SP) {
+        const float dtis = (float)(1.0 / sqrt(ctx->dt));
+        return evflag ? launch_pair_t<float, 1>(ctx, ctx->coeff_sp.p, dtis, range, accumulate, fuse_final, groupbit)
+                      : launch_pair_t<float, 0>(ctx, ctx->coeff_sp.p, dtis, range, accumulate, fuse_final, groupbit);
+    }
+    const double dtis = 1.0 / sqrt(ctx->dt);
+    return evflag ? launch_pair_t<double, 1>(ctx, ctx->coeff_dp.p, dtis, range, accumulate, fuse_final, groupbit)
+                  : launch_pair_t<double, 0>(ctx, ctx->coeff_dp.p, dtis, range, accumulate, fuse_final, groupbit);
 }
 
 int eval_gaussian(meso_ctx *ctx, int n, const uint32_t *si, const uint32_t *sj, float *osp, double *odp)

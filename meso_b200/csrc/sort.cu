@@ -40,18 +40,19 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const K *__restrict
     hist[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of m entries by one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) k_scan_exclusive(uint32_t *__restrict__ a, int m)
+// One CTA per digit: exclusive scan of that digit's row hist[d][0..nblk) in place, row total to totals[d].
+// (256 short independent scans instead of one long serial one.)
+__global__ void __launch_bounds__(256) k_scan_rows(uint32_t *__restrict__ hist, uint32_t *__restrict__ totals, int nblk)
 {
-    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t warp_sum[8];
     __shared__ uint32_t carry_s;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    uint32_t *row = hist + (size_t)blockIdx.x * nblk;
     if (t == 0) carry_s = 0;
     __syncthreads();
-    // strip-mined so that loads stay coalesced: 1024 consecutive entries per iteration
-    for (int base = 0; base < m; base += 1024) {
+    for (int base = 0; base < nblk; base += 256) {
         int i = base + t;
-        uint32_t v = i < m ? a[i] : 0u, x = v;
+        uint32_t v = i < nblk ? row[i] : 0u, x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -59,36 +60,43 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(uint32_t *__restrict__ 
         }
         if (lane == 31) warp_sum[w] = x;
         __syncthreads();
-        if (w == 0) {
-            uint32_t s = warp_sum[lane], z = s;
+        uint32_t pre = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
-                if (lane >= o) z += y;
-            }
-            warp_sum[lane] = z - s;   // exclusive
-        }
+        for (int ww = 0; ww < 8; ww++) pre += (ww < w) ? warp_sum[ww] : 0u;
+        uint32_t excl = carry_s + pre + x - v;
+        if (i < nblk) row[i] = excl;
         __syncthreads();
-        uint32_t carry = carry_s;
-        uint32_t excl = carry + warp_sum[w] + x - v;
-        if (i < m) a[i] = excl;
-        __syncthreads();
-        if (t == 1023) carry_s = excl + v;
+        if (t == 255) carry_s = excl + v;
         __syncthreads();
     }
+    if (t == 0) totals[blockIdx.x] = carry_s;
 }
 
 template <typename K>
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const K *__restrict__ key_in, const int *__restrict__ val_in,
                                                                 K *__restrict__ key_out, int *__restrict__ val_out,
                                                                 const int *__restrict__ d_n, const uint32_t *__restrict__ hist,
-                                                                int shift)
+                                                                const uint32_t *__restrict__ totals, int shift)
 {
     __shared__ uint32_t warp_hist[SORT_WARPS][256];
     __shared__ uint32_t gbase[256], cur_base[256];
+    __shared__ uint32_t wtot[SORT_WARPS];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    gbase[t] = hist[t * gridDim.x + blockIdx.x];
+    {   // digit base = exclusive scan of the 256 digit totals (thread t owns digit t) + this CTA's offset inside the digit
+        uint32_t v = totals[t], x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wtot[w] = x;
+        __syncthreads();
+        uint32_t pre = 0;
+#pragma unroll
+        for (int ww = 0; ww < SORT_WARPS; ww++) pre += (ww < w) ? wtot[ww] : 0u;
+        gbase[t] = pre + x - v + hist[t * gridDim.x + blockIdx.x];
+    }
     int beg, end;
     block_span(*d_n, beg, end);
     for (int chunk = beg; chunk < end; chunk += SORT_CHUNK) {
@@ -145,12 +153,13 @@ template <typename K>
 static int sort_impl(meso_ctx *ctx, K *&key, int *&val, K *&key_alt, int *&val_alt, const int *d_n, size_t cap, int bits)
 {
     const int nblk = grid_for(ctx, 4);
-    if (!ctx->sort.hist.reserve((size_t)256 * nblk)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
+    if (!ctx->sort.hist.reserve((size_t)256 * nblk + 256)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
     (void)cap;
     for (int shift = 0; shift < bits; shift += 8) {
         k_radix_hist<K><<<nblk, SORT_THREADS, 0, ctx->stream>>>(key, d_n, ctx->sort.hist.p, shift);
-        k_scan_exclusive<<<1, 1024, 0, ctx->stream>>>(ctx->sort.hist.p, 256 * nblk);
-        k_radix_scatter<K><<<nblk, SORT_THREADS, 0, ctx->stream>>>(key, val, key_alt, val_alt, d_n, ctx->sort.hist.p, shift);
+        uint32_t *totals = ctx->sort.hist.p + (size_t)256 * nblk;
+        k_scan_rows<<<256, 256, 0, ctx->stream>>>(ctx->sort.hist.p, totals, nblk);
+        k_radix_scatter<K><<<nblk, SORT_THREADS, 0, ctx->stream>>>(key, val, key_alt, val_alt, d_n, ctx->sort.hist.p, totals, shift);
         K *tk = key; key = key_alt; key_alt = tk;
         int *tv = val; val = val_alt; val_alt = tv;
     }
@@ -162,7 +171,8 @@ static int sort_impl(meso_ctx *ctx, K *&key, int *&val, K *&key_alt, int *&val_a
 // pairs (the DevBuf pointers are swapped with the scratch buffers when the pass count is odd).
 int sort_pairs_u64(meso_ctx *ctx, DevBuf<uint64_t> &key, DevBuf<int> &val, const int *d_n, size_t cap, int bits)
 {
-    if (!ctx->sort.key_alt.reserve(key.cap) || !ctx->sort.val_alt.reserve(val.cap)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
+    // size the scratch by the LOGICAL capacity: buffers are swapped below, so sizing by key.cap would ratchet up
+    if (!ctx->sort.key_alt.reserve(cap) || !ctx->sort.val_alt.reserve(cap)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
     uint64_t *k = key.p, *ka = ctx->sort.key_alt.p;
     int *v = val.p, *va = ctx->sort.val_alt.p;
     int rc = sort_impl<uint64_t>(ctx, k, v, ka, va, d_n, cap, bits);
