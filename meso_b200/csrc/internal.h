@@ -121,6 +121,8 @@ struct meso_ctx {
     meso::DevBuf<uint64_t> cell_key;          // sort key (cell id) per atom
     meso::DevBuf<int> cell_of, cell_atoms, cell_start;
     meso::DevBuf<unsigned char> stencil;      // [ncell][32]
+    meso::DevBuf<float4> cell_xyzj;           // cell-ordered {x,y,z,bits(atom index)}
+    meso::DevBuf<int2> cell_runs;             // [ncell][27] {first position, count} per stencil cell
     // neighbor list
     meso::DevBuf<int> pair_count, pair_table;
     size_t table_rows = 0;

@@ -236,6 +236,18 @@ def test_non_periodic_dimension_and_tiny_box():
     m.close()
 
 
+def test_dense_fluid_rows_longer_than_the_staging_queue():
+    """rho = 8: ~72 stored neighbors per atom (> 60 staging slots, > 2 table tiles): exercises the spill/join path of the
+    list build, the 32-slot tile wrap of the transposed table and the early-drain path of the force kernel."""
+    x = workload.dpd_fluid(6, rho=8, seed=13)
+    for precision in ("sp", "dp"):
+        m, w = make_pair(6, precision, x=x)
+        m.setup(); w.setup()
+        assert w.neighbors()[0].max() > 64 and w.counts()["n_col"] == 320
+        assert_state_identical(m, w, precision=precision, tol=2e-5 if precision == "sp" else 1e-11)
+        m.close()
+
+
 def test_atoms_on_cell_and_box_boundaries():
     x = workload.dpd_fluid(6, seed=2)
     x[:50] = np.round(x[:50])            # exactly on unit-lattice planes, including 0.0
