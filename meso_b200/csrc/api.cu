@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 using namespace meso;
 
@@ -99,6 +100,11 @@ extern "C" int meso_create(meso_ctx **out, int device)
         delete ctx;
         return MESO_ECUDA;
     }
+    cudaEventCreateWithFlags(&ctx->ev_fwd_begin, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_fwd_end, cudaEventDisableTiming);
+    // MESO_FORCE_COMM_PATH=1 runs the message-based halo path (pack -> [NCCL] -> unpack, side-stream overlap) even on one rank
+    const char *fc = getenv("MESO_FORCE_COMM_PATH");
+    ctx->comm_path = fc && fc[0] == '1';
     cudaMemsetAsync(ctx->d_counts, 0, sizeof(Counts), ctx->stream);
     memset(ctx->h_counts, 0, sizeof(Counts));
     *out = ctx;
@@ -113,6 +119,8 @@ extern "C" void meso_destroy(meso_ctx *ctx)
     comm_destroy(ctx);
     drain_timers(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev_fwd_begin) cudaEventDestroy(ctx->ev_fwd_begin);
+    if (ctx->ev_fwd_end) cudaEventDestroy(ctx->ev_fwd_end);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -223,6 +231,7 @@ extern "C" int meso_set_decomposition(meso_ctx *ctx, int rank, const int procgri
     if (n > 1) {
         if (!nccl_id) FAIL(MESO_EINVAL, "meso_set_decomposition: nranks > 1 needs an ncclUniqueId");
         TRY(comm_init(ctx, nccl_id));
+        ctx->comm_path = true;
     }
     return MESO_OK;
 }
@@ -333,6 +342,7 @@ static int ensure_capacity(meso_ctx *ctx, size_t nlocal)
     size_t nloc_cap = (ctx->nranks > 1) ? nlocal + nlocal / 8 + 1024 : nlocal;
     size_t cap = nloc_cap + nghost;
     if (cap <= ctx->cap) return MESO_OK;
+    ctx->nloc_cap = nloc_cap;
     bool ok = true;
     for (int d = 0; d < 3; d++)
         ok = ok && ctx->x[d].reserve(cap) && ctx->v[d].reserve(cap) && ctx->f[d].reserve(cap) && ctx->xa[d].reserve(cap) && ctx->va[d].reserve(cap);
@@ -466,11 +476,18 @@ static int rebuild_impl(meso_ctx *ctx)
         size_t need = ctx->table_rows * (size_t)ctx->n_col;
         if (!ctx->pair_table.reserve(need)) FAIL(MESO_ECUDA, "out of device memory (pair table)");
     }
-    if (ctx->nranks > 1) FAIL(MESO_EINVAL, "multi-rank rebuild is not available in this build");
     {
         PhaseTimer t(ctx, MESO_T_REBUILD);
-        TRY(launch_reorder(ctx));
-        TRY(launch_borders(ctx));
+        if (ctx->comm_path) {
+            // Domain::pbc -> Comm::exchange -> sort_local -> Comm::borders (UM/mvv_meso.cu:283-316), all on device
+            TRY(launch_pbc(ctx));
+            TRY(launch_exchange_multi(ctx));
+            TRY(launch_reorder(ctx));
+            TRY(launch_borders_multi(ctx));
+        } else {
+            TRY(launch_reorder(ctx));        // the key kernel wraps as it goes
+            TRY(launch_borders(ctx));
+        }
     }
     {
         PhaseTimer t(ctx, MESO_T_NEIGH);
@@ -494,6 +511,7 @@ extern "C" int meso_forward_comm(meso_ctx *ctx)
     TRY(ready(ctx));
     PhaseTimer t(ctx, MESO_T_FORWARD);
     // phase API keeps the reference's order: ghosts' fp64 x,v are refreshed, packing happens in meso_pair_compute
+    if (ctx->comm_path) return launch_forward_multi(ctx, ctx->stream);
     return launch_forward(ctx, true);
 }
 
@@ -566,8 +584,29 @@ extern "C" int meso_run(meso_ctx *ctx, int nsteps, int groupbit)
             PhaseTimer t(ctx, MESO_T_INTEGRATE);
             TRY(launch_initial_integrate(ctx, groupbit, !rebuild));
         }
-        if (rebuild) TRY(rebuild_impl(ctx));                 // gather + ghost kernels emit this step's packed views
-        else {
+        if (rebuild) {
+            TRY(rebuild_impl(ctx));                          // gather + ghost kernels emit this step's packed views
+        } else if (ctx->comm_path) {
+            // halo refresh on the side stream, overlapped with the bulk force kernel (UM/mvv_meso.cu:338-376):
+            // bulk particles have no ghost neighbors, border particles wait for the refreshed ghosts
+            MESO_CUDA(cudaEventRecord(ctx->ev_fwd_begin, ctx->stream));
+            MESO_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fwd_begin, 0));
+            TRY(launch_forward_multi(ctx, ctx->side));
+            MESO_CUDA(cudaEventRecord(ctx->ev_fwd_end, ctx->side));
+            {
+                PhaseTimer t(ctx, MESO_T_PAIR);
+                TRY(launch_pair(ctx, MESO_BULK, 0, false, true, groupbit));
+            }
+            {
+                PhaseTimer t(ctx, MESO_T_FORWARD);           // exposed (non-overlapped) part of the halo refresh
+                MESO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fwd_end, 0));
+            }
+            {
+                PhaseTimer t(ctx, MESO_T_PAIR);
+                TRY(launch_pair(ctx, MESO_BORDER, 0, false, true, groupbit));
+            }
+            continue;
+        } else {
             PhaseTimer t(ctx, MESO_T_FORWARD);
             TRY(launch_forward(ctx, false));
         }

@@ -1,8 +1,23 @@
-// comm.cu -- inter-rank plumbing (NCCL over NVLink).  Replaces the reference's host MPI +
-// pinned staging (UM/comm_meso.cu:135-147,385-402; src/comm.cpp:686-753; MPI_Allreduce in
-// UM/compute_temp_meso.cu:97).
+// comm.cu -- spatial decomposition across GPUs: migration, ghost creation and the per-step halo
+// refresh, with NCCL send/recv over NVLink.
+//
+// Reference path (host MPI through pinned staging buffers, every step):
+//   MesoComm::exchange                UM/comm_meso.cu:256-420        (migration, per dimension)
+//   MesoComm::borders                 UM/comm_meso.cu:41-186         (ghost creation, 6 swaps)
+//   Comm::forward_comm                src/comm.cpp:686-753           (ghost x,v refresh, 6 swaps)
+//   pack/unpack_{border,comm}_vel     UM/atom_vec_dpd_atomic_meso.cu:61-243
+//   MPI_Allreduce of thermo scalars   UM/compute_temp_meso.cu:97
+// The swap structure (3 dimensions x {to-lower, to-upper}, later dimensions forwarding earlier
+// ghosts) is kept, because it fixes the ghost ORDER and with it the neighbor-list order.  What
+// changes: selection, packing and unpacking are device kernels (ordered stream compaction, no
+// atomics); messages are fixed-capacity with the record count in a header, so neither side ever
+// needs a host round trip to size a message -- the whole rebuild and every step stay asynchronous;
+// a swap whose partner is this rank itself (procgrid[d] == 1) unpacks straight from its own send
+// buffer; the per-step refresh runs on a side stream so that it overlaps the bulk force kernel.
 #include "internal.h"
+#include "device_math.cuh"
 #include <nccl.h>
+#include <algorithm>
 #include <cstring>
 
 namespace meso {
@@ -15,6 +30,14 @@ namespace meso {
             return MESO_ENCCL;                                                            \
         }                                                                                 \
     } while (0)
+
+struct SoA3 { double *c[3]; };
+static inline SoA3 soa(DevBuf<double> *b) { SoA3 s; for (int d = 0; d < 3; d++) s.c[d] = b[d].p; return s; }
+
+constexpr int REC = 8;            // doubles per record (64 B); record 0 of every message is the header {count}
+constexpr int CT = 256;           // threads
+constexpr int CI = 4;             // items per thread
+constexpr int CTILE = CT * CI;
 
 int comm_init(meso_ctx *ctx, const void *nccl_id)
 {
@@ -39,11 +62,498 @@ int comm_allreduce_sum(meso_ctx *ctx, double *host_vals, int n)
 {
     if (ctx->nranks == 1) return MESO_OK;
     if (!ctx->nccl) { ctx->err = "communicator not initialised"; return MESO_ENCCL; }
-    if (!ctx->partial.reserve(64)) { ctx->err = "out of device memory"; return MESO_ECUDA; }
-    MESO_CUDA(cudaMemcpyAsync(ctx->partial.p, host_vals, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    MESO_NCCL(ncclAllReduce(ctx->partial.p, ctx->partial.p, n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
-    MESO_CUDA(cudaMemcpyAsync(host_vals, ctx->partial.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->reduce_buf.reserve(64)) { ctx->err = "out of device memory"; return MESO_ECUDA; }
+    MESO_CUDA(cudaMemcpyAsync(ctx->reduce_buf.p, host_vals, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    MESO_NCCL(ncclAllReduce(ctx->reduce_buf.p, ctx->reduce_buf.p, n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+    MESO_CUDA(cudaMemcpyAsync(host_vals, ctx->reduce_buf.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MESO_OK;
+}
+
+// ------------------------------------------------------------------ generic ordered 2-way compaction
+// flags a,b per candidate in [first,last); tile counts -> exclusive scan -> ranks.  Used for (lo,hi) slabs
+// and for (left,right) leavers.
+struct Flags { bool a, b; };
+
+template <typename F>
+__device__ __forceinline__ void tile_count(F flag, int first, int last, int2 *tile_counts, int ntiles)
+{
+    __shared__ int sa[CT / 32], sb[CT / 32];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int na = 0, nb = 0;
+        const int base = first + tile * CTILE;
+#pragma unroll
+        for (int r = 0; r < CI; r++) {
+            const int i = base + r * CT + threadIdx.x;
+            if (i < last) { Flags f = flag(i); na += f.a; nb += f.b; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
+        if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = na; sb[threadIdx.x >> 5] = nb; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int a = 0, b = 0;
+            for (int w = 0; w < CT / 32; w++) { a += sa[w]; b += sb[w]; }
+            tile_counts[tile] = make_int2(a, b);
+        }
+        __syncthreads();
+    }
+}
+
+// single CTA: exclusive scan of `used` tile counts; totals to tot[0..1]
+__device__ __forceinline__ int2 scan_tiles(int2 *tile_counts, int used)
+{
+    __shared__ int2 wsum[32];
+    __shared__ int2 carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = make_int2(0, 0);
+    __syncthreads();
+    for (int base = 0; base < used; base += 1024) {
+        const int i = base + t;
+        int2 v = (i < used) ? tile_counts[i] : make_int2(0, 0), x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int ya = __shfl_up_sync(0xffffffffu, x.x, o), yb = __shfl_up_sync(0xffffffffu, x.y, o);
+            if (lane >= o) { x.x += ya; x.y += yb; }
+        }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int2 s = wsum[lane], z = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int ya = __shfl_up_sync(0xffffffffu, z.x, o), yb = __shfl_up_sync(0xffffffffu, z.y, o);
+                if (lane >= o) { z.x += ya; z.y += yb; }
+            }
+            wsum[lane] = make_int2(z.x - s.x, z.y - s.y);
+        }
+        __syncthreads();
+        const int2 c = carry_s;
+        const int2 e = make_int2(c.x + wsum[w].x + x.x - v.x, c.y + wsum[w].y + x.y - v.y);
+        if (i < used) tile_counts[i] = e;
+        __syncthreads();
+        if (t == 1023) carry_s = make_int2(e.x + v.x, e.y + v.y);
+        __syncthreads();
+    }
+    return carry_s;
+}
+
+// rank of candidate i inside its tile for both flags (blocked order: round r covers CT consecutive candidates)
+struct TileRank {
+    int2 run;       // running totals of previous rounds in this tile
+};
+
+// ------------------------------------------------------------------ ghosts (borders)
+__device__ __forceinline__ Flags slab_flags(double xd, const Box &box, int d)
+{
+    Flags f;
+    f.a = box.sendflag[2 * d] && xd <= box.slab_lo_hi[d];
+    f.b = box.sendflag[2 * d + 1] && xd >= box.slab_hi_lo[d];
+    return f;
+}
+
+__global__ void __launch_bounds__(CT) k_mr_border_count(const double *__restrict__ xd, const Counts *__restrict__ cnt,
+                                                        int2 *__restrict__ tile_counts, Box box, int d, int ntiles)
+{
+    const int first = cnt->n_bulk, last = cnt->nlocal + cnt->nghost;
+    tile_count([&](int i) { return slab_flags(xd[i], box, d); }, first, last, tile_counts, ntiles);
+}
+
+__global__ void __launch_bounds__(1024) k_mr_border_scan(int2 *__restrict__ tile_counts, Counts *__restrict__ cnt, double *__restrict__ send_lo,
+                                                         double *__restrict__ send_hi, int d, int swap_cap)
+{
+    const int first = cnt->n_bulk, last = cnt->nlocal + cnt->nghost;
+    const int used = (max(last - first, 0) + CTILE - 1) / CTILE;
+    int2 tot = scan_tiles(tile_counts, used);
+    if (threadIdx.x == 0) {
+        if (tot.x > swap_cap || tot.y > swap_cap) { cnt->err |= 1; tot.x = min(tot.x, swap_cap); tot.y = min(tot.y, swap_cap); }
+        cnt->send_n[2 * d] = tot.x; cnt->send_n[2 * d + 1] = tot.y;
+        reinterpret_cast<int *>(send_lo)[0] = tot.x;           // message headers
+        reinterpret_cast<int *>(send_hi)[0] = tot.y;
+    }
+}
+
+// pack_border_vel (UM/atom_vec_dpd_atomic_meso.cu:61-100): record = {x+shift (3), v (3), tag|type, mask|signature}
+__global__ void __launch_bounds__(CT) k_mr_border_pack(SoA3 x, SoA3 v, const int *__restrict__ tag, const int *__restrict__ type,
+                                                       const int *__restrict__ mask, const float4 *__restrict__ veloc4,
+                                                       const Counts *__restrict__ cnt, const int2 *__restrict__ tile_counts,
+                                                       double *__restrict__ send_lo, double *__restrict__ send_hi,
+                                                       int *__restrict__ list_lo, int *__restrict__ list_hi, Box box, int d, int ntiles,
+                                                       int swap_cap)
+{
+    __shared__ int2 wsum[CT / 32];
+    const int first = cnt->n_bulk, last = cnt->nlocal + cnt->nghost;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int base = first + tile * CTILE;
+        if (base >= last) break;
+        int2 run = tile_counts[tile];
+#pragma unroll
+        for (int r = 0; r < CI; r++) {
+            const int i = base + r * CT + threadIdx.x;
+            Flags f{false, false};
+            double xi[3] = {0, 0, 0};
+            if (i < last) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) xi[q] = x.c[q][i];
+                f = slab_flags(xi[d], box, d);
+            }
+            const uint32_t ba = __ballot_sync(0xffffffffu, f.a), bb = __ballot_sync(0xffffffffu, f.b);
+            if (lane == 0) wsum[w] = make_int2(__popc(ba), __popc(bb));
+            __syncthreads();
+            int2 pre = make_int2(0, 0), tot = make_int2(0, 0);
+#pragma unroll
+            for (int ww = 0; ww < CT / 32; ww++) {
+                const int2 c = wsum[ww];
+                if (ww < w) { pre.x += c.x; pre.y += c.y; }
+                tot.x += c.x; tot.y += c.y;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                if (!(side ? f.b : f.a)) continue;
+                const int k = side ? run.y + pre.y + __popc(bb & lt) : run.x + pre.x + __popc(ba & lt);
+                if (k >= swap_cap) continue;
+                const int pbc = box.pbc[2 * d + side];
+                double xg[3] = {xi[0], xi[1], xi[2]};
+                if (pbc) xg[d] = pbc > 0 ? xi[d] + box.prd[d] : xi[d] - box.prd[d];   // x + pbc*prd
+                double *rec = (side ? send_hi : send_lo) + (size_t)(k + 1) * REC;
+                rec[0] = xg[0]; rec[1] = xg[1]; rec[2] = xg[2];
+                rec[3] = v.c[0][i]; rec[4] = v.c[1][i]; rec[5] = v.c[2][i];
+                reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
+                reinterpret_cast<int2 *>(rec)[7] = make_int2(mask[i], __float_as_int(veloc4[i].w));
+                (side ? list_hi : list_lo)[k] = i;
+            }
+            run.x += tot.x; run.y += tot.y;
+        }
+    }
+}
+
+// publishes the ghost ranges of the two swaps of dimension d from the received headers
+__global__ void k_mr_border_advance(Counts *cnt, const double *recv_a, const double *recv_b, int d, int cap)
+{
+    int na = reinterpret_cast<const int *>(recv_a)[0], nb = reinterpret_cast<const int *>(recv_b)[0];
+    const int last = cnt->nlocal + cnt->nghost;
+    if (last + na + nb > cap) { cnt->err |= 1; na = 0; nb = 0; }
+    cnt->swap_first[2 * d] = last;          cnt->swap_n[2 * d] = na;
+    cnt->swap_first[2 * d + 1] = last + na; cnt->swap_n[2 * d + 1] = nb;
+    cnt->nghost += na + nb;
+    cnt->nall = cnt->nlocal + cnt->nghost;
+}
+
+// unpack_border_vel (UM/atom_vec_dpd_atomic_meso.cu:137-163) + packing of the new ghosts
+__global__ void __launch_bounds__(256) k_mr_border_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
+                                                          float4 *__restrict__ coord4, float4 *__restrict__ veloc4,
+                                                          const Counts *__restrict__ cnt, const double *__restrict__ recv_a,
+                                                          const double *__restrict__ recv_b, Box box, int d)
+{
+    const int na = cnt->swap_n[2 * d], n = na + cnt->swap_n[2 * d + 1], g0 = cnt->swap_first[2 * d];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double *rec = (k < na) ? recv_a + (size_t)(k + 1) * REC : recv_b + (size_t)(k - na + 1) * REC;
+        const int g = g0 + k;
+        const double xx = rec[0], yy = rec[1], zz = rec[2], vx = rec[3], vy = rec[4], vz = rec[5];
+        const int2 tt = reinterpret_cast<const int2 *>(rec)[6], ms = reinterpret_cast<const int2 *>(rec)[7];
+        x.c[0][g] = xx; x.c[1][g] = yy; x.c[2][g] = zz;
+        v.c[0][g] = vx; v.c[1][g] = vy; v.c[2][g] = vz;
+        tag[g] = tt.x; type[g] = tt.y; mask[g] = ms.x;
+        float4 c, w;
+        c.x = (float)(xx - box.centre[0]); c.y = (float)(yy - box.centre[1]); c.z = (float)(zz - box.centre[2]);
+        c.w = __int_as_float(tt.y - 1);
+        w.x = (float)vx; w.y = (float)vy; w.z = (float)vz; w.w = __int_as_float(ms.y);
+        coord4[g] = c; veloc4[g] = w;
+    }
+}
+
+// ------------------------------------------------------------------ per-step forward (pack_comm_vel / unpack_comm_vel)
+__global__ void __launch_bounds__(256) k_mr_forward_pack(SoA3 x, SoA3 v, const float4 *__restrict__ veloc4, const Counts *__restrict__ cnt,
+                                                         const int *__restrict__ list_lo, const int *__restrict__ list_hi,
+                                                         double *__restrict__ send_lo, double *__restrict__ send_hi, Box box, int d)
+{
+    const int na = cnt->send_n[2 * d], n = na + cnt->send_n[2 * d + 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        reinterpret_cast<int *>(send_lo)[0] = na;
+        reinterpret_cast<int *>(send_hi)[0] = n - na;
+    }
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int side = k >= na;
+        const int kk = side ? k - na : k;
+        const int i = (side ? list_hi : list_lo)[kk];
+        const int pbc = box.pbc[2 * d + side];
+        double *rec = (side ? send_hi : send_lo) + (size_t)(kk + 1) * REC;
+        double xg[3] = {x.c[0][i], x.c[1][i], x.c[2][i]};
+        if (pbc) xg[d] = pbc > 0 ? xg[d] + box.prd[d] : xg[d] - box.prd[d];
+        rec[0] = xg[0]; rec[1] = xg[1]; rec[2] = xg[2];
+        rec[3] = v.c[0][i]; rec[4] = v.c[1][i]; rec[5] = v.c[2][i];
+        reinterpret_cast<int2 *>(rec)[7] = make_int2(0, __float_as_int(veloc4[i].w));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mr_forward_unpack(SoA3 x, SoA3 v, const int *__restrict__ type, float4 *__restrict__ coord4,
+                                                           float4 *__restrict__ veloc4, Counts *__restrict__ cnt,
+                                                           const double *__restrict__ recv_a, const double *__restrict__ recv_b, Box box, int d)
+{
+    const int na = cnt->swap_n[2 * d], n = na + cnt->swap_n[2 * d + 1], g0 = cnt->swap_first[2 * d];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // the sender's list must still be the one that created these ghosts
+        if (reinterpret_cast<const int *>(recv_a)[0] != na || reinterpret_cast<const int *>(recv_b)[0] != n - na) atomicOr(&cnt->err, 16);
+    }
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double *rec = (k < na) ? recv_a + (size_t)(k + 1) * REC : recv_b + (size_t)(k - na + 1) * REC;
+        const int g = g0 + k;
+        const double xx = rec[0], yy = rec[1], zz = rec[2], vx = rec[3], vy = rec[4], vz = rec[5];
+        x.c[0][g] = xx; x.c[1][g] = yy; x.c[2][g] = zz;
+        v.c[0][g] = vx; v.c[1][g] = vy; v.c[2][g] = vz;
+        float4 c, w;
+        c.x = (float)(xx - box.centre[0]); c.y = (float)(yy - box.centre[1]); c.z = (float)(zz - box.centre[2]);
+        c.w = __int_as_float(type[g] - 1);
+        w.x = (float)vx; w.y = (float)vy; w.z = (float)vz; w.w = __int_as_float(reinterpret_cast<const int2 *>(rec)[7].y);
+        coord4[g] = c; veloc4[g] = w;
+    }
+}
+
+// ------------------------------------------------------------------ migration (exchange)
+// leaving test `x >= hi || x < lo`, direction by the minimum image of x - mid (UM/comm_meso.cu:303-330)
+__device__ __forceinline__ Flags leave_flags(double xd, const Box &box, int d)
+{
+    Flags f{false, false};
+    if (xd >= box.subhi[d] || xd < box.sublo[d]) {
+        double dist = xd - 0.5 * (box.sublo[d] + box.subhi[d]);
+        if (box.periodic[d] && fabs(dist) > 0.5 * box.prd[d]) dist += dist < 0.0 ? box.prd[d] : -box.prd[d];
+        f.a = dist < 0;
+        f.b = !f.a;
+    }
+    return f;
+}
+
+__global__ void __launch_bounds__(CT) k_mr_exch_count(const double *__restrict__ xd, const Counts *__restrict__ cnt,
+                                                      int2 *__restrict__ tile_counts, Box box, int d, int ntiles)
+{
+    tile_count([&](int i) { return leave_flags(xd[i], box, d); }, 0, cnt->nlocal, tile_counts, ntiles);
+}
+
+__global__ void __launch_bounds__(1024) k_mr_exch_scan(int2 *__restrict__ tile_counts, Counts *__restrict__ cnt, double *__restrict__ send_l,
+                                                       double *__restrict__ send_r, int exch_cap)
+{
+    const int used = (cnt->nlocal + CTILE - 1) / CTILE;
+    int2 tot = scan_tiles(tile_counts, used);
+    if (threadIdx.x == 0) {
+        if (tot.x > exch_cap || tot.y > exch_cap) cnt->err |= 8;      // would lose atoms
+        cnt->exch_n[0] = min(tot.x, exch_cap); cnt->exch_n[1] = min(tot.y, exch_cap);
+        reinterpret_cast<int *>(send_l)[0] = cnt->exch_n[0];
+        reinterpret_cast<int *>(send_r)[0] = cnt->exch_n[1];
+    }
+}
+
+// stayers are compacted in order into the alternate arrays; leavers become records {x(3), v(3), tag|type, mask|image}
+__global__ void __launch_bounds__(CT) k_mr_exch_scatter(SoA3 x, SoA3 v, const int *__restrict__ tag, const int *__restrict__ type,
+                                                        const int *__restrict__ mask, const int *__restrict__ image, SoA3 xo, SoA3 vo,
+                                                        int *__restrict__ tago, int *__restrict__ typeo, int *__restrict__ masko,
+                                                        int *__restrict__ imageo, const Counts *__restrict__ cnt,
+                                                        const int2 *__restrict__ tile_counts, double *__restrict__ send_l,
+                                                        double *__restrict__ send_r, Box box, int d, int ntiles, int exch_cap)
+{
+    __shared__ int2 wsum[CT / 32];
+    const int last = cnt->nlocal;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int base = tile * CTILE;
+        if (base >= last) break;
+        int2 run = tile_counts[tile];
+#pragma unroll
+        for (int r = 0; r < CI; r++) {
+            const int i = base + r * CT + threadIdx.x;
+            Flags f{false, false};
+            if (i < last) f = leave_flags(x.c[d][i], box, d);
+            const uint32_t ba = __ballot_sync(0xffffffffu, f.a), bb = __ballot_sync(0xffffffffu, f.b);
+            if (lane == 0) wsum[w] = make_int2(__popc(ba), __popc(bb));
+            __syncthreads();
+            int2 pre = make_int2(0, 0), tot = make_int2(0, 0);
+#pragma unroll
+            for (int ww = 0; ww < CT / 32; ww++) {
+                const int2 c = wsum[ww];
+                if (ww < w) { pre.x += c.x; pre.y += c.y; }
+                tot.x += c.x; tot.y += c.y;
+            }
+            __syncthreads();
+            if (i < last) {
+                const int ka = run.x + pre.x + __popc(ba & lt), kb = run.y + pre.y + __popc(bb & lt);
+                if (!f.a && !f.b) {
+                    const int p = i - ka - kb;                  // stable: stayers keep their relative order
+#pragma unroll
+                    for (int q = 0; q < 3; q++) { xo.c[q][p] = x.c[q][i]; vo.c[q][p] = v.c[q][i]; }
+                    tago[p] = tag[i]; typeo[p] = type[i]; masko[p] = mask[i]; imageo[p] = image[i];
+                } else {
+                    const int k = f.a ? ka : kb;
+                    if (k < exch_cap) {
+                        double *rec = (f.a ? send_l : send_r) + (size_t)(k + 1) * REC;
+#pragma unroll
+                        for (int q = 0; q < 3; q++) { rec[q] = x.c[q][i]; rec[3 + q] = v.c[q][i]; }
+                        reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
+                        reinterpret_cast<int2 *>(rec)[7] = make_int2(mask[i], image[i]);
+                    }
+                }
+            }
+            run.x += tot.x; run.y += tot.y;
+        }
+    }
+}
+
+__global__ void k_mr_exch_shrink(Counts *cnt) { cnt->nlocal -= cnt->exch_n[0] + cnt->exch_n[1]; }
+
+// arrivals are appended: first the upper neighbor's left-movers, then the lower neighbor's right-movers
+// (UM/comm_meso.cu:385-417); an arrival outside [lo,hi) in this dimension is dropped there too ("rejected")
+__global__ void __launch_bounds__(256) k_mr_exch_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
+                                                        int *__restrict__ image, Counts *__restrict__ cnt, const double *__restrict__ recv_a,
+                                                        const double *__restrict__ recv_b, Box box, int d, int nloc_cap)
+{
+    const int na = reinterpret_cast<const int *>(recv_a)[0], n = na + reinterpret_cast<const int *>(recv_b)[0];
+    const int base = cnt->nlocal;
+    if (base + n > nloc_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&cnt->err, 8); return; }
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double *rec = (k < na) ? recv_a + (size_t)(k + 1) * REC : recv_b + (size_t)(k - na + 1) * REC;
+        const int p = base + k;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { x.c[q][p] = rec[q]; v.c[q][p] = rec[3 + q]; }
+        const int2 tt = reinterpret_cast<const int2 *>(rec)[6], mi = reinterpret_cast<const int2 *>(rec)[7];
+        tag[p] = tt.x; type[p] = tt.y; mask[p] = mi.x; image[p] = mi.y;
+        if (!(rec[d] >= box.sublo[d] && rec[d] < box.subhi[d])) atomicOr(&cnt->err, 8);
+    }
+}
+
+__global__ void k_mr_exch_grow(Counts *cnt, const double *recv_a, const double *recv_b)
+{
+    cnt->nlocal += reinterpret_cast<const int *>(recv_a)[0] + reinterpret_cast<const int *>(recv_b)[0];
+    cnt->nall = cnt->nlocal;
+}
+
+// ------------------------------------------------------------------ host drivers
+static int ensure_comm_buffers(meso_ctx *ctx)
+{
+    // slab of width cutghost over the largest (ghost-extended) face, at the brick's density, with head room
+    const Box &b = ctx->box;
+    double w[3], vol = 1.0;
+    for (int d = 0; d < 3; d++) { w[d] = b.subhi[d] - b.sublo[d]; vol *= w[d]; }
+    const double dens = std::max(1.0, (double)ctx->nlocal_host / vol);
+    double face = 0;
+    for (int d = 0; d < 3; d++) {
+        double a = 1.0;
+        for (int q = 0; q < 3; q++) if (q != d) a *= w[q] + 2.0 * ctx->cutneighmax;
+        face = std::max(face, a);
+    }
+    int swap_cap = (int)(face * ctx->cutneighmax * dens * 1.5) + 4096;
+    int exch_cap = std::max(8192, ctx->nlocal_host / 8);
+    if (swap_cap <= ctx->swap_cap && exch_cap <= ctx->exch_cap) return MESO_OK;
+    ctx->swap_cap = std::max(ctx->swap_cap, swap_cap);
+    ctx->exch_cap = std::max(ctx->exch_cap, exch_cap);
+    const size_t msg = (size_t)(std::max(ctx->swap_cap, ctx->exch_cap) + 1) * REC;
+    bool ok = true;
+    for (int s = 0; s < 2; s++) ok = ok && ctx->send_buf[s].reserve(msg) && ctx->recv_buf[s].reserve(msg);
+    for (int s = 0; s < 6; s++) ok = ok && ctx->sendlist[s].reserve((size_t)ctx->swap_cap);
+    const size_t ntiles = (ctx->cap + CTILE - 1) / CTILE;
+    ok = ok && ctx->tile_counts.reserve(ntiles * 2 + 16);
+    if (!ok) { ctx->err = "out of device memory (halo buffers)"; return MESO_ECUDA; }
+    return MESO_OK;
+}
+
+// one dimension's pair of messages: mine to lower/upper neighbor, theirs from upper/lower.  Self-partnered
+// dimensions alias the receive pointers to the send buffers (no copy, no NCCL).
+static int swap_messages(meso_ctx *ctx, int d, size_t ndoubles, cudaStream_t st, const double *&recv_a, const double *&recv_b)
+{
+    if (ctx->procgrid[d] == 1) { recv_a = ctx->send_buf[0].p; recv_b = ctx->send_buf[1].p; return MESO_OK; }
+    ncclComm_t comm = (ncclComm_t)ctx->nccl;
+    const int lower = ctx->procneigh[d][0], upper = ctx->procneigh[d][1];
+    MESO_NCCL(ncclGroupStart());
+    MESO_NCCL(ncclSend(ctx->send_buf[0].p, ndoubles, ncclDouble, lower, comm, st));
+    MESO_NCCL(ncclRecv(ctx->recv_buf[0].p, ndoubles, ncclDouble, upper, comm, st));
+    MESO_NCCL(ncclSend(ctx->send_buf[1].p, ndoubles, ncclDouble, upper, comm, st));
+    MESO_NCCL(ncclRecv(ctx->recv_buf[1].p, ndoubles, ncclDouble, lower, comm, st));
+    MESO_NCCL(ncclGroupEnd());
+    recv_a = ctx->recv_buf[0].p; recv_b = ctx->recv_buf[1].p;
+    return MESO_OK;
+}
+
+int launch_exchange_multi(meso_ctx *ctx)
+{
+    int rc = ensure_comm_buffers(ctx);
+    if (rc) return rc;
+    const Box &box = ctx->box;
+    const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
+    int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
+    cudaStream_t st = ctx->stream;
+    for (int d = 0; d < 3; d++) {
+        if (ctx->procgrid[d] == 1) continue;        // the periodic wrap already put every atom back into the brick
+        k_mr_exch_count<<<grid_for(ctx, 4), CT, 0, st>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
+        k_mr_exch_scan<<<1, 1024, 0, st>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->exch_cap);
+        k_mr_exch_scatter<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
+                                                         soa(ctx->xa), soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p, ctx->imagea.p,
+                                                         ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d, ntiles, ctx->exch_cap);
+        for (int q = 0; q < 3; q++) { std::swap(ctx->x[q].p, ctx->xa[q].p); std::swap(ctx->v[q].p, ctx->va[q].p); }
+        std::swap(ctx->tag.p, ctx->taga.p); std::swap(ctx->type.p, ctx->typea.p);
+        std::swap(ctx->mask.p, ctx->maska.p); std::swap(ctx->image.p, ctx->imagea.p);
+        k_mr_exch_shrink<<<1, 1, 0, st>>>(ctx->d_counts);
+        const double *ra, *rb;
+        rc = swap_messages(ctx, d, (size_t)(ctx->exch_cap + 1) * REC, st, ra, rb);
+        if (rc) return rc;
+        k_mr_exch_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
+                                                        ctx->d_counts, ra, rb, box, d, (int)ctx->nloc_cap);
+        k_mr_exch_grow<<<1, 1, 0, st>>>(ctx->d_counts, ra, rb);
+    }
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+__global__ void k_mr_reset_ghosts(Counts *cnt)
+{
+    cnt->nghost = 0;
+    cnt->nall = cnt->nlocal;
+    cnt->max_pair = 0;
+    for (int s = 0; s < 6; s++) { cnt->swap_first[s] = cnt->nlocal; cnt->swap_n[s] = 0; cnt->send_n[s] = 0; }
+}
+
+int launch_borders_multi(meso_ctx *ctx)
+{
+    int rc = ensure_comm_buffers(ctx);
+    if (rc) return rc;
+    const Box &box = ctx->box;
+    const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
+    int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
+    cudaStream_t st = ctx->stream;
+    k_mr_reset_ghosts<<<1, 1, 0, st>>>(ctx->d_counts);
+    for (int d = 0; d < 3; d++) {
+        if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1] && ctx->procgrid[d] == 1) continue;
+        k_mr_border_count<<<grid_for(ctx, 4), CT, 0, st>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
+        k_mr_border_scan<<<1, 1024, 0, st>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, d, ctx->swap_cap);
+        k_mr_border_pack<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->veloc4.p,
+                                                        ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->sendlist[2 * d].p,
+                                                        ctx->sendlist[2 * d + 1].p, box, d, ntiles, ctx->swap_cap);
+        const double *ra, *rb;
+        rc = swap_messages(ctx, d, (size_t)(ctx->swap_cap + 1) * REC, st, ra, rb);
+        if (rc) return rc;
+        k_mr_border_advance<<<1, 1, 0, st>>>(ctx->d_counts, ra, rb, d, (int)ctx->cap);
+        k_mr_border_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->coord4.p,
+                                                          ctx->veloc4.p, ctx->d_counts, ra, rb, box, d);
+    }
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+// per-step ghost refresh on stream `st` (the side stream when it overlaps the bulk force kernel)
+int launch_forward_multi(meso_ctx *ctx, cudaStream_t st)
+{
+    const Box &box = ctx->box;
+    for (int d = 0; d < 3; d++) {
+        if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1] && ctx->procgrid[d] == 1) continue;
+        k_mr_forward_pack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->veloc4.p, ctx->d_counts, ctx->sendlist[2 * d].p,
+                                                         ctx->sendlist[2 * d + 1].p, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d);
+        const double *ra, *rb;
+        int rc = swap_messages(ctx, d, (size_t)(ctx->swap_cap + 1) * REC, st, ra, rb);
+        if (rc) return rc;
+        k_mr_forward_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
+                                                           ra, rb, box, d);
+    }
+    MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
 

@@ -24,6 +24,8 @@ struct Counts {
     int err;                        // bit 0: ghost capacity, 1: pair table overflow, 2: join overlap, 3: lost atom
     int max_pair;
     int nall;                       // nlocal + nghost
+    int send_n[6];                  // atoms this rank sends in each border swap (== swap_n on a self-partnered swap)
+    int exch_n[2];                  // migration: leavers to the lower / upper neighbor in the current dimension
     int pad[1];
 };
 
@@ -117,6 +119,13 @@ struct meso_ctx {
     meso::DevBuf<int> ghost_root;             // per ghost g: local source index
     meso::DevBuf<int> ghost_shift;            // per ghost g: packed shift code (2 bits per dim)
     meso::DevBuf<int> tile_counts;            // compaction scratch
+    // multi-rank halo
+    bool comm_path = false;                   // use the message-based border/forward path (always when nranks > 1)
+    int swap_cap = 0, exch_cap = 0;           // records per halo / migration message
+    size_t nloc_cap = 0;                      // capacity for local atoms
+    meso::DevBuf<double> send_buf[2], recv_buf[2], reduce_buf;
+    meso::DevBuf<int> sendlist[6];
+    cudaEvent_t ev_fwd_begin = nullptr, ev_fwd_end = nullptr;
     // cells
     meso::DevBuf<uint64_t> cell_key;          // sort key (cell id) per atom
     meso::DevBuf<int> cell_of, cell_atoms, cell_start;
@@ -156,12 +165,19 @@ namespace meso {
 
 // kernels are persistent grid-stride: one launch shape for any n (counts are device-side)
 inline int grid_for(const meso_ctx *ctx, int blocks_per_sm) { return ctx->sm_count * blocks_per_sm; }
+// host-side upper bound of the local atom count (exact on one rank; the local capacity when atoms can migrate)
+inline size_t nlocal_bound(const meso_ctx *ctx) { return ctx->nranks > 1 ? ctx->nloc_cap : (size_t)ctx->nlocal_host; }
 
 // ---- sort.cu
 // ---- reorder.cu
+int launch_pbc(meso_ctx *ctx);         // periodic wrap + image flags only (before migration)
 int launch_reorder(meso_ctx *ctx);     // pbc + key + sort + gather(+pack)
 int launch_borders(meso_ctx *ctx);     // ghost creation (single rank: periodic images)
 int launch_forward(meso_ctx *ctx, bool full);     // per-step ghost refresh
+// ---- comm.cu
+int launch_exchange_multi(meso_ctx *ctx);
+int launch_borders_multi(meso_ctx *ctx);
+int launch_forward_multi(meso_ctx *ctx, cudaStream_t st);
 // ---- neighbor.cu
 int launch_setup_bins(meso_ctx *ctx);
 int launch_neighbor_build(meso_ctx *ctx);

@@ -248,7 +248,7 @@ int launch_neighbor_build(meso_ctx *ctx)
     float rc2_core = (float)pow(ctx->cutneighmax - ctx->skin, 2.0);   // UM/neigh_build_meso.cu:296-297
     float rc2_tail = (float)pow(ctx->cutneighmax, 2.0);
     {
-        int grid = std::max(1, std::min((ctx->nlocal_host + 127) / 128 + 1, ctx->sm_count * 4096));
+        int grid = std::max(1, std::min((int)((nlocal_bound(ctx) + 127) / 128) + 1, ctx->sm_count * 4096));
         k_build_neighbors<<<grid, 128, 0, ctx->stream>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
                                                       ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail);
     }

@@ -277,7 +277,7 @@ static int launch_pair_t(meso_ctx *ctx, const REAL *coeff, REAL dtis, int range,
     const double dtf = 0.5 * ctx->dt;   // ftm2v = 1 in lj units (FixNVEMeso::init, UM/fix_nve_meso.cu:42-46)
     const size_t sh = (((size_t)nt * nt * NCOEFF * sizeof(REAL) + 15) & ~(size_t)15) + (size_t)(PAIR_THREADS / 32) * QDEPTH * 32 * sizeof(int);
     // one CTA per 128 particles (host-side upper bound of the range); the grid-stride loop covers any excess
-    int grid = (int)(((size_t)ctx->nlocal_host + PAIR_THREADS - 1) / PAIR_THREADS) + 1;
+    int grid = (int)((nlocal_bound(ctx) + PAIR_THREADS - 1) / PAIR_THREADS) + 1;
     grid = std::max(1, std::min(grid, ctx->sm_count * 4096));
     static bool attr_done = false;
     if (!attr_done) {

@@ -66,6 +66,34 @@ __global__ void __launch_bounds__(256) k_reorder_key(SoA3 x, int *__restrict__ i
     }
 }
 
+// periodic wrap + image flags only (Domain::pbc before Comm::exchange, UM/mvv_meso.cu:283-290)
+__global__ void __launch_bounds__(256) k_pbc(SoA3 x, int *__restrict__ image, const Counts *__restrict__ cnt, Box box)
+{
+    const int n = cnt->nlocal;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int img = image[i];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            if (!box.periodic[d]) continue;
+            double xd = x.c[d][i];
+            const int sh = 10 * d;
+            if (xd < box.boxlo[d]) {
+                xd += box.prd[d];
+                int idim = (img >> sh) & 1023;
+                img = (img ^ (idim << sh)) | (((idim - 1) & 1023) << sh);
+            }
+            if (xd >= box.boxhi[d]) {
+                xd -= box.prd[d];
+                xd = fmax(xd, box.boxlo[d]);
+                int idim = (img >> sh) & 1023;
+                img = (img ^ (idim << sh)) | (((idim + 1) & 1023) << sh);
+            }
+            x.c[d][i] = xd;
+        }
+        image[i] = img;
+    }
+}
+
 // ------------------------------------------------------------------ gather into sorted order (+ pack)
 __global__ void __launch_bounds__(256) k_gather(SoA3c x, SoA3c v, const int *__restrict__ tag, const int *__restrict__ type,
                                                 const int *__restrict__ mask, const int *__restrict__ image, SoA3 xo, SoA3 vo,
@@ -308,6 +336,13 @@ __global__ void __launch_bounds__(256) k_forward_self(SoA3 x, SoA3 v, float4 *__
 // ------------------------------------------------------------------ host drivers
 static inline SoA3 soa(DevBuf<double> *b) { SoA3 s; for (int d = 0; d < 3; d++) s.c[d] = b[d].p; return s; }
 static inline SoA3c soac(DevBuf<double> *b) { SoA3c s; for (int d = 0; d < 3; d++) s.c[d] = b[d].p; return s; }
+
+int launch_pbc(meso_ctx *ctx)
+{
+    k_pbc<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), ctx->image.p, ctx->d_counts, ctx->box);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
 
 int launch_reorder(meso_ctx *ctx)
 {
