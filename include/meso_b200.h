@@ -66,6 +66,8 @@ int meso_pair_dpd_settings(meso_ctx *ctx, int precision, double cut_global, int 
  * MesoPairDPD::prepare_coeff UM/pair_dpd_meso.cu:68-89, layout UM/pair_dpd_meso.h:15-24 */
 int meso_pair_dpd_coeff(meso_ctx *ctx, const double *coeff7);
 int meso_set_timestep_size(meso_ctx *ctx, double dt);     /* update->dt; FixNVEMeso::reset_dt */
+/* force->ftm2v of the host's unit system (FixNVEMeso::init UM/fix_nve_meso.cu:42-46: dtf = 0.5*dt*ftm2v); default 1 (lj) */
+int meso_set_force_units(meso_ctx *ctx, double ftm2v);
 int meso_set_ntimestep(meso_ctx *ctx, int64_t ntimestep); /* update->ntimestep */
 int64_t meso_get_ntimestep(meso_ctx *ctx);
 
@@ -78,6 +80,9 @@ int meso_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, const double *
  * Returns after the copy completed. */
 int meso_atoms_download(meso_ctx *ctx, int nmax, double *x, double *v, double *f, int *tag, int *type,
                         int *mask, int *image);
+/* page-lock / release a borrowed host array in place: Pinned<T>, UM/memory_meso.h:224-243 (cudaHostRegister) */
+int meso_host_register(meso_ctx *ctx, void *ptr, uint64_t bytes);
+int meso_host_unregister(meso_ctx *ctx, void *ptr);
 /* counts after the last rebuild (host mirror; syncs the stream) */
 int meso_counts(meso_ctx *ctx, int *nlocal, int *nghost, int *n_bulk, int *n_border);
 int64_t meso_natoms_global(meso_ctx *ctx);
@@ -101,6 +106,9 @@ int meso_pair_compute(meso_ctx *ctx, int range, int eflag, int vflag);
 int meso_final_integrate(meso_ctx *ctx, int groupbit);
 /* MesoComputeTemp::compute_scalar UM/compute_temp_meso.cu:77-101: sum_i m v^2 over group (all ranks), and group count */
 int meso_compute_ke(meso_ctx *ctx, int groupbit, double *mv2_sum, double *count);
+/* local_only = 1: meso_compute_ke / meso_compute_virial return this rank's part only, for a host that sums over its
+ * own MPI ranks (MPI_Allreduce in UM/compute_temp_meso.cu:97); default 0 = summed over all ranks of the decomposition */
+int meso_set_reduce_scope(meso_ctx *ctx, int local_only);
 /* virial[6] (xx,yy,zz,xy,xz,yz) and pair energy summed over local atoms, all ranks
  * (the reference accumulates per-atom virial UM/pair_dpd_meso.cu:180-186 but never reduces it) */
 int meso_compute_virial(meso_ctx *ctx, double virial6[6], double *e_pair);

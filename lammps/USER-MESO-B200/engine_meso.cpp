@@ -1,0 +1,212 @@
+#include "mpi.h"
+#include "stdlib.h"
+#include "string.h"
+#include "engine_meso.h"
+#include "meso_bridge.h"
+#include "atom.h"
+#include "atom_vec.h"
+#include "comm.h"
+#include "domain.h"
+#include "error.h"
+#include "force.h"
+#include "neighbor.h"
+#include "timer.h"
+#include "update.h"
+
+using namespace LAMMPS_NS;
+
+/* ---------------------------------------------------------------------- */
+
+MesoDevice::MesoDevice(LAMMPS *lmp, int device, std::string profile) :
+  Pointers(lmp), dummy(false), ctx(NULL), profile_mode(profile),
+  profile_lo(0), profile_hi(0), profiling(false), on_device(false), npinned(0), pinned_nmax(0)
+{
+  int ndev = meso_device_count();
+  if (ndev <= 0)
+    error->one(FLERR,"<MESO> no CUDA device found: USER-MESO-B200 has no CPU path (run with -meso off for stock styles)");
+  if (device < 0 || device >= ndev) error->one(FLERR,"<MESO> -device index out of range");
+  int rc = meso_create(&ctx,device);
+  if (rc != MESO_OK) {
+    char msg[512];
+    sprintf(msg,"<MESO> cannot create device context: %s",meso_last_error(NULL));
+    error->one(FLERR,msg);
+  }
+  if (profile_mode.compare(0,8,"interval") == 0) {
+    const char *s = profile_mode.c_str() + 8;
+    profile_lo = ATOBIGINT(s);
+    const char *dash = strchr(s,'-');
+    profile_hi = dash ? ATOBIGINT(dash+1) : profile_lo;
+  } else if (profile_mode == "all") {
+    meso_profiler(ctx,1);
+    profiling = true;
+  }
+}
+
+MesoDevice::~MesoDevice()
+{
+  if (ctx) {
+    if (profiling) meso_profiler(ctx,0);
+    unpin_host_arrays();
+    meso_destroy(ctx);
+  }
+}
+
+void MesoDevice::check(int rc, const char *file, int line)
+{
+  if (rc == MESO_OK) return;
+  char msg[1024];
+  const char *txt = meso_last_error(ctx);
+  sprintf(msg,"<MESO> device library error %d: %.900s",rc,txt ? txt : "(no message)");
+  error->one(file,line,msg);
+}
+
+/* ----------------------------------------------------------------------
+   everything the library must know that is not per-atom data
+------------------------------------------------------------------------- */
+
+void MesoDevice::push_settings()
+{
+  if (domain->triclinic) error->all(FLERR,"<MESO> triclinic domain not supported in USER-MESO");
+  if (domain->dimension != 3) error->all(FLERR,"<MESO> USER-MESO-B200 needs a 3d simulation");
+  int periodic[3] = {domain->xperiodic, domain->yperiodic, domain->zperiodic};
+  check(meso_set_box(ctx,domain->boxlo,domain->boxhi,periodic),FLERR);
+
+  if (comm->nprocs > 1) {
+    // one MPI rank per GPU: the ranks share an ncclUniqueId and keep LAMMPS' brick layout
+    char id[128];
+    if (comm->me == 0) check(meso_comm_unique_id(id),FLERR);
+    MPI_Bcast(id,128,MPI_CHAR,0,world);
+    int expect = (comm->myloc[0]*comm->procgrid[1] + comm->myloc[1])*comm->procgrid[2] + comm->myloc[2];
+    if (expect != comm->me)
+      error->all(FLERR,"<MESO> processor mapping must be x-major (processors * * * map xyz is not supported)");
+    check(meso_set_decomposition(ctx,comm->me,comm->procgrid,id),FLERR);
+    check(meso_set_reduce_scope(ctx,1),FLERR);      // LAMMPS computes do their own MPI_Allreduce
+  }
+
+  if (atom->mass == NULL) error->all(FLERR,"<MESO> per-type masses are required");
+  for (int i = 1; i <= atom->ntypes; i++)
+    if (!atom->mass_setflag[i]) error->all(FLERR,"All masses are not set");
+  check(meso_set_types(ctx,atom->ntypes,atom->mass),FLERR);
+
+  if (neighbor->delay != 0 || neighbor->dist_check != 0)
+    error->all(FLERR,"<MESO> USER-MESO-B200 rebuilds on a fixed cadence: use neigh_modify delay 0 every N check no");
+  check(meso_set_neighbor(ctx,neighbor->skin,neighbor->every),FLERR);
+  check(meso_set_timestep_size(ctx,update->dt),FLERR);
+  check(meso_set_force_units(ctx,force->ftm2v),FLERR);
+  check(meso_set_ntimestep(ctx,(int64_t) update->ntimestep),FLERR);
+}
+
+/* ---------------------------------------------------------------------- */
+
+void MesoDevice::pin_host_arrays()
+{
+  if (pinned_nmax == atom->nmax && npinned) return;
+  unpin_host_arrays();
+  const uint64_t n = (uint64_t) atom->nmax;
+  void *p[7] = {atom->x ? atom->x[0] : NULL, atom->v ? atom->v[0] : NULL, atom->f ? atom->f[0] : NULL,
+                atom->tag, atom->type, atom->mask, atom->image};
+  const uint64_t bytes[7] = {24*n,24*n,24*n,4*n,4*n,4*n,sizeof(tagint)*n};
+  for (int k = 0; k < 7; k++) {
+    if (!p[k]) continue;
+    check(meso_host_register(ctx,p[k],bytes[k]),FLERR);
+    pinned[npinned++] = p[k];
+  }
+  pinned_nmax = atom->nmax;
+}
+
+void MesoDevice::unpin_host_arrays()
+{
+  for (int k = 0; k < npinned; k++) meso_host_unregister(ctx,pinned[k]);
+  npinned = 0;
+  pinned_nmax = 0;
+}
+
+void MesoDevice::upload_atoms()
+{
+  if (sizeof(tagint) != sizeof(int))
+    error->all(FLERR,"<MESO> USER-MESO-B200 needs 32-bit image flags (default -DLAMMPS_SMALLBIG)");
+  pin_host_arrays();
+  const int n = atom->nlocal;
+  check(meso_atoms_upload(ctx,n,n ? atom->x[0] : NULL,n ? atom->v[0] : NULL,atom->tag,atom->type,atom->mask,
+                          (const int *) atom->image),FLERR);
+  on_device = true;
+}
+
+void MesoDevice::download_atoms()
+{
+  if (!on_device) return;
+  int nlocal = 0;
+  check(meso_counts(ctx,&nlocal,NULL,NULL,NULL),FLERR);
+  if (nlocal > atom->nmax) {                     // atoms migrated in (multi-rank): grow the host arrays first
+    unpin_host_arrays();
+    while (nlocal > atom->nmax) atom->avec->grow(0);
+  }
+  pin_host_arrays();
+  check(meso_atoms_download(ctx,atom->nmax,atom->x[0],atom->v[0],atom->f[0],atom->tag,atom->type,atom->mask,
+                            (int *) atom->image),FLERR);
+  atom->nlocal = nlocal;
+  atom->nghost = 0;                              // ghosts exist on the device only
+  if (atom->map_style) { atom->map_init(); atom->map_set(); }   // the device reorders atoms at every rebuild
+}
+
+/* ---------------------------------------------------------------------- */
+
+void MesoDevice::profile_run_begin(bigint first_step)
+{
+  if (profile_mode == "loop" || profile_mode == "core") { meso_profiler(ctx,1); profiling = true; }
+  profile_step(first_step);
+}
+
+void MesoDevice::profile_step(bigint step)
+{
+  if (profile_mode.compare(0,8,"interval") != 0) return;
+  if (!profiling && step >= profile_lo && step < profile_hi) { meso_profiler(ctx,1); profiling = true; }
+  else if (profiling && step >= profile_hi) { meso_profiler(ctx,0); profiling = false; }
+}
+
+void MesoDevice::profile_run_end()
+{
+  if (profiling && profile_mode != "all") { meso_profiler(ctx,0); profiling = false; }
+}
+
+/* ---------------------------------------------------------------------- */
+
+void MesoDevice::timers_begin()
+{
+  double ms[MESO_T_COUNT];
+  int64_t calls[MESO_T_COUNT];
+  meso_timers_enable(ctx,1);
+  meso_timers_read(ctx,ms,calls,1);
+}
+
+void MesoDevice::timers_end()
+{
+  double ms[MESO_T_COUNT];
+  int64_t calls[MESO_T_COUNT];
+  if (meso_timers_read(ctx,ms,calls,1) != MESO_OK) return;
+  meso_timers_enable(ctx,0);
+  // Finish prints TIME_LOOP minus the categories as "Other": the integrator kernels stay there
+  timer->array[TIME_PAIR] += 1.0e-3*ms[MESO_T_PAIR];
+  timer->array[TIME_NEIGHBOR] += 1.0e-3*(ms[MESO_T_NEIGH] + ms[MESO_T_REBUILD]);
+  timer->array[TIME_COMM] += 1.0e-3*ms[MESO_T_FORWARD];
+  neighbor->ncalls += (int) calls[MESO_T_NEIGH];        // "Neighbor list builds" of Finish
+}
+
+/* ---------------------------------------------------------------------- */
+
+MesoDevice *MesoBridge::mdev(const char *who) const
+{
+  if (mlmp->meso_device == NULL) {
+    char msg[256];
+    sprintf(msg,"<MESO> %s needs the device runtime: do not combine it with -meso off",who);
+    mlmp->error->all(FLERR,msg);
+  }
+  return mlmp->meso_device;
+}
+
+meso_ctx *MesoBridge::mctx(const char *who) const { return mdev(who)->ctx; }
+
+void MesoBridge::mcheck(int rc, const char *file, int line) const
+{
+  if (rc != MESO_OK) mlmp->meso_device->check(rc,file,line);
+}

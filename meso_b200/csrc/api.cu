@@ -328,6 +328,33 @@ extern "C" int meso_set_timestep_size(meso_ctx *ctx, double dt)
     ctx->dt = dt;
     return MESO_OK;
 }
+extern "C" int meso_set_force_units(meso_ctx *ctx, double ftm2v)
+{
+    CHECK_CTX();
+    if (!(ftm2v > 0)) FAIL(MESO_EINVAL, "ftm2v must be positive");
+    ctx->ftm2v = ftm2v;
+    return MESO_OK;
+}
+extern "C" int meso_set_reduce_scope(meso_ctx *ctx, int local_only) { CHECK_CTX(); ctx->reduce_local = local_only != 0; return MESO_OK; }
+// page-lock a host array in place so uploads/downloads run at PCIe rate (Pinned<T>, UM/memory_meso.h:224-243)
+extern "C" int meso_host_register(meso_ctx *ctx, void *ptr, uint64_t bytes)
+{
+    CHECK_CTX();
+    if (!ptr || !bytes) return MESO_OK;
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return MESO_OK; }
+    MESO_CUDA(e);
+    return MESO_OK;
+}
+extern "C" int meso_host_unregister(meso_ctx *ctx, void *ptr)
+{
+    CHECK_CTX();
+    if (!ptr) return MESO_OK;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) cudaGetLastError();      // not registered: nothing to undo
+    return MESO_OK;
+}
 extern "C" int meso_set_ntimestep(meso_ctx *ctx, int64_t t) { CHECK_CTX(); ctx->ntimestep = t; return MESO_OK; }
 extern "C" int64_t meso_get_ntimestep(meso_ctx *ctx) { return ctx ? ctx->ntimestep : -1; }
 
@@ -539,7 +566,7 @@ extern "C" int meso_compute_ke(meso_ctx *ctx, int groupbit, double *mv2_sum, dou
     TRY(ready(ctx));
     double vals[2];
     TRY(launch_ke(ctx, groupbit, &vals[0], &vals[1]));
-    if (ctx->nranks > 1) TRY(comm_allreduce_sum(ctx, vals, 2));
+    if (ctx->nranks > 1 && !ctx->reduce_local) TRY(comm_allreduce_sum(ctx, vals, 2));
     if (mv2_sum) *mv2_sum = vals[0];
     if (count) *count = vals[1];
     return MESO_OK;
@@ -551,7 +578,7 @@ extern "C" int meso_compute_virial(meso_ctx *ctx, double virial6[6], double *e_p
     TRY(ready(ctx));
     double out[7];
     TRY(launch_virial_sum(ctx, out));
-    if (ctx->nranks > 1) TRY(comm_allreduce_sum(ctx, out, 7));
+    if (ctx->nranks > 1 && !ctx->reduce_local) TRY(comm_allreduce_sum(ctx, out, 7));
     if (virial6) memcpy(virial6, out, 6 * sizeof(double));
     if (e_pair) *e_pair = out[6];
     return MESO_OK;

@@ -177,7 +177,7 @@ static inline SoA3c soac(DevBuf<double> *b) { SoA3c s; for (int d = 0; d < 3; d+
 
 int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack)
 {
-    const double dtv = ctx->dt, dtf = 0.5 * ctx->dt;   // FixNVEMeso::init, UM/fix_nve_meso.cu:42-46 (ftm2v = 1, lj)
+    const double dtv = ctx->dt, dtf = 0.5 * ctx->dt * ctx->ftm2v;   // FixNVEMeso::init, UM/fix_nve_meso.cu:42-46
     if (pack)
         k_initial_integrate<1><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p,
                                                                        ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, ctx->veloc4.p,
@@ -193,7 +193,7 @@ int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack)
 int launch_final_integrate(meso_ctx *ctx, int groupbit)
 {
     k_final_integrate<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p, ctx->mass_dev.p,
-                                                              ctx->d_counts, 0.5 * ctx->dt, groupbit);
+                                                              ctx->d_counts, 0.5 * ctx->dt * ctx->ftm2v, groupbit);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

@@ -87,6 +87,8 @@ struct meso_ctx {
 
     // settings
     double skin = 0.3, cut_global = 1.0, cutneighmax = 1.3, dt = 0.005;
+    double ftm2v = 1.0;            // force->ftm2v of the host's unit system (1 in lj)
+    bool reduce_local = false;     // reductions return this rank's part only (an MPI host sums them itself)
     int every = 5, ago = 0;
     int64_t ntimestep = 0;
     int ntypes = 0;

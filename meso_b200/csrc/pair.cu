@@ -274,7 +274,7 @@ static int launch_pair_t(meso_ctx *ctx, const REAL *coeff, REAL dtis, int range,
     for (int d = 0; d < 3; d++) { f.c[d] = ctx->f[d].p; v.c[d] = ctx->v[d].p; }
     for (int q = 0; q < 6; q++) vir.c[q] = ctx->virial.p + (size_t)q * ctx->cap;
     const int nt = ctx->ntypes;
-    const double dtf = 0.5 * ctx->dt;   // ftm2v = 1 in lj units (FixNVEMeso::init, UM/fix_nve_meso.cu:42-46)
+    const double dtf = 0.5 * ctx->dt * ctx->ftm2v;   // FixNVEMeso::init, UM/fix_nve_meso.cu:42-46
     const size_t sh = (((size_t)nt * nt * NCOEFF * sizeof(REAL) + 15) & ~(size_t)15) + (size_t)(PAIR_THREADS / 32) * QDEPTH * 32 * sizeof(int);
     // one CTA per 128 particles (host-side upper bound of the range); the grid-stride loop covers any excess
     int grid = (int)((nlocal_bound(ctx) + PAIR_THREADS - 1) / PAIR_THREADS) + 1;

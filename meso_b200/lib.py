@@ -29,6 +29,10 @@ SIGNATURES = {
     "meso_pair_dpd_settings": (_i, [_vp, _i, _d, _i]),
     "meso_pair_dpd_coeff": (_i, [_vp, _pd]),
     "meso_set_timestep_size": (_i, [_vp, _d]),
+    "meso_set_force_units": (_i, [_vp, _d]),
+    "meso_set_reduce_scope": (_i, [_vp, _i]),
+    "meso_host_register": (_i, [_vp, _vp, _u64]),
+    "meso_host_unregister": (_i, [_vp, _vp]),
     "meso_set_ntimestep": (_i, [_vp, _i64]),
     "meso_get_ntimestep": (_i64, [_vp]),
     "meso_atoms_upload": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -1,0 +1,206 @@
+"""The reference's benchmark decks through the LAMMPS plugin surface (lammps/USER-MESO-B200 -> C ABI -> CUDA).
+
+lammps/_build/lmp_meso_b200 is the reference's own LAMMPS core (30 Sep 2013) compiled with this repository's
+package instead of the reference's USER-MESO (lammps/Makefile; built in the dev container, shipped to the GPU box).
+The decks below are example/simple/sp.run / dp.run command for command (atom_style dpd/atomic/meso, run_style
+mvv/meso, pair_style dpd/fast/meso | dpd/meso, compute temp/meso, fix nve/meso), plus a dump so that the
+trajectory can be compared with the same library driven through the Python mirror of the C ABI.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from meso_b200 import workload
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LMP = os.path.join(ROOT, "lammps", "_build", "lmp_meso_b200")
+
+DECK = """# example/simple/{prec}.run, box edge ${{case}}
+dimension       3
+units           lj
+atom_style      dpd/atomic/meso
+neighbor        0.3 bin
+neigh_modify    delay 0 every 5 check no
+read_data       ${{case}}.data
+run_style       mvv/meso
+pair_style      {pair} 1.0 419084618
+pair_coeff      1 1 15 4.5 3.0 1.0 1.0
+compute         mythermo all temp/meso
+velocity        all create 1.0 788662042 loop all
+fix             3 all nve/meso
+thermo_style    custom step temp {extra} cpu spcpu
+thermo          {thermo}
+thermo_modify   temp mythermo
+{dump}
+timestep        0.005
+run             {steps}
+"""
+DUMP = ("dump            d all custom {steps} traj.txt id x y z vx vy vz fx fy fz\n"
+        "dump_modify     d format \"%d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\"")
+
+
+def need_binary():
+    if not os.path.exists(LMP):
+        pytest.fail("lammps/_build/lmp_meso_b200 is missing: build it in the dev container (make -C lammps); it ships with the snapshot")
+
+
+def run_deck(tmp_path, L, prec, steps, thermo, extra="", dump=True, args=()):
+    workload.write_data(str(tmp_path / ("%d.data" % L)), workload.dpd_fluid(L), L)
+    deck = DECK.format(prec=prec, pair="dpd/fast/meso" if prec == "sp" else "dpd/meso", extra=extra, thermo=thermo, steps=steps,
+                       dump=DUMP.format(steps=steps) if dump else "")
+    (tmp_path / "in.run").write_text(deck)
+    out = subprocess.run([LMP, "-in", "in.run", "-var", "case", str(L), "-log", "none"] + list(args), cwd=str(tmp_path),
+                         capture_output=True, text=True, timeout=600)
+    return out
+
+
+def frames(path):
+    """{step: array sorted by id, columns id x y z vx vy vz fx fy fz}"""
+    out, lines = {}, open(path).read().split("\n")
+    i = 0
+    while i < len(lines):
+        if lines[i].startswith("ITEM: TIMESTEP"):
+            step, n = int(lines[i + 1]), int(lines[i + 3])
+            body = np.array([[float(t) for t in s.split()] for s in lines[i + 9:i + 9 + n]])
+            out[step] = body[np.argsort(body[:, 0])]
+            i += 9 + n
+        else:
+            i += 1
+    return out
+
+
+def thermo_rows(stdout, ncol):
+    rows, on = [], False
+    for s in stdout.split("\n"):
+        if s.startswith("Step "):
+            on = True
+            continue
+        if s.startswith("Loop time"):
+            on = False
+        t = s.split()
+        if on and len(t) == ncol:
+            try:
+                rows.append([float(v) for v in t])
+            except ValueError:
+                pass
+    return np.array(rows)
+
+
+def mirror(L, prec, fr0):
+    from meso_b200.engine import Meso
+    m = Meso(0)
+    m.box((0.0, 0.0, 0.0), (L, L, L))
+    m.masses([0.0, 1.0])
+    m.neighbor(0.3, "bin")
+    m.neigh_modify(delay=0, every=5, check=False)
+    m.pair_style("dpd/fast/meso" if prec == "sp" else "dpd/meso", 1.0, 419084618)
+    m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
+    m.timestep(0.005)
+    m.upload(np.ascontiguousarray(fr0[:, 1:4]), np.ascontiguousarray(fr0[:, 4:7]), tag=fr0[:, 0].astype(np.int32))
+    return m
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["sp", "dp"])
+def test_benchmark_deck_runs_unchanged_and_matches_the_c_abi_mirror(tmp_path, prec):
+    need_binary()
+    L, steps = 10, 20
+    out = run_deck(tmp_path, L, prec, steps, thermo=10)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "Loop time of" in out.stdout
+    th = thermo_rows(out.stdout, 4)
+    assert th.shape[0] == 3 and abs(th[0, 1] - 1.0) < 1e-12          # velocity create 1.0, read back through temp/meso
+    fr = frames(str(tmp_path / "traj.txt"))
+    assert sorted(fr) == [0, steps]
+    m = mirror(L, prec, fr[0])
+    m.setup()
+    a = m.download()
+    o = np.argsort(a["tag"])
+    assert np.array_equal(a["f"][o], fr[0][:, 7:10]), "setup forces differ between the LAMMPS-driven and the mirror-driven library"
+    m.run(steps)
+    a = m.download()
+    o = np.argsort(a["tag"])
+    assert np.array_equal(a["x"][o], fr[steps][:, 1:4])
+    assert np.array_equal(a["v"][o], fr[steps][:, 4:7])
+    assert np.array_equal(a["f"][o], fr[steps][:, 7:10])
+    assert abs(m.temperature() - th[-1, 1]) < 1e-6                      # thermo prints 8 significant digits
+    m.close()
+
+
+@pytest.mark.gpu
+def test_thermo_energy_and_pressure_go_through_the_phase_entry_points(tmp_path):
+    """`pe` and `press` make LAMMPS ask for energy/virial on thermo steps: those steps run phase by phase
+    (fix nve/meso -> meso_initial_integrate, pair->compute(eflag,vflag), ...), the others through meso_run."""
+    need_binary()
+    L, steps = 10, 20
+    out = run_deck(tmp_path, L, "dp", steps, thermo=10, extra="pe press")
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    th = thermo_rows(out.stdout, 6)
+    assert th.shape[0] == 3
+    fr = frames(str(tmp_path / "traj.txt"))
+    m = mirror(L, "dp", fr[0])
+    m.setup(eflag=1, vflag=1)
+    n = len(fr[0])
+    vol = float(L) ** 3
+
+    def pe_press():
+        vir, e = m.virial()
+        t = m.temperature()
+        return e / n, ((3 * n - 3) * t + vir[0] + vir[1] + vir[2]) / (3.0 * vol)   # thermo normalises pe by N (lj units)
+
+    pe0, p0 = pe_press()
+    assert abs(pe0 - th[0, 2]) < 2e-7 * abs(pe0) and abs(p0 - th[0, 3]) < 2e-7 * abs(p0), (pe0, p0, th[0])
+    m.run(steps - 1)
+    # last step with tallies, phase by phase
+    m.ntimestep = steps
+    m.initial_integrate()
+    if m.neighbor_decide():
+        m.rebuild()
+    else:
+        m.forward_comm()
+    m.force_clear(vflag=1)
+    m.pair_compute(eflag=1, vflag=1)
+    m.final_integrate()
+    pe1, p1 = pe_press()
+    assert abs(pe1 - th[-1, 2]) < 2e-7 * abs(pe1) and abs(p1 - th[-1, 3]) < 2e-7 * abs(p1), (pe1, p1, th[-1])
+    a = m.download()
+    o = np.argsort(a["tag"])
+    assert np.array_equal(a["x"][o], fr[steps][:, 1:4]) and np.array_equal(a["v"][o], fr[steps][:, 4:7])
+    # equilibrium DPD fluid at rho = 4, a = 15... just started from random positions: pressure is positive and O(10)
+    assert 5.0 < p1 < 80.0
+    m.close()
+
+
+@pytest.mark.gpu
+def test_deck_errors_match_the_reference_strings(tmp_path):
+    need_binary()
+    workload.write_data(str(tmp_path / "4.data"), workload.dpd_fluid(4), 4)
+    base = ("units lj\natom_style dpd/atomic/meso\nneighbor 0.3 bin\nneigh_modify delay 0 every 5 check no\nread_data 4.data\n"
+            "run_style mvv/meso\n")
+    cases = [("pair_style dpd/fast/meso 1.0\n", "Illegal pair_style command"),
+             ("pair_style dpd/meso 1.0 1\npair_coeff 1 1 15 4.5 3.0\n", "Incorrect args for pair coefficients"),
+             ("pair_style dpd/meso 1.0 1\nfix 3 all nve/meso\nrun 1\n", "All pair coeffs are not set"),
+             ("pair_style dpd/meso 1.0 1\npair_coeff 1 1 15 4.5 3.0 1.0\nfix 3 all nve\nrun 1\n", "does not act on device-resident atoms")]
+    for tail, msg in cases:
+        (tmp_path / "in.err").write_text(base + tail)
+        out = subprocess.run([LMP, "-in", "in.err", "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+        assert msg in out.stdout + out.stderr, (tail, out.stdout[-500:], out.stderr[-500:])
+
+
+def test_binary_keeps_stock_styles_with_meso_off(tmp_path):
+    """-meso off: the same binary is plain LAMMPS (and is what a CPU baseline would run); -meso on without a GPU fails loudly."""
+    if not os.path.exists(LMP):
+        pytest.skip("lammps/_build/lmp_meso_b200 not built (dev container: make -C lammps)")
+    workload.write_data(str(tmp_path / "4.data"), workload.dpd_fluid(4), 4)
+    (tmp_path / "in.stock").write_text("units lj\natom_style atomic\ncommunicate single vel yes\nneighbor 0.3 bin\nread_data 4.data\n"
+                                       "pair_style dpd 1.0 1.0 34387\npair_coeff 1 1 15 4.5 1.0\nvelocity all create 1.0 4928 loop all\n"
+                                       "fix 1 all nve\ntimestep 0.005\nrun 5\n")
+    out = subprocess.run([LMP, "-meso", "off", "-in", "in.stock", "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "Loop time of" in out.stdout, out.stdout[-800:] + out.stderr[-800:]
+    from meso_b200 import lib
+    if lib.load().meso_device_count() <= 0:
+        (tmp_path / "in.meso").write_text("units lj\natom_style dpd/atomic/meso\n")
+        out = subprocess.run([LMP, "-in", "in.meso", "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+        assert "no CUDA device found" in out.stdout + out.stderr
