@@ -105,6 +105,10 @@ extern "C" int meso_create(meso_ctx **out, int device)
     // MESO_FORCE_COMM_PATH=1 runs the message-based halo path (pack -> [NCCL] -> unpack, side-stream overlap) even on one rank
     const char *fc = getenv("MESO_FORCE_COMM_PATH");
     ctx->comm_path = fc && fc[0] == '1';
+    const char *po = getenv("MESO_PAIR_ONCE");               // 0: two-sided force kernel in meso_run (A/B measurements)
+    ctx->pair_once = !(po && po[0] == '0');
+    if (const char *e = getenv("MESO_PAIR_TEX")) ctx->pair_tex = atoi(e) & 3;
+    if (const char *e = getenv("MESO_NB_PER_ATOM")) ctx->nb_per_atom = e[0] == '1';
     cudaMemsetAsync(ctx->d_counts, 0, sizeof(Counts), ctx->stream);
     memset(ctx->h_counts, 0, sizeof(Counts));
     *out = ctx;
@@ -119,6 +123,8 @@ extern "C" void meso_destroy(meso_ctx *ctx)
     comm_destroy(ctx);
     drain_timers(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->tex_coord) cudaDestroyTextureObject(ctx->tex_coord);
+    if (ctx->tex_veloc) cudaDestroyTextureObject(ctx->tex_veloc);
     if (ctx->ev_fwd_begin) cudaEventDestroy(ctx->ev_fwd_begin);
     if (ctx->ev_fwd_end) cudaEventDestroy(ctx->ev_fwd_end);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
@@ -375,11 +381,29 @@ static int ensure_capacity(meso_ctx *ctx, size_t nlocal)
         ok = ok && ctx->x[d].reserve(cap) && ctx->v[d].reserve(cap) && ctx->f[d].reserve(cap) && ctx->xa[d].reserve(cap) && ctx->va[d].reserve(cap);
     ok = ok && ctx->tag.reserve(cap) && ctx->type.reserve(cap) && ctx->mask.reserve(cap) && ctx->image.reserve(cap) &&
          ctx->taga.reserve(cap) && ctx->typea.reserve(cap) && ctx->maska.reserve(cap) && ctx->imagea.reserve(cap) &&
-         ctx->coord4.reserve(cap) && ctx->veloc4.reserve(cap) && ctx->key.reserve(cap) && ctx->perm_from.reserve(cap) &&
+         ctx->coord4.reserve(cap + 1) && ctx->veloc4.reserve(cap + 1) && ctx->key.reserve(cap) && ctx->perm_from.reserve(cap) &&
          ctx->ghost_root.reserve(cap) && ctx->ghost_shift.reserve(cap) && ctx->cell_key.reserve(cap) && ctx->cell_of.reserve(cap) &&
          ctx->cell_atoms.reserve(cap) && ctx->e_pair.reserve(cap) && ctx->pair_count.reserve(cap);
     if (!ok) FAIL(MESO_ECUDA, "out of device memory growing the atom store");
     ctx->cap = cap;
+    {   // linear float4 textures over the packed views
+        for (cudaTextureObject_t *t : {&ctx->tex_coord, &ctx->tex_veloc}) if (*t) { cudaDestroyTextureObject(*t); *t = 0; }
+        cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+        cudaTextureDesc td; memset(&td, 0, sizeof td);
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        td.readMode = cudaReadModeElementType;
+        rd.res.linear.devPtr = ctx->coord4.p; rd.res.linear.sizeInBytes = (cap + 1) * sizeof(float4);
+        MESO_CUDA(cudaCreateTextureObject(&ctx->tex_coord, &rd, &td, nullptr));
+        rd.res.linear.devPtr = ctx->veloc4.p;
+        MESO_CUDA(cudaCreateTextureObject(&ctx->tex_veloc, &rd, &td, nullptr));
+    }
+    // the `far` record of the pair-once kernel: coord4[cap] = {3.4e38 (0x7f7f7f7f) x 3, type 0}
+    MESO_CUDA(cudaMemsetAsync(ctx->coord4.p + cap, 0x7f, 3 * sizeof(float), ctx->stream));
+    MESO_CUDA(cudaMemsetAsync(reinterpret_cast<float *>(ctx->coord4.p + cap) + 3, 0, sizeof(float), ctx->stream));   // .w = type 0
+    MESO_CUDA(cudaMemsetAsync(ctx->veloc4.p + cap, 0, sizeof(float4), ctx->stream));
+    if (!ctx->facc.reserve(cap)) FAIL(MESO_ECUDA, "out of device memory (force accumulator)");
+    MESO_CUDA(cudaMemsetAsync(ctx->facc.p, 0, ctx->facc.bytes(), ctx->stream));
     if (!ctx->virial.reserve(6 * ctx->cap)) FAIL(MESO_ECUDA, "out of device memory (virial)");
     ctx->table_rows = ((nloc_cap + 31) / 32) * 32;
     return MESO_OK;
@@ -401,7 +425,7 @@ extern "C" int meso_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, con
         MESO_CUDA(cudaMemcpyAsync(ctx->staging.p, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
         TRY(launch_deinterleave3(ctx, ctx->staging.p, ctx->v, nlocal));
     } else TRY(launch_zero3(ctx, ctx->v, nlocal));
-    TRY(launch_zero3(ctx, ctx->f, nlocal));
+    TRY(launch_zero3(ctx, ctx->f, (int)ctx->cap));       // whole capacity: f doubles as the fp64 pair-once accumulator
     if (tag) MESO_CUDA(cudaMemcpyAsync(ctx->tag.p, tag, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (type) MESO_CUDA(cudaMemcpyAsync(ctx->type.p, type, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (mask) MESO_CUDA(cudaMemcpyAsync(ctx->mask.p, mask, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -599,11 +623,66 @@ extern "C" int meso_setup(meso_ctx *ctx, int eflag, int vflag)
     return refresh_counts(ctx);
 }
 
+// The run loop with every local pair evaluated once (pair.cu:k_dpd_once).  Forces are reduced into an accumulator
+// (facc for dpd/fast/meso, f itself for dpd/meso) that is complete only when the whole force phase has finished, so the
+// second half-kick moves out of the force kernel's epilogue into the next step's streaming pass (integrate.cu:
+// k_step_integrate).  Kernels per ordinary step stay at three; on return f holds the last step's force in fp64 and the
+// accumulator is zero again, so the phase entry points, downloads and reductions see the same state as before.
+static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
+{
+    const bool sp = ctx->precision == MESO_SP;
+    bool pending = false;                                    // the previous step's second half-kick is still owed
+    for (int s = 0; s < nsteps; s++) {
+        ctx->ntimestep++;                                    // UM/mvv_meso.cu:256
+        const bool rebuild = meso_neighbor_decide(ctx) != 0;
+        {
+            PhaseTimer t(ctx, MESO_T_INTEGRATE);
+            // fp32: first step reads f (accumulator already zero), later steps read and clear facc;
+            // fp64: f is the accumulator: read and clear it every step
+            TRY(launch_step_integrate(ctx, groupbit, pending, true, !rebuild, sp && pending, sp ? pending : true, false));
+        }
+        pending = true;
+        if (rebuild) {
+            TRY(rebuild_impl(ctx));                          // gather + ghost kernels emit this step's packed views
+        } else if (ctx->comm_path) {
+            // halo refresh on the side stream, overlapped with the bulk force kernel (UM/mvv_meso.cu:338-376)
+            MESO_CUDA(cudaEventRecord(ctx->ev_fwd_begin, ctx->stream));
+            MESO_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fwd_begin, 0));
+            TRY(launch_forward_multi(ctx, ctx->side));
+            MESO_CUDA(cudaEventRecord(ctx->ev_fwd_end, ctx->side));
+            {
+                PhaseTimer t(ctx, MESO_T_PAIR);
+                TRY(launch_pair_once(ctx, MESO_BULK));
+            }
+            {
+                PhaseTimer t(ctx, MESO_T_FORWARD);           // exposed (non-overlapped) part of the halo refresh
+                MESO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fwd_end, 0));
+            }
+            {
+                PhaseTimer t(ctx, MESO_T_PAIR);
+                TRY(launch_pair_once(ctx, MESO_BORDER));
+            }
+            continue;
+        } else {
+            PhaseTimer t(ctx, MESO_T_FORWARD);
+            TRY(launch_forward(ctx, false));
+        }
+        PhaseTimer t(ctx, MESO_T_PAIR);
+        TRY(launch_pair_once(ctx, MESO_LOCAL));
+    }
+    if (pending) {
+        PhaseTimer t(ctx, MESO_T_INTEGRATE);                 // last step's second half-kick; f <- force, accumulator cleared
+        TRY(launch_step_integrate(ctx, groupbit, true, false, false, sp, sp, sp));
+    }
+    return MESO_OK;
+}
+
 extern "C" int meso_run(meso_ctx *ctx, int nsteps, int groupbit)
 {
     CHECK_CTX();
     TRY(ready(ctx));
     if (!ctx->setup_done) FAIL(MESO_EINVAL, "meso_run: call meso_setup first");
+    if (ctx->pair_once) return run_pair_once(ctx, nsteps, groupbit);
     for (int s = 0; s < nsteps; s++) {
         ctx->ntimestep++;                                    // UM/mvv_meso.cu:256
         const bool rebuild = meso_neighbor_decide(ctx) != 0;

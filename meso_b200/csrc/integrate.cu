@@ -49,6 +49,68 @@ __global__ void __launch_bounds__(256) k_initial_integrate(SoA3 x, SoA3 v, SoA3c
     }
 }
 
+// Step boundary of the fused run loop (api.cu:meso_run): the second half-kick of step k-1 and the first half-kick + drift
+// (+ pack + signature) of step k read the same force, so one streaming pass does both.  The force comes from the fp32
+// accumulator of the pair-once kernel (facc, src_acc) or from the fp64 arrays; the source is cleared for the next
+// reduction and/or mirrored into f when the run returns to the caller.  Each half is the reference's own fma
+// (UM/fix_nve_meso.cu:83-92,171-176), so results equal the unfused sequence bit for bit.
+template <int PACK>
+__global__ void __launch_bounds__(256) k_step_integrate(SoA3 x, SoA3 v, SoA3 f, float4 *__restrict__ facc, const int *__restrict__ mask,
+                                                        const int *__restrict__ type, const int *__restrict__ tag,
+                                                        const double *__restrict__ mass, float4 *__restrict__ coord4,
+                                                        float4 *__restrict__ veloc4, const Counts *__restrict__ cnt, Box box, double dtf,
+                                                        double dtv, int groupbit, uint32_t seed_now, int do_final, int do_initial,
+                                                        int src_acc, int zero_src, int write_f)
+{
+    const int n = cnt->nlocal;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        // all loads first: the arrays are not __restrict__ (x, v, f are read and written), so a store in the middle
+        // would serialise the remaining loads behind it
+        const int ty = type[i], mk = mask[i];
+        const int tg = PACK ? tag[i] : 0;
+        double ff[3], xx[3], vv[3];
+        if (src_acc) {
+            const float4 a = facc[i];
+            ff[0] = (double)a.x; ff[1] = (double)a.y; ff[2] = (double)a.z;
+        } else {
+#pragma unroll
+            for (int d = 0; d < 3; d++) ff[d] = f.c[d][i];
+        }
+#pragma unroll
+        for (int d = 0; d < 3; d++) { vv[d] = v.c[d][i]; xx[d] = do_initial ? x.c[d][i] : 0.; }
+        const double ms = mass[ty];
+        if (mk & groupbit) {
+            const double dtfm = __dmul_rn(dtf, rcp_nr(ms));
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                if (do_final) vv[d] = __fma_rn(dtfm, ff[d], vv[d]);
+                if (do_initial) {
+                    vv[d] = __fma_rn(dtfm, ff[d], vv[d]);
+                    xx[d] = __fma_rn(dtv, vv[d], xx[d]);
+                }
+            }
+        }
+        // stores
+        if (src_acc && zero_src) facc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (write_f || (!src_acc && zero_src)) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) f.c[d][i] = write_f ? ff[d] : 0.;
+        }
+        if (mk & groupbit) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) { v.c[d][i] = vv[d]; if (do_initial) x.c[d][i] = xx[d]; }
+        }
+        if (PACK) {
+            float4 c, w;
+            c.x = (float)(xx[0] - box.centre[0]); c.y = (float)(xx[1] - box.centre[1]); c.z = (float)(xx[2] - box.centre[2]);
+            c.w = __int_as_float(ty - 1);
+            w.x = (float)vv[0]; w.y = (float)vv[1]; w.z = (float)vv[2];
+            w.w = __uint_as_float(signature(seed_now, tg, w.x, w.y, w.z));
+            coord4[i] = c; veloc4[i] = w;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_final_integrate(SoA3 v, SoA3c f, const int *__restrict__ mask, const int *__restrict__ type,
                                                          const double *__restrict__ mass, const Counts *__restrict__ cnt, double dtf,
                                                          int groupbit)
@@ -186,6 +248,24 @@ int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack)
         k_initial_integrate<0><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p,
                                                                        ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, ctx->veloc4.p,
                                                                        ctx->d_counts, ctx->box, dtf, dtv, groupbit, 0u);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+int launch_step_integrate(meso_ctx *ctx, int groupbit, bool do_final, bool do_initial, bool pack, bool src_acc, bool zero_src, bool write_f)
+{
+    const double dtv = ctx->dt, dtf = 0.5 * ctx->dt * ctx->ftm2v;
+    pack = pack && do_initial;
+    if (pack)
+        k_step_integrate<1><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), soa(ctx->f), ctx->facc.p, ctx->mask.p, ctx->type.p,
+                                                                    ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
+                                                                    ctx->box, dtf, dtv, groupbit, seed_now(ctx), do_final, do_initial, src_acc,
+                                                                    zero_src, write_f);
+    else
+        k_step_integrate<0><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), soa(ctx->f), ctx->facc.p, ctx->mask.p, ctx->type.p,
+                                                                    ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
+                                                                    ctx->box, dtf, dtv, groupbit, 0u, do_final, do_initial, src_acc, zero_src,
+                                                                    write_f);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

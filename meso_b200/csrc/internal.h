@@ -106,6 +106,11 @@ struct meso_ctx {
     meso::DevBuf<double> x[3], v[3], f[3], xa[3], va[3];
     meso::DevBuf<int> tag, type, mask, image, taga, typea, maska, imagea;
     meso::DevBuf<float4> coord4, veloc4;
+    meso::DevBuf<float4> facc;                // fp32 per-atom force accumulator of the pair-once kernel (zero between uses)
+    cudaTextureObject_t tex_coord = 0, tex_veloc = 0;   // linear float4 textures over coord4 / veloc4 (gather-path experiments)
+    int pair_tex = 2;                         // which gathers of the pair-once kernel use the texture data pipe (MESO_PAIR_TEX)
+    bool nb_per_atom = false;                 // MESO_NB_PER_ATOM=1: thread-per-atom neighbor build everywhere
+    bool pair_once = true;                    // meso_run evaluates each local pair once (MESO_PAIR_ONCE=0: two-sided kernel)
     meso::DevBuf<double> virial, e_pair;      // [6][cap] SoA, [cap]
     meso::DevBuf<double> mass_dev;            // [ntypes+1]
     meso::DevBuf<float> coeff_sp;
@@ -136,6 +141,7 @@ struct meso_ctx {
     meso::DevBuf<int2> cell_runs;             // [ncell][27] {first position, count} per stencil cell
     // neighbor list
     meso::DevBuf<int> pair_count, pair_table;
+    meso::DevBuf<int> nb_fixup;               // != 0: some cell's candidate list exceeded the warp-per-cell window
     size_t table_rows = 0;
 
     // reductions
@@ -186,9 +192,13 @@ int launch_neighbor_build(meso_ctx *ctx);
 // ---- pair.cu
 int launch_pack(meso_ctx *ctx, int range);
 int launch_pair(meso_ctx *ctx, int range, int evflag, bool accumulate, bool fuse_final, int groupbit);
+int launch_pair_once(meso_ctx *ctx, int range);
 // ---- integrate.cu
 int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack);
 int launch_final_integrate(meso_ctx *ctx, int groupbit);
+// fused step boundary: [second half-kick of the previous step] + [first half-kick + drift (+ pack) of this step];
+// force source = facc (fp32 accumulator) or f; optionally mirrors the force into f and clears the source
+int launch_step_integrate(meso_ctx *ctx, int groupbit, bool do_final, bool do_initial, bool pack, bool src_acc, bool zero_src, bool write_f);
 int launch_ke(meso_ctx *ctx, int groupbit, double *mv2, double *count);
 int launch_virial_sum(meso_ctx *ctx, double out7[7]);
 int launch_clear(meso_ctx *ctx, int range, int vflag);

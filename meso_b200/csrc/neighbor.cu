@@ -17,6 +17,8 @@
 #include "internal.h"
 #include "device_math.cuh"
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 namespace meso {
 
@@ -116,9 +118,9 @@ __device__ __forceinline__ size_t slot(int i, int k, int n_col)
     return (size_t)((i & ~31) + (k & 31)) * (size_t)n_col + (size_t)((k >> 5) * 32 + (i & 31));
 }
 
-constexpr int NB_BATCH = 4;     // candidates tested per iteration (independent 16-byte loads in flight)
 constexpr int NB_THREADS = 128;
-constexpr int NB_DEPTH = 64;    // per-lane staging slots: core hits grow from the front, skin hits from the back
+// NB_BATCH: candidates tested per iteration (independent 16-byte loads in flight);
+// NB_DEPTH: per-lane staging slots (core hits grow from the front, skin hits from the back)
 
 // One thread owns one local atom.  In-range candidates are staged in a per-lane two-ended queue in shared
 // memory (column layout [slot][lane]: bank == lane, no conflicts, no atomics), which costs 3 issue slots per
@@ -127,17 +129,22 @@ constexpr int NB_DEPTH = 64;    // per-lane staging slots: core hits grow from t
 // final position (reverse encounter order after the core entries) and the reference's join pass disappears.
 // Rows denser than the queue (> 60 hits, never at rho = 4) take the spill path: core entries are flushed
 // forward, skin entries backward from slot n_col-1 as in the reference, and joined at the end.
+template <int NB_DEPTH, int NB_BATCH>
 __global__ void __launch_bounds__(NB_THREADS) k_build_neighbors(const float4 *__restrict__ coord4, const int *__restrict__ cell_of,
                                                                 const int2 *__restrict__ runs, const float4 *__restrict__ cell_xyzj,
                                                                 int *__restrict__ pair_count, int *__restrict__ pair_table,
-                                                                Counts *__restrict__ cnt, int n_col, float rc2_core, float rc2_tail)
+                                                                Counts *__restrict__ cnt, int n_col, float rc2_core, float rc2_tail,
+                                                                const int *__restrict__ fixup)
 {
     __shared__ int stage[NB_THREADS / 32][NB_DEPTH][32];
+    // fix-up mode: only the rows the warp-per-cell kernel marked (pair_count == -1); nothing to do when no cell was marked
+    if (fixup && *fixup == 0) return;
     int(*qq)[32] = stage[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int nlocal = cnt->nlocal;
     int worst = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+        if (fixup && pair_count[i] >= 0) continue;
         const float4 ci = coord4[i];
         const int2 *my = runs + (size_t)cell_of[i] * 27;
         int *row0 = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
@@ -201,6 +208,236 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_neighbors(const float4 *__
     if ((threadIdx.x & 31) == 0 && worst > 0) atomicMax(&cnt->max_pair, worst);
 }
 
+// ------------------------------------------------------------------ build, one warp per cell (default)
+// The thread-per-atom kernel above spends ~38 issue slots and ~10 L1 tag lookups per distance test: every lane
+// walks its own cell's candidate runs, so each float4 load touches ~10 different 128-byte lines and every hit is a
+// predicated shared-memory push.  Here a warp owns one cell and the roles are swapped, as in the reference
+// (UM/neigh_build_meso.cu:58-117), but without its shared counters, sentinel, join and transpose passes:
+//   fetch : lanes = 32 consecutive CANDIDATES of the cell's concatenated stencil list (the non-empty runs in stencil
+//           order).  The run of position t comes from one warp OR-reduction per chunk: bit (start_k - t0) of M marks the
+//           runs starting inside the chunk, so k(t0 + lane) = #runs before t0 + popc(M & lanemask_le) - 1.  One
+//           coalesced 16-byte load per candidate; two chunks are held in registers as packed pairs.
+//   test  : the cell's own atoms (<= 32 per pass) are broadcast one by one from shared memory; the distance test of two
+//           candidates is 6 packed fp32x2 instructions (FADD2/FMUL2/FFMA2: same IEEE operations in the same order as
+//           the scalar chain) and the 32 results of a chunk become two ballots (r <= r_n, r <= r_n - skin), stored by
+//           lane 0: ~0.3 issue slots per test and no per-hit memory traffic.
+//   count : lane m clears its own bit (j != i), prefix-sums its ballots over the chunks and publishes the row totals.
+//   emit  : the (atom, chunk) ballots are spread over all 32 lanes (32/pow2(n) lanes per atom); every entry goes straight
+//           to its final slot of the tile-transposed table: core entries ascending from slot 0, skin entries in reverse
+//           encounter order behind them -- bit-identical rows, counts and layout.
+// Cells whose candidate list exceeds the shared-memory window (local density >~ 1.5x the mean) are marked and rebuilt by
+// the thread-per-atom kernel in fix-up mode, so capacity never changes results.
+constexpr int NC_WARPS = 4;
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// shared memory per warp: 1408 B + 16 B x t_cap
+//   mxy[32]  float4 {x, x, y, y}    mz[32] float2 {z, z}    mi[32] int (atom index of member m)
+//   tot[32]  int2 {n_core, n_tot}    cfirst[32], coffs[32] int (non-empty runs)
+//   masks[m][pair] uint4 {within A, core A, within B, core B}      (8 B x t_cap)
+//   pre[m][chunk]  uint {core entries before the chunk | skin entries before the chunk << 16}   (4 B x t_cap)
+//   candj[t] int                                                                               (4 B x t_cap)
+__global__ void __launch_bounds__(NC_WARPS * 32) k_build_neighbors_cell(const int *__restrict__ cell_start, const int2 *__restrict__ runs,
+                                                                        const float4 *__restrict__ cell_xyzj,
+                                                                        int *__restrict__ pair_count, int *__restrict__ pair_table,
+                                                                        Counts *__restrict__ cnt, int *__restrict__ fixup, int ncell,
+                                                                        int n_col, float rc2_core, float rc2_tail, int t_cap)
+{
+    extern __shared__ __align__(16) unsigned char nb_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int npair_cap = t_cap >> 6;                                 // chunk pairs per member row
+    unsigned char *base = nb_smem + ((size_t)1408 + (size_t)16 * t_cap) * wid;
+    float4 *mxy = reinterpret_cast<float4 *>(base);
+    float2 *mz = reinterpret_cast<float2 *>(base + 512);
+    int *mis = reinterpret_cast<int *>(base + 768);
+    int2 *tot = reinterpret_cast<int2 *>(base + 896);
+    int *cfirst = reinterpret_cast<int *>(base + 1152);
+    int *coffs = reinterpret_cast<int *>(base + 1280);
+    uint4 *masks = reinterpret_cast<uint4 *>(base + 1408);
+    unsigned *pre = reinterpret_cast<unsigned *>(base + 1408 + (size_t)8 * t_cap);
+    int *candj = reinterpret_cast<int *>(base + 1408 + (size_t)12 * t_cap);
+    const unsigned full = 0xffffffffu, le = 0xffffffffu >> (31 - lane);
+    const int nlocal = cnt->nlocal;
+    int worst = 0;
+    for (int c = blockIdx.x * NC_WARPS + wid; c < ncell; c += gridDim.x * NC_WARPS) {
+        const int cs = cell_start[c], nc = cell_start[c + 1] - cs;
+        if (nc == 0) continue;
+        // atoms of a cell are in ascending index order and locals precede ghosts: a cell whose first atom is a ghost has no rows
+        if (__float_as_int(cell_xyzj[cs].w) >= nlocal) continue;
+        // ---- the cell's stencil runs, compacted to the non-empty ones (stencil order kept)
+        const int2 run = lane < 27 ? runs[(size_t)c * 27 + lane] : make_int2(0, 0);
+        int incl = run.y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int T = __shfl_sync(full, incl, 31);
+        const unsigned nonempty = __ballot_sync(full, run.y > 0);
+        const int nne = __popc(nonempty);
+        __syncwarp();
+        if (run.y > 0) {
+            const int k = __popc(nonempty & (le >> 1));
+            cfirst[k] = run.x - (incl - run.y);                       // first position minus list offset
+            coffs[k] = incl - run.y;
+        }
+        __syncwarp();
+        // lane k keeps the list offset of the k-th non-empty run (strictly increasing); lanes >= nne: never inside a chunk
+        const int coff = lane < nne ? coffs[lane] : 0x3fffffff;
+        const unsigned ownb = __ballot_sync(full, run.y > 0 && run.x == cs);
+        const int own_off = __shfl_sync(full, incl - run.y, (__ffs(ownb) - 1) & 31);
+        const bool too_long = T > t_cap;                              // falls back to the thread-per-atom kernel
+        const int nch = too_long ? 0 : (T + 31) >> 5, ncp = (nch + 1) >> 1;
+        __syncwarp();
+        for (int m0 = 0; m0 < nc; m0 += 32) {
+            const int ng = min(32, nc - m0);
+            float4 me = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+            if (lane < ng) me = cell_xyzj[cs + m0 + lane];
+            const int mi = __float_as_int(me.w);
+            mxy[lane] = make_float4(me.x, me.x, me.y, me.y);
+            mz[lane] = make_float2(me.z, me.z);
+            mis[lane] = mi;
+            __syncwarp();
+            if (too_long) {
+                if (lane < ng && mi < nlocal) { pair_count[mi] = -1; *fixup = 1; }
+                continue;
+            }
+            // ---- fetch + test, two chunks (A, B) per pass
+            int nb = 0;                                               // runs starting before the current chunk
+            for (int cp = 0; cp < ncp; cp++) {
+                unsigned long long nx, ny, nz;                        // packed negated candidate coordinates {A, B}
+                {
+                    float4 cd[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int t0 = (2 * cp + h) * 32, t = t0 + lane;
+                        const unsigned d = (unsigned)(coff - t0);
+                        const unsigned M = __reduce_or_sync(full, d < 32u ? 1u << d : 0u);
+                        const int k = nb + __popc(M & le) - 1;
+                        nb += __popc(M);
+                        cd[h] = make_float4(3.0e18f, 3.0e18f, 3.0e18f, __int_as_float(-1));
+                        if (t < T) cd[h] = cell_xyzj[cfirst[k] + t];
+                        candj[t] = __float_as_int(cd[h].w);
+                    }
+                    nx = pack2(-cd[0].x, -cd[1].x); ny = pack2(-cd[0].y, -cd[1].y); nz = pack2(-cd[0].z, -cd[1].z);
+                }
+                uint4 *mrow = masks + cp;
+#pragma unroll 4
+                for (int m = 0; m < ng; m++) {
+                    const float4 a = mxy[m];
+                    const float2 zz = mz[m];
+                    const unsigned long long dx = add2(pack2(a.x, a.y), nx), dy = add2(pack2(a.z, a.w), ny), dz = add2(pack2(zz.x, zz.y), nz);
+                    const unsigned long long r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));       // UM/neigh_build_meso.cu:86-89
+                    float rA, rB;
+                    unpack2(r2, rA, rB);
+                    uint4 bb;
+                    bb.x = __ballot_sync(full, rA <= rc2_tail); bb.y = __ballot_sync(full, rA <= rc2_core);
+                    bb.z = __ballot_sync(full, rB <= rc2_tail); bb.w = __ballot_sync(full, rB <= rc2_core);
+                    if (lane == 0) mrow[m * npair_cap] = bb;
+                }
+            }
+            __syncwarp();
+            // ---- count: lane = member; clear my own bit, prefix over chunks, totals
+            if (lane < ng) {
+                const int ts = own_off + m0 + lane;                   // my own position in the candidate list (j != i)
+                int ncore = 0, nskin = 0;
+                for (int cp = 0; cp < ncp; cp++) {
+                    uint4 bb = masks[lane * npair_cap + cp];
+                    if ((ts >> 6) == cp) {
+                        const unsigned bit = ~(1u << (ts & 31));
+                        if (ts & 32) { bb.z &= bit; bb.w &= bit; } else { bb.x &= bit; bb.y &= bit; }
+                        masks[lane * npair_cap + cp] = bb;
+                    }
+                    pre[lane * (2 * npair_cap) + 2 * cp] = (unsigned)ncore | ((unsigned)nskin << 16);
+                    ncore += __popc(bb.y); nskin += __popc(bb.x & ~bb.y);
+                    pre[lane * (2 * npair_cap) + 2 * cp + 1] = (unsigned)ncore | ((unsigned)nskin << 16);
+                    ncore += __popc(bb.w); nskin += __popc(bb.z & ~bb.w);
+                }
+                int n_tot = ncore + nskin;
+                if (mi < nlocal) {
+                    if (n_tot > n_col) { atomicOr(&cnt->err, 2); n_tot = -min(ncore, n_col) - 1; }   // overflow: core entries only (as above)
+                    pair_count[mi] = n_tot < 0 ? -n_tot - 1 : n_tot;
+                    worst = max(worst, n_tot < 0 ? -n_tot - 1 : n_tot);
+                }
+                tot[lane] = make_int2(ncore, n_tot);
+            }
+            __syncwarp();
+            // ---- emit: the ng x nch (member, chunk) ballots are dealt round-robin to the 32 lanes; a lane pops one entry
+            //      per iteration and refills from its next item when its ballot is exhausted, so the warp runs
+            //      max_lane(entries) iterations whatever the distribution of hits over chunks
+            {
+                const int nitems = ng * nch;
+                int item = lane;
+                int ch = (int)((float)lane * (1.0f / (float)ng) + 1.0e-4f), m = lane - ch * ng;   // lane = ch * ng + m (exact for lane < 32)
+                const int dch = 32 / ng, dm = 32 - dch * ng;                                        // advance of (ch, m) per 32 items
+                unsigned hits = 0, corem = 0;
+                int kc = 0, ks = 0;
+                int *row0 = pair_table;
+                const int *cj = candj;
+                while (true) {
+                    if (hits == 0) {
+                        if (item >= nitems) break;
+                        const int am = mis[m];
+                        const int2 tt = tot[m];
+                        const uint2 mk = reinterpret_cast<const uint2 *>(masks + m * npair_cap + (ch >> 1))[ch & 1];
+                        const unsigned pw = pre[m * (2 * npair_cap) + ch];
+                        const bool overflow = tt.y < 0;
+                        const int n_tot = overflow ? -tt.y - 1 : tt.y;
+                        kc = pw & 0xffffu; ks = n_tot - 1 - (int)(pw >> 16);
+                        corem = mk.y;
+                        hits = am < nlocal ? (overflow ? mk.y & ((kc < n_col) ? 0xffffffffu : 0u) : mk.x) : 0u;
+                        if (overflow && hits) {                                   // keep the first n_col core entries only
+                            while (kc + __popc(hits) > n_col) hits &= ~(0x80000000u >> __clz(hits));
+                        }
+                        row0 = pair_table + (size_t)(am & ~31) * (size_t)n_col + (am & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
+                        cj = candj + ch * 32;
+                        item += 32; ch += dch; m += dm;
+                        if (m >= ng) { m -= ng; ch++; }
+                        continue;
+                    }
+                    const int b = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const bool is_core = (corem >> b) & 1u;
+                    const int k = is_core ? kc : ks;
+                    kc += is_core ? 1 : 0; ks -= is_core ? 0 : 1;
+                    row0[(k & 31) * n_col + (k & ~31)] = cj[b];
+                }
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) worst = max(worst, __shfl_xor_sync(full, worst, o));
+    if (lane == 0 && worst > 0) atomicMax(&cnt->max_pair, worst);
+}
+
 // ------------------------------------------------------------------ host drivers
 int launch_setup_bins(meso_ctx *ctx)
 {
@@ -247,10 +484,41 @@ int launch_neighbor_build(meso_ctx *ctx)
     k_cell_runs<<<(box.ncell * 27 + 255) / 256, 256, 0, ctx->stream>>>(ctx->stencil.p, ctx->cell_start.p, ctx->cell_runs.p, box);
     float rc2_core = (float)pow(ctx->cutneighmax - ctx->skin, 2.0);   // UM/neigh_build_meso.cu:296-297
     float rc2_tail = (float)pow(ctx->cutneighmax, 2.0);
-    {
-        int grid = std::max(1, std::min((int)((nlocal_bound(ctx) + 127) / 128) + 1, ctx->sm_count * 4096));
-        k_build_neighbors<<<grid, 128, 0, ctx->stream>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
-                                                      ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail);
+    const bool per_atom = ctx->nb_per_atom;
+    int grid_atoms = std::max(1, std::min((int)((nlocal_bound(ctx) + 127) / 128) + 1, ctx->sm_count * 4096));
+    if (!per_atom) {
+        // candidate window per cell: 1.25x the expected stencil population (+64), whole chunk pairs
+        double cellvol = box.binsize[0] * box.binsize[1] * box.binsize[2], vol = 1.0;
+        for (int d = 0; d < 3; d++) vol *= box.subhi[d] - box.sublo[d];
+        const double t_exp = 27.0 * cellvol * std::max(ctx->nlocal_host / vol, 1.0);
+        int t_cap = ((int)(1.25 * t_exp) + 64 + 63) / 64 * 64;
+        t_cap = std::max(256, std::min(t_cap, 2048));
+        if (const char *e = getenv("MESO_NB_TCAP")) t_cap = std::max(64, atoi(e) / 64 * 64);      // tests: force the fix-up path
+        const size_t sh = (size_t)NC_WARPS * (1408 + (size_t)16 * t_cap);
+        static size_t sh_set = 0;
+        if (sh > sh_set) {
+            MESO_CUDA(cudaFuncSetAttribute(k_build_neighbors_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+            sh_set = sh;
+        }
+        if (!ctx->nb_fixup.reserve(1)) { ctx->err = "neighbor: out of device memory"; return MESO_ECUDA; }
+        MESO_CUDA(cudaMemsetAsync(ctx->nb_fixup.p, 0, sizeof(int), ctx->stream));
+        const int grid = std::max(1, std::min((box.ncell + NC_WARPS - 1) / NC_WARPS, ctx->sm_count * 64));
+        k_build_neighbors_cell<<<grid, NC_WARPS * 32, sh, ctx->stream>>>(ctx->cell_start.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
+                                                                        ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p, box.ncell, ctx->n_col,
+                                                                        rc2_core, rc2_tail, t_cap);
+        k_build_neighbors<64, 4><<<grid_atoms, 128, 0, ctx->stream>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
+                                                                   ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, ctx->nb_fixup.p);
+    } else {
+#define MESO_NB_ARGS ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p, ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, nullptr
+        const char *ve = getenv("MESO_NB_VARIANT");
+        switch (ve ? atoi(ve) : 0) {
+        case 1: k_build_neighbors<48, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS); break;
+        case 2: k_build_neighbors<48, 8><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS); break;
+        case 3: k_build_neighbors<40, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS); break;
+        case 4: k_build_neighbors<64, 8><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS); break;
+        default: k_build_neighbors<64, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS);
+        }
+#undef MESO_NB_ARGS
     }
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;

@@ -22,6 +22,7 @@
 #include "internal.h"
 #include "device_math.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace meso {
 
@@ -222,6 +223,206 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_dpd(const float4 *__restrict__
     }
 }
 
+// ------------------------------------------------------------------ force, each local pair evaluated ONCE
+// The reference evaluates every pair from both sides (newton off, full list): F_ij and F_ji come from two
+// separate runs of TEA + Box-Muller + force.  Every term of the pair force is antisymmetric bit for bit in
+// (i,j): d = r_i - r_j negates exactly, rsq, rinv, d.dv and the Gaussian (keyed on (max,min) of the two
+// signatures) are identical from both sides -- so F_ji == -F_ij to the last bit and one evaluation serves both
+// atoms.  The full, reference-ordered table stays the only list; a lane owns the pair (i,j), j local, iff
+//      (i+j) odd ? i < j : i > j          (balanced: every atom owns ~half of its in-range neighbors)
+// and pairs with a ghost j are always evaluated by i (the ghost's owner evaluates the mirror pair itself,
+// exactly as before: no reverse communication).  The j side is updated with ONE 16-byte vector reduction
+// (red.global.add.v4.f32 -> REDG.E.ADD.F32x4, resolved in L2) into a float4 accumulator per atom that the
+// integrator consumes and clears; the fp64 style reduces into the fp64 force arrays (REDG.E.ADD.F64).
+// Only the order of the fp32 additions differs from the two-sided kernel (each addend is bit-identical).
+constexpr int QD1 = 24;          // per-lane FIFO depth (mean owned in-range count at rho = 4 is 8.4, max over a warp ~14)
+
+template <typename REAL> struct Coef1 { REAL cut, cutsq, cutinv, expw, a0, gamma, sigma; };
+
+// facc[j] += {a, b, c, 0} if pred (predicated REDG.E.ADD.F32x4: no branch around the reduction)
+__device__ __forceinline__ void red_add_v4_if(bool pred, float4 *p, float a, float b, float c)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+                 ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(0.f), "r"((int)pred) : "memory");
+}
+
+__device__ __forceinline__ void sts32(unsigned addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds32(unsigned addr) { int v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+
+// ONE_TYPE: a single atom type -> the 7 coefficients arrive as kernel parameters (constant bank operands, no shared-memory
+// lookups per candidate / per pair); POW1: every exponent is 1 -> wr = wc (pow(x,1) == x, result-identical).
+// GMODE (experiment knob, MESO_PAIR_TEX): bit 0 = scan-phase coordinate gathers, bit 1 = drain-phase gathers go through the
+// texture data pipe (tex.1d.v4.f32.s32 on a linear texture object over the same buffers) instead of the LSU data pipe
+template <typename REAL, bool ONE_TYPE, bool POW1, int GMODE>
+__global__ void __launch_bounds__(PAIR_THREADS) k_dpd_once(cudaTextureObject_t tex_c, cudaTextureObject_t tex_v,
+                                                           const float4 *__restrict__ coord4, const float4 *__restrict__ veloc4,
+                                                           const int *__restrict__ pair_count, const int *__restrict__ pair_table,
+                                                           float4 *__restrict__ facc, SoA3 f, const REAL *__restrict__ coeff,
+                                                           const Coef1<REAL> k1, const Counts *__restrict__ cnt, int n_col, int n_type,
+                                                           REAL dt_inv_sqrt, int range, int far)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int queue_s[PAIR_THREADS / 32][QD1][32];
+    REAL *cf = reinterpret_cast<REAL *>(smem_raw);
+    if (!ONE_TYPE) {
+        const int ncf = n_type * n_type * NCOEFF;
+        for (int p = threadIdx.x; p < ncf; p += blockDim.x) cf[p] = coeff[p];
+        __syncthreads();
+    }
+    // 32-bit shared-window address of this lane's FIFO column (entry q lives at qbase + q*128: bank == lane)
+    const unsigned qbase = (unsigned)__cvta_generic_to_shared(&queue_s[threadIdx.x >> 5][0][threadIdx.x & 31]);
+    const unsigned full = 0xffffffffu;
+    const int nlocal = cnt->nlocal;
+    const int p_beg = (range & MESO_BULK) ? 0 : cnt->n_bulk;
+    const int p_end = (range & MESO_BORDER) ? nlocal : cnt->n_bulk;
+    const ptrdiff_t step4 = (ptrdiff_t)SCAN_CHUNK * n_col, wrap = 32 - (ptrdiff_t)32 * n_col;
+    for (int i = (p_beg & ~31) + blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < p_end; i += gridDim.x * blockDim.x) {
+        const bool active = i >= p_beg && i < p_end;
+        // masked-off table slots (beyond the row, not owned by this lane) gather the `far` slot: one coordinate record at
+        // ~3.4e38 kept behind the atoms, so rsq = +inf fails the cutoff test without a validity flag, and all masked
+        // lanes of a warp read the same 16 bytes (one L1 tag lookup instead of a scattered line each)
+        const int self = active ? i : far;
+        const float4 c1 = coord4[self], v1 = veloc4[self];
+        const int n_pair = active ? pair_count[i] : 0;
+        const int nmax = __reduce_max_sync(full, n_pair);
+        const REAL *cf1 = cf + (ONE_TYPE ? 0 : __float_as_uint(c1.w) * n_type * NCOEFF);
+        REAL fx = 0, fy = 0, fz = 0;
+        unsigned qp = qbase;                                // FIFO write address
+
+        auto one_pair = [&](const float4 c2, const float4 v2, int j) {
+            if constexpr (sizeof(REAL) == 4) {
+                const float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
+                const float rsq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                const float rn = gaussian_sp_fast(__float_as_uint(v1.w), __float_as_uint(v2.w));
+                const float rinv = rsqrt_approx(rsq);
+                const float r = rsq * rinv;
+                const float dvx = v1.x - v2.x, dvy = v1.y - v2.y, dvz = v1.z - v2.z;
+                const float dot = dx * dvx + dy * dvy + dz * dvz;
+                float cutinv, ew, a0, gamma, sigma;
+                if (ONE_TYPE) { cutinv = k1.cutinv; ew = k1.expw; a0 = k1.a0; gamma = k1.gamma; sigma = k1.sigma; }
+                else {
+                    const float *kk = cf1 + __float_as_uint(c2.w) * NCOEFF;
+                    cutinv = kk[P_CUTINV]; ew = kk[P_EXPW]; a0 = kk[P_A0]; gamma = kk[P_GAMMA]; sigma = kk[P_SIGMA];
+                }
+                const float wc = 1.0f - r * cutinv;
+                const float wr = (POW1 || ew == 1.0f) ? wc : __powf(wc, ew);
+                float fpair = a0 * wc - (gamma * wr * wr * dot * rinv) + (sigma * wr * rn * dt_inv_sqrt);
+                const float nf = -(fpair * rinv);             // -fpair: the j side's addend is computed directly, the i side subtracts it
+                const float qx = dx * nf, qy = dy * nf, qz = dz * nf;
+                red_add_v4_if(j < nlocal, facc + j, qx, qy, qz);
+                fx -= qx; fy -= qy; fz -= qz;
+            } else {
+                const double dx = (double)__fsub_rn(c1.x, c2.x), dy = (double)__fsub_rn(c1.y, c2.y), dz = (double)__fsub_rn(c1.z, c2.z);
+                const double rsq = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+                const double rn = gaussian_dp(__float_as_uint(v1.w), __float_as_uint(v2.w));
+                const double rinv = rsqrt(rsq);
+                const double r = rsq * rinv;
+                const double dvx = (double)__fsub_rn(v1.x, v2.x), dvy = (double)__fsub_rn(v1.y, v2.y), dvz = (double)__fsub_rn(v1.z, v2.z);
+                const double dot = __fma_rn(dz, dvz, __fma_rn(dy, dvy, __dmul_rn(dx, dvx)));
+                double cutinv, ew, a0, gamma, sigma;
+                if (ONE_TYPE) { cutinv = k1.cutinv; ew = k1.expw; a0 = k1.a0; gamma = k1.gamma; sigma = k1.sigma; }
+                else {
+                    const double *kk = cf1 + __float_as_uint(c2.w) * NCOEFF;
+                    cutinv = kk[P_CUTINV]; ew = kk[P_EXPW]; a0 = kk[P_A0]; gamma = kk[P_GAMMA]; sigma = kk[P_SIGMA];
+                }
+                const double wc = 1.0 - r * cutinv;
+                const double wr = pow_poly(wc, ew);           // the reference's polynomial pow, also for expw == 1 (bit parity)
+                double fpair = a0 * wc - (gamma * wr * wr * dot * rinv) + (sigma * wr * rn * dt_inv_sqrt);
+                fpair *= rinv;
+                const double px = dx * fpair, py = dy * fpair, pz = dz * fpair;
+                if (j < nlocal) { atomicAdd(f.c[0] + j, -px); atomicAdd(f.c[1] + j, -py); atomicAdd(f.c[2] + j, -pz); }
+                fx += px; fy += py; fz += pz;
+            }
+        };
+
+        // ---- drain: pop my FIFO; the next entry's two gathers are in flight during the current pair's math
+        auto drain = [&]() {
+            const int qlen = (int)(qp - qbase) >> 7;
+            const int m = __reduce_max_sync(full, qlen);
+            int jn = qlen > 0 ? lds32(qbase) : far;
+            float4 c2n, v2n;
+            if (GMODE & 2) { c2n = tex1Dfetch<float4>(tex_c, jn); v2n = tex1Dfetch<float4>(tex_v, jn); }
+            else { c2n = coord4[jn]; v2n = veloc4[jn]; }
+#pragma unroll 2
+            for (int q = 0; q < m; q++) {
+                const float4 c2 = c2n, v2 = v2n;
+                const int j = jn;
+                jn = (q + 1 < qlen) ? lds32(qbase + (q + 1) * 128) : far;
+                if (GMODE & 2) { c2n = tex1Dfetch<float4>(tex_c, jn); v2n = tex1Dfetch<float4>(tex_v, jn); }
+                else { c2n = coord4[jn]; v2n = veloc4[jn]; }
+                if (q < qlen) one_pair(c2, v2, j);
+            }
+            qp = qbase;
+        };
+
+        // ---- scan: SCAN_CHUNK slots per step; slot(k) = tp[(k&31)*n_col + (k>>5)*32], walked with one running pointer.
+        // Ownership and validity fold into one sign test: d = j - i, key = d + (d << 31) = d * 0x80000001 has the sign bit
+        // (d odd ? d > 0 : d < 0); nlocal-1-j is negative for ghosts; k - n_pair is negative inside the row.
+        const int *pk = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);
+        const unsigned key_c = 0u - (unsigned)i * 0x80000001u;
+        const int nlm1 = nlocal - 1;
+        auto load_chunk = [&](int k0, int (&jj)[SCAN_CHUNK]) {
+            if (k0 < nmax) {
+                const int kn = k0 - n_pair;
+#pragma unroll
+                for (int u = 0; u < SCAN_CHUNK; u++) {
+                    const int j = __ldcs(pk + (ptrdiff_t)u * n_col);
+                    const unsigned key = (unsigned)j * 0x80000001u + key_c;
+                    const int take = (int)((key | (unsigned)(nlm1 - j)) & (unsigned)(kn + u));
+                    jj[u] = take < 0 ? j : far;
+                }
+                pk += step4;
+                if (((k0 + SCAN_CHUNK) & 31) == 0) pk += wrap;
+            } else {
+#pragma unroll
+                for (int u = 0; u < SCAN_CHUNK; u++) jj[u] = far;
+            }
+        };
+        auto test_chunk = [&](const int (&jc)[SCAN_CHUNK]) {
+            float4 c2[SCAN_CHUNK];
+#pragma unroll
+            for (int u = 0; u < SCAN_CHUNK; u++) c2[u] = (GMODE & 1) ? tex1Dfetch<float4>(tex_c, jc[u]) : coord4[jc[u]];
+#pragma unroll
+            for (int u = 0; u < SCAN_CHUNK; u++) {
+                REAL cutsq;
+                if (ONE_TYPE) cutsq = k1.cutsq; else cutsq = cf1[__float_as_uint(c2[u].w) * NCOEFF + P_CUTSQ];
+                bool hit;
+                if constexpr (sizeof(REAL) == 4) {
+                    const float dx = c1.x - c2[u].x, dy = c1.y - c2[u].y, dz = c1.z - c2[u].z;
+                    const float rsq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                    hit = rsq < cutsq && rsq >= 1.0E-20f;            // UM/pair_dpd_fast_meso.cu:143
+                } else {
+                    const double dx = (double)__fsub_rn(c1.x, c2[u].x), dy = (double)__fsub_rn(c1.y, c2[u].y), dz = (double)__fsub_rn(c1.z, c2[u].z);
+                    const double rsq = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+                    hit = rsq < cutsq && rsq >= 1.0E-20;             // UM/pair_dpd_meso.cu:143
+                }
+                if (hit) { sts32(qp, jc[u]); qp += 128; }
+            }
+        };
+        // two chunks per iteration with explicit double buffering: the index loads of the chunk after next are in flight
+        // while the current chunk's gathers and distance tests run (no register shuffling between iterations)
+        int ja[SCAN_CHUNK], jb[SCAN_CHUNK];
+        load_chunk(0, ja);
+        int k0 = 0;
+        do {
+            // scan until the row ends or some lane's FIFO could overflow within the next two chunks (rare)
+            while (k0 < nmax && !__any_sync(full, qp > qbase + (QD1 - 2 * SCAN_CHUNK) * 128)) {
+                load_chunk(k0 + SCAN_CHUNK, jb);
+                test_chunk(ja);
+                load_chunk(k0 + 2 * SCAN_CHUNK, ja);
+                test_chunk(jb);
+                k0 += 2 * SCAN_CHUNK;
+            }
+            drain();
+        } while (k0 < nmax);
+
+        if (active) {
+            if constexpr (sizeof(REAL) == 4) red_add_v4_if(true, facc + i, fx, fy, fz);
+            else { atomicAdd(f.c[0] + i, fx); atomicAdd(f.c[1] + i, fy); atomicAdd(f.c[2] + i, fz); }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ parity helpers (A8, A9)
 __global__ void k_eval_gaussian(int n, const uint32_t *si, const uint32_t *sj, float *osp, double *odp)
 {
@@ -301,6 +502,42 @@ int launch_pair(meso_ctx *ctx, int range, int evflag, bool accumulate, bool fuse
     const double dtis = 1.0 / sqrt(ctx->dt);
     return evflag ? launch_pair_t<double, 1>(ctx, ctx->coeff_dp.p, dtis, range, accumulate, fuse_final, groupbit)
                   : launch_pair_t<double, 0>(ctx, ctx->coeff_dp.p, dtis, range, accumulate, fuse_final, groupbit);
+}
+
+template <typename REAL>
+static int launch_pair_once_t(meso_ctx *ctx, const REAL *coeff, REAL dtis, int range)
+{
+    SoA3 f;
+    for (int d = 0; d < 3; d++) f.c[d] = ctx->f[d].p;
+    const int nt = ctx->ntypes;
+    Coef1<REAL> k1;
+    k1.cut = (REAL)ctx->coeff[P_CUT]; k1.cutsq = (REAL)ctx->coeff[P_CUTSQ]; k1.cutinv = (REAL)ctx->coeff[P_CUTINV];
+    k1.expw = (REAL)ctx->coeff[P_EXPW]; k1.a0 = (REAL)ctx->coeff[P_A0]; k1.gamma = (REAL)ctx->coeff[P_GAMMA]; k1.sigma = (REAL)ctx->coeff[P_SIGMA];
+    int grid = (int)((nlocal_bound(ctx) + PAIR_THREADS - 1) / PAIR_THREADS) + 1;
+    grid = std::max(1, std::min(grid, ctx->sm_count * 4096));
+    bool pow1 = true;
+    for (int t = 0; t < nt * nt; t++) pow1 = pow1 && ctx->coeff[(size_t)t * NCOEFF + P_EXPW] == 1.0;
+#define MESO_ONCE_ARGS ctx->tex_coord, ctx->tex_veloc, ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, ctx->facc.p, f, coeff, k1, ctx->d_counts, ctx->n_col, nt, dtis, range, (int)ctx->cap
+    const int gmode = ctx->pair_tex;
+    if (nt == 1 && pow1) {
+        switch (gmode) {
+        case 1: k_dpd_once<REAL, true, true, 1><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS); break;
+        case 2: k_dpd_once<REAL, true, true, 2><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS); break;
+        case 3: k_dpd_once<REAL, true, true, 3><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS); break;
+        default: k_dpd_once<REAL, true, true, 0><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS);
+        }
+    } else if (nt == 1) k_dpd_once<REAL, true, false, 0><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS);
+    else k_dpd_once<REAL, false, false, 0><<<grid, PAIR_THREADS, (size_t)nt * nt * NCOEFF * sizeof(REAL), ctx->stream>>>(MESO_ONCE_ARGS);
+#undef MESO_ONCE_ARGS
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+// each owned pair once, no energy/virial tally; the accumulator (facc for fp32, f for fp64) must be zero on entry
+int launch_pair_once(meso_ctx *ctx, int range)
+{
+    if (ctx->precision == MESO_SP) return launch_pair_once_t<float>(ctx, ctx->coeff_sp.p, (float)(1.0 / sqrt(ctx->dt)), range);
+    return launch_pair_once_t<double>(ctx, ctx->coeff_dp.p, 1.0 / sqrt(ctx->dt), range);
 }
 
 int eval_gaussian(meso_ctx *ctx, int n, const uint32_t *si, const uint32_t *sj, float *osp, double *odp)

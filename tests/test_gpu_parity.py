@@ -248,6 +248,30 @@ def test_dense_fluid_rows_longer_than_the_staging_queue():
         m.close()
 
 
+@pytest.mark.parametrize("tcap", ["64", "384"])
+def test_neighbor_build_window_overflow_falls_back_per_atom(monkeypatch, tcap):
+    """cells whose candidate list exceeds the warp-per-cell kernel's shared-memory window are rebuilt by the
+    thread-per-atom kernel in fix-up mode: all cells (window 64) or a mix (window 384 at ~364 +- 20 candidates)."""
+    monkeypatch.setenv("MESO_NB_TCAP", tcap)
+    m, w = make_pair(9, "dp")
+    m.setup(); w.setup()
+    assert_state_identical(m, w, precision="dp")
+    m.run(6); w.run(6)
+    cntg, rowsg = m.neighbors()
+    cnto, rowso = w.neighbors()
+    mask = np.arange(rowso.shape[1])[None, :] < cnto[:, None]
+    assert np.array_equal(cntg, cnto) and np.array_equal(rowsg[mask], rowso[mask])
+    m.close()
+
+
+def test_neighbor_build_per_atom_kernel_matches(monkeypatch):
+    monkeypatch.setenv("MESO_NB_PER_ATOM", "1")
+    m, w = make_pair(10, "sp")
+    m.setup(); w.setup()
+    assert_state_identical(m, w, precision="sp")
+    m.close()
+
+
 def test_atoms_on_cell_and_box_boundaries():
     x = workload.dpd_fluid(6, seed=2)
     x[:50] = np.round(x[:50])            # exactly on unit-lattice planes, including 0.0
@@ -325,8 +349,12 @@ def test_dp_trajectory_lockstep_12_steps():
     m.close()
 
 
-def test_phase_api_equals_fused_run():
-    """ModifiedVerlet::run spelled phase by phase (bulk/border split, separate clears) == meso_run, bit for bit."""
+def test_phase_api_equals_fused_run(monkeypatch):
+    """ModifiedVerlet::run spelled phase by phase (bulk/border split, separate clears) == meso_run, bit for bit, when
+    meso_run uses the same two-sided force kernel as the phase entry points (MESO_PAIR_ONCE=0).  The default run loop
+    evaluates each local pair once and reduces with atomics, so there only the summation order differs:
+    see test_pair_once_run_matches_two_sided_and_oracle."""
+    monkeypatch.setenv("MESO_PAIR_ONCE", "0")
     B, O, LOC = lib.MESO_BULK, lib.MESO_BORDER, lib.MESO_LOCAL
     for precision in ("sp", "dp"):
         a, _ = make_pair(8, precision)
@@ -353,6 +381,52 @@ def test_phase_api_equals_fused_run():
         a.close(); b.close()
 
 
+def test_pair_once_run_matches_two_sided_and_oracle(monkeypatch):
+    """The default run loop (pair.cu:k_dpd_once: each local pair evaluated once, j side reduced with REDG, second
+    half-kick fused into the next step's streaming pass) against the two-sided kernel and the oracle.
+    One step from the same state: x and the half-kicked v are bit-identical (they depend on the setup force only),
+    the new force agrees to the fp tolerance (every addend is bit-identical, only the summation order differs).
+    fp64 additionally stays locked over 11 steps / two rebuilds (x, v to 1e-10, lists + signatures bit-exact in
+    test_dp_trajectory_lockstep_12_steps); fp32 trajectories cannot be locked (RNG keys on fp32 velocity bits)."""
+    for precision, tol in (("sp", SP_TOL), ("dp", DP_TOL)):
+        for ntypes in (1, 2):
+            kw = {}
+            if ntypes == 2:
+                n = 4 * 9 ** 3
+                kw = dict(ntypes=2, types=(np.arange(n) % 2 + 1).astype(np.int32), mass=[0.0, 1.0, 2.5],
+                          coeff=[(1, 1, (15, 4.5, 3.0, 1.0, 1.0)), (1, 2, (20, 3.0, 2.0, 0.5, 0.9)), (2, 2, (25, 5.0, 3.2, 2.0, 1.0))])
+            monkeypatch.setenv("MESO_PAIR_ONCE", "1")
+            a, w = make_pair(9, precision, **kw)
+            monkeypatch.setenv("MESO_PAIR_ONCE", "0")
+            b, _ = make_pair(9, precision, **kw)
+            a.setup(); b.setup(); w.setup()
+            a.run(1); b.run(1); w.run(1)
+            da, db, ao = a.download(), b.download(), w.atoms()
+            assert np.array_equal(da["x"], db["x"]) and np.array_equal(da["tag"], db["tag"])
+            e_ab = force_err(da["f"], db["f"])
+            assert e_ab <= tol, (precision, ntypes, e_ab)
+            if precision == "dp":
+                assert force_err(da["f"], ao["f"]) <= 1e-10
+            else:
+                # vs the oracle a few atoms draw different random numbers: the setup forces agree to 1e-6 only (MUFU), so
+                # the half-kicked fp32 velocity of a handful of atoms rounds across one of the signature's mantissa bits
+                mag = np.linalg.norm(ao["f"], axis=1)
+                derr = np.linalg.norm(da["f"] - ao["f"], axis=1) / np.maximum(mag, mag.mean())
+                assert (derr > tol).mean() <= 0.12 and np.median(derr) <= tol, (derr > tol).sum()   # ~0.25 % of atoms flip x ~17 pairs each
+            assert np.abs(da["v"] - db["v"]).max() <= 0.5 * 0.005 * 40 * tol * 10
+            # pairwise antisymmetry; pairs across the periodic boundary see separately fp32-packed image coordinates on
+            # the two sides (|dF| ~ 1e-7 |F| each, also in the oracle), everything else cancels to rounding
+            assert np.abs(da["f"].sum(0)).max() < 5e-3
+            assert np.abs(da["f"].sum(0) - ao["f"][:len(da["f"])].sum(0)).max() < (1e-3 if precision == "sp" else 1e-8)
+            # a second run call: the accumulator was handed back clean and f holds the fp64 mirror
+            a.run(4); b.run(4)
+            if precision == "dp":
+                da, db = a.download(), b.download()
+                assert np.abs(da["x"] - db["x"]).max() < 1e-10 and np.abs(da["v"] - db["v"]).max() < 1e-10
+                assert force_err(da["f"], db["f"]) < 1e-9
+            a.close(); b.close()
+
+
 def test_message_based_halo_path_on_one_rank(monkeypatch):
     """MESO_FORCE_COMM_PATH=1: the multi-GPU halo code (ordered pack -> message -> unpack, sendlists, side-stream
     overlap of the refresh with the bulk force kernel) with every swap partnered to the rank itself.  No migration
@@ -377,7 +451,8 @@ def test_message_based_halo_path_on_one_rank(monkeypatch):
             gg = m.ghosts()
             assert np.array_equal(gg["tag"], ao["tag"][nl:])
         m.close()
-    # and the two halo implementations agree with each other bit for bit over a run
+    # and the two halo implementations agree with each other bit for bit over a run (deterministic two-sided kernel)
+    monkeypatch.setenv("MESO_PAIR_ONCE", "0")
     a, _ = make_pair(8, "sp")
     monkeypatch.setenv("MESO_FORCE_COMM_PATH", "0")
     b, _ = make_pair(8, "sp")
@@ -387,6 +462,16 @@ def test_message_based_halo_path_on_one_rank(monkeypatch):
     for k in ("x", "v", "f", "tag"):
         assert np.array_equal(da[k], db[k]), k
     a.close(); b.close()
+    # same in the default pair-once loop (bulk kernel || halo, then border kernel, both reducing into one accumulator): fp64, 1e-10
+    monkeypatch.setenv("MESO_PAIR_ONCE", "1")
+    monkeypatch.setenv("MESO_FORCE_COMM_PATH", "1")
+    a, w = make_pair(8, "dp")
+    a.setup(); w.setup()
+    a.run(12); w.run(12)
+    da, ao = a.download(), w.atoms()
+    assert np.array_equal(da["tag"], ao["tag"][:ao["nlocal"]])
+    assert np.abs(da["x"] - ao["x"][:ao["nlocal"]]).max() < 1e-10 and np.abs(da["v"] - ao["v"][:ao["nlocal"]]).max() < 1e-10
+    a.close()
 
 
 def test_sp_run_then_oracle_force_from_device_state():

@@ -46,13 +46,13 @@ def need_binary():
         pytest.fail("lammps/_build/lmp_meso_b200 is missing: build it in the dev container (make -C lammps); it ships with the snapshot")
 
 
-def run_deck(tmp_path, L, prec, steps, thermo, extra="", dump=True, args=()):
+def run_deck(tmp_path, L, prec, steps, thermo, extra="", dump=True, args=(), env=None):
     workload.write_data(str(tmp_path / ("%d.data" % L)), workload.dpd_fluid(L), L)
     deck = DECK.format(prec=prec, pair="dpd/fast/meso" if prec == "sp" else "dpd/meso", extra=extra, thermo=thermo, steps=steps,
                        dump=DUMP.format(steps=steps) if dump else "")
     (tmp_path / "in.run").write_text(deck)
     out = subprocess.run([LMP, "-in", "in.run", "-var", "case", str(L), "-log", "none"] + list(args), cwd=str(tmp_path),
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     return out
 
 
@@ -104,10 +104,13 @@ def mirror(L, prec, fr0):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("prec", ["sp", "dp"])
-def test_benchmark_deck_runs_unchanged_and_matches_the_c_abi_mirror(tmp_path, prec):
+def test_benchmark_deck_runs_unchanged_and_matches_the_c_abi_mirror(tmp_path, prec, monkeypatch):
+    """bit-for-bit with the deterministic two-sided force kernel (MESO_PAIR_ONCE=0) in both processes; the default
+    pair-once loop reduces with atomics (summation order varies run to run) and is compared on observables below"""
     need_binary()
     L, steps = 10, 20
-    out = run_deck(tmp_path, L, prec, steps, thermo=10)
+    monkeypatch.setenv("MESO_PAIR_ONCE", "0")
+    out = run_deck(tmp_path, L, prec, steps, thermo=10, env={"MESO_PAIR_ONCE": "0"})
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "Loop time of" in out.stdout
     th = thermo_rows(out.stdout, 4)
@@ -127,6 +130,16 @@ def test_benchmark_deck_runs_unchanged_and_matches_the_c_abi_mirror(tmp_path, pr
     assert np.array_equal(a["f"][o], fr[steps][:, 7:10])
     assert abs(m.temperature() - th[-1, 1]) < 1e-6                      # thermo prints 8 significant digits
     m.close()
+    # default loop (each pair once): same deck, same thermo trace to the fp tolerance of the path
+    d2 = tmp_path / "once"
+    d2.mkdir()
+    out2 = run_deck(d2, L, prec, steps, thermo=10, env={"MESO_PAIR_ONCE": "1"})
+    assert out2.returncode == 0, out2.stdout[-2000:] + out2.stderr[-2000:]
+    th2 = thermo_rows(out2.stdout, 4)
+    assert np.abs(th2[:, 1] - th[:, 1]).max() < (2e-3 if prec == "sp" else 1e-7), (th2[:, 1], th[:, 1])
+    fr2 = frames(str(d2 / "traj.txt"))
+    if prec == "dp":
+        assert np.abs(fr2[steps][:, 1:7] - fr[steps][:, 1:7]).max() < 1e-9
 
 
 @pytest.mark.gpu
