@@ -445,6 +445,7 @@ extern "C" int meso_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, con
     ctx->bins_ready = false;
     ctx->setup_done = false;
     ctx->f_cleared = true;
+    ctx->comm_caps_agreed = false;
     return MESO_OK;
 }
 

@@ -444,6 +444,20 @@ static int ensure_comm_buffers(meso_ctx *ctx)
     }
     int swap_cap = (int)(face * ctx->cutneighmax * dens * 1.5) + 4096;
     int exch_cap = std::max(8192, ctx->nlocal_host / 8);
+    if (ctx->nranks > 1 && !ctx->comm_caps_agreed) {
+        // message sizes are part of the protocol: every rank must use the same capacities (ranks own slightly different
+        // atom counts, so the local estimates can differ).  One max-reduction at the first rebuild after an upload,
+        // which every rank reaches at the same point.
+        double caps[2] = {(double)swap_cap, (double)exch_cap};
+        if (!ctx->reduce_buf.reserve(64)) { ctx->err = "out of device memory"; return MESO_ECUDA; }
+        MESO_CUDA(cudaMemcpyAsync(ctx->reduce_buf.p, caps, sizeof caps, cudaMemcpyHostToDevice, ctx->stream));
+        MESO_NCCL(ncclAllReduce(ctx->reduce_buf.p, ctx->reduce_buf.p, 2, ncclDouble, ncclMax, (ncclComm_t)ctx->nccl, ctx->stream));
+        MESO_CUDA(cudaMemcpyAsync(caps, ctx->reduce_buf.p, sizeof caps, cudaMemcpyDeviceToHost, ctx->stream));
+        MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+        swap_cap = (int)caps[0]; exch_cap = (int)caps[1];
+        ctx->swap_cap = 0; ctx->exch_cap = 0;                 // adopt the agreed sizes exactly
+        ctx->comm_caps_agreed = true;
+    } else if (ctx->nranks > 1) return MESO_OK;               // agreed sizes stay until the next upload
     if (swap_cap <= ctx->swap_cap && exch_cap <= ctx->exch_cap) return MESO_OK;
     ctx->swap_cap = std::max(ctx->swap_cap, swap_cap);
     ctx->exch_cap = std::max(ctx->exch_cap, exch_cap);

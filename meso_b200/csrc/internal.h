@@ -109,7 +109,7 @@ struct meso_ctx {
     meso::DevBuf<float4> facc;                // fp32 per-atom force accumulator of the pair-once kernel (zero between uses)
     cudaTextureObject_t tex_coord = 0, tex_veloc = 0;   // linear float4 textures over coord4 / veloc4 (gather-path experiments)
     int pair_tex = 2;                         // which gathers of the pair-once kernel use the texture data pipe (MESO_PAIR_TEX)
-    bool nb_per_atom = false;                 // MESO_NB_PER_ATOM=1: thread-per-atom neighbor build everywhere
+    bool nb_per_atom = true;                  // thread-per-atom neighbor build (MESO_NB_PER_ATOM=0: warp-per-cell ballot kernel + per-atom fix-up)
     bool pair_once = true;                    // meso_run evaluates each local pair once (MESO_PAIR_ONCE=0: two-sided kernel)
     meso::DevBuf<double> virial, e_pair;      // [6][cap] SoA, [cap]
     meso::DevBuf<double> mass_dev;            // [ntypes+1]
@@ -129,6 +129,7 @@ struct meso_ctx {
     // multi-rank halo
     bool comm_path = false;                   // use the message-based border/forward path (always when nranks > 1)
     int swap_cap = 0, exch_cap = 0;           // records per halo / migration message
+    bool comm_caps_agreed = false;            // capacities were max-reduced over the ranks since the last upload
     size_t nloc_cap = 0;                      // capacity for local atoms
     meso::DevBuf<double> send_buf[2], recv_buf[2], reduce_buf;
     meso::DevBuf<int> sendlist[6];

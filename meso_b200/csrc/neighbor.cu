@@ -510,14 +510,7 @@ int launch_neighbor_build(meso_ctx *ctx)
                                                                    ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, ctx->nb_fixup.p);
     } else {
 #define MESO_NB_ARGS ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p, ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, nullptr
-        const char *ve = getenv("MESO_NB_VARIANT");
-        switch (ve ? atoi(ve) : 0) {
-        case 1: k_build_neighbors<48, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS); break;
-        case 2: k_build_neighbors<48, 8><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS); break;
-        case 3: k_build_neighbors<40, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS); break;
-        case 4: k_build_neighbors<64, 8><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS); break;
-        default: k_build_neighbors<64, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS);
-        }
+        k_build_neighbors<48, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS);   // 48 slots: 9 CTAs/SM; 40 spills too often, 56+ loses occupancy (measured)
 #undef MESO_NB_ARGS
     }
     MESO_CUDA(cudaGetLastError());

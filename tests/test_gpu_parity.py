@@ -253,6 +253,7 @@ def test_neighbor_build_window_overflow_falls_back_per_atom(monkeypatch, tcap):
     """cells whose candidate list exceeds the warp-per-cell kernel's shared-memory window are rebuilt by the
     thread-per-atom kernel in fix-up mode: all cells (window 64) or a mix (window 384 at ~364 +- 20 candidates)."""
     monkeypatch.setenv("MESO_NB_TCAP", tcap)
+    monkeypatch.setenv("MESO_NB_PER_ATOM", "0")
     m, w = make_pair(9, "dp")
     m.setup(); w.setup()
     assert_state_identical(m, w, precision="dp")
@@ -264,11 +265,18 @@ def test_neighbor_build_window_overflow_falls_back_per_atom(monkeypatch, tcap):
     m.close()
 
 
-def test_neighbor_build_per_atom_kernel_matches(monkeypatch):
-    monkeypatch.setenv("MESO_NB_PER_ATOM", "1")
-    m, w = make_pair(10, "sp")
+@pytest.mark.parametrize("L", [10, (7, 9, 12)])
+def test_neighbor_build_warp_per_cell_kernel_matches(monkeypatch, L):
+    """the alternative build (one warp per cell, ballots, packed fp32x2 tests) gives the same table bit for bit"""
+    monkeypatch.setenv("MESO_NB_PER_ATOM", "0")
+    m, w = make_pair(L, "sp")
     m.setup(); w.setup()
     assert_state_identical(m, w, precision="sp")
+    m.close()
+    x = workload.dpd_fluid(6, rho=8, seed=13)               # dense rows, several chunk pairs, > 32 atoms in some cells
+    m, w = make_pair(6, "dp", x=x)
+    m.setup(); w.setup()
+    assert_state_identical(m, w, precision="dp", tol=1e-11)
     m.close()
 
 

@@ -136,19 +136,23 @@ def test_benchmark_deck_runs_unchanged_and_matches_the_c_abi_mirror(tmp_path, pr
     out2 = run_deck(d2, L, prec, steps, thermo=10, env={"MESO_PAIR_ONCE": "1"})
     assert out2.returncode == 0, out2.stdout[-2000:] + out2.stderr[-2000:]
     th2 = thermo_rows(out2.stdout, 4)
-    assert np.abs(th2[:, 1] - th[:, 1]).max() < (2e-3 if prec == "sp" else 1e-7), (th2[:, 1], th[:, 1])
+    # fp32: a few atoms per step draw different random numbers (RNG keys on fp32 velocity bits): T of 4000 atoms agrees statistically
+    assert np.abs(th2[:, 1] - th[:, 1]).max() < (6e-2 if prec == "sp" else 1e-7), (th2[:, 1], th[:, 1])
     fr2 = frames(str(d2 / "traj.txt"))
     if prec == "dp":
         assert np.abs(fr2[steps][:, 1:7] - fr[steps][:, 1:7]).max() < 1e-9
 
 
 @pytest.mark.gpu
-def test_thermo_energy_and_pressure_go_through_the_phase_entry_points(tmp_path):
+@pytest.mark.parametrize("once", ["0", "1"])
+def test_thermo_energy_and_pressure_go_through_the_phase_entry_points(tmp_path, monkeypatch, once):
     """`pe` and `press` make LAMMPS ask for energy/virial on thermo steps: those steps run phase by phase
     (fix nve/meso -> meso_initial_integrate, pair->compute(eflag,vflag), ...), the others through meso_run."""
     need_binary()
+    # once = 0: deterministic two-sided kernel in meso_run, bit-for-bit; once = 1 (default loop): fp64 atomics, 1e-9
     L, steps = 10, 20
-    out = run_deck(tmp_path, L, "dp", steps, thermo=10, extra="pe press")
+    monkeypatch.setenv("MESO_PAIR_ONCE", once)
+    out = run_deck(tmp_path, L, "dp", steps, thermo=10, extra="pe press", env={"MESO_PAIR_ONCE": once})
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     th = thermo_rows(out.stdout, 6)
     assert th.shape[0] == 3
@@ -180,7 +184,10 @@ def test_thermo_energy_and_pressure_go_through_the_phase_entry_points(tmp_path):
     assert abs(pe1 - th[-1, 2]) < 2e-7 * abs(pe1) and abs(p1 - th[-1, 3]) < 2e-7 * abs(p1), (pe1, p1, th[-1])
     a = m.download()
     o = np.argsort(a["tag"])
-    assert np.array_equal(a["x"][o], fr[steps][:, 1:4]) and np.array_equal(a["v"][o], fr[steps][:, 4:7])
+    if once == "0":
+        assert np.array_equal(a["x"][o], fr[steps][:, 1:4]) and np.array_equal(a["v"][o], fr[steps][:, 4:7])
+    else:
+        assert np.abs(a["x"][o] - fr[steps][:, 1:4]).max() < 1e-9 and np.abs(a["v"][o] - fr[steps][:, 4:7]).max() < 1e-9
     # equilibrium DPD fluid at rho = 4, a = 15... just started from random positions: pressure is positive and O(10)
     assert 5.0 < p1 < 80.0
     m.close()
