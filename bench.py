@@ -184,9 +184,11 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
-    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) out of it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so that banners printed by
+    # native libraries (NCCL prints its version on this pool's boxes) cannot end up in front of the JSON
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from meso_b200 import workload
@@ -271,7 +273,8 @@ def main():
     once = os.environ.get("MESO_PAIR_ONCE", "1") != "0"
     pair_ms, pair_calls = tm["pair"]
     b_force = 4.0 * n_bar + 32.0 + 24.0                        # algorithmic bytes per particle per force evaluation
-    achieved = b_force * nloc / (pair_ms / max(pair_calls, 1) * 1e-3) / 1e9
+    # per rank: every step evaluates the force on all nloc particles (one launch on 1 GPU; bulk + border launches on N > 1)
+    achieved = b_force * nloc * args.steps / (pair_ms * 1e-3) / 1e9
     traffic = None
     tp_path = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
     if os.path.exists(tp_path):
@@ -280,7 +283,7 @@ def main():
         ("float" if args.precision == "sp" else "double")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_particle": b_force, "particles_per_launch": nloc,
+                "algorithmic_bytes_per_particle": b_force, "particles_per_launch": nloc * args.steps / max(pair_calls, 1),
                 "avg_launch_ms": pair_ms / max(pair_calls, 1), "share_of_step": pair_ms / ms,
                 "note": "not HBM-bound: the kernel saturates the L1 data pipe (l1tex__data_pipe_lsu_wavefronts ~78 % of peak, one tag "
                         "lookup per ~1.7 gathered neighbors) with the issue slots at ~56 %; see DESIGN.md s3 and profiles/"}
@@ -339,7 +342,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(L)
     if rank == 0:
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -91,8 +91,12 @@ extern "C" int meso_create(meso_ctx **out, int device)
     meso_ctx *ctx = new meso_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+    // the halo stream outranks the compute stream: its pack / NCCL / unpack CTAs are placed as soon as SM slots free up
+    // instead of queueing behind the ~8000 CTAs of the bulk force kernel they are meant to overlap
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaMalloc(&ctx->d_counts, sizeof(Counts)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counts, sizeof(Counts)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_result, 16 * sizeof(double)) != cudaSuccess) {
@@ -102,6 +106,7 @@ extern "C" int meso_create(meso_ctx **out, int device)
     }
     cudaEventCreateWithFlags(&ctx->ev_fwd_begin, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_fwd_end, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming);
     // MESO_FORCE_COMM_PATH=1 runs the message-based halo path (pack -> [NCCL] -> unpack, side-stream overlap) even on one rank
     const char *fc = getenv("MESO_FORCE_COMM_PATH");
     ctx->comm_path = fc && fc[0] == '1';
@@ -127,6 +132,7 @@ extern "C" void meso_destroy(meso_ctx *ctx)
     if (ctx->tex_veloc) cudaDestroyTextureObject(ctx->tex_veloc);
     if (ctx->ev_fwd_begin) cudaEventDestroy(ctx->ev_fwd_begin);
     if (ctx->ev_fwd_end) cudaEventDestroy(ctx->ev_fwd_end);
+    if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -545,7 +551,10 @@ static int rebuild_impl(meso_ctx *ctx)
         PhaseTimer t(ctx, MESO_T_NEIGH);
         TRY(launch_neighbor_build(ctx));
     }
+    if (ctx->comm_path) TRY(comm_share_errors(ctx));
     MESO_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(Counts), cudaMemcpyDeviceToHost, ctx->stream));
+    MESO_CUDA(cudaEventRecord(ctx->ev_counts, ctx->stream));
+    ctx->fwd_counts_valid = false;
     ctx->ago = 0;
     return MESO_OK;
 }

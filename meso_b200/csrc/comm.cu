@@ -266,26 +266,29 @@ __global__ void __launch_bounds__(256) k_mr_border_unpack(SoA3 x, SoA3 v, int *_
 }
 
 // ------------------------------------------------------------------ per-step forward (pack_comm_vel / unpack_comm_vel)
-__global__ void __launch_bounds__(256) k_mr_forward_pack(SoA3 x, SoA3 v, const float4 *__restrict__ veloc4, const Counts *__restrict__ cnt,
+// Forward records are 40 bytes: {x + shift (3 x fp64), veloc4 = fp32 v + this step's signature}.  The force kernel reads
+// ghosts only through the packed views, and a ghost's packed velocity is what later dimensions forward, so the fp64 ghost
+// velocity is simply the widened fp32 value.  Messages carry exactly the records of the send lists built at the last
+// rebuild (sizes known to both sides from that rebuild's counts): no headers, no padding.
+constexpr int RECF = 5;
+
+__global__ void __launch_bounds__(256) k_mr_forward_pack(SoA3 x, const float4 *__restrict__ veloc4, const Counts *__restrict__ cnt,
                                                          const int *__restrict__ list_lo, const int *__restrict__ list_hi,
                                                          double *__restrict__ send_lo, double *__restrict__ send_hi, Box box, int d)
 {
     const int na = cnt->send_n[2 * d], n = na + cnt->send_n[2 * d + 1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        reinterpret_cast<int *>(send_lo)[0] = na;
-        reinterpret_cast<int *>(send_hi)[0] = n - na;
-    }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int side = k >= na;
         const int kk = side ? k - na : k;
         const int i = (side ? list_hi : list_lo)[kk];
         const int pbc = box.pbc[2 * d + side];
-        double *rec = (side ? send_hi : send_lo) + (size_t)(kk + 1) * REC;
+        double *rec = (side ? send_hi : send_lo) + (size_t)kk * RECF;
         double xg[3] = {x.c[0][i], x.c[1][i], x.c[2][i]};
         if (pbc) xg[d] = pbc > 0 ? xg[d] + box.prd[d] : xg[d] - box.prd[d];
         rec[0] = xg[0]; rec[1] = xg[1]; rec[2] = xg[2];
-        rec[3] = v.c[0][i]; rec[4] = v.c[1][i]; rec[5] = v.c[2][i];
-        reinterpret_cast<int2 *>(rec)[7] = make_int2(0, __float_as_int(veloc4[i].w));
+        const float4 w = veloc4[i];
+        reinterpret_cast<float2 *>(rec)[3] = make_float2(w.x, w.y);
+        reinterpret_cast<float2 *>(rec)[4] = make_float2(w.z, w.w);
     }
 }
 
@@ -294,21 +297,17 @@ __global__ void __launch_bounds__(256) k_mr_forward_unpack(SoA3 x, SoA3 v, const
                                                            const double *__restrict__ recv_a, const double *__restrict__ recv_b, Box box, int d)
 {
     const int na = cnt->swap_n[2 * d], n = na + cnt->swap_n[2 * d + 1], g0 = cnt->swap_first[2 * d];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        // the sender's list must still be the one that created these ghosts
-        if (reinterpret_cast<const int *>(recv_a)[0] != na || reinterpret_cast<const int *>(recv_b)[0] != n - na) atomicOr(&cnt->err, 16);
-    }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const double *rec = (k < na) ? recv_a + (size_t)(k + 1) * REC : recv_b + (size_t)(k - na + 1) * REC;
+        const double *rec = (k < na) ? recv_a + (size_t)k * RECF : recv_b + (size_t)(k - na) * RECF;
         const int g = g0 + k;
-        const double xx = rec[0], yy = rec[1], zz = rec[2], vx = rec[3], vy = rec[4], vz = rec[5];
+        const double xx = rec[0], yy = rec[1], zz = rec[2];
+        const float2 w01 = reinterpret_cast<const float2 *>(rec)[3], w23 = reinterpret_cast<const float2 *>(rec)[4];
         x.c[0][g] = xx; x.c[1][g] = yy; x.c[2][g] = zz;
-        v.c[0][g] = vx; v.c[1][g] = vy; v.c[2][g] = vz;
-        float4 c, w;
+        v.c[0][g] = (double)w01.x; v.c[1][g] = (double)w01.y; v.c[2][g] = (double)w23.x;
+        float4 c;
         c.x = (float)(xx - box.centre[0]); c.y = (float)(yy - box.centre[1]); c.z = (float)(zz - box.centre[2]);
         c.w = __int_as_float(type[g] - 1);
-        w.x = (float)vx; w.y = (float)vy; w.z = (float)vz; w.w = __int_as_float(reinterpret_cast<const int2 *>(rec)[7].y);
-        coord4[g] = c; veloc4[g] = w;
+        coord4[g] = c; veloc4[g] = make_float4(w01.x, w01.y, w23.x, w23.y);
     }
 }
 
@@ -442,8 +441,10 @@ static int ensure_comm_buffers(meso_ctx *ctx)
         for (int q = 0; q < 3; q++) if (q != d) a *= w[q] + 2.0 * ctx->cutneighmax;
         face = std::max(face, a);
     }
-    int swap_cap = (int)(face * ctx->cutneighmax * dens * 1.5) + 4096;
-    int exch_cap = std::max(8192, ctx->nlocal_host / 8);
+    // ghosts of one swap: slab of width cutghost over the ghost-extended face (+20 %, density fluctuations are ~1 % at this size);
+    // leavers per dimension and rebuild: a layer |v| * every * dt thick, ~0.1 % of the brick -- 1/64 is ample; overflow sets err
+    int swap_cap = (int)(face * ctx->cutneighmax * dens * 1.2) + 4096;
+    int exch_cap = std::max(8192, ctx->nlocal_host / 64);
     if (ctx->nranks > 1 && !ctx->comm_caps_agreed) {
         // message sizes are part of the protocol: every rank must use the same capacities (ranks own slightly different
         // atom counts, so the local estimates can differ).  One max-reduction at the first rebuild after an upload,
@@ -473,19 +474,24 @@ static int ensure_comm_buffers(meso_ctx *ctx)
 
 // one dimension's pair of messages: mine to lower/upper neighbor, theirs from upper/lower.  Self-partnered
 // dimensions alias the receive pointers to the send buffers (no copy, no NCCL).
-static int swap_messages(meso_ctx *ctx, int d, size_t ndoubles, cudaStream_t st, const double *&recv_a, const double *&recv_b)
+static int swap_messages4(meso_ctx *ctx, int d, size_t send_lo, size_t send_hi, size_t recv_up, size_t recv_lo, cudaStream_t st,
+                          const double *&recv_a, const double *&recv_b)
 {
     if (ctx->procgrid[d] == 1) { recv_a = ctx->send_buf[0].p; recv_b = ctx->send_buf[1].p; return MESO_OK; }
     ncclComm_t comm = (ncclComm_t)ctx->nccl;
     const int lower = ctx->procneigh[d][0], upper = ctx->procneigh[d][1];
     MESO_NCCL(ncclGroupStart());
-    MESO_NCCL(ncclSend(ctx->send_buf[0].p, ndoubles, ncclDouble, lower, comm, st));
-    MESO_NCCL(ncclRecv(ctx->recv_buf[0].p, ndoubles, ncclDouble, upper, comm, st));
-    MESO_NCCL(ncclSend(ctx->send_buf[1].p, ndoubles, ncclDouble, upper, comm, st));
-    MESO_NCCL(ncclRecv(ctx->recv_buf[1].p, ndoubles, ncclDouble, lower, comm, st));
+    if (send_lo) MESO_NCCL(ncclSend(ctx->send_buf[0].p, send_lo, ncclDouble, lower, comm, st));
+    if (recv_up) MESO_NCCL(ncclRecv(ctx->recv_buf[0].p, recv_up, ncclDouble, upper, comm, st));
+    if (send_hi) MESO_NCCL(ncclSend(ctx->send_buf[1].p, send_hi, ncclDouble, upper, comm, st));
+    if (recv_lo) MESO_NCCL(ncclRecv(ctx->recv_buf[1].p, recv_lo, ncclDouble, lower, comm, st));
     MESO_NCCL(ncclGroupEnd());
     recv_a = ctx->recv_buf[0].p; recv_b = ctx->recv_buf[1].p;
     return MESO_OK;
+}
+static int swap_messages(meso_ctx *ctx, int d, size_t ndoubles, cudaStream_t st, const double *&recv_a, const double *&recv_b)
+{
+    return swap_messages4(ctx, d, ndoubles, ndoubles, ndoubles, ndoubles, st, recv_a, recv_b);
 }
 
 int launch_exchange_multi(meso_ctx *ctx)
@@ -553,16 +559,39 @@ int launch_borders_multi(meso_ctx *ctx)
     return MESO_OK;
 }
 
-// per-step ghost refresh on stream `st` (the side stream when it overlaps the bulk force kernel)
+int comm_share_errors(meso_ctx *ctx)
+{
+    Counts *c = ctx->d_counts;
+    MESO_CUDA(cudaMemcpyAsync(&c->err_any, &c->err, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->nranks > 1)
+        MESO_NCCL(ncclAllReduce(&c->err_any, &c->err_any, 1, ncclInt, ncclMax, (ncclComm_t)ctx->nccl, ctx->stream));
+    return MESO_OK;
+}
+
+// per-step ghost refresh on stream `st` (the side stream when it overlaps the bulk force kernel).  Message sizes come from
+// the counts of the rebuild that built the send lists: the host waits once per rebuild for that (tiny) copy; the
+// sender's send_n[s] equals the receiver's swap_n[s] by construction (it is the header the receiver unpacked).
 int launch_forward_multi(meso_ctx *ctx, cudaStream_t st)
 {
     const Box &box = ctx->box;
+    if (!ctx->fwd_counts_valid) {
+        MESO_CUDA(cudaEventSynchronize(ctx->ev_counts));
+        if (ctx->h_counts->err_any) {
+            // some rank overflowed a capacity during the rebuild: its ghost counts no longer match its partners' send lists.
+            // Every rank sees the same flag and stops here, before a size-mismatched message could block the others.
+            ctx->err = "device-side capacity error on some rank during the last rebuild (ghost / migration / pair-table capacity)";
+            return MESO_ECAPACITY;
+        }
+        for (int s = 0; s < 6; s++) { ctx->fwd_send_n[s] = ctx->h_counts->send_n[s]; ctx->fwd_recv_n[s] = ctx->h_counts->swap_n[s]; }
+        ctx->fwd_counts_valid = true;
+    }
     for (int d = 0; d < 3; d++) {
         if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1] && ctx->procgrid[d] == 1) continue;
-        k_mr_forward_pack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->veloc4.p, ctx->d_counts, ctx->sendlist[2 * d].p,
+        k_mr_forward_pack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, ctx->sendlist[2 * d].p,
                                                          ctx->sendlist[2 * d + 1].p, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d);
         const double *ra, *rb;
-        int rc = swap_messages(ctx, d, (size_t)(ctx->swap_cap + 1) * REC, st, ra, rb);
+        int rc = swap_messages4(ctx, d, (size_t)ctx->fwd_send_n[2 * d] * RECF, (size_t)ctx->fwd_send_n[2 * d + 1] * RECF,
+                                (size_t)ctx->fwd_recv_n[2 * d] * RECF, (size_t)ctx->fwd_recv_n[2 * d + 1] * RECF, st, ra, rb);
         if (rc) return rc;
         k_mr_forward_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
                                                            ra, rb, box, d);

@@ -26,7 +26,7 @@ struct Counts {
     int nall;                       // nlocal + nghost
     int send_n[6];                  // atoms this rank sends in each border swap (== swap_n on a self-partnered swap)
     int exch_n[2];                  // migration: leavers to the lower / upper neighbor in the current dimension
-    int pad[1];
+    int err_any;                    // max of `err` over all ranks at the last rebuild (multi-rank: every rank fails together)
 };
 
 struct Box {
@@ -134,6 +134,9 @@ struct meso_ctx {
     meso::DevBuf<double> send_buf[2], recv_buf[2], reduce_buf;
     meso::DevBuf<int> sendlist[6];
     cudaEvent_t ev_fwd_begin = nullptr, ev_fwd_end = nullptr;
+    cudaEvent_t ev_counts = nullptr;          // the pinned Counts mirror of the last rebuild has landed
+    bool fwd_counts_valid = false;            // fwd_send_n / fwd_recv_n describe the current send lists
+    int fwd_send_n[6] = {0}, fwd_recv_n[6] = {0};
     // cells
     meso::DevBuf<uint64_t> cell_key;          // sort key (cell id) per atom
     meso::DevBuf<int> cell_of, cell_atoms, cell_start;
@@ -187,6 +190,7 @@ int launch_forward(meso_ctx *ctx, bool full);     // per-step ghost refresh
 int launch_exchange_multi(meso_ctx *ctx);
 int launch_borders_multi(meso_ctx *ctx);
 int launch_forward_multi(meso_ctx *ctx, cudaStream_t st);
+int comm_share_errors(meso_ctx *ctx);   // Counts::err_any = max over ranks of Counts::err (stream-ordered, no host sync)
 // ---- neighbor.cu
 int launch_setup_bins(meso_ctx *ctx);
 int launch_neighbor_build(meso_ctx *ctx);
