@@ -113,6 +113,22 @@ int meso_set_reduce_scope(meso_ctx *ctx, int local_only);
  * (the reference accumulates per-atom virial UM/pair_dpd_meso.cu:180-186 but never reduces it) */
 int meso_compute_virial(meso_ctx *ctx, double virial6[6], double *e_pair);
 
+/* ---- bead-spring topology (single rank for now): atom_style dpd/bond/meso + bond_style harmonic/meso ---- */
+/* bond_coeff N k r0 for N = 1..nbondtypes, arrays [nbondtypes+1] (MesoBondHarmonic::alloc_coeff UM/bond_harmonic_meso.cu:34-44) */
+int meso_bond_harmonic_coeff(meso_ctx *ctx, int nbondtypes, const double *k, const double *r0);
+/* special_bonds lj <w12> ...: 1 keeps 1-2 pairs in the neighbor list, 0 filters them out
+ * (MesoNeighbor::filter_exclusion_meso UM/neigh_build_meso.cu:546-569) */
+int meso_set_special_bonds(meso_ctx *ctx, double lj12);
+/* per-atom bond table in LAMMPS' host layout (Atom::num_bond[i], bond_type[i][slot], bond_atom[i][slot] = partner TAG,
+ * rows of bond_per_atom ints), for the atoms just passed to meso_atoms_upload, newton_bond off (both atoms hold the bond):
+ * AtomVecDPDBond device table UM/atom_vec_dpd_bond_meso.h:33-36.  tag_max = largest tag (size of the tag -> index array,
+ * MesoAtom::map_set_device UM/atom_meso.cu:109-128). */
+int meso_bonds_upload(meso_ctx *ctx, int nlocal, int bond_per_atom, const int *num_bond, const int *bond_type,
+                      const int *bond_atom, int tag_max);
+/* MesoBondHarmonic::compute UM/bond_harmonic_meso.cu:119-170: f += bonded forces (tallies per-atom energy/virial if flagged) */
+int meso_bond_compute(meso_ctx *ctx, int eflag, int vflag);
+int meso_compute_bond_energy(meso_ctx *ctx, double *e_bond);
+
 /* ---- whole-run drivers (same results as the phase calls above, fewer launches) ---- */
 /* ModifiedVerlet::setup UM/mvv_meso.cu:139-219 */
 int meso_setup(meso_ctx *ctx, int eflag, int vflag);

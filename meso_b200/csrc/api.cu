@@ -151,6 +151,7 @@ static int check_device_flags(meso_ctx *ctx)
     if (e & 1) ctx->err += " ghost capacity exceeded;";
     if (e & 2) ctx->err += " pair table overflow (local density too high for n_col);";
     if (e & 8) ctx->err += " atom lost in migration;";
+    if (e & 32) ctx->err += " Bond atoms missing (a bond partner is neither local nor ghost);";
     return MESO_ECAPACITY;
 }
 
@@ -452,6 +453,7 @@ extern "C" int meso_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, con
     ctx->setup_done = false;
     ctx->f_cleared = true;
     ctx->comm_caps_agreed = false;
+    ctx->bond_per_atom = 0;                    // a bond table describes the atoms of ONE upload: re-send it with meso_bonds_upload
     return MESO_OK;
 }
 
@@ -541,15 +543,19 @@ static int rebuild_impl(meso_ctx *ctx)
             TRY(launch_pbc(ctx));
             TRY(launch_exchange_multi(ctx));
             TRY(launch_reorder(ctx));
+            TRY(launch_bonds_gather(ctx));
             TRY(launch_borders_multi(ctx));
         } else {
             TRY(launch_reorder(ctx));        // the key kernel wraps as it goes
+            TRY(launch_bonds_gather(ctx));
             TRY(launch_borders(ctx));
         }
+        TRY(launch_bonds_map(ctx));          // map_set_device + bond_all, UM/mvv_meso.cu:316, UM/neighbor_meso.cu:136-159
     }
     {
         PhaseTimer t(ctx, MESO_T_NEIGH);
         TRY(launch_neighbor_build(ctx));
+        TRY(launch_bonds_filter(ctx));       // filter_exclusion_meso, UM/neigh_build_meso.cu:546-569
     }
     if (ctx->comm_path) TRY(comm_share_errors(ctx));
     MESO_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(Counts), cudaMemcpyDeviceToHost, ctx->stream));
@@ -618,6 +624,74 @@ extern "C" int meso_compute_virial(meso_ctx *ctx, double virial6[6], double *e_p
     return MESO_OK;
 }
 
+// ---------------------------------------------------------------- bonded topology
+extern "C" int meso_bond_harmonic_coeff(meso_ctx *ctx, int nbondtypes, const double *k, const double *r0)
+{
+    CHECK_CTX();
+    if (nbondtypes < 1 || !k || !r0) FAIL(MESO_EINVAL, "Incorrect args for bond coefficients");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->bond_k_dev.reserve(nbondtypes + 1) || !ctx->bond_r0_dev.reserve(nbondtypes + 1)) FAIL(MESO_ECUDA, "out of device memory");
+    MESO_CUDA(cudaMemcpyAsync(ctx->bond_k_dev.p, k, sizeof(double) * (nbondtypes + 1), cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaMemcpyAsync(ctx->bond_r0_dev.p, r0, sizeof(double) * (nbondtypes + 1), cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->nbondtypes = nbondtypes;
+    return MESO_OK;
+}
+
+extern "C" int meso_set_special_bonds(meso_ctx *ctx, double lj12)
+{
+    CHECK_CTX();
+    if (lj12 != 0.0 && lj12 != 1.0) FAIL(MESO_EINVAL, "special_bonds: only lj weights 0 (1-2 pairs excluded) and 1 (kept) are supported");
+    ctx->special_lj12 = lj12;
+    return MESO_OK;
+}
+
+extern "C" int meso_bonds_upload(meso_ctx *ctx, int nlocal, int bond_per_atom, const int *num_bond, const int *bond_type,
+                                 const int *bond_atom, int tag_max)
+{
+    CHECK_CTX();
+    if (ctx->nranks > 1) FAIL(MESO_EINVAL, "bonded topology is single-rank for now (the table does not ride the migration messages yet)");
+    if (nlocal != ctx->nlocal_host) FAIL(MESO_EINVAL, "meso_bonds_upload: call right after meso_atoms_upload with the same atoms");
+    if (bond_per_atom < 0 || (bond_per_atom > 0 && (!num_bond || !bond_type || !bond_atom))) FAIL(MESO_EINVAL, "meso_bonds_upload: bad arguments");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    ctx->bond_per_atom = bond_per_atom;
+    ctx->map_tag_max = tag_max;
+    if (bond_per_atom == 0) return MESO_OK;
+    TRY(bonds_reserve(ctx));
+    // LAMMPS rows [atom][slot] -> column-major [slot][atom] of {partner tag, type}
+    std::vector<int2> col((size_t)ctx->cap * bond_per_atom, make_int2(0, 0));
+    for (int i = 0; i < nlocal; i++) {
+        if (num_bond[i] < 0 || num_bond[i] > bond_per_atom) FAIL(MESO_EINVAL, "meso_bonds_upload: num_bond exceeds bond_per_atom");
+        for (int p = 0; p < num_bond[i]; p++)
+            col[(size_t)p * ctx->cap + i] = make_int2(bond_atom[(size_t)i * bond_per_atom + p], bond_type[(size_t)i * bond_per_atom + p]);
+    }
+    MESO_CUDA(cudaMemcpyAsync(ctx->nbond.p, num_bond, sizeof(int) * nlocal, cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaMemcpyAsync(ctx->bonds.p, col.data(), sizeof(int2) * col.size(), cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->setup_done = false;
+    return MESO_OK;
+}
+
+// force->bond->compute (UM/mvv_meso.cu:387-389): adds the bonded forces of the local atoms into f
+extern "C" int meso_bond_compute(meso_ctx *ctx, int eflag, int vflag)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    PhaseTimer t(ctx, MESO_T_PAIR);
+    return launch_bond_force(ctx, eflag || vflag, false);
+}
+
+// sum of the per-atom bond energies of the last evflag evaluation (MesoBondHarmonic: e_bond = e/2 per atom)
+extern "C" int meso_compute_bond_energy(meso_ctx *ctx, double *e_bond)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    double e = 0.;
+    TRY(launch_bond_energy_sum(ctx, &e));
+    if (e_bond) *e_bond = e;
+    return MESO_OK;
+}
+
 // ---------------------------------------------------------------- whole-run drivers
 extern "C" int meso_setup(meso_ctx *ctx, int eflag, int vflag)
 {
@@ -628,6 +702,7 @@ extern "C" int meso_setup(meso_ctx *ctx, int eflag, int vflag)
     {
         PhaseTimer t(ctx, MESO_T_PAIR);                      // force_clear + pair->compute (UM/mvv_meso.cu:191-197)
         TRY(launch_pair(ctx, MESO_LOCAL, eflag || vflag, false, false, 0));
+        TRY(launch_bond_force(ctx, eflag || vflag, false));   // force->bond->compute, UM/mvv_meso.cu:198-201
     }
     ctx->setup_done = true;
     return refresh_counts(ctx);
@@ -640,16 +715,22 @@ extern "C" int meso_setup(meso_ctx *ctx, int eflag, int vflag)
 // accumulator is zero again, so the phase entry points, downloads and reductions see the same state as before.
 static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
 {
-    const bool sp = ctx->precision == MESO_SP;
+    // accumulator: facc for the fp32 pair-once kernel; otherwise f itself (fp64 pair-once kernel, or the two-sided kernel in
+    // accumulate mode when bonded forces force this loop with MESO_PAIR_ONCE=0)
+    const bool acc_facc = ctx->precision == MESO_SP && ctx->pair_once;
+    auto pair = [&](int range) -> int {
+        if (ctx->pair_once) return launch_pair_once(ctx, range);
+        return launch_pair(ctx, range, 0, true, false, 0);
+    };
     bool pending = false;                                    // the previous step's second half-kick is still owed
     for (int s = 0; s < nsteps; s++) {
         ctx->ntimestep++;                                    // UM/mvv_meso.cu:256
         const bool rebuild = meso_neighbor_decide(ctx) != 0;
         {
             PhaseTimer t(ctx, MESO_T_INTEGRATE);
-            // fp32: first step reads f (accumulator already zero), later steps read and clear facc;
-            // fp64: f is the accumulator: read and clear it every step
-            TRY(launch_step_integrate(ctx, groupbit, pending, true, !rebuild, sp && pending, sp ? pending : true, false));
+            // facc: the first step reads f (accumulator already zero), later steps read and clear facc;
+            // f as accumulator: read and clear it every step
+            TRY(launch_step_integrate(ctx, groupbit, pending, true, !rebuild, acc_facc && pending, acc_facc ? pending : true, false));
         }
         pending = true;
         if (rebuild) {
@@ -662,7 +743,7 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
             MESO_CUDA(cudaEventRecord(ctx->ev_fwd_end, ctx->side));
             {
                 PhaseTimer t(ctx, MESO_T_PAIR);
-                TRY(launch_pair_once(ctx, MESO_BULK));
+                TRY(pair(MESO_BULK));
             }
             {
                 PhaseTimer t(ctx, MESO_T_FORWARD);           // exposed (non-overlapped) part of the halo refresh
@@ -670,7 +751,8 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
             }
             {
                 PhaseTimer t(ctx, MESO_T_PAIR);
-                TRY(launch_pair_once(ctx, MESO_BORDER));
+                TRY(pair(MESO_BORDER));
+                TRY(launch_bond_force(ctx, 0, acc_facc));
             }
             continue;
         } else {
@@ -678,11 +760,12 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
             TRY(launch_forward(ctx, false));
         }
         PhaseTimer t(ctx, MESO_T_PAIR);
-        TRY(launch_pair_once(ctx, MESO_LOCAL));
+        TRY(pair(MESO_LOCAL));
+        TRY(launch_bond_force(ctx, 0, acc_facc));            // bonded forces join the same accumulator (UM/mvv_meso.cu:387-389)
     }
     if (pending) {
         PhaseTimer t(ctx, MESO_T_INTEGRATE);                 // last step's second half-kick; f <- force, accumulator cleared
-        TRY(launch_step_integrate(ctx, groupbit, true, false, false, sp, sp, sp));
+        TRY(launch_step_integrate(ctx, groupbit, true, false, false, acc_facc, acc_facc, acc_facc));
     }
     return MESO_OK;
 }
@@ -692,7 +775,7 @@ extern "C" int meso_run(meso_ctx *ctx, int nsteps, int groupbit)
     CHECK_CTX();
     TRY(ready(ctx));
     if (!ctx->setup_done) FAIL(MESO_EINVAL, "meso_run: call meso_setup first");
-    if (ctx->pair_once) return run_pair_once(ctx, nsteps, groupbit);
+    if (ctx->pair_once || bonds_active(ctx)) return run_pair_once(ctx, nsteps, groupbit);   // bonded forces need the unfused second half-kick
     for (int s = 0; s < nsteps; s++) {
         ctx->ntimestep++;                                    // UM/mvv_meso.cu:256
         const bool rebuild = meso_neighbor_decide(ctx) != 0;

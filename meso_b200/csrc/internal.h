@@ -88,7 +88,14 @@ struct meso_ctx {
     // settings
     double skin = 0.3, cut_global = 1.0, cutneighmax = 1.3, dt = 0.005;
     double ftm2v = 1.0;            // force->ftm2v of the host's unit system (1 in lj)
-    bool reduce_local = false;     // reductions return this rank's part only (an MPI host sums them itself)
+    bool reduce_local = false;     // bead-spring topology (bond.cu): column-major [slot][atom] table of {partner tag, bond type}
+    int bond_per_atom = 0, nbondtypes = 0, map_tag_max = 0;
+    double special_lj12 = 1.0;                // special_bonds lj weight of 1-2 pairs: 1 keeps them in the list, 0 filters them out
+    meso::DevBuf<int> nbond, nbond_alt;
+    meso::DevBuf<int2> bonds, bonds_alt, bonds_mapped;
+    meso::DevBuf<unsigned> tag_map;
+    meso::DevBuf<double> bond_k_dev, bond_r0_dev, e_bond;
+    // reductions return this rank's part only (an MPI host sums them itself)
     int every = 5, ago = 0;
     int64_t ntimestep = 0;
     int ntypes = 0;
@@ -198,6 +205,14 @@ int launch_neighbor_build(meso_ctx *ctx);
 int launch_pack(meso_ctx *ctx, int range);
 int launch_pair(meso_ctx *ctx, int range, int evflag, bool accumulate, bool fuse_final, int groupbit);
 int launch_pair_once(meso_ctx *ctx, int range);
+// ---- bond.cu
+bool bonds_active(const meso_ctx *ctx);
+int bonds_reserve(meso_ctx *ctx);
+int launch_bonds_gather(meso_ctx *ctx);                 // after launch_reorder
+int launch_bonds_map(meso_ctx *ctx);                    // after the ghosts exist
+int launch_bonds_filter(meso_ctx *ctx);                 // after the neighbor build
+int launch_bond_force(meso_ctx *ctx, int evflag, bool into_facc);
+int launch_bond_energy_sum(meso_ctx *ctx, double *e);
 // ---- integrate.cu
 int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack);
 int launch_final_integrate(meso_ctx *ctx, int groupbit);

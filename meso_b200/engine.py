@@ -140,6 +140,43 @@ class Meso:
         v, tag, type, mask, image = c(v, np.float64), c(tag, np.int32), c(type, np.int32), c(mask, np.int32), c(image, np.int32)
         self._chk(self.L.meso_atoms_upload(self.h, x.shape[0], _ptr(x), _ptr(v), _ptr(tag), _ptr(type), _ptr(mask), _ptr(image)))
 
+    # ---- bead-spring topology: bond_style harmonic/meso, bond_coeff, special_bonds, Bonds section ------------
+    def bond_style(self, style, nbondtypes):
+        if style != "harmonic/meso":
+            raise MesoError("Invalid bond style")
+        self._bond_k = np.zeros(nbondtypes + 1)
+        self._bond_r0 = np.zeros(nbondtypes + 1)
+        self._bond_set = np.zeros(nbondtypes + 1, dtype=bool)
+
+    def bond_coeff(self, n, k, r0):
+        """bond_coeff N K r0: E = K (r - r0)^2 (UM/bond_harmonic_meso.cu, src/MOLECULE/bond_harmonic.cpp)"""
+        if getattr(self, "_bond_k", None) is None or not 1 <= n < len(self._bond_k):
+            raise MesoError("Incorrect args for bond coefficients")
+        self._bond_k[n], self._bond_r0[n], self._bond_set[n] = k, r0, True
+        if self._bond_set[1:].all():
+            self._chk(self.L.meso_bond_harmonic_coeff(self.h, len(self._bond_k) - 1, self._bond_k.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      self._bond_r0.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def special_bonds(self, lj12):
+        self._chk(self.L.meso_set_special_bonds(self.h, float(lj12)))
+
+    def bonds(self, num_bond, bond_type, bond_atom, tag_max=None):
+        """per-atom table in LAMMPS' layout (rows [atom][slot]; bond_atom = partner TAG), same atom order as upload()"""
+        num_bond = np.ascontiguousarray(num_bond, np.int32)
+        bond_type = np.ascontiguousarray(bond_type, np.int32).reshape(len(num_bond), -1)
+        bond_atom = np.ascontiguousarray(bond_atom, np.int32).reshape(len(num_bond), -1)
+        if tag_max is None:
+            tag_max = int(max(len(num_bond), bond_atom.max(initial=0)))
+        self._chk(self.L.meso_bonds_upload(self.h, len(num_bond), bond_type.shape[1], _ptr(num_bond), _ptr(bond_type), _ptr(bond_atom),
+                                           int(tag_max)))
+
+    def bond_compute(self, eflag=0, vflag=0): self._chk(self.L.meso_bond_compute(self.h, eflag, vflag))
+
+    def bond_energy(self):
+        e = C.c_double()
+        self._chk(self.L.meso_compute_bond_energy(self.h, C.byref(e)))
+        return e.value
+
     def counts(self):
         v = [C.c_int() for _ in range(4)]
         self._chk(self.L.meso_counts(self.h, *[C.byref(a) for a in v]))

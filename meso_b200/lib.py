@@ -48,6 +48,11 @@ SIGNATURES = {
     "meso_final_integrate": (_i, [_vp, _i]),
     "meso_compute_ke": (_i, [_vp, _i, _pd, _pd]),
     "meso_compute_virial": (_i, [_vp, _pd, _pd]),
+    "meso_bond_harmonic_coeff": (_i, [_vp, _i, _pd, _pd]),
+    "meso_set_special_bonds": (_i, [_vp, _d]),
+    "meso_bonds_upload": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i]),
+    "meso_bond_compute": (_i, [_vp, _i, _i]),
+    "meso_compute_bond_energy": (_i, [_vp, _pd]),
     "meso_setup": (_i, [_vp, _i, _i]),
     "meso_run": (_i, [_vp, _i, _i]),
     "meso_export_bins": (_i, [_vp, _pi, _pd, _pd, _pi]),

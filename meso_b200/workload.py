@@ -84,3 +84,37 @@ def read_data(path):
                 [0.0] + [masses.get(t, 1.0) for t in range(1, ntypes + 1)]
         i += 1
     raise ValueError("no Atoms section in %s" % path)
+
+
+def polymer_melt(L, chain_len=8, rho=4, bond_len=0.7, seed=20140902, solvent_frac=0.5):
+    """Bead-spring chains in DPD solvent (BASELINE configs[4] flavour): `solvent_frac` of the rho*L^3 beads are free
+    solvent (type 1), the rest form linear chains of `chain_len` beads (type 2) grown as random walks of step
+    `bond_len` and wrapped into the box.  Returns x, type, tag and the per-atom bond table in LAMMPS' newton_bond-off
+    layout (both partners hold each bond): num_bond[n], bond_type[n][2], bond_atom[n][2] (partner tags)."""
+    rng = np.random.default_rng(seed)
+    n = int(rho * L ** 3)
+    nchain = int(n * (1.0 - solvent_frac)) // chain_len
+    npoly = nchain * chain_len
+    nsolv = n - npoly
+    x = np.empty((n, 3))
+    typ = np.ones(n, np.int32)
+    x[:nsolv] = rng.random((nsolv, 3)) * L
+    start = rng.random((nchain, 3)) * L
+    steps = rng.normal(size=(nchain, chain_len - 1, 3))
+    steps *= bond_len / np.linalg.norm(steps, axis=2, keepdims=True)
+    walk = np.concatenate([start[:, None, :], start[:, None, :] + np.cumsum(steps, axis=1)], axis=1)
+    x[nsolv:] = np.mod(walk.reshape(-1, 3), L)
+    typ[nsolv:] = 2
+    tag = np.arange(1, n + 1, dtype=np.int32)
+    num_bond = np.zeros(n, np.int32)
+    bond_type = np.zeros((n, 2), np.int32)
+    bond_atom = np.zeros((n, 2), np.int32)
+    for c in range(nchain):
+        base = nsolv + c * chain_len
+        for b in range(chain_len - 1):
+            i, j = base + b, base + b + 1
+            for a, o in ((i, j), (j, i)):
+                bond_type[a, num_bond[a]] = 1
+                bond_atom[a, num_bond[a]] = tag[o]
+                num_bond[a] += 1
+    return x, typ, tag, num_bond, bond_type, bond_atom

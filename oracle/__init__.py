@@ -77,6 +77,11 @@ def lib():
         "orc_get_stencil": (i32, [C.c_void_p, i32, i32, C.c_void_p]),
         "orc_get_neighbors": (None, [C.c_void_p, i32, C.c_void_p, C.c_void_p]),
         "orc_get_neighbors_transposed": (None, [C.c_void_p, i32, C.c_void_p]),
+        "orc_world_set_bonds": (i32, [C.c_void_p, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "orc_set_bond_coeff": (None, [C.c_void_p, i32, C.c_void_p, C.c_void_p]),
+        "orc_set_special_lj12": (None, [C.c_void_p, f64]),
+        "orc_bond_compute": (None, [C.c_void_p, i32, i32]),
+        "orc_bond_energy": (f64, [C.c_void_p]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -154,6 +159,20 @@ class World:
         c = lambda a, t: None if a is None else np.ascontiguousarray(a, dtype=t)
         v, tag, type, mask, image = c(v, np.float64), c(tag, np.int32), c(type, np.int32), c(mask, np.int32), c(image, np.int32)
         self._chk(self.L.orc_world_set_atoms(self.h, n, _p(x), _p(v), _p(tag), _p(type), _p(mask), _p(image)))
+
+    def set_bonds(self, num_bond, bond_type, bond_atom, tag=None, k=None, r0=None, special_lj12=1.0):
+        """per-atom bond tables (LAMMPS layout, same atom order as set_atoms) + bond_coeff arrays [nbondtypes+1]"""
+        num_bond = np.ascontiguousarray(num_bond, np.int32)
+        bond_type = np.ascontiguousarray(bond_type, np.int32).reshape(len(num_bond), -1)
+        bond_atom = np.ascontiguousarray(bond_atom, np.int32).reshape(len(num_bond), -1)
+        tag = None if tag is None else np.ascontiguousarray(tag, np.int32)
+        self._chk(self.L.orc_world_set_bonds(self.h, len(num_bond), bond_type.shape[1], _p(tag), _p(num_bond), _p(bond_type), _p(bond_atom)))
+        k, r0 = np.ascontiguousarray(k, np.float64), np.ascontiguousarray(r0, np.float64)
+        self.L.orc_set_bond_coeff(self.h, len(k) - 1, _p(k), _p(r0))
+        self.L.orc_set_special_lj12(self.h, float(special_lj12))
+
+    def bond_compute(self, eflag=0, vflag=0): self.L.orc_bond_compute(self.h, eflag, vflag)
+    def bond_energy(self): return self.L.orc_bond_energy(self.h)
 
     def setup(self, eflag=0, vflag=0):
         self._chk(self.L.orc_world_setup(self.h, eflag, vflag))

@@ -270,7 +270,7 @@ typedef struct {
 
     int nlocal, nghost, nmax, n_bulk, n_border;
     double *x, *v, *f; int *tag, *type, *mask, *image;
-    double *virial, *e_pair;
+    double *virial, *e_pair, *e_bond;
     float *coord4, *veloc4;
 
     int m[3]; double binsize[3], bininv[3];
@@ -293,6 +293,10 @@ struct orc_world {
     uint32_t seed; double dt; int every, ago; long ntimestep;
     int precision;
     orc_rank *rk;
+    /* bead-spring topology, keyed by TAG (a bond is a property of the atom, wherever the rank arrays keep it) */
+    int bond_per_atom, tag_max, nbondtypes; double special_lj12;
+    int *num_bond, *bond_type, *bond_atom;      /* [tag_max+1], [tag_max+1][bond_per_atom] */
+    double *bond_k, *bond_r0;                   /* [nbondtypes+1] */
 };
 
 static int rank_of(const orc_world *w, int ix, int iy, int iz)
@@ -313,6 +317,7 @@ static void rank_grow(orc_rank *r, int n)
     r->image = realloc(r->image, sizeof(int) * nm);
     r->virial = realloc(r->virial, sizeof(double) * 6 * nm);
     r->e_pair = realloc(r->e_pair, sizeof(double) * nm);
+    r->e_bond = realloc(r->e_bond, sizeof(double) * nm);
     r->coord4 = realloc(r->coord4, sizeof(float) * 4 * nm);
     r->veloc4 = realloc(r->veloc4, sizeof(float) * 4 * nm);
     r->cell_id = realloc(r->cell_id, sizeof(int) * nm);
@@ -377,6 +382,7 @@ orc_world *orc_world_create(const double boxlo[3], const double boxhi[3],
                             uint32_t seed, double dt, int precision)
 {
     orc_world *w = calloc(1, sizeof *w);
+    w->special_lj12 = 1.0;
     for (int d = 0; d < 3; d++) {
         w->boxlo[d] = boxlo[d]; w->boxhi[d] = boxhi[d]; w->prd[d] = boxhi[d] - boxlo[d];
         w->periodic[d] = periodic[d]; w->procgrid[d] = procgrid[d];
@@ -424,6 +430,7 @@ void orc_world_destroy(orc_world *w)
         free(r->buf_l); free(r->buf_r);
         for (int s = 0; s < 6; s++) free(r->swap[s].sendlist);
     }
+    free(w->num_bond); free(w->bond_type); free(w->bond_atom); free(w->bond_k); free(w->bond_r0);
     free(w->rk); free(w->mass); free(w->coeff); free(w);
 }
 
@@ -884,6 +891,8 @@ static int neighbor_build(orc_world *w, orc_rank *r)
     return 0;
 }
 
+static void filter_exclusion(const orc_world *w, orc_rank *r);
+
 int orc_rebuild(orc_world *w)
 {
     for (int ir = 0; ir < w->nranks; ir++) {
@@ -895,6 +904,8 @@ int orc_rebuild(orc_world *w)
     for (int ir = 0; ir < w->nranks; ir++) sort_local(w, &w->rk[ir]);
     borders(w);
     for (int ir = 0; ir < w->nranks; ir++) if (neighbor_build(w, &w->rk[ir])) return -1;
+    if (w->bond_per_atom > 0 && w->special_lj12 == 0.0)
+        for (int ir = 0; ir < w->nranks; ir++) filter_exclusion(w, &w->rk[ir]);
     w->ago = 0;
     return 0;
 }
@@ -1062,6 +1073,116 @@ double orc_temperature(orc_world *w, int groupbit)
 }
 
 /* ---------------------------------------------------------------------- */
+/* bead-spring topology                                 */
+/* ---------------------------------------------------------------------- */
+int orc_world_set_bonds(orc_world *w, int n, int bond_per_atom, const int *tag, const int *num_bond,
+                        const int *bond_type, const int *bond_atom)
+{
+    int tmax = 0;
+    for (int i = 0; i < n; i++) { int t = tag ? tag[i] : i + 1; if (t > tmax) tmax = t; }
+    free(w->num_bond); free(w->bond_type); free(w->bond_atom);
+    w->bond_per_atom = bond_per_atom; w->tag_max = tmax;
+    w->num_bond = calloc(tmax + 1, sizeof(int));
+    w->bond_type = calloc((size_t)(tmax + 1) * (bond_per_atom > 0 ? bond_per_atom : 1), sizeof(int));
+    w->bond_atom = calloc((size_t)(tmax + 1) * (bond_per_atom > 0 ? bond_per_atom : 1), sizeof(int));
+    for (int i = 0; i < n; i++) {
+        int t = tag ? tag[i] : i + 1;
+        if (num_bond[i] > bond_per_atom) FAIL("num_bond exceeds bond_per_atom for atom %d", i);
+        w->num_bond[t] = num_bond[i];
+        for (int p = 0; p < num_bond[i]; p++) {
+            w->bond_type[(size_t)t * bond_per_atom + p] = bond_type[(size_t)i * bond_per_atom + p];
+            w->bond_atom[(size_t)t * bond_per_atom + p] = bond_atom[(size_t)i * bond_per_atom + p];
+        }
+    }
+    return 0;
+}
+
+void orc_set_bond_coeff(orc_world *w, int nbondtypes, const double *k, const double *r0)
+{
+    free(w->bond_k); free(w->bond_r0);
+    w->nbondtypes = nbondtypes;
+    w->bond_k = malloc(sizeof(double) * (nbondtypes + 1)); w->bond_r0 = malloc(sizeof(double) * (nbondtypes + 1));
+    memcpy(w->bond_k, k, sizeof(double) * (nbondtypes + 1)); memcpy(w->bond_r0, r0, sizeof(double) * (nbondtypes + 1));
+}
+
+void orc_set_special_lj12(orc_world *w, double v) { w->special_lj12 = v; }
+
+static int bonds_on(const orc_world *w) { return w->bond_per_atom > 0 && w->nbondtypes > 0; }
+
+static double minimum_image(double dr, double p)          /* UM/math_meso.h:148-152 */
+{
+    double p_half = p * 0.5;
+    return dr + (dr > -p_half ? (dr < p_half ? 0.0 : -p) : p);
+}
+
+/* gpu_filter_exclusion, UM/neigh_build_meso.cu:497-544, for special_bonds lj 0: bonded partners (by tag) leave the row */
+static void filter_exclusion(const orc_world *w, orc_rank *r)
+{
+    for (int i = 0; i < r->nlocal; i++) {
+        int t = r->tag[i], nb = w->num_bond[t];
+        if (!nb) continue;
+        int *row = r->pair_rows + (size_t)i * r->n_col, keep = 0;
+        for (int k = 0; k < r->pair_count[i]; k++) {
+            int tj = r->tag[row[k]], ok = 1;
+            for (int p = 0; p < nb; p++) if (w->bond_atom[(size_t)t * w->bond_per_atom + p] == tj) ok = 0;
+            if (ok) row[keep++] = row[k];
+        }
+        r->pair_count[i] = keep;
+    }
+}
+
+/* gpu_bond_harmonic, UM/bond_harmonic_meso.cu:46-117; partner = lowest index holding the tag (gpu_set_map's atomicMin,
+ * UM/atom_meso.cu:74-82), minimum image on the packed fp32 coordinates */
+void orc_bond_compute(orc_world *w, int eflag, int vflag)
+{
+    if (!bonds_on(w)) return;
+    int ev = eflag || vflag;
+    for (int ir = 0; ir < w->nranks; ir++) {
+        orc_rank *r = &w->rk[ir];
+        int nall = r->nlocal + r->nghost;
+        int *map = malloc(sizeof(int) * (w->tag_max + 1));
+        for (int t = 0; t <= w->tag_max; t++) map[t] = -1;
+        for (int i = nall - 1; i >= 0; i--) if (r->tag[i] >= 0 && r->tag[i] <= w->tag_max) map[r->tag[i]] = i;
+        double period[3];
+        for (int d = 0; d < 3; d++) period[d] = w->periodic[d] ? w->prd[d] : 0.0;
+        for (int i = 0; i < r->nlocal; i++) {
+            int t = r->tag[i], nb = w->num_bond[t];
+            const float *c1 = r->coord4 + 4 * i;
+            double fx = 0, fy = 0, fz = 0, e = 0;
+            for (int p = 0; p < nb; p++) {
+                int j = map[w->bond_atom[(size_t)t * w->bond_per_atom + p]], ty = w->bond_type[(size_t)t * w->bond_per_atom + p];
+                if (j < 0) continue;
+                const float *c2 = r->coord4 + 4 * j;
+                double dx = minimum_image((double)(float)(c2[0] - c1[0]), period[0]);
+                double dy = minimum_image((double)(float)(c2[1] - c1[1]), period[1]);
+                double dz = minimum_image((double)(float)(c2[2] - c1[2]), period[2]);
+                double rsq = dx * dx + dy * dy + dz * dz;
+                double rinv = 1.0 / sqrt(rsq), rr = rinv * rsq, dr = rr - w->bond_r0[ty];
+                double fbond = 2.0 * w->bond_k[ty] * dr * rinv;
+                fx += dx * fbond; fy += dy * fbond; fz += dz * fbond;
+                e += w->bond_k[ty] * dr * dr;
+            }
+            r->f[3 * i] += fx; r->f[3 * i + 1] += fy; r->f[3 * i + 2] += fz;
+            if (ev) {
+                double *vv = r->virial + 6 * i;
+                vv[0] += c1[0] * fx; vv[1] += c1[1] * fy; vv[2] += c1[2] * fz;
+                vv[3] += c1[0] * fy; vv[4] += c1[0] * fz; vv[5] += c1[1] * fz;
+                r->e_bond[i] = e * 0.5;
+            }
+        }
+        free(map);
+    }
+}
+
+double orc_bond_energy(orc_world *w)
+{
+    double e = 0;
+    if (!bonds_on(w)) return 0;
+    for (int ir = 0; ir < w->nranks; ir++) for (int i = 0; i < w->rk[ir].nlocal; i++) e += w->rk[ir].e_bond[i];
+    return e;
+}
+
+/* ---------------------------------------------------------------------- */
 /* drivers: ModifiedVerlet::setup / ::run, UM/mvv_meso.cu:139-219,243-425  */
 /* ---------------------------------------------------------------------- */
 int orc_world_setup(orc_world *w, int eflag, int vflag)
@@ -1070,6 +1191,7 @@ int orc_world_setup(orc_world *w, int eflag, int vflag)
     if (orc_rebuild(w)) return -1;
     orc_force_clear(w);
     orc_pair_compute(w, eflag, vflag);
+    orc_bond_compute(w, eflag, vflag);
     return 0;
 }
 
@@ -1083,6 +1205,7 @@ int orc_world_run(orc_world *w, int nsteps, int eflag, int vflag)
         else orc_forward_comm(w);
         orc_force_clear(w);
         orc_pair_compute(w, eflag, vflag);
+        orc_bond_compute(w, eflag, vflag);
         orc_final_integrate(w, 1);
     }
     return 0;

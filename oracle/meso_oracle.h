@@ -84,6 +84,15 @@ double orc_temperature(orc_world *w, int groupbit);        /* scalar T, lj units
 void orc_set_timestep(orc_world *w, long ntimestep);
 long orc_get_timestep(orc_world *w);
 
+/* bead-spring topology: per-atom tables in LAMMPS' layout for the atoms of set_atoms (same order);
+ * harmonic bonds UM/bond_harmonic_meso.cu:46-117, exclusion filter UM/neigh_build_meso.cu:497-544 */
+int  orc_world_set_bonds(orc_world *w, int n, int bond_per_atom, const int *tag, const int *num_bond,
+                         const int *bond_type, const int *bond_atom);
+void orc_set_bond_coeff(orc_world *w, int nbondtypes, const double *k, const double *r0);
+void orc_set_special_lj12(orc_world *w, double v);
+void orc_bond_compute(orc_world *w, int eflag, int vflag);
+double orc_bond_energy(orc_world *w);
+
 /* queries (rank r) */
 int  orc_nranks(orc_world *w);
 void orc_counts(orc_world *w, int r, int *nlocal, int *nghost, int *n_bulk,

@@ -561,3 +561,73 @@ def test_full_size_properties(L, precision):
     T = m.temperature()
     assert 0.5 < T < 2.5
     m.close()
+
+
+# ------------------------------------------------------------------ bead-spring polymers
+def make_polymer_pair(L, precision, lj12=1.0, monkeypatch=None, once="1"):
+    x, typ, tag, nb, bt, ba = workload.polymer_melt(L, chain_len=8, seed=5)
+    v = workload.maxwell_velocities(len(x))
+    coeff = [(1, 1, (25, 4.5, 3.0, 1.0, 1.0)), (1, 2, (40, 4.5, 3.0, 1.0, 1.0)), (2, 2, (25, 4.5, 3.0, 1.0, 1.0))]
+    m, w = make_pair(L, precision, ntypes=2, mass=[0.0, 1.0, 1.0], coeff=coeff, types=typ, x=x, v=v, tag=tag)
+    m.bond_style("harmonic/meso", 1)
+    m.bond_coeff(1, 50.0, 0.5)
+    m.special_bonds(lj12)
+    m.bonds(nb, bt, ba)
+    w.set_bonds(nb, bt, ba, tag=tag, k=[0.0, 50.0], r0=[0.0, 0.5], special_lj12=lj12)
+    return m, w
+
+
+@pytest.mark.parametrize("lj12", [1.0, 0.0])
+def test_polymer_setup_forces_table_and_bond_energy(lj12):
+    """atom_style dpd/bond/meso + bond_style harmonic/meso: bond table rides the reorder, tag map, harmonic bonds,
+    1-2 exclusion filter: rows (order included) bit-exact, forces and bond energy to the fp64 bar."""
+    for precision in ("dp", "sp"):
+        m, w = make_polymer_pair(8, precision, lj12)
+        m.setup(eflag=1, vflag=1); w.setup(eflag=1, vflag=1)
+        assert_state_identical(m, w, precision=precision, tol=2e-5 if precision == "sp" else 1e-11)
+        eg, eo = m.bond_energy(), w.bond_energy()
+        assert abs(eg - eo) < 1e-10 * abs(eo), (eg, eo)
+        vg, _ = m.per_atom_virial()
+        vo, _ = w.virial()
+        assert np.abs(vg - vo).max() < (1e-3 if precision == "sp" else 1e-8)
+        m.close()
+
+
+@pytest.mark.parametrize("once", ["1", "0"])
+def test_polymer_trajectory_fp64_lockstep(monkeypatch, once):
+    """12 steps / two rebuilds of bead-spring chains in solvent: both run loops (pair-once + REDG, and the two-sided
+    kernel accumulating into f) stay on the oracle's fp64 trajectory; bond tables survive the reorder."""
+    monkeypatch.setenv("MESO_PAIR_ONCE", once)
+    m, w = make_polymer_pair(8, "dp")
+    m.setup(); w.setup()
+    m.run(12); w.run(12)
+    ag, ao = m.download(), w.atoms()
+    nl = ao["nlocal"]
+    assert np.array_equal(ag["tag"], ao["tag"][:nl])
+    assert np.abs(ag["x"] - ao["x"][:nl]).max() < 1e-9 and np.abs(ag["v"] - ao["v"][:nl]).max() < 1e-9
+    assert force_err(ag["f"], ao["f"]) < 1e-9
+    # and in fp32: chains stay bonded (no bond stretches beyond a few r0) and the thermostat holds T
+    m.close()
+    m, _ = make_polymer_pair(8, "sp")
+    m.setup()
+    m.run(200)
+    d = m.download(("x", "tag"))
+    assert 0.5 < m.temperature() < 1.6
+    m.bond_compute(1, 0)
+    assert m.bond_energy() < 50.0 * 0.5 * 4 * 8 ** 3            # mean bond extension well below r0
+    m.close()
+
+
+def test_bonds_refused_on_a_decomposition_and_missing_partner_flagged():
+    x, typ, tag, nb, bt, ba = workload.polymer_melt(6, chain_len=4, seed=9)
+    m, _ = make_pair(6, "dp", ntypes=2, mass=[0.0, 1.0, 1.0], types=typ, x=x, tag=tag,
+                     coeff=[("*", "*", (25, 4.5, 3.0, 1.0, 1.0))])
+    m.bond_style("harmonic/meso", 1)
+    m.bond_coeff(1, 50.0, 0.5)
+    ba2 = ba.copy()
+    ba2[np.flatnonzero(nb > 0)[0], 0] = len(x) + 7            # a partner tag nobody owns
+    m.bonds(nb, bt, ba2, tag_max=len(x) + 8)
+    with pytest.raises(MesoError, match="Bond atoms missing"):
+        m.setup()
+        m.sync()
+    m.close()

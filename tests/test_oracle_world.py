@@ -164,3 +164,44 @@ def test_nve_energy_drift_conservative():
     w.run(40, 1, 1)
     e1 = etot()
     assert abs(e1 - e0) < 2e-3 * abs(e0), (e0, e1)
+
+
+def test_harmonic_bonds_and_exclusion_filter_against_direct_evaluation():
+    """the oracle's gpu_bond_harmonic / gpu_filter_exclusion restatement against a direct numpy
+    evaluation by tag (minimum image), on bead-spring chains in solvent."""
+    from meso_b200 import workload
+    L, k, r0 = 6, 50.0, 0.5
+    x, typ, tag, nb, bt, ba = workload.polymer_melt(L, chain_len=6, seed=3)
+    n = len(x)
+    coeff = np.array([[1, 1, 1, 1, 25, 4.5, 3.0]] * 4, dtype=float)
+
+    def world(lj12):
+        w = oracle.World((0, 0, 0), (L, L, L), ntypes=2, mass=[0, 1, 1], coeff=coeff, precision=1)
+        w.set_atoms(x, np.zeros_like(x), tag=tag, type=typ)
+        w.set_bonds(nb, bt, ba, tag=tag, k=[0, k], r0=[0, r0], special_lj12=lj12)
+        w.rebuild()
+        return w
+
+    w = world(1.0)
+    w.force_clear(); w.bond_compute(1, 1)
+    a = w.atoms()
+    pos = np.empty((n + 1, 3)); pos[a["tag"][:n]] = a["x"][:n]
+    E, F = 0.0, np.zeros((n + 1, 3))
+    for i in range(n):
+        for p in range(nb[i]):
+            d = pos[ba[i, p]] - pos[tag[i]]
+            d -= L * np.round(d / L)
+            r = np.linalg.norm(d)
+            E += 0.5 * k * (r - r0) ** 2                      # each bond is held by both atoms: e_bond = e/2 per atom
+            F[tag[i]] += 2 * k * (r - r0) / r * d
+    Fo = np.empty((n + 1, 3)); Fo[a["tag"][:n]] = a["f"]
+    assert abs(w.bond_energy() - E) < 1e-5 * E                # fp32-packed coordinates
+    assert np.abs(F[1:] - Fo[1:]).max() < 2e-4 and np.abs(a["f"].sum(0)).max() < 1e-9
+    c_all, rows_all = w.neighbors()
+    c_ex, rows_ex = world(0.0).neighbors()
+    assert c_all.sum() - c_ex.sum() == nb.sum()               # every bond partner is within r_n here and leaves the row
+    t = a["tag"]
+    for i in np.flatnonzero(nb[a["tag"][:n] - 1] > 0)[:50]:
+        partners = set(ba[t[i] - 1, :nb[t[i] - 1]].tolist())
+        kept = [j for j in rows_all[i, :c_all[i]] if t[j] not in partners]
+        assert kept == rows_ex[i, :c_ex[i]].tolist()          # survivors keep their order
