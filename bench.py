@@ -35,40 +35,70 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region"""
+    """SM clock + throttle reasons sampled through NVML every few ms; only samples that fall inside the timed region
+    (mark_begin .. mark_end) are reported.  Falls back to one nvidia-smi query if NVML cannot be loaded."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.period, self.stop_flag, self.rows = index, period, False, []
+        self.t0 = self.t1 = None
+        self.h = self.nv = None
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.h, self.nv = pynvml.nvmlDeviceGetHandleByIndex(phys), pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                 stdout=subprocess.PIPE, text=True)
-        except Exception:
+        if self.h is None:
             return
-        self.p = p
-        for line in p.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
-            if self.stop_flag:
-                break
-        p.kill()
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:
+                try:
+                    self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), 0))
+                except Exception:
+                    break
+            time.sleep(self.period)
+
+    def mark_begin(self): self.t0 = time.perf_counter()
+    def mark_end(self): self.t1 = time.perf_counter()
 
     def summary(self):
         self.stop_flag = True
-        time.sleep(0.15)
+        if self.is_alive():
+            self.join(timeout=1.0)
+        if self.h is None:
+            return self._smi_once()
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])] or self.rows[-3:]
+        sm = [r[1] for r in rows]
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": [n for n, b in self.REASONS if bits & b], "samples": len(sm), "source": "nvml, %g ms period, timed region only" % (1e3 * self.period)}
+
+    def _smi_once(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p.kill()
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().split("\n")[0]
+            r = [t.strip() for t in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(r[0]), "sm_max_mhz": float(r[1]), "reasons": [n for i, n in enumerate(names) if r[2 + i].lower().startswith("active")],
+                    "samples": 1, "source": "nvidia-smi after the timed region (NVML unavailable)"}
         except Exception:
-            pass
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
 
 
 def procgrid_for(n):
@@ -251,10 +281,12 @@ def main():
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record(stream)
     m.run(args.steps)
     e1.record(stream)
     m.sync()
+    sampler.mark_end()
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.summary()

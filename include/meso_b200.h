@@ -129,6 +129,25 @@ int meso_bonds_upload(meso_ctx *ctx, int nlocal, int bond_per_atom, const int *n
 int meso_bond_compute(meso_ctx *ctx, int eflag, int vflag);
 int meso_compute_bond_energy(meso_ctx *ctx, double *e_bond);
 
+/* ---- device-resident fixes of the channel decks: each call registers one fix and returns its handle (>= 0) ---- */
+/* fix ID group wall/meso [x] [y] [z] d <d> f <f> (MesoFixWall, UM/fix_wall_meso.cu:20-46): dims bit 0/1/2 = x/y/z;
+ * post_force: f -/+= F erfcf(sqrt3 (h - d/2)/d) within d of the box faces (:74-117); bounce-forward at the faces in
+ * pre_exchange and end_of_step (:147-238) */
+int meso_fix_wall(meso_ctx *ctx, int groupbit, int dims, double d, double f);
+/* fix ID group solid_bound/meso [x] [y] [z] rho5rc1s1 (MesoFixSolidBound, UM/fix_solid_bound_meso.cu:20-46;
+ * force_kernel 1 = Rho5rc1s1, UM/fix_solid_bound_meso.h:42-63) */
+int meso_fix_solid_bound(meso_ctx *ctx, int groupbit, int dims, int force_kernel);
+/* fix ID group addforce/meso fx fy fz (MesoFixAddForce, UM/fix_addforce_meso.cu:20-90) */
+int meso_fix_addforce(meso_ctx *ctx, int groupbit, double fx, double fy, double fz);
+/* fix ID group pois/meso <dim_ortho> <dim_force> <strength> [bisect_frac = 0.5] (MesoFixPoiseuille,
+ * UM/fix_poiseuille_meso.cu:20-113): +strength below the bisection plane, -strength above it */
+int meso_fix_pois(meso_ctx *ctx, int groupbit, int dim_ortho, int dim_force, double strength, double bisect_frac);
+int meso_fix_clear(meso_ctx *ctx);                                  /* unfix: drops every registered fix */
+/* hooks for a host that drives the step by phases (Modify::post_force / pre_exchange / end_of_step, UM/mvv_meso.cu:273,396,399);
+ * handle < 0 applies every registered fix in registration order.  meso_setup and meso_run call them themselves. */
+int meso_fix_post_force(meso_ctx *ctx, int handle);
+int meso_fix_bounce(meso_ctx *ctx, int handle);
+
 /* ---- whole-run drivers (same results as the phase calls above, fewer launches) ---- */
 /* ModifiedVerlet::setup UM/mvv_meso.cu:139-219 */
 int meso_setup(meso_ctx *ctx, int eflag, int vflag);

@@ -692,6 +692,83 @@ extern "C" int meso_compute_bond_energy(meso_ctx *ctx, double *e_bond)
     return MESO_OK;
 }
 
+// ---------------------------------------------------------------- device-resident fixes
+static int fix_register(meso_ctx *ctx, const meso::FixOp &op)
+{
+    meso::FixList &fl = ctx->fixes;
+    if (fl.n >= meso::MAX_FIX) FAIL(MESO_EINVAL, "too many device-resident fixes (limit 8)");
+    fl.op[fl.n] = op;
+    if (op.kind == meso::FIX_WALL || op.kind == meso::FIX_SOLID_BOUND) fl.nbounce++;
+    fl.nforce++;
+    return fl.n++;
+}
+
+extern "C" int meso_fix_wall(meso_ctx *ctx, int groupbit, int dims, double d, double f)
+{
+    CHECK_CTX();
+    if ((dims & 7) == 0) FAIL(MESO_EINVAL, "Incomplete fix wall command: insufficient arguments");
+    meso::FixOp op{};
+    op.kind = meso::FIX_WALL; op.groupbit = groupbit; op.dims = dims & 7;
+    op.p[0] = d; op.p[1] = 1.0 / d; op.p[2] = f;                 // MesoFixWall::boundary_force passes d, 1.0 / d, f
+    return fix_register(ctx, op);
+}
+
+extern "C" int meso_fix_solid_bound(meso_ctx *ctx, int groupbit, int dims, int force_kernel)
+{
+    CHECK_CTX();
+    if ((dims & 7) == 0) FAIL(MESO_EINVAL, "Incomplete fix wall command: dimension unspecified");
+    if (force_kernel != 1) FAIL(MESO_EINVAL, "Incomplete fix wall command: force kernel unspecified");
+    meso::FixOp op{};
+    op.kind = meso::FIX_SOLID_BOUND; op.groupbit = groupbit; op.dims = dims & 7; op.aux = force_kernel;
+    return fix_register(ctx, op);
+}
+
+extern "C" int meso_fix_addforce(meso_ctx *ctx, int groupbit, double fx, double fy, double fz)
+{
+    CHECK_CTX();
+    meso::FixOp op{};
+    op.kind = meso::FIX_ADDFORCE; op.groupbit = groupbit;
+    op.p[0] = fx; op.p[1] = fy; op.p[2] = fz;
+    return fix_register(ctx, op);
+}
+
+extern "C" int meso_fix_pois(meso_ctx *ctx, int groupbit, int dim_ortho, int dim_force, double strength, double bisect_frac)
+{
+    CHECK_CTX();
+    if (dim_ortho < 0 || dim_ortho > 2 || dim_force < 0 || dim_force > 2) FAIL(MESO_EINVAL, "Illegal fix CUDAPoiseuille command");
+    meso::FixOp op{};
+    op.kind = meso::FIX_POIS; op.groupbit = groupbit; op.dims = dim_ortho | (dim_force << 2);
+    op.p[0] = strength; op.p[1] = bisect_frac;
+    return fix_register(ctx, op);
+}
+
+extern "C" int meso_fix_clear(meso_ctx *ctx)
+{
+    CHECK_CTX();
+    ctx->fixes = meso::FixList{};
+    return MESO_OK;
+}
+
+// modify->post_force for fix `handle` (< 0: all, in registration order): f += wall / body forces of the local atoms
+extern "C" int meso_fix_post_force(meso_ctx *ctx, int handle)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    if (handle >= ctx->fixes.n) FAIL(MESO_EINVAL, "meso_fix_post_force: no such fix");
+    PhaseTimer t(ctx, MESO_T_INTEGRATE);
+    return launch_fix_post_force(ctx, handle, false);
+}
+
+// the pre_exchange / end_of_step hook of wall/meso and solid_bound/meso: bounce-forward at the box faces
+extern "C" int meso_fix_bounce(meso_ctx *ctx, int handle)
+{
+    CHECK_CTX();
+    TRY(ready(ctx));
+    if (handle >= ctx->fixes.n) FAIL(MESO_EINVAL, "meso_fix_bounce: no such fix");
+    PhaseTimer t(ctx, MESO_T_INTEGRATE);
+    return launch_fix_bounce(ctx, handle);
+}
+
 // ---------------------------------------------------------------- whole-run drivers
 extern "C" int meso_setup(meso_ctx *ctx, int eflag, int vflag)
 {
@@ -703,6 +780,7 @@ extern "C" int meso_setup(meso_ctx *ctx, int eflag, int vflag)
         PhaseTimer t(ctx, MESO_T_PAIR);                      // force_clear + pair->compute (UM/mvv_meso.cu:191-197)
         TRY(launch_pair(ctx, MESO_LOCAL, eflag || vflag, false, false, 0));
         TRY(launch_bond_force(ctx, eflag || vflag, false));   // force->bond->compute, UM/mvv_meso.cu:198-201
+        TRY(launch_fix_post_force(ctx, -1, false));           // modify->setup -> Fix::setup -> post_force, UM/mvv_meso.cu:212
     }
     ctx->setup_done = true;
     return refresh_counts(ctx);
@@ -730,7 +808,7 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
             PhaseTimer t(ctx, MESO_T_INTEGRATE);
             // facc: the first step reads f (accumulator already zero), later steps read and clear facc;
             // f as accumulator: read and clear it every step
-            TRY(launch_step_integrate(ctx, groupbit, pending, true, !rebuild, acc_facc && pending, acc_facc ? pending : true, false));
+            TRY(launch_step_integrate(ctx, groupbit, pending, true, !rebuild, acc_facc && pending, acc_facc ? pending : true, false, rebuild));
         }
         pending = true;
         if (rebuild) {
@@ -753,6 +831,7 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
                 PhaseTimer t(ctx, MESO_T_PAIR);
                 TRY(pair(MESO_BORDER));
                 TRY(launch_bond_force(ctx, 0, acc_facc));
+                TRY(launch_fix_post_force(ctx, -1, acc_facc));
             }
             continue;
         } else {
@@ -762,6 +841,7 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
         PhaseTimer t(ctx, MESO_T_PAIR);
         TRY(pair(MESO_LOCAL));
         TRY(launch_bond_force(ctx, 0, acc_facc));            // bonded forces join the same accumulator (UM/mvv_meso.cu:387-389)
+        TRY(launch_fix_post_force(ctx, -1, acc_facc));       // modify->post_force (UM/mvv_meso.cu:396)
     }
     if (pending) {
         PhaseTimer t(ctx, MESO_T_INTEGRATE);                 // last step's second half-kick; f <- force, accumulator cleared
@@ -775,7 +855,8 @@ extern "C" int meso_run(meso_ctx *ctx, int nsteps, int groupbit)
     CHECK_CTX();
     TRY(ready(ctx));
     if (!ctx->setup_done) FAIL(MESO_EINVAL, "meso_run: call meso_setup first");
-    if (ctx->pair_once || bonds_active(ctx)) return run_pair_once(ctx, nsteps, groupbit);   // bonded forces need the unfused second half-kick
+    // bonded forces and post_force fixes need the unfused second half-kick
+    if (ctx->pair_once || bonds_active(ctx) || ctx->fixes.n > 0) return run_pair_once(ctx, nsteps, groupbit);
     for (int s = 0; s < nsteps; s++) {
         ctx->ntimestep++;                                    // UM/mvv_meso.cu:256
         const bool rebuild = meso_neighbor_decide(ctx) != 0;

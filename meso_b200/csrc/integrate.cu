@@ -9,6 +9,7 @@
 // (the reference re-reads x, v, type and tag in a separate gpu_merge_xvt pass).
 #include "internal.h"
 #include "device_math.cuh"
+#include "fix_device.cuh"
 
 namespace meso {
 
@@ -54,13 +55,16 @@ __global__ void __launch_bounds__(256) k_initial_integrate(SoA3 x, SoA3 v, SoA3c
 // accumulator of the pair-once kernel (facc, src_acc) or from the fp64 arrays; the source is cleared for the next
 // reduction and/or mirrored into f when the run returns to the caller.  Each half is the reference's own fma
 // (UM/fix_nve_meso.cu:83-92,171-176), so results equal the unfused sequence bit for bit.
-template <int PACK>
+// FIX: wall fixes are registered (fix.cu).  Their end_of_step bounce-forward of step k-1 sits between the two kicks and their
+// pre_exchange bounce (re-neighbouring steps) follows the drift -- per atom the same operation sequence as the reference's
+// separate kernels (UM/mvv_meso.cu:262-275,398-402), so the fusion is exact.
+template <int PACK, int FIX>
 __global__ void __launch_bounds__(256) k_step_integrate(SoA3 x, SoA3 v, SoA3 f, float4 *__restrict__ facc, const int *__restrict__ mask,
                                                         const int *__restrict__ type, const int *__restrict__ tag,
                                                         const double *__restrict__ mass, float4 *__restrict__ coord4,
                                                         float4 *__restrict__ veloc4, const Counts *__restrict__ cnt, Box box, double dtf,
                                                         double dtv, int groupbit, uint32_t seed_now, int do_final, int do_initial,
-                                                        int src_acc, int zero_src, int write_f)
+                                                        int src_acc, int zero_src, int write_f, FixList fl, int bounce_after)
 {
     const int n = cnt->nlocal;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -77,9 +81,29 @@ __global__ void __launch_bounds__(256) k_step_integrate(SoA3 x, SoA3 v, SoA3 f, 
             for (int d = 0; d < 3; d++) ff[d] = f.c[d][i];
         }
 #pragma unroll
-        for (int d = 0; d < 3; d++) { vv[d] = v.c[d][i]; xx[d] = do_initial ? x.c[d][i] : 0.; }
+        for (int d = 0; d < 3; d++) { vv[d] = v.c[d][i]; xx[d] = (do_initial || FIX) ? x.c[d][i] : 0.; }
         const double ms = mass[ty];
-        if (mk & groupbit) {
+        if (FIX) {
+            const bool grp = (mk & groupbit) != 0;
+            const double dtfm = __dmul_rn(dtf, rcp_nr(ms));
+            if (do_final) {
+                if (grp) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) vv[d] = __fma_rn(dtfm, ff[d], vv[d]);
+                }
+                fix_bounce_all(fl, box, mk, xx, vv);                  // end_of_step of the previous step
+            }
+            if (do_initial) {
+                if (grp) {
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        vv[d] = __fma_rn(dtfm, ff[d], vv[d]);
+                        xx[d] = __fma_rn(dtv, vv[d], xx[d]);
+                    }
+                }
+                if (bounce_after) fix_bounce_all(fl, box, mk, xx, vv);   // pre_exchange of this (re-neighbouring) step
+            }
+        } else if (mk & groupbit) {
             const double dtfm = __dmul_rn(dtf, rcp_nr(ms));
 #pragma unroll
             for (int d = 0; d < 3; d++) {
@@ -96,9 +120,9 @@ __global__ void __launch_bounds__(256) k_step_integrate(SoA3 x, SoA3 v, SoA3 f, 
 #pragma unroll
             for (int d = 0; d < 3; d++) f.c[d][i] = write_f ? ff[d] : 0.;
         }
-        if (mk & groupbit) {
+        if (FIX || (mk & groupbit)) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) { v.c[d][i] = vv[d]; if (do_initial) x.c[d][i] = xx[d]; }
+            for (int d = 0; d < 3; d++) { v.c[d][i] = vv[d]; if (do_initial || FIX) x.c[d][i] = xx[d]; }
         }
         if (PACK) {
             float4 c, w;
@@ -252,20 +276,21 @@ int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack)
     return MESO_OK;
 }
 
-int launch_step_integrate(meso_ctx *ctx, int groupbit, bool do_final, bool do_initial, bool pack, bool src_acc, bool zero_src, bool write_f)
+int launch_step_integrate(meso_ctx *ctx, int groupbit, bool do_final, bool do_initial, bool pack, bool src_acc, bool zero_src, bool write_f,
+                          bool bounce_after)
 {
     const double dtv = ctx->dt, dtf = 0.5 * ctx->dt * ctx->ftm2v;
     pack = pack && do_initial;
-    if (pack)
-        k_step_integrate<1><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), soa(ctx->f), ctx->facc.p, ctx->mask.p, ctx->type.p,
-                                                                    ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
-                                                                    ctx->box, dtf, dtv, groupbit, seed_now(ctx), do_final, do_initial, src_acc,
-                                                                    zero_src, write_f);
-    else
-        k_step_integrate<0><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), soa(ctx->f), ctx->facc.p, ctx->mask.p, ctx->type.p,
-                                                                    ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
-                                                                    ctx->box, dtf, dtv, groupbit, 0u, do_final, do_initial, src_acc, zero_src,
-                                                                    write_f);
+    const bool fix = ctx->fixes.nbounce > 0;
+#define MESO_STEP_ARGS soa(ctx->x), soa(ctx->v), soa(ctx->f), ctx->facc.p, ctx->mask.p, ctx->type.p, ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, \
+                       ctx->veloc4.p, ctx->d_counts, ctx->box, dtf, dtv, groupbit, pack ? seed_now(ctx) : 0u, do_final, do_initial, src_acc,        \
+                       zero_src, write_f, ctx->fixes, bounce_after
+    const int g = grid_for(ctx, 8);
+    if (pack && fix) k_step_integrate<1, 1><<<g, 256, 0, ctx->stream>>>(MESO_STEP_ARGS);
+    else if (pack) k_step_integrate<1, 0><<<g, 256, 0, ctx->stream>>>(MESO_STEP_ARGS);
+    else if (fix) k_step_integrate<0, 1><<<g, 256, 0, ctx->stream>>>(MESO_STEP_ARGS);
+    else k_step_integrate<0, 0><<<g, 256, 0, ctx->stream>>>(MESO_STEP_ARGS);
+#undef MESO_STEP_ARGS
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

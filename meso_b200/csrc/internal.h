@@ -68,6 +68,20 @@ struct SortScratch {
     DevBuf<uint32_t> hist;     // [256][ntiles]
 };
 
+// device-resident fixes of the channel decks: wall/meso, solid_bound/meso, addforce/meso, pois/meso.
+// The list is small and travels to the kernels by value (constant bank), so one streaming pass applies all of them.
+enum { FIX_WALL = 1, FIX_SOLID_BOUND = 2, FIX_ADDFORCE = 3, FIX_POIS = 4, MAX_FIX = 8 };
+struct FixOp {
+    int kind, groupbit;
+    int dims;                       // wall / solid_bound: bit d = walls across dimension d;  pois: dim_ortho | dim_force << 2
+    int aux;                        // solid_bound: force kernel id (1 = rho5rc1s1)
+    double p[4];                    // wall: {d, 1/d, f};  addforce: {fx, fy, fz};  pois: {strength, bisect_frac}
+};
+struct FixList {
+    int n, nbounce, nforce, pad;
+    FixOp op[MAX_FIX];
+};
+
 enum { NCOEFF = 7, P_CUT = 0, P_CUTSQ, P_CUTINV, P_EXPW, P_A0, P_GAMMA, P_SIGMA };
 
 }  // namespace meso
@@ -163,6 +177,9 @@ struct meso_ctx {
     bool f_cleared = true, v_cleared = true;
     bool setup_done = false;
 
+    // device-resident fixes (fix.cu)
+    meso::FixList fixes{};
+
     // timers
     bool timers_on = false;
     double t_ms[MESO_T_COUNT] = {0};
@@ -213,12 +230,17 @@ int launch_bonds_map(meso_ctx *ctx);                    // after the ghosts exis
 int launch_bonds_filter(meso_ctx *ctx);                 // after the neighbor build
 int launch_bond_force(meso_ctx *ctx, int evflag, bool into_facc);
 int launch_bond_energy_sum(meso_ctx *ctx, double *e);
+// ---- fix.cu
+int launch_fix_post_force(meso_ctx *ctx, int handle, bool into_facc);   // handle < 0: every registered fix, in order
+int launch_fix_bounce(meso_ctx *ctx, int handle);
 // ---- integrate.cu
 int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack);
 int launch_final_integrate(meso_ctx *ctx, int groupbit);
 // fused step boundary: [second half-kick of the previous step] + [first half-kick + drift (+ pack) of this step];
 // force source = facc (fp32 accumulator) or f; optionally mirrors the force into f and clears the source
-int launch_step_integrate(meso_ctx *ctx, int groupbit, bool do_final, bool do_initial, bool pack, bool src_acc, bool zero_src, bool write_f);
+// bounce_after: wall fixes reflect once more after the drift (their pre_exchange hook on a re-neighbouring step)
+int launch_step_integrate(meso_ctx *ctx, int groupbit, bool do_final, bool do_initial, bool pack, bool src_acc, bool zero_src, bool write_f,
+                          bool bounce_after = false);
 int launch_ke(meso_ctx *ctx, int groupbit, double *mv2, double *count);
 int launch_virial_sum(meso_ctx *ctx, double out7[7]);
 int launch_clear(meso_ctx *ctx, int range, int vflag);

@@ -177,6 +177,57 @@ class Meso:
         self._chk(self.L.meso_compute_bond_energy(self.h, C.byref(e)))
         return e.value
 
+    # ---- fix wall/meso | solid_bound/meso | addforce/meso | pois/meso: same argument grammar as the reference ----------
+    def fix(self, style, *args, groupbit=1):
+        """fix ID group <style> args... (the ID and group words are implied: groupbit selects the atoms).  Returns the handle."""
+        args = [str(a) for a in args]
+        narg = len(args) + 3                                          # the reference counts ID, group and style
+        if style == "wall/meso":                                     # UM/fix_wall_meso.cu:24-46
+            if narg < 6:
+                raise MesoError("Illegal fix MesoFixWall command")
+            d = f = 0.0
+            dims, i = 0, 0
+            while i < len(args):
+                a = args[i]
+                if a in ("d", "f"):
+                    i += 1
+                    if i >= len(args):
+                        raise MesoError("Incomplete fix wall command after '%s'" % a)
+                    if a == "d":
+                        d = float(args[i])
+                    else:
+                        f = float(args[i])
+                elif a in ("x", "y", "z"):
+                    dims |= 1 << "xyz".index(a)
+                i += 1
+            if not dims:
+                raise MesoError("Incomplete fix wall command: insufficient arguments")
+            return self._chk(self.L.meso_fix_wall(self.h, groupbit, dims, d, f))
+        if style == "solid_bound/meso":                              # UM/fix_solid_bound_meso.cu:24-45
+            if narg < 4:
+                raise MesoError("Illegal fix MesoFixSolidBound command")
+            dims = sum(1 << "xyz".index(a) for a in set(args) if a in ("x", "y", "z"))
+            if not dims:
+                raise MesoError("Incomplete fix wall command: dimension unspecified")
+            if "rho5rc1s1" not in args:
+                raise MesoError("Incomplete fix wall command: force kernel unspecified")
+            return self._chk(self.L.meso_fix_solid_bound(self.h, groupbit, dims, 1))
+        if style == "addforce/meso":                                 # UM/fix_addforce_meso.cu:24-32
+            if narg < 6:
+                raise MesoError("Illegal fix addforce/meso command")
+            return self._chk(self.L.meso_fix_addforce(self.h, groupbit, *(float(a) for a in args[:3])))
+        if style == "pois/meso":                                     # UM/fix_poiseuille_meso.cu:24-42
+            if narg < 6:
+                raise MesoError("Illegal fix CUDAPoiseuille command")
+            dim = lambda a: int(a) if a[0].isdigit() else "xyz".index(a[0])
+            frac = float(args[3]) if len(args) > 3 else 0.5
+            return self._chk(self.L.meso_fix_pois(self.h, groupbit, dim(args[0]), dim(args[1]), float(args[2]), frac))
+        raise MesoError("Invalid fix style")
+
+    def unfix_all(self): self._chk(self.L.meso_fix_clear(self.h))
+    def fix_post_force(self, handle=-1): self._chk(self.L.meso_fix_post_force(self.h, handle))
+    def fix_bounce(self, handle=-1): self._chk(self.L.meso_fix_bounce(self.h, handle))
+
     def counts(self):
         v = [C.c_int() for _ in range(4)]
         self._chk(self.L.meso_counts(self.h, *[C.byref(a) for a in v]))

@@ -53,6 +53,13 @@ SIGNATURES = {
     "meso_bonds_upload": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i]),
     "meso_bond_compute": (_i, [_vp, _i, _i]),
     "meso_compute_bond_energy": (_i, [_vp, _pd]),
+    "meso_fix_wall": (_i, [_vp, _i, _i, _d, _d]),
+    "meso_fix_solid_bound": (_i, [_vp, _i, _i, _i]),
+    "meso_fix_addforce": (_i, [_vp, _i, _d, _d, _d]),
+    "meso_fix_pois": (_i, [_vp, _i, _i, _i, _d, _d]),
+    "meso_fix_clear": (_i, [_vp]),
+    "meso_fix_post_force": (_i, [_vp, _i]),
+    "meso_fix_bounce": (_i, [_vp, _i]),
     "meso_setup": (_i, [_vp, _i, _i]),
     "meso_run": (_i, [_vp, _i, _i]),
     "meso_export_bins": (_i, [_vp, _pi, _pd, _pd, _pi]),

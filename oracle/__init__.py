@@ -82,6 +82,11 @@ def lib():
         "orc_set_special_lj12": (None, [C.c_void_p, f64]),
         "orc_bond_compute": (None, [C.c_void_p, i32, i32]),
         "orc_bond_energy": (f64, [C.c_void_p]),
+        "orc_fix_add": (i32, [C.c_void_p, i32, i32, i32, P(f64)]),
+        "orc_fix_clear": (None, [C.c_void_p]),
+        "orc_fix_post_force": (None, [C.c_void_p, i32]),
+        "orc_fix_bounce": (None, [C.c_void_p, i32]),
+        "orc_set_integrate_group": (None, [C.c_void_p, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -173,6 +178,24 @@ class World:
 
     def bond_compute(self, eflag=0, vflag=0): self.L.orc_bond_compute(self.h, eflag, vflag)
     def bond_energy(self): return self.L.orc_bond_energy(self.h)
+
+    # channel fixes, argument meaning of the reference's constructors (UM/fix_wall_meso.cu:24-46 etc.)
+    def _fix(self, kind, groupbit, dims, p):
+        h = self.L.orc_fix_add(self.h, kind, groupbit, dims, (f64 * 4)(*(list(p) + [0.0] * (4 - len(p)))))
+        if h < 0:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return h
+
+    def fix_wall(self, dims, d, f, groupbit=1): return self._fix(1, groupbit, sum(1 << "xyz".index(a) for a in dims), [d, f])
+    def fix_solid_bound(self, dims, groupbit=1): return self._fix(2, groupbit, sum(1 << "xyz".index(a) for a in dims), [])
+    def fix_addforce(self, fx, fy, fz, groupbit=1): return self._fix(3, groupbit, 0, [fx, fy, fz])
+
+    def fix_pois(self, dim_ortho, dim_force, strength, bisect_frac=0.5, groupbit=1):
+        return self._fix(4, groupbit, dim_ortho | (dim_force << 2), [strength, bisect_frac])
+
+    def fix_post_force(self, only=-1): self.L.orc_fix_post_force(self.h, only)
+    def fix_bounce(self, only=-1): self.L.orc_fix_bounce(self.h, only)
+    def integrate_group(self, groupbit): self.L.orc_set_integrate_group(self.h, groupbit)
 
     def setup(self, eflag=0, vflag=0):
         self._chk(self.L.orc_world_setup(self.h, eflag, vflag))

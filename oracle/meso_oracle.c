@@ -297,6 +297,9 @@ struct orc_world {
     int bond_per_atom, tag_max, nbondtypes; double special_lj12;
     int *num_bond, *bond_type, *bond_atom;      /* [tag_max+1], [tag_max+1][bond_per_atom] */
     double *bond_k, *bond_r0;                   /* [nbondtypes+1] */
+    /* channel fixes, in registration order */
+    int nfix; struct { int kind, groupbit, dims; double p[4]; } fix[8];
+    int integrate_groupbit;                     /* group of the deck's fix nve/meso (0 = unset -> 1) */
 };
 
 static int rank_of(const orc_world *w, int ix, int iy, int iz)
@@ -1183,6 +1186,105 @@ double orc_bond_energy(orc_world *w)
 }
 
 /* ---------------------------------------------------------------------- */
+/* channel fixes                                        */
+/* ---------------------------------------------------------------------- */
+enum { FIX_WALL = 1, FIX_SOLID_BOUND = 2, FIX_ADDFORCE = 3, FIX_POIS = 4 };
+
+int orc_fix_add(orc_world *w, int kind, int groupbit, int dims, const double *p4)
+{
+    if (w->nfix >= 8) FAIL("too many fixes");
+    w->fix[w->nfix].kind = kind; w->fix[w->nfix].groupbit = groupbit; w->fix[w->nfix].dims = dims;
+    for (int q = 0; q < 4; q++) w->fix[w->nfix].p[q] = p4 ? p4[q] : 0.0;
+    return w->nfix++;
+}
+void orc_fix_clear(orc_world *w) { w->nfix = 0; }
+void orc_set_integrate_group(orc_world *w, int groupbit) { w->integrate_groupbit = groupbit; }
+
+/* Rho5rc1s1::operator(), UM/fix_solid_bound_meso.h:42-56 (nvcc contracts every s*h + c of the Horner form into one fma) */
+static double rho5rc1s1(double h)
+{
+    double s = +0.282625;
+    s = fma(s, h, -1.39021);
+    s = fma(s, h, +2.70259);
+    s = fma(s, h, -2.47678);
+    s = fma(s, h, +0.863184);
+    s = fma(s, h, +0.0664266);
+    s = fma(s, h, +0.0247250);
+    s = fma(s, h, +0.00856667);
+    s = fma(s, h, -0.116714);
+    s = fma(s * h, h, 0.0355959);
+    return 75.0 * 6.2831853071796 * s;
+}
+
+/* Modify::post_force over the registered fixes: gpu_fix_wall_force UM/fix_wall_meso.cu:74-117, gpu_fix_solid_wall_force
+ * UM/fix_solid_bound_meso.cu:72-113, gpu_fix_add_force UM/fix_addforce_meso.cu:72-90, gpu_fix_pois_post_force
+ * UM/fix_poiseuille_meso.cu:71-92.  only < 0: all fixes */
+void orc_fix_post_force(orc_world *w, int only)
+{
+    const double SQRT3 = 1.732050808;
+    for (int k = 0; k < w->nfix; k++) {
+        if (only >= 0 && only != k) continue;
+        const int kind = w->fix[k].kind, gb = w->fix[k].groupbit, dims = w->fix[k].dims;
+        const double *p = w->fix[k].p;
+        for (int ir = 0; ir < w->nranks; ir++) {
+            orc_rank *r = &w->rk[ir];
+            for (int i = 0; i < r->nlocal; i++) {
+                if (!(r->mask[i] & gb)) continue;
+                double *f = r->f + 3 * i; const double *x = r->x + 3 * i;
+                if (kind == FIX_WALL) {
+                    double d = p[0], dinv = 1.0 / d, ff = p[1];
+                    if (ff == 0.0) continue;
+                    for (int a = 0; a < 3; a++) {
+                        if (!((dims >> a) & 1)) continue;
+                        double h = x[a] - w->boxlo[a];
+                        if (h <= d) f[a] = fma(ff, (double)erfcf((float)((h - 0.5 * d) * dinv * SQRT3)), f[a]);
+                        h = w->boxhi[a] - x[a];
+                        if (h <= d) f[a] = fma(-ff, (double)erfcf((float)((h - 0.5 * d) * dinv * SQRT3)), f[a]);
+                    }
+                } else if (kind == FIX_SOLID_BOUND) {
+                    for (int a = 0; a < 3; a++) {
+                        if (!((dims >> a) & 1)) continue;
+                        double h = x[a] - w->boxlo[a];
+                        if (h <= 1.0) f[a] += rho5rc1s1(h);
+                        h = w->boxhi[a] - x[a];
+                        if (h <= 1.0) f[a] -= rho5rc1s1(h);
+                    }
+                } else if (kind == FIX_ADDFORCE) {
+                    f[0] += p[0]; f[1] += p[1]; f[2] += p[2];
+                } else if (kind == FIX_POIS) {
+                    int dim_ortho = dims & 3, dim_force = (dims >> 2) & 3;
+                    double lower = w->boxlo[dim_ortho], upper = w->boxhi[dim_ortho];
+                    double bisect = p[1] * upper + (1.0 - p[1]) * lower, rr = x[dim_ortho];
+                    if ((rr < bisect && rr >= lower) || rr >= upper) f[dim_force] += p[0];
+                    else f[dim_force] -= p[0];
+                }
+            }
+        }
+    }
+}
+
+/* bounce-forward, gpu_fix_wall_bounce UM/fix_wall_meso.cu:147-193 (= gpu_fix_solid_wall_bounce) */
+void orc_fix_bounce(orc_world *w, int only)
+{
+    for (int k = 0; k < w->nfix; k++) {
+        if (only >= 0 && only != k) continue;
+        if (w->fix[k].kind != FIX_WALL && w->fix[k].kind != FIX_SOLID_BOUND) continue;
+        for (int ir = 0; ir < w->nranks; ir++) {
+            orc_rank *r = &w->rk[ir];
+            for (int i = 0; i < r->nlocal; i++) {
+                if (!(r->mask[i] & w->fix[k].groupbit)) continue;
+                for (int a = 0; a < 3; a++) {
+                    if (!((w->fix[k].dims >> a) & 1)) continue;
+                    double *x = r->x + 3 * i + a, *v = r->v + 3 * i + a;
+                    if (*x <= w->boxlo[a]) { *v = fabs(*v); *x = 2. * w->boxlo[a] - *x; }
+                    else if (*x >= w->boxhi[a]) { *v = -fabs(*v); *x = 2. * w->boxhi[a] - *x; }
+                }
+            }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------- */
 /* drivers: ModifiedVerlet::setup / ::run, UM/mvv_meso.cu:139-219,243-425  */
 /* ---------------------------------------------------------------------- */
 int orc_world_setup(orc_world *w, int eflag, int vflag)
@@ -1192,21 +1294,28 @@ int orc_world_setup(orc_world *w, int eflag, int vflag)
     orc_force_clear(w);
     orc_pair_compute(w, eflag, vflag);
     orc_bond_compute(w, eflag, vflag);
+    orc_fix_post_force(w, -1);                     /* modify->setup -> Fix::setup -> post_force (UM/fix_wall_meso.cu:66-72) */
     return 0;
 }
 
 int orc_world_run(orc_world *w, int nsteps, int eflag, int vflag)
 {
+    const int gb = w->integrate_groupbit ? w->integrate_groupbit : 1;
     for (int s = 0; s < nsteps; s++) {
         w->ntimestep++;
-        orc_initial_integrate(w, 1);
+        orc_initial_integrate(w, gb);
         w->ago++;                                  /* Neighbor::decide, neighbor.cpp:1216-1231 (delay 0, check no) */
-        if (w->ago % w->every == 0) { if (orc_rebuild(w)) return -1; }
+        if (w->ago % w->every == 0) {
+            orc_fix_bounce(w, -1);                 /* modify->pre_exchange, UM/mvv_meso.cu:273 */
+            if (orc_rebuild(w)) return -1;
+        }
         else orc_forward_comm(w);
         orc_force_clear(w);
         orc_pair_compute(w, eflag, vflag);
         orc_bond_compute(w, eflag, vflag);
-        orc_final_integrate(w, 1);
+        orc_fix_post_force(w, -1);                 /* modify->post_force, UM/mvv_meso.cu:396 */
+        orc_final_integrate(w, gb);
+        orc_fix_bounce(w, -1);                     /* modify->end_of_step, UM/mvv_meso.cu:399 */
     }
     return 0;
 }

@@ -93,6 +93,15 @@ void orc_set_special_lj12(orc_world *w, double v);
 void orc_bond_compute(orc_world *w, int eflag, int vflag);
 double orc_bond_energy(orc_world *w);
 
+/* channel fixes: kind 1 wall/meso {d, f}, 2 solid_bound/meso (rho5rc1s1), 3 addforce/meso {fx,fy,fz},
+ * 4 pois/meso {strength, bisect_frac} with dims = dim_ortho | dim_force << 2; wall kinds: dims bit a = walls across a.
+ * UM/fix_wall_meso.cu, UM/fix_solid_bound_meso.{h,cu}, UM/fix_addforce_meso.cu, UM/fix_poiseuille_meso.cu */
+int  orc_fix_add(orc_world *w, int kind, int groupbit, int dims, const double *p4);
+void orc_fix_clear(orc_world *w);
+void orc_fix_post_force(orc_world *w, int only);   /* only < 0: every fix in registration order */
+void orc_fix_bounce(orc_world *w, int only);
+void orc_set_integrate_group(orc_world *w, int groupbit);   /* group of fix nve/meso used by orc_world_run (default 1) */
+
 /* queries (rank r) */
 int  orc_nranks(orc_world *w);
 void orc_counts(orc_world *w, int r, int *nlocal, int *nghost, int *n_bulk,

@@ -1,0 +1,214 @@
+"""Channel fixes: wall/meso, solid_bound/meso, addforce/meso, pois/meso.
+
+CPU part: the oracle's restatement against an independent numpy evaluation of the reference formulas
+(UM/fix_wall_meso.cu:74-193, UM/fix_solid_bound_meso.h:42-56, UM/fix_addforce_meso.cu:72-90,
+UM/fix_poiseuille_meso.cu:71-92) and the properties a wall has (nothing ends up outside, reflections are involutions).
+GPU part: the CUDA hooks and the fused run loop against the oracle -- fp64 arithmetic, so the bar is 1e-12 on the
+force hooks (1e-6 on the erfcf wall: CUDA's and glibc's erfcf differ in the last ulp) and bit-exact on the bounce.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from meso_b200 import workload
+
+L = 8
+D_WALL, F_WALL = 0.5, 20.0
+
+
+def channel_atoms(seed=11, hot=1.0):
+    x = workload.dpd_fluid(L, seed=seed)
+    v = workload.maxwell_velocities(len(x), seed=seed + 1) * hot
+    mask = np.where(np.arange(len(x)) % 3 == 0, 3, 1).astype(np.int32)     # every third atom is also in group bit 2
+    return x, v, mask
+
+
+def channel_world(precision=1, fixes=("solid", "add", "pois"), hot=1.0, gamma_sigma=True):
+    x, v, mask = channel_atoms(hot=hot)
+    g, s = (4.5, 3.0) if gamma_sigma else (0.0, 0.0)
+    w = oracle.World((0, 0, 0), (L, L, L), periodic=(1, 1, 0), precision=precision, coeff=oracle.default_coeff(1, 15.0, g, s))
+    w.set_atoms(x, v, mask=mask)
+    add_fixes(w, fixes, oracle_side=True)
+    return w, x, v, mask
+
+
+def add_fixes(o, fixes, oracle_side):
+    """the same fix list on the oracle World or on the Meso mirror (which takes the reference's argument grammar)"""
+    for f in fixes:
+        if f == "wall":
+            o.fix_wall("z", D_WALL, F_WALL) if oracle_side else o.fix("wall/meso", "z", "d", D_WALL, "f", F_WALL)
+        elif f == "solid":
+            o.fix_solid_bound("z") if oracle_side else o.fix("solid_bound/meso", "z", "rho5rc1s1")
+        elif f == "add":
+            o.fix_addforce(0.25, -0.5, 0.0, groupbit=2) if oracle_side else o.fix("addforce/meso", 0.25, -0.5, 0.0, groupbit=2)
+        elif f == "pois":
+            o.fix_pois(2, 0, 0.3) if oracle_side else o.fix("pois/meso", "z", "x", 0.3)
+
+
+def rho5(h):
+    s = 0.282625
+    for c in (-1.39021, 2.70259, -2.47678, 0.863184, 0.0664266, 0.0247250, 0.00856667, -0.116714):
+        s = s * h + c
+    return 75.0 * 6.2831853071796 * (s * h * h + 0.0355959)
+
+
+def test_oracle_post_force_matches_numpy_formulas():
+    from scipy.special import erfc
+    w, x, v, mask = channel_world(fixes=("wall", "solid", "add", "pois"))
+    w.setup()                                        # includes Fix::setup -> post_force
+    a = w.atoms()
+    nl = a["nlocal"]
+    f_all = a["f"][:nl].copy()
+    w.force_clear(); w.pair_compute()
+    f_pair = w.atoms()["f"][:nl]
+    df = f_all - f_pair
+    xs, mk = a["x"][:nl], a["mask"][:nl]
+    want = np.zeros_like(df)
+    z = xs[:, 2]
+    lo, hi = z, L - z
+    arg = lambda h: ((h - 0.5 * D_WALL) / D_WALL * 1.732050808).astype(np.float32)
+    want[:, 2] += np.where(lo <= D_WALL, F_WALL * erfc(arg(lo)).astype(np.float32), 0.0)
+    want[:, 2] -= np.where(hi <= D_WALL, F_WALL * erfc(arg(hi)).astype(np.float32), 0.0)
+    want[:, 2] += np.where(lo <= 1.0, rho5(lo), 0.0) - np.where(hi <= 1.0, rho5(hi), 0.0)
+    want[:, 0] += np.where(mk & 2, 0.25, 0.0)
+    want[:, 1] += np.where(mk & 2, -0.5, 0.0)
+    want[:, 0] += np.where(z < 0.5 * L, 0.3, -0.3)
+    assert np.abs(df - want).max() < 1e-5 * np.abs(want).max()
+    assert np.abs(df[:, :2] - want[:, :2]).max() < 1e-12          # no erfcf in x, y
+
+
+def test_oracle_bounce_is_a_reflection_and_walls_confine():
+    w, x, v, mask = channel_world(fixes=("wall",), hot=3.0)
+    w.setup()
+    w.run(60)
+    a = w.atoms()
+    z = a["x"][:a["nlocal"], 2]
+    assert z.min() > 0.0 and z.max() < L, (z.min(), z.max())
+    assert a["nlocal"] == len(x)
+    # one explicit reflection: an atom put outside comes back mirrored with its velocity pointing inwards
+    w2 = oracle.World((0, 0, 0), (L, L, L), periodic=(1, 1, 0))
+    w2.set_atoms(np.array([[1.0, 1.0, 0.25], [2.0, 2.0, L - 0.5], [3.0, 3.0, 4.0]]), np.array([[0, 0, -100.0], [0, 0, 200.0], [1.0, 1.0, 1.0]]))
+    w2.fix_wall("z", 0.0, 0.0)
+    w2.initial_integrate()                           # f = 0: pure drift by 0.005 v, two atoms end up beyond the walls
+    w2.fix_bounce()
+    b = w2.atoms()
+    order = np.argsort(b["tag"][:3])
+    assert np.allclose(b["x"][:3][order][:, 2], [0.25, L - 0.5, 4.005]) and np.allclose(b["v"][:3][order][:, 2], [100.0, -200.0, 1.0])
+
+
+def test_oracle_poiseuille_drives_counterflow_and_addforce_adds_momentum():
+    w, x, v, mask = channel_world(fixes=("wall", "pois"), precision=0)
+    w.setup()
+    w.run(150)
+    a = w.atoms()
+    nl = a["nlocal"]
+    z, vx = a["x"][:nl, 2], a["v"][:nl, 0]
+    assert vx[z < 0.5 * L].mean() > 0.05 and vx[z >= 0.5 * L].mean() < -0.05
+    w, x, v, mask = channel_world(fixes=("solid", "add"), precision=1, gamma_sigma=False)
+    w.setup()
+    p0 = w.atoms()["v"][:len(x)].sum(axis=0)
+    w.run(10)
+    a = w.atoms()
+    assert a["nlocal"] == len(x)
+    p1 = a["v"][:len(x)].sum(axis=0)
+    n2 = int((mask & 2).astype(bool).sum())
+    # dp/dt = sum of the added forces: n2 * (0.25, -0.5) over 10 steps of 0.005 -- conservative pair forces cancel (to the
+    # fp32 packing of the coordinates), the walls act along z only
+    assert np.allclose((p1 - p0)[:2], np.array([0.25, -0.5]) * n2 * 10 * 0.005, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ GPU parity
+def gpu_pair(precision, fixes, hot=1.0):
+    from meso_b200.engine import Meso
+    x, v, mask = channel_atoms(hot=hot)
+    m = Meso(0)
+    m.box((0.0, 0.0, 0.0), (L, L, L), (1, 1, 0))
+    m.masses([0.0, 1.0])
+    m.neighbor(0.3, "bin")
+    m.neigh_modify(delay=0, every=5, check=False)
+    m.pair_style("dpd/fast/meso" if precision == "sp" else "dpd/meso", 1.0, 419084618)
+    m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
+    m.timestep(0.005)
+    m.upload(x, v, mask=mask)
+    add_fixes(m, fixes, oracle_side=False)
+    w, _, _, _ = channel_world(1 if precision == "dp" else 0, fixes, hot=hot)
+    return m, w
+
+
+def rel_err(a, b):
+    d = np.linalg.norm(a - b, axis=1)
+    mag = np.linalg.norm(b, axis=1)
+    return float((d / np.maximum(mag, mag.mean())).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixes,tol", [(("solid", "add", "pois"), 1e-12), (("wall",), 1e-6), (("wall", "solid", "add", "pois"), 1e-6)])
+def test_gpu_setup_post_force_matches_oracle(fixes, tol):
+    m, w = gpu_pair("dp", fixes)
+    m.setup(); w.setup()
+    ag, ao = m.download(), w.atoms()
+    nl = ao["nlocal"]
+    assert np.array_equal(ag["tag"], ao["tag"][:nl])
+    assert rel_err(ag["f"], ao["f"][:nl]) < tol
+    # the stand-alone hook adds the same amount again, fix by fix
+    for h in range(len(fixes)):
+        m.fix_post_force(h); w.fix_post_force(h)
+    assert rel_err(m.download(("f",))["f"], w.atoms()["f"][:nl]) < tol
+    m.close()
+
+
+@pytest.mark.gpu
+def test_gpu_bounce_hook_bit_exact():
+    m, w = gpu_pair("dp", ("wall", "solid"), hot=4.0)
+    m._push_coeff()
+    for _ in range(3):                                # no setup: f = 0, pure fp64 drift (bit-identical inputs for the bounce)
+        m.initial_integrate(); w.initial_integrate()
+    xg0 = m.download(("x",))["x"]
+    assert (xg0[:, 2] < 0).any() or (xg0[:, 2] > L).any(), "test needs atoms beyond the walls"
+    m.fix_bounce(); w.fix_bounce()
+    ag, ao = m.download(("x", "v")), w.atoms()
+    nl = ao["nlocal"]
+    assert np.array_equal(ag["x"], ao["x"][:nl]) and np.array_equal(ag["v"], ao["v"][:nl])
+    assert ag["x"][:, 2].min() >= 0 and ag["x"][:, 2].max() <= L
+    m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("once", ["1", "0"])
+def test_gpu_channel_trajectory_fp64_lockstep(monkeypatch, once):
+    """17 steps (three rebuilds) of a driven channel: bounce fused into the step-boundary pass, post_force hook after the
+    pair kernel, in both run loops; x, v stay on the oracle's fp64 trajectory and nobody leaves the channel."""
+    monkeypatch.setenv("MESO_PAIR_ONCE", once)
+    m, w = gpu_pair("dp", ("solid", "add", "pois"), hot=2.0)
+    m.setup(); w.setup()
+    m.run(17); w.run(17)
+    ag, ao = m.download(), w.atoms()
+    nl = ao["nlocal"]
+    assert nl == len(ag["tag"]) and np.array_equal(ag["tag"], ao["tag"][:nl])
+    assert np.abs(ag["x"] - ao["x"][:nl]).max() < 1e-9 and np.abs(ag["v"] - ao["v"][:nl]).max() < 1e-9
+    assert rel_err(ag["f"], ao["f"][:nl]) < 1e-9
+    assert ag["x"][:, 2].min() > 0 and ag["x"][:, 2].max() < L
+    m.close()
+
+
+@pytest.mark.gpu
+def test_gpu_channel_fp32_flow_profile_and_grammar_errors():
+    from meso_b200.engine import MesoError
+    m, w = gpu_pair("sp", ("wall", "pois"))
+    m.setup()
+    m.run(300)
+    a = m.download(("x", "v"))
+    z, vx = a["x"][:, 2], a["v"][:, 0]
+    assert z.min() > 0 and z.max() < L
+    assert vx[z < 0.5 * L].mean() > 0.05 and vx[z >= 0.5 * L].mean() < -0.05     # counter-flowing Poiseuille halves
+    assert 0.7 < m.temperature() < 1.6
+    for args, msg in ((("wall/meso", "z"), "Illegal fix MesoFixWall"), (("wall/meso", "d", 1.0, "f", 2.0), "insufficient arguments"),
+                      (("wall/meso", "z", "f", 1.0, "d"), "after 'd'"), (("solid_bound/meso", "z"), "force kernel unspecified"),
+                      (("solid_bound/meso", "rho5rc1s1"), "dimension unspecified"), (("addforce/meso", 1.0, 2.0), "Illegal fix addforce/meso"),
+                      (("pois/meso", "z", "x"), "Illegal fix CUDAPoiseuille"), (("nope/meso",), "Invalid fix style")):
+        with pytest.raises(MesoError, match=msg):
+            m.fix(*args)
+    m.unfix_all()
+    m.close()
