@@ -2,6 +2,7 @@
 #include "mvv_meso.h"
 #include "engine_meso.h"
 #include "fix_nve_meso.h"
+#include "fix_resident_meso.h"
 #include "pair_dpd_meso.h"
 #include "atom.h"
 #include "comm.h"
@@ -56,7 +57,9 @@ void ModifiedVerlet::init()
     error->all(FLERR,"<MESO> bonded styles are not part of USER-MESO-B200 yet");
 
   // every fix acts on device-resident atoms, so it has to be a /meso style;
-  // exactly one nve/meso and nothing else on the step path => the fused run loop
+  // exactly one nve/meso plus fixes that live in the library's own fix list => the fused run loop.
+  // The list is rebuilt by the fixes' init() (Modify::init runs after this function).
+  MESO_CALL(meso_fix_clear(mctx("run_style mvv/meso")));
   int n_nve = 0, others = 0, gbit = -1;
   for (int i = 0; i < modify->nfix; i++) {
     Fix *fix = modify->fix[i];
@@ -69,7 +72,7 @@ void ModifiedVerlet::init()
     }
     FixNVEMeso *nve = dynamic_cast<FixNVEMeso *>(fix);
     if (nve) { n_nve++; gbit = nve->group_bit(); }
-    else others++;
+    else if (dynamic_cast<MesoFixResident *>(fix) == NULL) others++;
   }
   fused_groupbit = (n_nve == 1 && others == 0) ? gbit : -1;
 }
@@ -120,6 +123,7 @@ void ModifiedVerlet::setup_minimal(int flag)
   ev_set(update->ntimestep);
   force_clear();
   force->pair->compute(eflag,vflag);
+  MESO_CALL(meso_fix_post_force(dev->ctx,-1));      // Fix::setup -> post_force of the device-resident fixes
   modify->setup(vflag);
   update->setupflag = 0;
 }

@@ -193,6 +193,81 @@ def test_thermo_energy_and_pressure_go_through_the_phase_entry_points(tmp_path, 
     m.close()
 
 
+CHANNEL_DECK = """# driven channel: walls across z, counter-flowing body force (SURVEY.md s8f N2)
+dimension       3
+units           lj
+boundary        p p f
+atom_style      dpd/atomic/meso
+neighbor        0.3 bin
+neigh_modify    delay 0 every 5 check no
+read_data       {L}.data
+run_style       mvv/meso
+pair_style      dpd/meso 1.0 419084618
+pair_coeff      1 1 15 4.5 3.0 1.0 1.0
+compute         mythermo all temp/meso
+velocity        all create 1.0 788662042 loop all
+fix             3 all nve/meso
+fix             4 all wall/meso z d 0.5 f 20.0
+fix             5 all pois/meso z x 0.3
+fix             6 all addforce/meso 0.0 0.1 0.0
+thermo_style    custom step temp {extra} cpu
+thermo          10
+thermo_modify   temp mythermo
+{dump}
+timestep        0.005
+run             {steps}
+"""
+
+
+@pytest.mark.gpu
+def test_channel_deck_with_device_resident_fixes(tmp_path, monkeypatch):
+    """wall/meso + pois/meso + addforce/meso next to nve/meso: the fused loop applies the library's fix list (bit-for-bit
+    with the C-ABI mirror given the same list); with `pe press` in the thermo line the thermo steps go through the fixes'
+    own post_force / pre_exchange / end_of_step hooks and land on the same trajectory."""
+    need_binary()
+    monkeypatch.setenv("MESO_PAIR_ONCE", "0")        # deterministic two-sided kernel in both processes (read at meso_create)
+    L, steps = 8, 20
+    workload.write_data(str(tmp_path / ("%d.data" % L)), workload.dpd_fluid(L), L)
+
+    def run(extra, sub):
+        d = tmp_path / sub
+        d.mkdir()
+        os.symlink(str(tmp_path / ("%d.data" % L)), str(d / ("%d.data" % L)))
+        (d / "in.run").write_text(CHANNEL_DECK.format(L=L, extra=extra, steps=steps, dump=DUMP.format(steps=steps)))
+        out = subprocess.run([LMP, "-in", "in.run", "-log", "none"], cwd=str(d), capture_output=True, text=True, timeout=600,
+                             env=dict(os.environ, MESO_PAIR_ONCE="0"))
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        return frames(str(d / "traj.txt")), out
+
+    fr, out = run("", "fused")
+    from meso_b200.engine import Meso
+    m = Meso(0)
+    m.box((0.0, 0.0, 0.0), (L, L, L), (1, 1, 0))
+    m.masses([0.0, 1.0])
+    m.neighbor(0.3, "bin")
+    m.neigh_modify(delay=0, every=5, check=False)
+    m.pair_style("dpd/meso", 1.0, 419084618)
+    m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
+    m.timestep(0.005)
+    m.upload(np.ascontiguousarray(fr[0][:, 1:4]), np.ascontiguousarray(fr[0][:, 4:7]), tag=fr[0][:, 0].astype(np.int32))
+    m.fix("wall/meso", "z", "d", 0.5, "f", 20.0)
+    m.fix("pois/meso", "z", "x", 0.3)
+    m.fix("addforce/meso", 0.0, 0.1, 0.0)
+    m.setup()
+    a = m.download()
+    o = np.argsort(a["tag"])
+    assert np.array_equal(a["f"][o], fr[0][:, 7:10]), "setup forces (pair + fix post_force) differ"
+    m.run(steps)
+    a = m.download()
+    o = np.argsort(a["tag"])
+    assert np.array_equal(a["x"][o], fr[steps][:, 1:4]) and np.array_equal(a["v"][o], fr[steps][:, 4:7])
+    assert np.array_equal(a["f"][o], fr[steps][:, 7:10])
+    assert a["x"][:, 2].min() > 0 and a["x"][:, 2].max() < L
+    m.close()
+    fr2, out2 = run("pe press", "phases")
+    assert np.abs(fr2[steps][:, 1:7] - fr[steps][:, 1:7]).max() < 1e-9
+
+
 @pytest.mark.gpu
 def test_deck_errors_match_the_reference_strings(tmp_path):
     need_binary()
