@@ -113,7 +113,9 @@ int meso_set_reduce_scope(meso_ctx *ctx, int local_only);
  * (the reference accumulates per-atom virial UM/pair_dpd_meso.cu:180-186 but never reduces it) */
 int meso_compute_virial(meso_ctx *ctx, double virial6[6], double *e_pair);
 
-/* ---- bead-spring topology (single rank for now): atom_style dpd/bond/meso + bond_style harmonic/meso ---- */
+/* ---- bead-spring topology: atom_style dpd/bond/meso + bond_style harmonic/meso ----
+ * On a decomposition every rank makes the same calls with the same bond_per_atom / tag_max (a rank without bonded atoms
+ * passes its zero counts): the table rides the migration messages, partners across a brick face are found among the ghosts. */
 /* bond_coeff N k r0 for N = 1..nbondtypes, arrays [nbondtypes+1] (MesoBondHarmonic::alloc_coeff UM/bond_harmonic_meso.cu:34-44) */
 int meso_bond_harmonic_coeff(meso_ctx *ctx, int nbondtypes, const double *k, const double *r0);
 /* special_bonds lj <w12> ...: 1 keeps 1-2 pairs in the neighbor list, 0 filters them out
@@ -127,7 +129,7 @@ int meso_bonds_upload(meso_ctx *ctx, int nlocal, int bond_per_atom, const int *n
                       const int *bond_atom, int tag_max);
 /* MesoBondHarmonic::compute UM/bond_harmonic_meso.cu:119-170: f += bonded forces (tallies per-atom energy/virial if flagged) */
 int meso_bond_compute(meso_ctx *ctx, int eflag, int vflag);
-int meso_compute_bond_energy(meso_ctx *ctx, double *e_bond);
+int meso_compute_bond_energy(meso_ctx *ctx, double *e_bond);   /* all ranks (collective) unless meso_set_reduce_scope(1) */
 
 /* ---- device-resident fixes of the channel decks: each call registers one fix and returns its handle (>= 0) ---- */
 /* fix ID group wall/meso [x] [y] [z] d <d> f <f> (MesoFixWall, UM/fix_wall_meso.cu:20-46): dims bit 0/1/2 = x/y/z;

@@ -650,7 +650,6 @@ extern "C" int meso_bonds_upload(meso_ctx *ctx, int nlocal, int bond_per_atom, c
                                  const int *bond_atom, int tag_max)
 {
     CHECK_CTX();
-    if (ctx->nranks > 1) FAIL(MESO_EINVAL, "bonded topology is single-rank for now (the table does not ride the migration messages yet)");
     if (nlocal != ctx->nlocal_host) FAIL(MESO_EINVAL, "meso_bonds_upload: call right after meso_atoms_upload with the same atoms");
     if (bond_per_atom < 0 || (bond_per_atom > 0 && (!num_bond || !bond_type || !bond_atom))) FAIL(MESO_EINVAL, "meso_bonds_upload: bad arguments");
     MESO_CUDA(cudaSetDevice(ctx->device));
@@ -688,6 +687,7 @@ extern "C" int meso_compute_bond_energy(meso_ctx *ctx, double *e_bond)
     TRY(ready(ctx));
     double e = 0.;
     TRY(launch_bond_energy_sum(ctx, &e));
+    if (ctx->nranks > 1 && !ctx->reduce_local) TRY(comm_allreduce_sum(ctx, &e, 1));   // collective: every rank calls
     if (e_bond) *e_bond = e;
     return MESO_OK;
 }

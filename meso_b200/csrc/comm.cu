@@ -18,6 +18,7 @@
 #include "device_math.cuh"
 #include <nccl.h>
 #include <algorithm>
+#include <climits>
 #include <cstring>
 
 namespace meso {
@@ -350,7 +351,8 @@ __global__ void __launch_bounds__(CT) k_mr_exch_scatter(SoA3 x, SoA3 v, const in
                                                         int *__restrict__ tago, int *__restrict__ typeo, int *__restrict__ masko,
                                                         int *__restrict__ imageo, const Counts *__restrict__ cnt,
                                                         const int2 *__restrict__ tile_counts, double *__restrict__ send_l,
-                                                        double *__restrict__ send_r, Box box, int d, int ntiles, int exch_cap)
+                                                        double *__restrict__ send_r, Box box, int d, int ntiles, int exch_cap,
+                                                        int *__restrict__ dest)
 {
     __shared__ int2 wsum[CT / 32];
     const int last = cnt->nlocal;
@@ -383,8 +385,10 @@ __global__ void __launch_bounds__(CT) k_mr_exch_scatter(SoA3 x, SoA3 v, const in
 #pragma unroll
                     for (int q = 0; q < 3; q++) { xo.c[q][p] = x.c[q][i]; vo.c[q][p] = v.c[q][i]; }
                     tago[p] = tag[i]; typeo[p] = type[i]; masko[p] = mask[i]; imageo[p] = image[i];
+                    if (dest) dest[i] = p;
                 } else {
                     const int k = f.a ? ka : kb;
+                    if (dest) dest[i] = k < exch_cap ? -(2 * k + (f.a ? 0 : 1)) - 1 : INT_MIN;   // record k of the left / right message
                     if (k < exch_cap) {
                         double *rec = (f.a ? send_l : send_r) + (size_t)(k + 1) * REC;
 #pragma unroll
@@ -425,6 +429,45 @@ __global__ void k_mr_exch_grow(Counts *cnt, const double *recv_a, const double *
 {
     cnt->nlocal += reinterpret_cast<const int *>(recv_a)[0] + reinterpret_cast<const int *>(recv_b)[0];
     cnt->nall = cnt->nlocal;
+}
+
+// bead-spring topology rides the migration (AtomVecDPDBond::pack_exchange / unpack_exchange, UM/atom_vec_dpd_bond_meso.cu):
+// a second message per direction, records of (1 + bond_per_atom) int2 = {nbond, 0}, {partner tag, bond type}..., in the
+// order of the atom records; stayers are compacted with the destination map the atom scatter wrote
+__global__ void __launch_bounds__(256) k_mr_exch_bonds_scatter(const int *__restrict__ dest, const int *__restrict__ nbond,
+                                                               const int2 *__restrict__ bonds, int *__restrict__ nbond_o,
+                                                               int2 *__restrict__ bonds_o, int2 *__restrict__ send_l, int2 *__restrict__ send_r,
+                                                               const Counts *__restrict__ cnt, size_t padding, int bpa)
+{
+    const int n = cnt->nlocal;                                   // still the count before the leavers were removed
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int dd = dest[i], nb = nbond[i];
+        if (dd >= 0) {
+            nbond_o[dd] = nb;
+            for (int q = 0; q < nb; q++) bonds_o[dd + q * padding] = bonds[i + q * padding];
+        } else if (dd != INT_MIN) {
+            const int sidx = -(dd + 1), k = sidx >> 1;
+            int2 *rec = ((sidx & 1) ? send_r : send_l) + (size_t)k * (1 + bpa);
+            rec[0] = make_int2(nb, 0);
+            for (int q = 0; q < nb; q++) rec[1 + q] = bonds[i + q * padding];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mr_exch_bonds_unpack(int *__restrict__ nbond, int2 *__restrict__ bonds, const Counts *__restrict__ cnt,
+                                                              const double *__restrict__ hdr_a, const double *__restrict__ hdr_b,
+                                                              const int2 *__restrict__ recv_a, const int2 *__restrict__ recv_b, size_t padding,
+                                                              int bpa, int nloc_cap)
+{
+    const int na = reinterpret_cast<const int *>(hdr_a)[0], n = na + reinterpret_cast<const int *>(hdr_b)[0];
+    const int base = cnt->nlocal;                                // arrivals are appended; k_mr_exch_grow runs after this kernel
+    if (base + n > nloc_cap) return;                             // flagged by k_mr_exch_unpack
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int2 *rec = (k < na) ? recv_a + (size_t)k * (1 + bpa) : recv_b + (size_t)(k - na) * (1 + bpa);
+        const int p = base + k, nb = min(max(rec[0].x, 0), bpa);
+        nbond[p] = nb;
+        for (int q = 0; q < nb; q++) bonds[p + q * padding] = rec[1 + q];
+    }
 }
 
 // ------------------------------------------------------------------ host drivers
@@ -502,13 +545,28 @@ int launch_exchange_multi(meso_ctx *ctx)
     const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
     int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
     cudaStream_t st = ctx->stream;
+    const bool bonded = bonds_active(ctx);
+    const int bpa = ctx->bond_per_atom;
+    const size_t bond_msg = (size_t)ctx->exch_cap * (size_t)(1 + bpa);      // int2 records per bond message
+    if (bonded) {
+        bool ok = ctx->exch_dest.reserve(ctx->cap);
+        for (int q = 0; q < 2; q++) ok = ok && ctx->bond_send[q].reserve(bond_msg) && ctx->bond_recv[q].reserve(bond_msg);
+        if (!ok) { ctx->err = "out of device memory (bond migration buffers)"; return MESO_ECUDA; }
+    }
     for (int d = 0; d < 3; d++) {
         if (ctx->procgrid[d] == 1) continue;        // the periodic wrap already put every atom back into the brick
         k_mr_exch_count<<<grid_for(ctx, 4), CT, 0, st>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
         k_mr_exch_scan<<<1, 1024, 0, st>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->exch_cap);
         k_mr_exch_scatter<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
                                                          soa(ctx->xa), soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p, ctx->imagea.p,
-                                                         ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d, ntiles, ctx->exch_cap);
+                                                         ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d, ntiles, ctx->exch_cap,
+                                                         bonded ? ctx->exch_dest.p : nullptr);
+        if (bonded) {
+            k_mr_exch_bonds_scatter<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->exch_dest.p, ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p,
+                                                                   ctx->bond_send[0].p, ctx->bond_send[1].p, ctx->d_counts, ctx->cap, bpa);
+            std::swap(ctx->nbond.p, ctx->nbond_alt.p); std::swap(ctx->nbond.cap, ctx->nbond_alt.cap);
+            std::swap(ctx->bonds.p, ctx->bonds_alt.p); std::swap(ctx->bonds.cap, ctx->bonds_alt.cap);
+        }
         for (int q = 0; q < 3; q++) { std::swap(ctx->x[q].p, ctx->xa[q].p); std::swap(ctx->v[q].p, ctx->va[q].p); }
         std::swap(ctx->tag.p, ctx->taga.p); std::swap(ctx->type.p, ctx->typea.p);
         std::swap(ctx->mask.p, ctx->maska.p); std::swap(ctx->image.p, ctx->imagea.p);
@@ -518,6 +576,18 @@ int launch_exchange_multi(meso_ctx *ctx)
         if (rc) return rc;
         k_mr_exch_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
                                                         ctx->d_counts, ra, rb, box, d, (int)ctx->nloc_cap);
+        if (bonded) {
+            ncclComm_t comm = (ncclComm_t)ctx->nccl;
+            const size_t nint = bond_msg * 2;
+            MESO_NCCL(ncclGroupStart());
+            MESO_NCCL(ncclSend(ctx->bond_send[0].p, nint, ncclInt, ctx->procneigh[d][0], comm, st));
+            MESO_NCCL(ncclRecv(ctx->bond_recv[0].p, nint, ncclInt, ctx->procneigh[d][1], comm, st));
+            MESO_NCCL(ncclSend(ctx->bond_send[1].p, nint, ncclInt, ctx->procneigh[d][1], comm, st));
+            MESO_NCCL(ncclRecv(ctx->bond_recv[1].p, nint, ncclInt, ctx->procneigh[d][0], comm, st));
+            MESO_NCCL(ncclGroupEnd());
+            k_mr_exch_bonds_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->nbond.p, ctx->bonds.p, ctx->d_counts, ra, rb, ctx->bond_recv[0].p,
+                                                                  ctx->bond_recv[1].p, ctx->cap, bpa, (int)ctx->nloc_cap);
+        }
         k_mr_exch_grow<<<1, 1, 0, st>>>(ctx->d_counts, ra, rb);
     }
     MESO_CUDA(cudaGetLastError());

@@ -108,6 +108,8 @@ struct meso_ctx {
     meso::DevBuf<int> nbond, nbond_alt;
     meso::DevBuf<int2> bonds, bonds_alt, bonds_mapped;
     meso::DevBuf<unsigned> tag_map;
+    meso::DevBuf<int> exch_dest;               // migration: where each local atom went (stayer slot / message record)
+    meso::DevBuf<int2> bond_send[2], bond_recv[2];
     meso::DevBuf<double> bond_k_dev, bond_r0_dev, e_bond;
     // reductions return this rank's part only (an MPI host sums them itself)
     int every = 5, ago = 0;

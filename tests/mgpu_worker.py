@@ -23,6 +23,7 @@ ap.add_argument("--L", type=int, nargs="+", default=[12])
 ap.add_argument("--grid", type=int, nargs=3, default=None)
 ap.add_argument("--steps", type=int, default=12)
 ap.add_argument("--backend", default="nccl")
+ap.add_argument("--polymer", action="store_true", help="bead-spring chains in solvent (bond table rides the migration, ghost partners)")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -33,15 +34,23 @@ from bench import procgrid_for  # noqa: E402
 grid = tuple(a.grid) if a.grid else procgrid_for(world)
 assert grid[0] * grid[1] * grid[2] == world
 dims = tuple(a.L) * 3 if len(a.L) == 1 else tuple(a.L)
-x = workload.dpd_fluid(dims if len(set(dims)) > 1 else dims[0])
-v = workload.maxwell_velocities(len(x))
-tag = np.arange(1, len(x) + 1, dtype=np.int32)
+if a.polymer:
+    assert len(set(dims)) == 1
+    x, typ, tag, nbond, btype, batom = workload.polymer_melt(dims[0], chain_len=8, seed=5)
+    ntypes, coeff = 2, np.array([[1, 1, 1, 1, 25, 4.5, 3.0], [1, 1, 1, 1, 40, 4.5, 3.0], [1, 1, 1, 1, 40, 4.5, 3.0], [1, 1, 1, 1, 25, 4.5, 3.0]], float)
+else:
+    x = workload.dpd_fluid(dims if len(set(dims)) > 1 else dims[0])
+    tag = np.arange(1, len(x) + 1, dtype=np.int32)
+    typ, ntypes, coeff = np.ones(len(x), np.int32), 1, None
+v = workload.maxwell_velocities(len(x)) * (2.0 if a.polymer else 1.0)      # hotter chains: more migration within the run
 
 
 def check(precision):
-    w = oracle.World((0, 0, 0), dims, procgrid=grid, precision=1 if precision == "dp" else 0)
-    w.set_atoms(x, v, tag=tag)
-    w.setup()
+    w = oracle.World((0, 0, 0), dims, procgrid=grid, precision=1 if precision == "dp" else 0, ntypes=ntypes, coeff=coeff)
+    w.set_atoms(x, v, tag=tag, type=typ)
+    if a.polymer:
+        w.set_bonds(nbond, btype, batom, tag=tag, k=[0.0, 50.0], r0=[0.0, 0.5], special_lj12=0.0)
+    w.setup(eflag=1, vflag=1)
     ao = w.atoms(rank)
     nl = ao["nlocal"]
     # this rank's atoms, in the oracle's pre-sort (file) order: select by ownership from the global arrays
@@ -54,14 +63,22 @@ def check(precision):
     ids = [Meso.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     m.decomposition(rank, grid, ids[0])
-    m.masses([0.0, 1.0])
+    m.masses([0.0] + [1.0] * ntypes)
     m.neighbor(0.3, "bin")
     m.neigh_modify(delay=0, every=5, check=False)
     m.pair_style("dpd/fast/meso" if precision == "sp" else "dpd/meso", 1.0, 419084618)
-    m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
+    if a.polymer:
+        m.pair_coeff(1, 1, 25, 4.5, 3.0, 1.0, 1.0); m.pair_coeff(1, 2, 40, 4.5, 3.0, 1.0, 1.0); m.pair_coeff(2, 2, 25, 4.5, 3.0, 1.0, 1.0)
+    else:
+        m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
     m.timestep(0.005)
-    m.upload(x[mine], v[mine], tag=tag[mine])
-    m.setup()
+    m.upload(x[mine], v[mine], tag=tag[mine], type=typ[mine])
+    if a.polymer:
+        m.bond_style("harmonic/meso", 1)
+        m.bond_coeff(1, 50.0, 0.5)
+        m.special_bonds(0.0)
+        m.bonds(nbond[mine], btype[mine], batom[mine], tag_max=len(x))
+    m.setup(eflag=1, vflag=1)
     cg, co = m.counts(), w.counts(rank)
     for k in ("nlocal", "nghost", "n_bulk", "n_border"):
         assert cg[k] == co[k], (rank, k, cg, co)
@@ -80,7 +97,10 @@ def check(precision):
     assert np.array_equal(c4g.view(np.uint32), c4o.view(np.uint32)) and np.array_equal(v4g.view(np.uint32), v4o.view(np.uint32))
     mag = np.linalg.norm(ao["f"], axis=1)
     err = (np.linalg.norm(ag["f"] - ao["f"], axis=1) / np.maximum(mag, mag.mean())).max()
-    assert err <= (1e-5 if precision == "sp" else 1e-12), err
+    assert err <= ((2e-5 if a.polymer else 1e-5) if precision == "sp" else (1e-11 if a.polymer else 1e-12)), err
+    if a.polymer:
+        eb = m.bond_energy()                         # summed over the ranks by the library (collective call)
+        assert abs(eb - w.bond_energy()) < 1e-10 * abs(w.bond_energy()), (eb, w.bond_energy())
     assert m.L.meso_natoms_global(m.h) == len(x)
     t_g, t_o = m.temperature(), w.temperature()
     assert abs(t_g - t_o) < 1e-12, (t_g, t_o)
@@ -105,7 +125,7 @@ def check(precision):
     else:
         m.run(a.steps)
         t = m.temperature()
-        assert 0.5 < t < 3.0, t
+        assert 0.5 < t < (6.0 if a.polymer else 3.0), t      # the polymer case starts at T = 4 (velocities doubled)
     m.close()
     return err
 
@@ -114,5 +134,6 @@ for precision in ("dp", "sp"):
     e = check(precision)
     dist.barrier()
     if rank == 0:
-        print("mgpu parity OK: %d ranks grid %s box %s %s (force err %.2e)" % (world, grid, dims, precision, e), flush=True)
+        print("mgpu parity OK: %d ranks grid %s box %s %s%s (force err %.2e)" % (world, grid, dims, precision, " polymer" if a.polymer else "", e),
+              flush=True)
 dist.destroy_process_group()
