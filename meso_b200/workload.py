@@ -50,6 +50,41 @@ def write_data(path, x, L, types=None, ntypes=1, masses=None):
             f.write("%d %d %.9e %.9e %.9e\n" % (i + 1, types[i], x[i, 0], x[i, 1], x[i, 2]))
 
 
+def write_data_bond(path, x, L, types, ntypes, num_bond, bond_type, bond_atom, masses=None, nbondtypes=1):
+    """LAMMPS data file for atom_style bond / dpd/bond/meso (Atoms lines `id mol type x y z`, Bonds section).  The per-atom
+    table is in the newton_bond-off layout (both partners hold each bond); the file lists every bond once (a < b)."""
+    Lx, Ly, Lz = (L, L, L) if np.isscalar(L) else L
+    n = len(x)
+    masses = [1.0] * ntypes if masses is None else masses
+    bonds = []
+    for i in range(n):
+        for p in range(int(num_bond[i])):
+            j = int(bond_atom[i][p])
+            if i + 1 < j:
+                bonds.append((int(bond_type[i][p]), i + 1, j))
+    # molecule id: chain number for bonded beads (consecutive tags), 0 for solvent
+    mol = np.zeros(n, dtype=int)
+    cur = 0
+    for i in range(n):
+        if num_bond[i] == 0:
+            continue
+        if i == 0 or num_bond[i - 1] == 0 or (i + 1) not in [int(t) for t in bond_atom[i - 1][:num_bond[i - 1]]]:
+            cur += 1
+        mol[i] = cur
+    with open(path, "w") as f:
+        f.write("LAMMPS\n\n%d atoms\n%d bonds\n\n%d atom types\n%d bond types\n\n" % (n, len(bonds), ntypes, nbondtypes))
+        f.write("0 %g xlo xhi\n0 %g ylo yhi\n0 %g zlo zhi\n\nMasses\n\n" % (Lx, Ly, Lz))
+        for t, m in enumerate(masses):
+            f.write("%d %f\n" % (t + 1, m))
+        f.write("\nAtoms\n\n")
+        for i in range(n):
+            f.write("%d %d %d %.9e %.9e %.9e\n" % (i + 1, mol[i], types[i], x[i, 0], x[i, 1], x[i, 2]))
+        f.write("\nBonds\n\n")
+        for k, (t, a, b) in enumerate(bonds):
+            f.write("%d %d %d %d\n" % (k + 1, t, a, b))
+    return len(bonds)
+
+
 def read_data(path):
     """Minimal reader for the files above: returns (x, tag, type, boxlo, boxhi, masses)."""
     with open(path) as f:
@@ -104,6 +139,8 @@ def polymer_melt(L, chain_len=8, rho=4, bond_len=0.7, seed=20140902, solvent_fra
     steps *= bond_len / np.linalg.norm(steps, axis=2, keepdims=True)
     walk = np.concatenate([start[:, None, :], start[:, None, :] + np.cumsum(steps, axis=1)], axis=1)
     x[nsolv:] = np.mod(walk.reshape(-1, 3), L)
+    x = np.round(x, 9)                       # same text round trip as a %.9e data file
+    x[x >= L] = 0.0
     typ[nsolv:] = 2
     tag = np.arange(1, n + 1, dtype=np.int32)
     num_bond = np.zeros(n, np.int32)

@@ -205,3 +205,29 @@ def test_harmonic_bonds_and_exclusion_filter_against_direct_evaluation():
         partners = set(ba[t[i] - 1, :nb[t[i] - 1]].tolist())
         kept = [j for j in rows_all[i, :c_all[i]] if t[j] not in partners]
         assert kept == rows_ex[i, :c_ex[i]].tolist()          # survivors keep their order
+
+
+@pytest.mark.parametrize("lj12", [1, 0])
+def test_polymer_forces_match_stock_lammps_bond_harmonic(lj12):
+    """SURVEY.md s8f N1 pin: conservative pair + harmonic bond forces of bead-spring chains against stock LAMMPS
+    (atom_style bond, bond_style harmonic of src/MOLECULE, pair_style dpd gamma = 0; fixture made by
+    tests/golden/make_lammps_bond_golden.py), with 1-2 pairs kept (special_bonds lj 1 1 1) and excluded (lj 0 1 1).
+    The MESO styles work on fl32(x - centre): 1e-5 relative, as for the plain fluid."""
+    from meso_b200 import workload
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stock_polymer_conservative_L6.npz"))
+    L = int(g["L"])
+    x, typ, tag, nb, bt, ba = workload.polymer_melt(L, chain_len=int(g["chain_len"]), seed=int(g["seed"]))
+    coeff = np.array([[1, 1, 1, 1, 25, 0, 0], [1, 1, 1, 1, 40, 0, 0], [1, 1, 1, 1, 40, 0, 0], [1, 1, 1, 1, 25, 0, 0]], dtype=float)
+    for precision in (0, 1):
+        w = oracle.World((0, 0, 0), (L, L, L), ntypes=2, mass=[0, 1, 1], coeff=coeff, precision=precision)
+        w.set_atoms(x, np.zeros_like(x), tag=tag, type=typ)
+        w.set_bonds(nb, bt, ba, tag=tag, k=[0, float(g["k"])], r0=[0, float(g["r0"])], special_lj12=float(lj12))
+        w.setup(eflag=1, vflag=1)
+        f = by_tag(w)
+        ref = g["f_lj%d" % lj12]
+        mag = np.linalg.norm(ref, axis=1)
+        err = (np.linalg.norm(f - ref, axis=1) / np.maximum(mag, mag.mean())).max()
+        assert err <= 1e-5, (precision, err)
+        assert abs(w.bond_energy() - float(g["ebond_lj%d" % lj12])) < 1e-5 * float(g["ebond_lj%d" % lj12])
+        _, e = w.virial()
+        assert abs(e.sum() - float(g["evdwl_lj%d" % lj12])) < 1e-5 * float(g["evdwl_lj%d" % lj12])
