@@ -6,6 +6,7 @@
 #include "force.h"
 #include "modify.h"
 #include "pair.h"
+#include "bond.h"
 #include "update.h"
 
 using namespace LAMMPS_NS;
@@ -18,13 +19,14 @@ MesoComputePE::MesoComputePE(LAMMPS *lmp, int narg, char **arg) : Compute(lmp,na
   extscalar = 1;
   peflag = 1;
   timeflag = 1;
-  pairflag = thermoflag = 1;
+  pairflag = bondflag = thermoflag = 1;
   if (narg > 3) {
-    pairflag = thermoflag = 0;
+    pairflag = bondflag = thermoflag = 0;
     for (int iarg = 3; iarg < narg; iarg++) {
       if (strcmp(arg[iarg],"pair") == 0) pairflag = 1;
+      else if (strcmp(arg[iarg],"bond") == 0) bondflag = 1;
       else if (strcmp(arg[iarg],"thermo") == 0) thermoflag = 1;
-      else error->all(FLERR,"<MESO> compute pe/meso knows the keywords pair and thermo");
+      else error->all(FLERR,"<MESO> compute pe/meso knows the keywords pair, bond and thermo");
     }
   }
 }
@@ -37,6 +39,7 @@ double MesoComputePE::compute_scalar()
   // the pair style filled eng_vdwl from the device reduction (MesoPairDPD::tally_from_device)
   double one = 0.0;
   if (pairflag && force->pair) one += force->pair->eng_vdwl + force->pair->eng_coul;
+  if (bondflag && force->bond) one += force->bond->energy;
   MPI_Allreduce(&one,&scalar,1,MPI_DOUBLE,MPI_SUM,world);
 
   if (pairflag && force->pair && force->pair->tail_flag)

@@ -22,7 +22,7 @@ class MesoComputePE : public Compute {
   virtual double compute_scalar();
 
  private:
-  int pairflag, thermoflag;
+  int pairflag, bondflag, thermoflag;
 };
 
 }

@@ -19,7 +19,8 @@ using namespace LAMMPS_NS;
 
 MesoDevice::MesoDevice(LAMMPS *lmp, int device, std::string profile) :
   Pointers(lmp), dummy(false), ctx(NULL), profile_mode(profile),
-  profile_lo(0), profile_hi(0), profiling(false), on_device(false), npinned(0), pinned_nmax(0)
+  profile_lo(0), profile_hi(0), profiling(false), on_device(false), npinned(0), pinned_nmax(0),
+  bonded(false), topo_tag_max(0), topo_bpa(0), topo_maxspecial(0)
 {
   int ndev = meso_device_count();
   if (ndev <= 0)
@@ -87,6 +88,7 @@ void MesoDevice::push_settings()
   for (int i = 1; i <= atom->ntypes; i++)
     if (!atom->mass_setflag[i]) error->all(FLERR,"All masses are not set");
   check(meso_set_types(ctx,atom->ntypes,atom->mass),FLERR);
+  if (atom->molecular) check(meso_set_special_bonds(ctx,force->special_lj[1]),FLERR);
 
   if (neighbor->delay != 0 || neighbor->dist_check != 0)
     error->all(FLERR,"<MESO> USER-MESO-B200 rebuilds on a fixed cadence: use neigh_modify delay 0 every N check no");
@@ -129,7 +131,63 @@ void MesoDevice::upload_atoms()
   const int n = atom->nlocal;
   check(meso_atoms_upload(ctx,n,n ? atom->x[0] : NULL,n ? atom->v[0] : NULL,atom->tag,atom->type,atom->mask,
                           (const int *) atom->image),FLERR);
+  upload_topology(n);
   on_device = true;
+}
+
+/* per-atom bond table -> device (AtomVecDPDBond::transfer_bond, UM/atom_vec_dpd_bond_meso.cu); newton_bond must have
+   been off when the data file was read, so that both atoms of a bond hold it (UM/mvv_meso.cu:96-103 forces it off) */
+void MesoDevice::upload_topology(int n)
+{
+  bonded = atom->molecular && atom->avec->bonds_allow && atom->bond_per_atom > 0 && atom->num_bond != NULL;
+  if (!bonded) return;
+  const int bpa = atom->bond_per_atom, ms = atom->maxspecial;
+  bigint held = 0;
+  int tmax = 0;
+  for (int i = 0; i < n; i++) { held += atom->num_bond[i]; if (atom->tag[i] > tmax) tmax = atom->tag[i]; }
+  bigint held_all = held;
+  int tmax_all = tmax;
+  MPI_Allreduce(&held,&held_all,1,MPI_LMP_BIGINT,MPI_SUM,world);
+  MPI_Allreduce(&tmax,&tmax_all,1,MPI_INT,MPI_MAX,world);
+  if (held_all != 2*atom->nbonds)
+    error->all(FLERR,"<MESO> bonds must be stored by both atoms: put `newton off` before read_data");
+  topo_tag_max = tmax_all; topo_bpa = bpa; topo_maxspecial = ms;
+  topo_molecule.assign(tmax_all+1,0);
+  topo_num_bond.assign(tmax_all+1,0);
+  topo_bond_type.assign((size_t)(tmax_all+1)*bpa,0);
+  topo_bond_atom.assign((size_t)(tmax_all+1)*bpa,0);
+  topo_nspecial.assign((size_t)(tmax_all+1)*3,0);
+  topo_special.assign((size_t)(tmax_all+1)*(ms > 0 ? ms : 1),0);
+  for (int i = 0; i < n; i++) {
+    const int t = atom->tag[i];
+    topo_molecule[t] = atom->molecule[i];
+    topo_num_bond[t] = atom->num_bond[i];
+    for (int p = 0; p < atom->num_bond[i]; p++) {
+      topo_bond_type[(size_t)t*bpa+p] = atom->bond_type[i][p];
+      topo_bond_atom[(size_t)t*bpa+p] = atom->bond_atom[i][p];
+    }
+    for (int p = 0; p < 3; p++) topo_nspecial[(size_t)t*3+p] = atom->nspecial[i][p];
+    for (int p = 0; p < atom->nspecial[i][2] && p < ms; p++) topo_special[(size_t)t*ms+p] = atom->special[i][p];
+  }
+  check(meso_bonds_upload(ctx,n,bpa,atom->num_bond,n ? atom->bond_type[0] : NULL,n ? atom->bond_atom[0] : NULL,tmax_all),FLERR);
+}
+
+void MesoDevice::restore_topology(int n)
+{
+  if (!bonded) return;
+  const int bpa = topo_bpa, ms = topo_maxspecial;
+  for (int i = 0; i < n; i++) {
+    const int t = atom->tag[i];
+    if (t < 0 || t > topo_tag_max) error->one(FLERR,"<MESO> atom tag outside the uploaded topology");
+    atom->molecule[i] = topo_molecule[t];
+    atom->num_bond[i] = topo_num_bond[t];
+    for (int p = 0; p < topo_num_bond[t]; p++) {
+      atom->bond_type[i][p] = topo_bond_type[(size_t)t*bpa+p];
+      atom->bond_atom[i][p] = topo_bond_atom[(size_t)t*bpa+p];
+    }
+    for (int p = 0; p < 3; p++) atom->nspecial[i][p] = topo_nspecial[(size_t)t*3+p];
+    for (int p = 0; p < atom->nspecial[i][2] && p < ms; p++) atom->special[i][p] = topo_special[(size_t)t*ms+p];
+  }
 }
 
 void MesoDevice::download_atoms()
@@ -146,6 +204,7 @@ void MesoDevice::download_atoms()
                             (int *) atom->image),FLERR);
   atom->nlocal = nlocal;
   atom->nghost = 0;                              // ghosts exist on the device only
+  restore_topology(nlocal);
   if (atom->map_style) { atom->map_init(); atom->map_set(); }   // the device reorders atoms at every rebuild
 }
 

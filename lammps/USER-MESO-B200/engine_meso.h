@@ -7,6 +7,7 @@
 #define LMP_MESO_ENGINE
 
 #include <string>
+#include <vector>
 #include "pointers.h"
 #include "meso_b200.h"
 
@@ -48,6 +49,13 @@ class MesoDevice : protected Pointers {
   int npinned, pinned_nmax;
   void pin_host_arrays();
   void unpin_host_arrays();
+  // bead-spring decks: host-only per-atom arrays (molecule, bond and special tables) keyed by tag at upload time,
+  // so that they can follow the device's reorder when the atoms come back
+  bool bonded;
+  int topo_tag_max, topo_bpa, topo_maxspecial;
+  std::vector<int> topo_molecule, topo_num_bond, topo_bond_type, topo_bond_atom, topo_nspecial, topo_special;
+  void upload_topology(int n);
+  void restore_topology(int n);
 };
 
 }

@@ -3,6 +3,7 @@
 #include "engine_meso.h"
 #include "fix_nve_meso.h"
 #include "fix_resident_meso.h"
+#include "bond_harmonic_meso.h"
 #include "pair_dpd_meso.h"
 #include "atom.h"
 #include "comm.h"
@@ -53,8 +54,10 @@ void ModifiedVerlet::init()
 
   dpd = dynamic_cast<MesoPairDPD *>(force->pair);
   if (dpd == NULL) error->all(FLERR,"<MESO> run_style mvv/meso needs pair_style dpd/meso or dpd/fast/meso");
-  if (force->bond || force->angle || force->dihedral || force->improper)
-    error->all(FLERR,"<MESO> bonded styles are not part of USER-MESO-B200 yet");
+  if (force->bond && dynamic_cast<MesoBondHarmonic *>(force->bond) == NULL)
+    error->all(FLERR,"<MESO> bond styles other than harmonic/meso are not part of USER-MESO-B200");
+  if (force->angle || force->dihedral || force->improper)
+    error->all(FLERR,"<MESO> angle, dihedral and improper styles are not part of USER-MESO-B200");
 
   // every fix acts on device-resident atoms, so it has to be a /meso style;
   // exactly one nve/meso plus fixes that live in the library's own fix list => the fused run loop.
@@ -94,12 +97,15 @@ void ModifiedVerlet::device_setup(int outflag)
 
   dev->push_settings();
   dpd->push_coeff();
+  MesoBondHarmonic *bond = dynamic_cast<MesoBondHarmonic *>(force->bond);
+  if (bond) bond->push_coeff();
   dev->upload_atoms();
 
   // wrap + reorder + ghosts + neighbor table + forces of step `ntimestep`, all on the device
   ev_set(update->ntimestep);
   MESO_CALL(meso_setup(dev->ctx,eflag,vflag));
   dpd->tally_from_device(eflag,vflag);
+  if (bond) bond->tally_from_device(eflag,vflag);
 
   modify->setup(vflag);
   if (outflag) {
@@ -123,6 +129,7 @@ void ModifiedVerlet::setup_minimal(int flag)
   ev_set(update->ntimestep);
   force_clear();
   force->pair->compute(eflag,vflag);
+  if (force->bond) force->bond->compute(eflag,vflag);
   MESO_CALL(meso_fix_post_force(dev->ctx,-1));      // Fix::setup -> post_force of the device-resident fixes
   modify->setup(vflag);
   update->setupflag = 0;
@@ -154,6 +161,7 @@ void ModifiedVerlet::step_by_phases(bigint ntimestep)
   force_clear();
   if (modify->n_pre_force) modify->pre_force(vflag);
   force->pair->compute(eflag,vflag);
+  if (force->bond) force->bond->compute(eflag,vflag);          // UM/mvv_meso.cu:385-393
   if (modify->n_post_force) modify->post_force(vflag);
   modify->final_integrate();
   if (modify->n_end_of_step) modify->end_of_step();

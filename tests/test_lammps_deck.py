@@ -268,6 +268,90 @@ def test_channel_deck_with_device_resident_fixes(tmp_path, monkeypatch):
     assert np.abs(fr2[steps][:, 1:7] - fr[steps][:, 1:7]).max() < 1e-9
 
 
+POLYMER_DECK = """# bead-spring chains in solvent (SURVEY.md s8f N1)
+dimension       3
+units           lj
+newton          off
+atom_style      dpd/bond/meso
+neighbor        0.3 bin
+neigh_modify    delay 0 every 5 check no
+read_data       p.data
+run_style       mvv/meso
+bond_style      harmonic/meso
+bond_coeff      1 50.0 0.5
+special_bonds   lj 0 1 1
+pair_style      dpd/meso 1.0 419084618
+pair_coeff      1 1 25 4.5 3.0 1.0 1.0
+pair_coeff      1 2 40 4.5 3.0 1.0 1.0
+pair_coeff      2 2 25 4.5 3.0 1.0 1.0
+compute         mythermo all temp/meso
+velocity        all create 1.0 788662042 loop all
+fix             3 all nve/meso
+thermo_style    custom step temp {extra} cpu
+thermo          10
+thermo_modify   temp mythermo norm no
+{dump}
+timestep        0.005
+run             {steps}
+"""
+
+
+@pytest.mark.gpu
+def test_polymer_deck_dpd_bond_meso_and_harmonic_meso(tmp_path, monkeypatch):
+    """atom_style dpd/bond/meso + bond_style harmonic/meso + special_bonds lj 0 through lmp_meso_b200: the Bonds section
+    reaches the device table, the fused loop adds the bonded forces, the host's bond arrays follow the device reorder
+    (the dump after 20 steps is by id), thermo's ebond / pe come from the device reductions."""
+    need_binary()
+    monkeypatch.setenv("MESO_PAIR_ONCE", "0")
+    L, steps = 8, 20
+    x, typ, tag, nb, bt, ba = workload.polymer_melt(L, chain_len=8, seed=5)
+    workload.write_data_bond(str(tmp_path / "p.data"), x, L, typ, 2, nb, bt, ba)
+
+    def run(extra, sub, ncol):
+        d = tmp_path / sub
+        d.mkdir()
+        os.symlink(str(tmp_path / "p.data"), str(d / "p.data"))
+        (d / "in.run").write_text(POLYMER_DECK.format(extra=extra, steps=steps, dump=DUMP.format(steps=steps)))
+        out = subprocess.run([LMP, "-in", "in.run", "-log", "none"], cwd=str(d), capture_output=True, text=True, timeout=600,
+                             env=dict(os.environ, MESO_PAIR_ONCE="0"))
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        return frames(str(d / "traj.txt")), thermo_rows(out.stdout, ncol)
+
+    fr, th = run("", "fused", 3)
+    from meso_b200.engine import Meso
+    m = Meso(0)
+    m.box((0.0, 0.0, 0.0), (L, L, L))
+    m.masses([0.0, 1.0, 1.0])
+    m.neighbor(0.3, "bin")
+    m.neigh_modify(delay=0, every=5, check=False)
+    m.pair_style("dpd/meso", 1.0, 419084618)
+    m.pair_coeff(1, 1, 25, 4.5, 3.0, 1.0, 1.0); m.pair_coeff(1, 2, 40, 4.5, 3.0, 1.0, 1.0); m.pair_coeff(2, 2, 25, 4.5, 3.0, 1.0, 1.0)
+    m.timestep(0.005)
+    assert np.array_equal(fr[0][:, 0].astype(np.int32), tag)
+    m.upload(np.ascontiguousarray(fr[0][:, 1:4]), np.ascontiguousarray(fr[0][:, 4:7]), tag=tag, type=typ)
+    m.bond_style("harmonic/meso", 1)
+    m.bond_coeff(1, 50.0, 0.5)
+    m.special_bonds(0.0)
+    m.bonds(nb, bt, ba)
+    m.setup(eflag=1, vflag=1)
+    a = m.download()
+    o = np.argsort(a["tag"])
+    assert np.array_equal(a["f"][o], fr[0][:, 7:10]), "setup forces (pair + bonds) differ"
+    eb0 = m.bond_energy()
+    _, ep0 = m.virial()
+    m.run(steps)
+    a = m.download()
+    o = np.argsort(a["tag"])
+    assert np.array_equal(a["x"][o], fr[steps][:, 1:4]) and np.array_equal(a["v"][o], fr[steps][:, 4:7])
+    assert np.array_equal(a["f"][o], fr[steps][:, 7:10])
+    m.close()
+    # thermo steps by phases, energies from the device reductions; the by-id dump proves the host bond arrays stayed aligned
+    fr2, th2 = run("ebond pe", "phases", 5)
+    assert np.abs(fr2[steps][:, 1:7] - fr[steps][:, 1:7]).max() < 1e-9
+    assert abs(th2[0, 2] - eb0) < 2e-7 * eb0 and abs(th2[0, 3] - (eb0 + ep0)) < 2e-7 * (eb0 + ep0), (th2[0], eb0, ep0)
+    assert 0 < th2[-1, 2] < eb0                      # the stretched start (bond length 0.7, r0 0.5) relaxes
+
+
 @pytest.mark.gpu
 def test_deck_errors_match_the_reference_strings(tmp_path):
     need_binary()
