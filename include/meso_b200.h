@@ -144,6 +144,13 @@ int meso_fix_addforce(meso_ctx *ctx, int groupbit, double fx, double fy, double 
 /* fix ID group pois/meso <dim_ortho> <dim_force> <strength> [bisect_frac = 0.5] (MesoFixPoiseuille,
  * UM/fix_poiseuille_meso.cu:20-113): +strength below the bisection plane, -strength above it */
 int meso_fix_pois(meso_ctx *ctx, int groupbit, int dim_ortho, int dim_force, double strength, double bisect_frac);
+/* fix ID group rdf/fast/meso output <file> nbin <n> [every <k>] [other <group>] (MesoFixRDFFast, UM/fix_rdf_fast_meso.cu:42-180):
+ * every `every` steps, in the post_force slot, histogram of the distances r < pair cutoff over the neighbor table between
+ * atoms of `groupbit` (rows) and `j_groupbit` (entries); call after meso_pair_dpd_settings (rc = the pair style's global cutoff) */
+int meso_fix_rdf(meso_ctx *ctx, int groupbit, int j_groupbit, int nbin, int every);
+/* accumulated pair counts per bin (as doubles), number of samples, sizes of the two groups (the inputs of MesoFixRDFFast::dump,
+ * UM/fix_rdf_fast_meso.cu:182-219); all ranks (collective) unless meso_set_reduce_scope(1) */
+int meso_fix_rdf_read(meso_ctx *ctx, int handle, int nbin, double *histogram, double *n_samples, double *ni, double *nj);
 int meso_fix_clear(meso_ctx *ctx);                                  /* unfix: drops every registered fix */
 /* hooks for a host that drives the step by phases (Modify::post_force / pre_exchange / end_of_step, UM/mvv_meso.cu:273,396,399);
  * handle < 0 applies every registered fix in registration order.  meso_setup and meso_run call them themselves. */

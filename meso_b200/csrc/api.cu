@@ -699,7 +699,7 @@ static int fix_register(meso_ctx *ctx, const meso::FixOp &op)
     if (fl.n >= meso::MAX_FIX) FAIL(MESO_EINVAL, "too many device-resident fixes (limit 8)");
     fl.op[fl.n] = op;
     if (op.kind == meso::FIX_WALL || op.kind == meso::FIX_SOLID_BOUND) fl.nbounce++;
-    fl.nforce++;
+    if (op.kind == meso::FIX_RDF) fl.nrdf++; else fl.nforce++;
     return fl.n++;
 }
 
@@ -742,6 +742,42 @@ extern "C" int meso_fix_pois(meso_ctx *ctx, int groupbit, int dim_ortho, int dim
     return fix_register(ctx, op);
 }
 
+// fix ID group rdf/fast/meso output <file> nbin <n> [every <k>] [other <group>]: samples in the post_force slot
+extern "C" int meso_fix_rdf(meso_ctx *ctx, int groupbit, int j_groupbit, int nbin, int every)
+{
+    CHECK_CTX();
+    if (nbin <= 0 || nbin > 8192) FAIL(MESO_EINVAL, "Incomplete compute rdf command: insufficient arguments");
+    if (every < 1) every = 1;
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    meso::FixOp op{};
+    op.kind = meso::FIX_RDF; op.groupbit = groupbit; op.aux = j_groupbit; op.dims = nbin;
+    op.p[0] = every; op.p[1] = ctx->cut_global;                  // MesoFixRDFFast::init: rc = force->pair->cutforce
+    const int h = fix_register(ctx, op);
+    if (h < 0) return h;
+    if (!ctx->rdf_hist[h].reserve((size_t)nbin + 2)) FAIL(MESO_ECUDA, "out of device memory (rdf histogram)");
+    MESO_CUDA(cudaMemsetAsync(ctx->rdf_hist[h].p, 0, sizeof(unsigned long long) * ((size_t)nbin + 2), ctx->stream));
+    ctx->rdf_samples[h] = 0;
+    return h;
+}
+
+// accumulated histogram[nbin] (pair counts, both directions), number of samples, sizes of the i and j groups; summed over
+// the ranks unless meso_set_reduce_scope(1).  g(r) follows as in MesoFixRDFFast::dump (UM/fix_rdf_fast_meso.cu:182-219).
+extern "C" int meso_fix_rdf_read(meso_ctx *ctx, int handle, int nbin, double *histogram, double *n_samples, double *ni, double *nj)
+{
+    CHECK_CTX();
+    if (handle < 0 || handle >= ctx->fixes.n || ctx->fixes.op[handle].kind != meso::FIX_RDF || nbin != ctx->fixes.op[handle].dims || !histogram)
+        FAIL(MESO_EINVAL, "meso_fix_rdf_read: not an rdf fix / wrong bin count");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    std::vector<double> buf((size_t)nbin + 2);
+    TRY(fix_rdf_read(ctx, handle, nbin, buf.data(), &buf[nbin], &buf[nbin + 1]));
+    if (ctx->nranks > 1 && !ctx->reduce_local) TRY(comm_allreduce_sum(ctx, buf.data(), nbin + 2));
+    memcpy(histogram, buf.data(), sizeof(double) * nbin);
+    if (n_samples) *n_samples = (double)ctx->rdf_samples[handle];
+    if (ni) *ni = buf[nbin];
+    if (nj) *nj = buf[nbin + 1];
+    return MESO_OK;
+}
+
 extern "C" int meso_fix_clear(meso_ctx *ctx)
 {
     CHECK_CTX();
@@ -756,7 +792,9 @@ extern "C" int meso_fix_post_force(meso_ctx *ctx, int handle)
     TRY(ready(ctx));
     if (handle >= ctx->fixes.n) FAIL(MESO_EINVAL, "meso_fix_post_force: no such fix");
     PhaseTimer t(ctx, MESO_T_INTEGRATE);
-    return launch_fix_post_force(ctx, handle, false);
+    if (handle >= 0 && ctx->fixes.op[handle].kind == meso::FIX_RDF) return launch_fix_rdf(ctx, handle);
+    TRY(launch_fix_post_force(ctx, handle, false));
+    return handle < 0 ? launch_fix_rdf(ctx, -1) : MESO_OK;
 }
 
 // the pre_exchange / end_of_step hook of wall/meso and solid_bound/meso: bounce-forward at the box faces
@@ -832,6 +870,7 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
                 TRY(pair(MESO_BORDER));
                 TRY(launch_bond_force(ctx, 0, acc_facc));
                 TRY(launch_fix_post_force(ctx, -1, acc_facc));
+                TRY(launch_fix_rdf(ctx, -1));
             }
             continue;
         } else {
@@ -842,6 +881,7 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
         TRY(pair(MESO_LOCAL));
         TRY(launch_bond_force(ctx, 0, acc_facc));            // bonded forces join the same accumulator (UM/mvv_meso.cu:387-389)
         TRY(launch_fix_post_force(ctx, -1, acc_facc));       // modify->post_force (UM/mvv_meso.cu:396)
+        TRY(launch_fix_rdf(ctx, -1));
     }
     if (pending) {
         PhaseTimer t(ctx, MESO_T_INTEGRATE);                 // last step's second half-kick; f <- force, accumulator cleared

@@ -63,7 +63,7 @@ int comm_allreduce_sum(meso_ctx *ctx, double *host_vals, int n)
 {
     if (ctx->nranks == 1) return MESO_OK;
     if (!ctx->nccl) { ctx->err = "communicator not initialised"; return MESO_ENCCL; }
-    if (!ctx->reduce_buf.reserve(64)) { ctx->err = "out of device memory"; return MESO_ECUDA; }
+    if (!ctx->reduce_buf.reserve(std::max(64, n))) { ctx->err = "out of device memory"; return MESO_ECUDA; }
     MESO_CUDA(cudaMemcpyAsync(ctx->reduce_buf.p, host_vals, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     MESO_NCCL(ncclAllReduce(ctx->reduce_buf.p, ctx->reduce_buf.p, n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
     MESO_CUDA(cudaMemcpyAsync(host_vals, ctx->reduce_buf.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));

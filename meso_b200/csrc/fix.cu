@@ -8,6 +8,7 @@
 // kernel count of the plain fluid plus one.
 #include "internal.h"
 #include "fix_device.cuh"
+#include <vector>
 
 namespace meso {
 
@@ -54,6 +55,90 @@ __global__ void __launch_bounds__(256) k_fix_bounce(SoA3 x, SoA3 v, const int *_
             for (int d = 0; d < 3; d++) { x.c[d][i] = xx[d]; v.c[d][i] = vv[d]; }
         }
     }
+}
+
+// ------------------------------------------------------------------ rdf/fast/meso
+// gpu_calc_rdf, UM/fix_rdf_fast_meso.cu:102-150: histogram of the pair distances r < rc over the stored neighbor table
+// (full list: every i-j pair is counted from both sides), fp32 on the packed coordinates, bin = floor(r nbin / rc).
+// One lane per row of the tile-transposed table (coalesced index loads), block-private histogram in shared memory,
+// flushed once per CTA into 64-bit global counters (the reference's 32-bit counters wrap after ~250 samples of 1M atoms).
+__global__ void __launch_bounds__(256) k_rdf(const float4 *__restrict__ coord4, const int *__restrict__ mask, const int *__restrict__ pair_count,
+                                             const int *__restrict__ pair_table, unsigned long long *__restrict__ hist,
+                                             const Counts *__restrict__ cnt, int n_col, float rc, float bin_sz_inv, int nbin, int groupi,
+                                             int groupj)
+{
+    extern __shared__ unsigned hist_local[];
+    for (int b = threadIdx.x; b < nbin; b += blockDim.x) hist_local[b] = 0;
+    __syncthreads();
+    const int n = cnt->nlocal;
+    const float rcsq = rc * rc;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!(mask[i] & groupi)) continue;
+        const float4 c1 = coord4[i];
+        const int n_pair = pair_count[i];
+        const int *row = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);
+        for (int k = 0; k < n_pair; k++) {
+            const int j = row[(size_t)(k & 31) * n_col + (k & ~31)];
+            if (groupj != 1 && !(mask[j] & groupj)) continue;          // group bit 1 is LAMMPS' `all`
+            const float4 c2 = coord4[j];
+            const float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
+            const float rsq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            if (rsq < rcsq) {
+                const float r = rsq * rsqrtf(rsq);
+                const int bid = (int)floorf(r * bin_sz_inv);
+                if (bid >= 0 && bid < nbin) atomicAdd(hist_local + bid, 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbin; b += blockDim.x)
+        if (hist_local[b]) atomicAdd(hist + b, (unsigned long long)hist_local[b]);
+}
+
+__global__ void __launch_bounds__(256) k_group_count(const int *__restrict__ mask, const Counts *__restrict__ cnt, int gi, int gj,
+                                                     unsigned long long *__restrict__ out2)
+{
+    const int n = cnt->nlocal;
+    unsigned a = 0, b = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int m = mask[i];
+        a += (m & gi) != 0; b += (m & gj) != 0;
+    }
+    a = __reduce_add_sync(0xffffffffu, a); b = __reduce_add_sync(0xffffffffu, b);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out2, (unsigned long long)a); atomicAdd(out2 + 1, (unsigned long long)b); }
+}
+
+int launch_fix_rdf(meso_ctx *ctx, int handle)
+{
+    if (ctx->fixes.nrdf == 0) return MESO_OK;
+    for (int k = 0; k < ctx->fixes.n; k++) {
+        const FixOp &o = ctx->fixes.op[k];
+        if (o.kind != FIX_RDF || (handle >= 0 && handle != k)) continue;
+        const int every = (int)o.p[0], nbin = o.dims;
+        if (every > 1 && ctx->ntimestep % every != 0) continue;       // UM/fix_rdf_fast_meso.cu:160
+        const float rc = (float)o.p[1];
+        k_rdf<<<grid_for(ctx, 4), 256, sizeof(unsigned) * nbin, ctx->stream>>>(ctx->coord4.p, ctx->mask.p, ctx->pair_count.p, ctx->pair_table.p,
+                                                                            ctx->rdf_hist[k].p, ctx->d_counts, ctx->n_col, rc, (float)nbin / rc,
+                                                                            nbin, o.groupbit, o.aux);
+        ctx->rdf_samples[k]++;
+    }
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+// histogram (as doubles) and the sizes of the two groups among this rank's local atoms
+int fix_rdf_read(meso_ctx *ctx, int handle, int nbin, double *hist, double *ni, double *nj)
+{
+    const FixOp &o = ctx->fixes.op[handle];
+    std::vector<unsigned long long> h((size_t)nbin + 2, 0ull);
+    unsigned long long *cnt2 = ctx->rdf_hist[handle].p + nbin;       // two spare counters behind the bins
+    MESO_CUDA(cudaMemsetAsync(cnt2, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    k_group_count<<<grid_for(ctx, 2), 256, 0, ctx->stream>>>(ctx->mask.p, ctx->d_counts, o.groupbit, o.aux, cnt2);
+    MESO_CUDA(cudaMemcpyAsync(h.data(), ctx->rdf_hist[handle].p, sizeof(unsigned long long) * (nbin + 2), cudaMemcpyDeviceToHost, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < nbin; b++) hist[b] = (double)h[b];
+    *ni = (double)h[nbin]; *nj = (double)h[nbin + 1];
+    return MESO_OK;
 }
 
 int launch_fix_post_force(meso_ctx *ctx, int handle, bool into_facc)

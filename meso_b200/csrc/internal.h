@@ -70,15 +70,16 @@ struct SortScratch {
 
 // device-resident fixes of the channel decks: wall/meso, solid_bound/meso, addforce/meso, pois/meso.
 // The list is small and travels to the kernels by value (constant bank), so one streaming pass applies all of them.
-enum { FIX_WALL = 1, FIX_SOLID_BOUND = 2, FIX_ADDFORCE = 3, FIX_POIS = 4, MAX_FIX = 8 };
+enum { FIX_WALL = 1, FIX_SOLID_BOUND = 2, FIX_ADDFORCE = 3, FIX_POIS = 4, FIX_RDF = 5, MAX_FIX = 8 };
 struct FixOp {
     int kind, groupbit;
     int dims;                       // wall / solid_bound: bit d = walls across dimension d;  pois: dim_ortho | dim_force << 2
-    int aux;                        // solid_bound: force kernel id (1 = rho5rc1s1)
+    int aux;                        // solid_bound: force kernel id (1 = rho5rc1s1);  rdf: group bit of the j atoms
+                                    // rdf: dims = nbin, p = {every, rc}
     double p[4];                    // wall: {d, 1/d, f};  addforce: {fx, fy, fz};  pois: {strength, bisect_frac}
 };
 struct FixList {
-    int n, nbounce, nforce, pad;
+    int n, nbounce, nforce, nrdf;
     FixOp op[MAX_FIX];
 };
 
@@ -181,6 +182,8 @@ struct meso_ctx {
 
     // device-resident fixes (fix.cu)
     meso::FixList fixes{};
+    meso::DevBuf<unsigned long long> rdf_hist[meso::MAX_FIX];   // rdf/fast/meso: pair counts per radial bin, accumulated over samples
+    int64_t rdf_samples[meso::MAX_FIX] = {0};
 
     // timers
     bool timers_on = false;
@@ -235,6 +238,8 @@ int launch_bond_energy_sum(meso_ctx *ctx, double *e);
 // ---- fix.cu
 int launch_fix_post_force(meso_ctx *ctx, int handle, bool into_facc);   // handle < 0: every registered fix, in order
 int launch_fix_bounce(meso_ctx *ctx, int handle);
+int launch_fix_rdf(meso_ctx *ctx, int handle);                          // samples every rdf fix whose cadence hits ctx->ntimestep
+int fix_rdf_read(meso_ctx *ctx, int handle, int nbin, double *hist, double *ni, double *nj);
 // ---- integrate.cu
 int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack);
 int launch_final_integrate(meso_ctx *ctx, int groupbit);

@@ -222,7 +222,51 @@ class Meso:
             dim = lambda a: int(a) if a[0].isdigit() else "xyz".index(a[0])
             frac = float(args[3]) if len(args) > 3 else 0.5
             return self._chk(self.L.meso_fix_pois(self.h, groupbit, dim(args[0]), dim(args[1]), float(args[2]), frac))
+        if style == "rdf/fast/meso":                                 # UM/fix_rdf_fast_meso.cu:42-75
+            output, nbin, every, other, i = "", 0, 1, groupbit, 0
+            while i < len(args):
+                a = args[i]
+                if a in ("output", "nbin", "every", "other"):
+                    i += 1
+                    if i >= len(args):
+                        raise MesoError("Incomplete compute vprof command after '%s'" % a)
+                    if a == "output":
+                        output = args[i]
+                    elif a == "nbin":
+                        nbin = int(args[i])
+                    elif a == "every":
+                        every = int(args[i])
+                    else:
+                        other = int(args[i])                         # the mirror takes the other group's bit directly
+                i += 1
+            if output == "" or nbin == 0:
+                raise MesoError("Incomplete compute rdf command: insufficient arguments")
+            h = self._chk(self.L.meso_fix_rdf(self.h, groupbit, other, nbin, every))
+            self._rdf = getattr(self, "_rdf", {})
+            self._rdf[h] = (output, nbin)
+            return h
         raise MesoError("Invalid fix style")
+
+    def rdf(self, handle, volume):
+        """(r, g(r), histogram, samples) with the normalisation of MesoFixRDFFast::dump (UM/fix_rdf_fast_meso.cu:182-219, pi = 3.1415)"""
+        output, nbin = self._rdf[handle]
+        hist = np.zeros(nbin)
+        ns, ni, nj = C.c_double(), C.c_double(), C.c_double()
+        self._chk(self.L.meso_fix_rdf_read(self.h, handle, nbin, hist.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ns), C.byref(ni), C.byref(nj)))
+        rc = self._cut_global
+        bin_sz = rc / nbin
+        i = np.arange(nbin)
+        freq = hist / max(ni.value, 1.0) / max(ns.value, 1.0)
+        shell = 4.0 / 3.0 * 3.1415 * ((bin_sz * (i + 1)) ** 3 - (bin_sz * i) ** 3)
+        g = freq / shell / (nj.value / volume)
+        return (i + 0.5) * bin_sz, g, hist, int(ns.value)
+
+    def rdf_dump(self, handle, volume):
+        """the file the reference writes when the fix is destroyed: `r <tab> g(r) <tab>` per bin, 15 significant digits"""
+        r, g, _, _ = self.rdf(handle, volume)
+        with open(self._rdf[handle][0], "w") as f:
+            for a, b in zip(r, g):
+                f.write("%.15g\t%.15g\t\n" % (a, b))
 
     def unfix_all(self): self._chk(self.L.meso_fix_clear(self.h))
     def fix_post_force(self, handle=-1): self._chk(self.L.meso_fix_post_force(self.h, handle))

@@ -57,6 +57,8 @@ SIGNATURES = {
     "meso_fix_solid_bound": (_i, [_vp, _i, _i, _i]),
     "meso_fix_addforce": (_i, [_vp, _i, _d, _d, _d]),
     "meso_fix_pois": (_i, [_vp, _i, _i, _i, _d, _d]),
+    "meso_fix_rdf": (_i, [_vp, _i, _i, _i, _i]),
+    "meso_fix_rdf_read": (_i, [_vp, _i, _i, _pd, _pd, _pd, _pd]),
     "meso_fix_clear": (_i, [_vp]),
     "meso_fix_post_force": (_i, [_vp, _i]),
     "meso_fix_bounce": (_i, [_vp, _i]),

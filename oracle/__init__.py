@@ -84,6 +84,7 @@ def lib():
         "orc_bond_energy": (f64, [C.c_void_p]),
         "orc_fix_add": (i32, [C.c_void_p, i32, i32, i32, P(f64)]),
         "orc_fix_clear": (None, [C.c_void_p]),
+        "orc_fix_rdf_read": (i32, [C.c_void_p, i32, P(f64), P(f64), P(f64), P(f64)]),
         "orc_fix_post_force": (None, [C.c_void_p, i32]),
         "orc_fix_bounce": (None, [C.c_void_p, i32]),
         "orc_set_integrate_group": (None, [C.c_void_p, i32]),
@@ -192,6 +193,19 @@ class World:
 
     def fix_pois(self, dim_ortho, dim_force, strength, bisect_frac=0.5, groupbit=1):
         return self._fix(4, groupbit, dim_ortho | (dim_force << 2), [strength, bisect_frac])
+
+    def fix_rdf(self, nbin, every=1, groupbit=1, other=None, rc=1.0):
+        self._rdf_nbin = getattr(self, "_rdf_nbin", {})
+        h = self._fix(5, groupbit, nbin, [every, groupbit if other is None else other, rc])
+        self._rdf_nbin[h] = nbin
+        return h
+
+    def rdf(self, handle):
+        """(histogram, samples, ni, nj)"""
+        hist = np.zeros(self._rdf_nbin[handle])
+        s, ni, nj = f64(), f64(), f64()
+        self._chk(self.L.orc_fix_rdf_read(self.h, handle, hist.ctypes.data_as(P(f64)), C.byref(s), C.byref(ni), C.byref(nj)))
+        return hist, int(s.value), ni.value, nj.value
 
     def fix_post_force(self, only=-1): self.L.orc_fix_post_force(self.h, only)
     def fix_bounce(self, only=-1): self.L.orc_fix_bounce(self.h, only)

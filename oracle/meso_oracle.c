@@ -298,7 +298,7 @@ struct orc_world {
     int *num_bond, *bond_type, *bond_atom;      /* [tag_max+1], [tag_max+1][bond_per_atom] */
     double *bond_k, *bond_r0;                   /* [nbondtypes+1] */
     /* channel fixes, in registration order */
-    int nfix; struct { int kind, groupbit, dims; double p[4]; } fix[8];
+    int nfix; struct { int kind, groupbit, dims; double p[4]; unsigned long long *hist; long samples; } fix[8];
     int integrate_groupbit;                     /* group of the deck's fix nve/meso (0 = unset -> 1) */
 };
 
@@ -434,6 +434,7 @@ void orc_world_destroy(orc_world *w)
         for (int s = 0; s < 6; s++) free(r->swap[s].sendlist);
     }
     free(w->num_bond); free(w->bond_type); free(w->bond_atom); free(w->bond_k); free(w->bond_r0);
+    for (int k = 0; k < w->nfix; k++) free(w->fix[k].hist);
     free(w->rk); free(w->mass); free(w->coeff); free(w);
 }
 
@@ -1188,16 +1189,66 @@ double orc_bond_energy(orc_world *w)
 /* ---------------------------------------------------------------------- */
 /* channel fixes                                        */
 /* ---------------------------------------------------------------------- */
-enum { FIX_WALL = 1, FIX_SOLID_BOUND = 2, FIX_ADDFORCE = 3, FIX_POIS = 4 };
+enum { FIX_WALL = 1, FIX_SOLID_BOUND = 2, FIX_ADDFORCE = 3, FIX_POIS = 4, FIX_RDF = 5 };
 
 int orc_fix_add(orc_world *w, int kind, int groupbit, int dims, const double *p4)
 {
     if (w->nfix >= 8) FAIL("too many fixes");
     w->fix[w->nfix].kind = kind; w->fix[w->nfix].groupbit = groupbit; w->fix[w->nfix].dims = dims;
     for (int q = 0; q < 4; q++) w->fix[w->nfix].p[q] = p4 ? p4[q] : 0.0;
+    w->fix[w->nfix].hist = NULL; w->fix[w->nfix].samples = 0;
+    if (kind == FIX_RDF) w->fix[w->nfix].hist = calloc(dims > 0 ? dims : 1, sizeof(unsigned long long));   /* dims = nbin */
     return w->nfix++;
 }
-void orc_fix_clear(orc_world *w) { w->nfix = 0; }
+void orc_fix_clear(orc_world *w)
+{
+    for (int k = 0; k < w->nfix; k++) { free(w->fix[k].hist); w->fix[k].hist = NULL; }
+    w->nfix = 0;
+}
+
+/* gpu_calc_rdf, UM/fix_rdf_fast_meso.cu:102-150: p = {every, j_groupbit, rc}; fp32 on the packed coordinates over the stored
+ * neighbor table, bin = floorf(r * nbin / rc) with r = rsq * rsqrtf(rsq) (rsqrtf is approximate on the device: a distance
+ * within an ulp of a bin edge may land in the neighboring bin there) */
+static void rdf_sample(orc_world *w, int k)
+{
+    const int nbin = w->fix[k].dims, gi = w->fix[k].groupbit, gj = (int)w->fix[k].p[1];
+    const float rc = (float)w->fix[k].p[2], bin_sz_inv = (float)nbin / rc;
+    for (int ir = 0; ir < w->nranks; ir++) {
+        orc_rank *r = &w->rk[ir];
+        for (int i = 0; i < r->nlocal; i++) {
+            if (!(r->mask[i] & gi)) continue;
+            const float *c1 = r->coord4 + 4 * i;
+            const int *row = r->pair_rows + (size_t)i * r->n_col;
+            for (int q = 0; q < r->pair_count[i]; q++) {
+                int j = row[q];
+                if (!(r->mask[j] & gj)) continue;
+                const float *c2 = r->coord4 + 4 * j;
+                float dx = c1[0] - c2[0], dy = c1[1] - c2[1], dz = c1[2] - c2[2];
+                float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (rsq < rc * rc) {
+                    float rr = rsq * (1.0f / sqrtf(rsq));
+                    int bid = (int)floorf(rr * bin_sz_inv);
+                    if (bid >= 0 && bid < nbin) w->fix[k].hist[bid]++;
+                }
+            }
+        }
+    }
+    w->fix[k].samples++;
+}
+
+/* histogram[nbin] as doubles, samples, sizes of the two groups */
+int orc_fix_rdf_read(orc_world *w, int k, double *hist, double *samples, double *ni, double *nj)
+{
+    if (k < 0 || k >= w->nfix || w->fix[k].kind != FIX_RDF) FAIL("not an rdf fix");
+    for (int b = 0; b < w->fix[k].dims; b++) hist[b] = (double)w->fix[k].hist[b];
+    *samples = (double)w->fix[k].samples; *ni = 0; *nj = 0;
+    for (int ir = 0; ir < w->nranks; ir++)
+        for (int i = 0; i < w->rk[ir].nlocal; i++) {
+            if (w->rk[ir].mask[i] & w->fix[k].groupbit) *ni += 1;
+            if (w->rk[ir].mask[i] & (int)w->fix[k].p[1]) *nj += 1;
+        }
+    return 0;
+}
 void orc_set_integrate_group(orc_world *w, int groupbit) { w->integrate_groupbit = groupbit; }
 
 /* Rho5rc1s1::operator(), UM/fix_solid_bound_meso.h:42-56 (nvcc contracts every s*h + c of the Horner form into one fma) */
@@ -1226,6 +1277,10 @@ void orc_fix_post_force(orc_world *w, int only)
         if (only >= 0 && only != k) continue;
         const int kind = w->fix[k].kind, gb = w->fix[k].groupbit, dims = w->fix[k].dims;
         const double *p = w->fix[k].p;
+        if (kind == FIX_RDF) {                      /* MesoFixRDFFast::post_force, UM/fix_rdf_fast_meso.cu:152-180 */
+            if (w->ntimestep % (long)(p[0] < 1 ? 1 : p[0]) == 0) rdf_sample(w, k);
+            continue;
+        }
         for (int ir = 0; ir < w->nranks; ir++) {
             orc_rank *r = &w->rk[ir];
             for (int i = 0; i < r->nlocal; i++) {
@@ -1294,7 +1349,8 @@ int orc_world_setup(orc_world *w, int eflag, int vflag)
     orc_force_clear(w);
     orc_pair_compute(w, eflag, vflag);
     orc_bond_compute(w, eflag, vflag);
-    orc_fix_post_force(w, -1);                     /* modify->setup -> Fix::setup -> post_force (UM/fix_wall_meso.cu:66-72) */
+    for (int k = 0; k < w->nfix; k++)              /* modify->setup -> Fix::setup -> post_force (UM/fix_wall_meso.cu:66-72); */
+        if (w->fix[k].kind != FIX_RDF) orc_fix_post_force(w, k);   /* MesoFixRDFFast::setup is empty */
     return 0;
 }
 

@@ -97,6 +97,8 @@ double orc_bond_energy(orc_world *w);
  * 4 pois/meso {strength, bisect_frac} with dims = dim_ortho | dim_force << 2; wall kinds: dims bit a = walls across a.
  * UM/fix_wall_meso.cu, UM/fix_solid_bound_meso.{h,cu}, UM/fix_addforce_meso.cu, UM/fix_poiseuille_meso.cu */
 int  orc_fix_add(orc_world *w, int kind, int groupbit, int dims, const double *p4);
+/* kind 5 rdf/fast/meso: dims = nbin, p = {every, j_groupbit, rc} (UM/fix_rdf_fast_meso.cu:102-180) */
+int  orc_fix_rdf_read(orc_world *w, int k, double *hist, double *samples, double *ni, double *nj);
 void orc_fix_clear(orc_world *w);
 void orc_fix_post_force(orc_world *w, int only);   /* only < 0: every fix in registration order */
 void orc_fix_bounce(orc_world *w, int only);

@@ -212,3 +212,132 @@ def test_gpu_channel_fp32_flow_profile_and_grammar_errors():
             m.fix(*args)
     m.unfix_all()
     m.close()
+
+
+# ------------------------------------------------------------------------------------------------ rdf/fast/meso
+GOLD_EQ = None
+
+
+def gold_eq():
+    global GOLD_EQ
+    if GOLD_EQ is None:
+        import os
+        GOLD_EQ = np.load(os.path.join(os.path.dirname(__file__), "golden", "stock_dpd_equilibrium_L10.npz"))
+    return GOLD_EQ
+
+
+def g_of_r(hist, samples, ni, nj, volume, rc=1.0):
+    nbin = len(hist)
+    b = rc / nbin
+    i = np.arange(nbin)
+    return hist / ni / samples / (4.0 / 3.0 * 3.1415 * ((b * (i + 1)) ** 3 - (b * i) ** 3)) / (nj / volume)
+
+
+def test_oracle_rdf_histogram_equals_brute_force_and_group_selection():
+    Lb = 6
+    x = workload.dpd_fluid(Lb)
+    mask = np.where(np.arange(len(x)) % 4 == 0, 3, 1).astype(np.int32)
+    w = oracle.World((0, 0, 0), (Lb, Lb, Lb))
+    w.set_atoms(x, workload.maxwell_velocities(len(x)), mask=mask)
+    h_all = w.fix_rdf(40)
+    h_sub = w.fix_rdf(40, groupbit=2, other=1)
+    w.setup()
+    assert w.rdf(h_all)[1] == 0                      # MesoFixRDFFast::setup is empty: no sample at setup
+    w.fix_post_force()
+    d = x[:, None, :] - x[None, :, :]
+    d -= Lb * np.round(d / Lb)
+    r = np.sqrt((d * d).sum(-1))
+    np.fill_diagonal(r, 9.0)
+    bf = np.histogram(r[r < 1.0], bins=40, range=(0, 1))[0]
+    hist, s, ni, nj = w.rdf(h_all)
+    assert s == 1 and ni == nj == len(x) and hist.sum() == bf.sum() and np.abs(hist - bf).max() <= 2   # fp32 distances at bin edges
+    sub = (mask & 2) != 0
+    bf2 = np.histogram(r[sub][r[sub] < 1.0], bins=40, range=(0, 1))[0]
+    hist2, s2, ni2, nj2 = w.rdf(h_sub)
+    assert ni2 == sub.sum() and nj2 == len(x) and hist2.sum() == bf2.sum() and np.abs(hist2 - bf2).max() <= 2
+
+
+def test_oracle_equilibrium_matches_stock_lammps_statistically():
+    """north_star check (4) on the CPU side: <T>, <P> and g(r) of the MESO algorithm (its own TEA random stream) against
+    stock pair_style dpd (RanMars stream) -- fixture from tests/golden/make_lammps_rdf_golden.py."""
+    g = gold_eq()
+    Lb = int(g["L"])
+    x = workload.dpd_fluid(Lb)
+    w = oracle.World((0, 0, 0), (Lb, Lb, Lb), precision=0)
+    w.set_atoms(x, workload.maxwell_velocities(len(x)))
+    w.setup()
+    w.run(500)
+    h = w.fix_rdf(int(g["nbin"]), every=10)
+    ts, ps = [], []
+    for _ in range(10):
+        w.run(49)
+        w.run(1, eflag=1, vflag=1)
+        vir, _ = w.virial()
+        t = w.temperature()
+        ts.append(t)
+        ps.append(((3 * len(x) - 3) * t + vir[:, :3].sum()) / (3.0 * Lb ** 3))
+    hist, s, ni, nj = w.rdf(h)
+    assert s == 50
+    gr = g_of_r(hist, s, ni, nj, float(Lb) ** 3)
+    sel = g["r"] > 0.3
+    assert np.abs(gr[sel] - g["g"][sel]).max() < 0.05, np.abs(gr[sel] - g["g"][sel]).max()
+    assert abs(np.mean(ts) - g["temp"].mean()) < 0.02 and abs(np.mean(ps) - g["press"].mean()) < 0.5, (np.mean(ts), np.mean(ps))
+
+
+@pytest.mark.gpu
+def test_gpu_rdf_matches_oracle_and_samples_on_cadence():
+    m, w = gpu_pair("sp", ())
+    hg = m.fix("rdf/fast/meso", "output", "unused.txt", "nbin", 64, "every", 5)
+    hg2 = m.fix("rdf/fast/meso", "output", "unused2.txt", "nbin", 32, "other", 2, groupbit=2)
+    ho = w.fix_rdf(64, every=5)
+    ho2 = w.fix_rdf(32, groupbit=2, other=2)
+    m.setup(); w.setup()
+    m.fix_post_force(); w.fix_post_force()           # ntimestep 0: both cadences hit
+    vol = float(L) ** 3
+    for (a, b) in ((hg, ho), (hg2, ho2)):
+        r, gr, hist_g, s_g = m.rdf(a, vol)
+        hist_o, s_o, ni, nj = w.rdf(b)
+        assert s_g == s_o == 1 and hist_g.sum() == hist_o.sum() and np.abs(hist_g - hist_o).max() <= 2, np.abs(hist_g - hist_o).max()
+        assert np.allclose(gr, g_of_r(hist_o, s_o, ni, nj, vol) * hist_g / np.maximum(hist_o, 1), rtol=1e-12, atol=1e-12)
+    m.run(20)
+    assert m.rdf(hg, vol)[3] == 1 + 4 and m.rdf(hg2, vol)[3] == 1 + 20     # steps 5, 10, 15, 20 / every step
+    m.close()
+
+
+@pytest.mark.gpu
+def test_gpu_equilibrium_temperature_pressure_rdf_match_stock_lammps():
+    """north_star check (4): trajectory observables of the CUDA path (fp32 style, pair-once loop) against stock LAMMPS."""
+    from meso_b200.engine import dpd_fluid_deck
+    g = gold_eq()
+    Lb = int(g["L"])
+    m = dpd_fluid_deck(Lb, "sp")
+    h = m.fix("rdf/fast/meso", "output", "unused.txt", "nbin", int(g["nbin"]), "every", 10)
+    m.setup()
+    m.run(1000)
+    base = m.rdf(h, float(Lb) ** 3)
+    ts, ps = [], []
+    n = 4 * Lb ** 3
+    for _ in range(40):
+        m.run(49)
+        # one step with tallies through the phase entry points
+        m.ntimestep = m.ntimestep + 1
+        m.initial_integrate()
+        if m.neighbor_decide():
+            m.rebuild()
+        else:
+            m.forward_comm()
+        m.force_clear(vflag=1)
+        m.pair_compute(eflag=1, vflag=1)
+        m.fix_post_force()
+        m.final_integrate()
+        vir, _ = m.virial()
+        t = m.temperature()
+        ts.append(t)
+        ps.append(((3 * n - 3) * t + vir[:3].sum()) / (3.0 * Lb ** 3))
+    r, gr, hist, s = m.rdf(h, float(Lb) ** 3)
+    hist, s = hist - base[2], s - base[3]
+    gr = g_of_r(hist, s, n, n, float(Lb) ** 3)
+    sel = g["r"] > 0.3
+    assert s == 200 and np.abs(gr[sel] - g["g"][sel]).max() < 0.03, np.abs(gr[sel] - g["g"][sel]).max()
+    assert abs(np.mean(ts) - g["temp"].mean()) < 0.01 and abs(np.mean(ps) - g["press"].mean()) < 0.25, (np.mean(ts), np.mean(ps))
+    m.close()

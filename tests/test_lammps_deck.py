@@ -210,6 +210,7 @@ fix             3 all nve/meso
 fix             4 all wall/meso z d 0.5 f 20.0
 fix             5 all pois/meso z x 0.3
 fix             6 all addforce/meso 0.0 0.1 0.0
+fix             7 all rdf/fast/meso output rdf.txt nbin 40 every 5
 thermo_style    custom step temp {extra} cpu
 thermo          10
 thermo_modify   temp mythermo
@@ -253,6 +254,7 @@ def test_channel_deck_with_device_resident_fixes(tmp_path, monkeypatch):
     m.fix("wall/meso", "z", "d", 0.5, "f", 20.0)
     m.fix("pois/meso", "z", "x", 0.3)
     m.fix("addforce/meso", 0.0, 0.1, 0.0)
+    hr = m.fix("rdf/fast/meso", "output", str(tmp_path / "rdf_mirror.txt"), "nbin", 40, "every", 5)
     m.setup()
     a = m.download()
     o = np.argsort(a["tag"])
@@ -263,8 +265,14 @@ def test_channel_deck_with_device_resident_fixes(tmp_path, monkeypatch):
     assert np.array_equal(a["x"][o], fr[steps][:, 1:4]) and np.array_equal(a["v"][o], fr[steps][:, 4:7])
     assert np.array_equal(a["f"][o], fr[steps][:, 7:10])
     assert a["x"][:, 2].min() > 0 and a["x"][:, 2].max() < L
+    # rdf/fast/meso: g(r) written when LAMMPS destroys the fix == the mirror's dump of the same four samples (steps 5..20)
+    m.rdf_dump(hr, float(L) ** 3)
+    assert m.rdf(hr, float(L) ** 3)[3] == 4
+    g_lmp, g_mir = np.loadtxt(str(tmp_path / "fused" / "rdf.txt")), np.loadtxt(str(tmp_path / "rdf_mirror.txt"))
+    assert g_lmp.shape == (40, 2) and np.allclose(g_lmp, g_mir, rtol=1e-12, atol=0) and g_lmp[:, 1].max() > 0.5
     m.close()
     fr2, out2 = run("pe press", "phases")
+    assert np.allclose(np.loadtxt(str(tmp_path / "phases" / "rdf.txt")), g_lmp, rtol=1e-12)   # sampled through Fix::post_force here
     assert np.abs(fr2[steps][:, 1:7] - fr[steps][:, 1:7]).max() < 1e-9
 
 
