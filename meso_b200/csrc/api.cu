@@ -113,6 +113,7 @@ extern "C" int meso_create(meso_ctx **out, int device)
     const char *po = getenv("MESO_PAIR_ONCE");               // 0: two-sided force kernel in meso_run (A/B measurements)
     ctx->pair_once = !(po && po[0] == '0');
     if (const char *e = getenv("MESO_PAIR_TEX")) ctx->pair_tex = atoi(e) & 3;
+    if (const char *e = getenv("MESO_HALO_ROUTES")) ctx->halo_routes = e[0] != '0';
     if (const char *e = getenv("MESO_NB_PER_ATOM")) ctx->nb_per_atom = e[0] == '1';
     cudaMemsetAsync(ctx->d_counts, 0, sizeof(Counts), ctx->stream);
     memset(ctx->h_counts, 0, sizeof(Counts));
@@ -212,6 +213,7 @@ static void update_subbox(meso_ctx *ctx)
 
 extern "C" int meso_set_box(meso_ctx *ctx, const double boxlo[3], const double boxhi[3], const int periodic[3])
 {
+    if (ctx) ctx->npeers = 0;
     CHECK_CTX();
     for (int d = 0; d < 3; d++) {
         if (!(boxhi[d] > boxlo[d])) FAIL(MESO_EINVAL, "meso_set_box: boxhi must exceed boxlo");
@@ -225,6 +227,7 @@ extern "C" int meso_set_box(meso_ctx *ctx, const double boxlo[3], const double b
 
 extern "C" int meso_set_decomposition(meso_ctx *ctx, int rank, const int procgrid[3], const void *nccl_id)
 {
+    if (ctx) ctx->npeers = 0;
     CHECK_CTX();
     int n = procgrid[0] * procgrid[1] * procgrid[2];
     if (n < 1 || rank < 0 || rank >= n) FAIL(MESO_EINVAL, "meso_set_decomposition: bad rank/procgrid");

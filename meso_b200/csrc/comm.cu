@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstring>
+#include <vector>
 
 namespace meso {
 
@@ -35,7 +36,8 @@ namespace meso {
 struct SoA3 { double *c[3]; };
 static inline SoA3 soa(DevBuf<double> *b) { SoA3 s; for (int d = 0; d < 3; d++) s.c[d] = b[d].p; return s; }
 
-constexpr int REC = 8;            // doubles per record (64 B); record 0 of every message is the header {count}
+constexpr int REC = 8;            // doubles per migration record (64 B); record 0 of every message is the header {count}
+constexpr int RECB = 9;           // doubles per border record: + {owner rank | shift code << 24, owner's local index}
 constexpr int CT = 256;           // threads
 constexpr int CI = 4;             // items per thread
 constexpr int CTILE = CT * CI;
@@ -180,10 +182,11 @@ __global__ void __launch_bounds__(CT) k_mr_border_pack(SoA3 x, SoA3 v, const int
                                                        const Counts *__restrict__ cnt, const int2 *__restrict__ tile_counts,
                                                        double *__restrict__ send_lo, double *__restrict__ send_hi,
                                                        int *__restrict__ list_lo, int *__restrict__ list_hi, Box box, int d, int ntiles,
-                                                       int swap_cap)
+                                                       int swap_cap, const int2 *__restrict__ ghost_origin, int my_rank)
 {
     __shared__ int2 wsum[CT / 32];
-    const int first = cnt->n_bulk, last = cnt->nlocal + cnt->nghost;
+    const int nlocal = cnt->nlocal;
+    const int first = cnt->n_bulk, last = nlocal + cnt->nghost;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -219,7 +222,12 @@ __global__ void __launch_bounds__(CT) k_mr_border_pack(SoA3 x, SoA3 v, const int
                 const int pbc = box.pbc[2 * d + side];
                 double xg[3] = {xi[0], xi[1], xi[2]};
                 if (pbc) xg[d] = pbc > 0 ? xi[d] + box.prd[d] : xi[d] - box.prd[d];   // x + pbc*prd
-                double *rec = (side ? send_hi : send_lo) + (size_t)(k + 1) * REC;
+                double *rec = (side ? send_hi : send_lo) + (size_t)(k + 1) * RECB;
+                // owner of this image: a local atom is its own, a forwarded ghost keeps the owner it arrived with;
+                // shift code 2 bits per dimension (1 = +prd, 2 = -prd), accumulated over the swaps it went through
+                int2 org = (i < nlocal) ? make_int2(my_rank, i) : ghost_origin[i - nlocal];
+                if (pbc) org.x |= (pbc > 0 ? 1 : 2) << (24 + 2 * d);
+                reinterpret_cast<int2 *>(rec)[8] = org;
                 rec[0] = xg[0]; rec[1] = xg[1]; rec[2] = xg[2];
                 rec[3] = v.c[0][i]; rec[4] = v.c[1][i]; rec[5] = v.c[2][i];
                 reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
@@ -247,12 +255,14 @@ __global__ void k_mr_border_advance(Counts *cnt, const double *recv_a, const dou
 __global__ void __launch_bounds__(256) k_mr_border_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
                                                           float4 *__restrict__ coord4, float4 *__restrict__ veloc4,
                                                           const Counts *__restrict__ cnt, const double *__restrict__ recv_a,
-                                                          const double *__restrict__ recv_b, Box box, int d)
+                                                          const double *__restrict__ recv_b, Box box, int d, int2 *__restrict__ ghost_origin)
 {
     const int na = cnt->swap_n[2 * d], n = na + cnt->swap_n[2 * d + 1], g0 = cnt->swap_first[2 * d];
+    const int nlocal = cnt->nlocal;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const double *rec = (k < na) ? recv_a + (size_t)(k + 1) * REC : recv_b + (size_t)(k - na + 1) * REC;
+        const double *rec = (k < na) ? recv_a + (size_t)(k + 1) * RECB : recv_b + (size_t)(k - na + 1) * RECB;
         const int g = g0 + k;
+        ghost_origin[g - nlocal] = reinterpret_cast<const int2 *>(rec)[8];
         const double xx = rec[0], yy = rec[1], zz = rec[2], vx = rec[3], vy = rec[4], vz = rec[5];
         const int2 tt = reinterpret_cast<const int2 *>(rec)[6], ms = reinterpret_cast<const int2 *>(rec)[7];
         x.c[0][g] = xx; x.c[1][g] = yy; x.c[2][g] = zz;
@@ -505,12 +515,12 @@ static int ensure_comm_buffers(meso_ctx *ctx)
     if (swap_cap <= ctx->swap_cap && exch_cap <= ctx->exch_cap) return MESO_OK;
     ctx->swap_cap = std::max(ctx->swap_cap, swap_cap);
     ctx->exch_cap = std::max(ctx->exch_cap, exch_cap);
-    const size_t msg = (size_t)(std::max(ctx->swap_cap, ctx->exch_cap) + 1) * REC;
+    const size_t msg = (size_t)(std::max(ctx->swap_cap, ctx->exch_cap) + 1) * RECB;
     bool ok = true;
     for (int s = 0; s < 2; s++) ok = ok && ctx->send_buf[s].reserve(msg) && ctx->recv_buf[s].reserve(msg);
     for (int s = 0; s < 6; s++) ok = ok && ctx->sendlist[s].reserve((size_t)ctx->swap_cap);
     const size_t ntiles = (ctx->cap + CTILE - 1) / CTILE;
-    ok = ok && ctx->tile_counts.reserve(ntiles * 2 + 16);
+    ok = ok && ctx->tile_counts.reserve(ntiles * 2 + 16) && ctx->ghost_origin.reserve(ctx->cap);
     if (!ok) { ctx->err = "out of device memory (halo buffers)"; return MESO_ECUDA; }
     return MESO_OK;
 }
@@ -594,6 +604,235 @@ int launch_exchange_multi(meso_ctx *ctx)
     return MESO_OK;
 }
 
+// ------------------------------------------------------------------ direct halo routes
+// The 3-phase creation above fixes WHICH images a rank holds and in WHAT order; it also forwards ghosts of earlier
+// dimensions, which makes the per-step refresh of the reference three dependent messages.  Every ghost record carries its
+// owner, so after the creation each rank groups its ghosts by owner rank, sends every owner the list {index, shift} it wants
+// refreshed (one message per peer, once per rebuild), and from then on a step's refresh is ONE pack kernel, ONE NCCL group
+// (a message per peer, exact size) and ONE unpack kernel.  Values are bit-identical to the forwarded ones: each coordinate is
+// shifted by at most one period, and the packed velocity/signature is copied.
+struct RouteTable {
+    int np, self;
+    const int2 *slist[27];      // what peer s asked me to send: [0] = {count, 0}, then {index, shift code}
+    const int *dst[27];         // ghost slot (0-based behind nlocal) of the k-th record peer s sends me
+    double *sbuf[27];           // staging of the records for peer s
+    const double *rbuf[27];     // records received from peer s (self: my own staging buffer)
+};
+
+__global__ void __launch_bounds__(256) k_route_build(const int2 *__restrict__ ghost_origin, const int *__restrict__ peer_slot, Counts *cnt,
+                                                     RouteTable rt, int2 *const *req, int *const *dst, int route_cap, int nranks)
+{
+    const int ng = cnt->nghost;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    // whole warps iterate together; the lanes that want the same peer share ONE atomic (a handful of counters would
+    // otherwise serialise ~10^5 same-address atomics)
+    for (int g0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; g0 < ng; g0 += gridDim.x * blockDim.x) {
+        const int g = g0 + lane;
+        int s = -1;
+        int2 o = make_int2(0, 0);
+        if (g < ng) {
+            o = ghost_origin[g];
+            const int r = o.x & 0xffffff;
+            s = (r >= 0 && r < nranks) ? peer_slot[r] : -1;
+            if (s < 0) atomicOr(&cnt->err, 1);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, s);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader && s >= 0) base = atomicAdd(&cnt->route_recv_n[s], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (s < 0) continue;
+        const int k = base + __popc(peers & lt);
+        if (k >= route_cap) { atomicOr(&cnt->err, 1); continue; }
+        req[s][k + 1] = make_int2(o.y, (o.x >> 24) & 63);
+        dst[s][k] = g;
+    }
+}
+
+__global__ void k_route_reset(Counts *cnt)
+{
+    if (threadIdx.x < 27) { cnt->route_recv_n[threadIdx.x] = 0; cnt->route_send_n[threadIdx.x] = 0; }
+}
+
+__global__ void k_route_headers(Counts *cnt, int2 *const *req, int np, int route_cap)
+{
+    const int s = threadIdx.x;
+    if (s < np) {
+        const int n = min(cnt->route_recv_n[s], route_cap);
+        cnt->route_recv_n[s] = n;
+        req[s][0] = make_int2(n, 0);
+    }
+}
+
+__global__ void k_route_adopt(Counts *cnt, RouteTable rt, int route_cap)
+{
+    const int s = threadIdx.x;
+    if (s < rt.np) {
+        int n = rt.slist[s][0].x;
+        if (n < 0 || n > route_cap) { atomicOr(&cnt->err, 1); n = 0; }
+        cnt->route_send_n[s] = n;
+    }
+}
+
+// records: {x + shift (3 x fp64), veloc4 = fp32 v + this step's signature} = 40 bytes, as in the forwarding refresh
+__global__ void __launch_bounds__(256) k_route_pack(SoA3 x, const float4 *__restrict__ veloc4, const Counts *__restrict__ cnt, RouteTable rt,
+                                                    Box box)
+{
+    const int s = blockIdx.y;
+    const int n = cnt->route_send_n[s];
+    const int2 *list = rt.slist[s] + 1;
+    double *buf = rt.sbuf[s];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int2 e = list[k];
+        const int i = e.x;
+        double xg[3] = {x.c[0][i], x.c[1][i], x.c[2][i]};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const int c = (e.y >> (2 * d)) & 3;
+            if (c) xg[d] = c == 1 ? xg[d] + box.prd[d] : xg[d] - box.prd[d];
+        }
+        double *rec = buf + (size_t)k * RECF;
+        rec[0] = xg[0]; rec[1] = xg[1]; rec[2] = xg[2];
+        const float4 w = veloc4[i];
+        reinterpret_cast<float2 *>(rec)[3] = make_float2(w.x, w.y);
+        reinterpret_cast<float2 *>(rec)[4] = make_float2(w.z, w.w);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_route_unpack(SoA3 x, SoA3 v, const int *__restrict__ type, float4 *__restrict__ coord4,
+                                                      float4 *__restrict__ veloc4, const Counts *__restrict__ cnt, RouteTable rt, Box box)
+{
+    const int s = blockIdx.y;
+    const int n = cnt->route_recv_n[s], nlocal = cnt->nlocal;
+    const int *dst = rt.dst[s];
+    const double *buf = rt.rbuf[s];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double *rec = buf + (size_t)k * RECF;
+        const int g = nlocal + dst[k];
+        const double xx = rec[0], yy = rec[1], zz = rec[2];
+        const float2 w01 = reinterpret_cast<const float2 *>(rec)[3], w23 = reinterpret_cast<const float2 *>(rec)[4];
+        x.c[0][g] = xx; x.c[1][g] = yy; x.c[2][g] = zz;
+        v.c[0][g] = (double)w01.x; v.c[1][g] = (double)w01.y; v.c[2][g] = (double)w23.x;
+        float4 c;
+        c.x = (float)(xx - box.centre[0]); c.y = (float)(yy - box.centre[1]); c.z = (float)(zz - box.centre[2]);
+        c.w = __int_as_float(type[g] - 1);
+        coord4[g] = c; veloc4[g] = make_float4(w01.x, w01.y, w23.x, w23.y);
+    }
+}
+
+// distinct ranks among this brick's 26 neighbors, plus itself (slot peer_self)
+int comm_build_peers(meso_ctx *ctx)
+{
+    const Box &b = ctx->box;
+    ctx->npeers = 0;
+    std::vector<int> slot((size_t)ctx->nranks, -1);
+    auto add = [&](int r) {
+        if (slot[r] >= 0) return;
+        slot[r] = ctx->npeers;
+        ctx->peer_rank[ctx->npeers++] = r;
+    };
+    add(ctx->rank);
+    ctx->peer_self = 0;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                int off[3] = {dx, dy, dz}, loc[3];
+                bool ok = true;
+                for (int d = 0; d < 3; d++) {
+                    loc[d] = ctx->myloc[d] + off[d];
+                    if (loc[d] < 0 || loc[d] >= ctx->procgrid[d]) {
+                        if (!b.periodic[d]) { ok = false; break; }
+                        loc[d] = (loc[d] + ctx->procgrid[d]) % ctx->procgrid[d];
+                    }
+                }
+                if (ok) add((loc[0] * ctx->procgrid[1] + loc[1]) * ctx->procgrid[2] + loc[2]);
+            }
+    if (!ctx->peer_slot.reserve((size_t)ctx->nranks)) { ctx->err = "out of device memory"; return MESO_ECUDA; }
+    MESO_CUDA(cudaMemcpyAsync(ctx->peer_slot.p, slot.data(), sizeof(int) * ctx->nranks, cudaMemcpyHostToDevice, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MESO_OK;
+}
+
+static int route_table(meso_ctx *ctx, RouteTable &rt)
+{
+    rt.np = ctx->npeers; rt.self = ctx->peer_self;
+    for (int s = 0; s < 27; s++) { rt.slist[s] = nullptr; rt.dst[s] = nullptr; rt.sbuf[s] = nullptr; rt.rbuf[s] = nullptr; }
+    for (int s = 0; s < ctx->npeers; s++) {
+        const bool self = s == ctx->peer_self;
+        rt.slist[s] = self ? ctx->route_req[s].p : ctx->route_send_list[s].p;     // my own requests are my own send list
+        rt.dst[s] = ctx->route_dst[s].p;
+        rt.sbuf[s] = ctx->route_sbuf[s].p;
+        rt.rbuf[s] = self ? ctx->route_sbuf[s].p : ctx->route_rbuf[s].p;
+    }
+    return MESO_OK;
+}
+
+// after the ghosts exist: group them by owner, exchange the request lists (once per rebuild)
+static int build_routes(meso_ctx *ctx)
+{
+    if (ctx->npeers == 0) { int rc = comm_build_peers(ctx); if (rc) return rc; }
+    const int np = ctx->npeers;
+    ctx->route_cap = 6 * ctx->swap_cap;           // a peer (or this rank itself, through periodic images) can own the ghosts of all six swaps
+    bool ok = true;
+    for (int s = 0; s < np; s++) {
+        ok = ok && ctx->route_req[s].reserve((size_t)ctx->route_cap + 1) && ctx->route_dst[s].reserve((size_t)ctx->route_cap) &&
+             ctx->route_sbuf[s].reserve((size_t)ctx->route_cap * RECF);
+        if (s != ctx->peer_self) ok = ok && ctx->route_send_list[s].reserve((size_t)ctx->route_cap + 1) && ctx->route_rbuf[s].reserve((size_t)ctx->route_cap * RECF);
+    }
+    // device-side pointer tables for the build kernel
+    ok = ok && ctx->route_ptrs.reserve(64);
+    if (!ok) { ctx->err = "out of device memory (halo routes)"; return MESO_ECUDA; }
+    void *hp[54];
+    for (int s = 0; s < 27; s++) { hp[s] = s < np ? (void *)ctx->route_req[s].p : nullptr; hp[27 + s] = s < np ? (void *)ctx->route_dst[s].p : nullptr; }
+    cudaStream_t st = ctx->stream;
+    MESO_CUDA(cudaMemcpyAsync(ctx->route_ptrs.p, hp, sizeof hp, cudaMemcpyHostToDevice, st));
+    RouteTable rt;
+    route_table(ctx, rt);
+    int2 *const *req = reinterpret_cast<int2 *const *>(ctx->route_ptrs.p);
+    int *const *dst = reinterpret_cast<int *const *>(ctx->route_ptrs.p + 27);
+    k_route_reset<<<1, 32, 0, st>>>(ctx->d_counts);
+    k_route_build<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->ghost_origin.p, ctx->peer_slot.p, ctx->d_counts, rt, req, dst, ctx->route_cap, ctx->nranks);
+    k_route_headers<<<1, 32, 0, st>>>(ctx->d_counts, req, np, ctx->route_cap);
+    if (np > 1) {
+        ncclComm_t comm = (ncclComm_t)ctx->nccl;
+        const size_t nint = ((size_t)ctx->route_cap + 1) * 2;
+        MESO_NCCL(ncclGroupStart());
+        for (int s = 0; s < np; s++) {
+            if (s == ctx->peer_self) continue;
+            MESO_NCCL(ncclSend(ctx->route_req[s].p, nint, ncclInt, ctx->peer_rank[s], comm, st));
+            MESO_NCCL(ncclRecv(ctx->route_send_list[s].p, nint, ncclInt, ctx->peer_rank[s], comm, st));
+        }
+        MESO_NCCL(ncclGroupEnd());
+    }
+    k_route_adopt<<<1, 32, 0, st>>>(ctx->d_counts, rt, ctx->route_cap);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+// per-step ghost refresh over the routes, on stream `st`
+static int forward_routes(meso_ctx *ctx, cudaStream_t st)
+{
+    const int np = ctx->npeers;
+    RouteTable rt;
+    route_table(ctx, rt);
+    const dim3 grid(ctx->sm_count, np);
+    k_route_pack<<<grid, 256, 0, st>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, rt, ctx->box);
+    if (np > 1) {
+        ncclComm_t comm = (ncclComm_t)ctx->nccl;
+        MESO_NCCL(ncclGroupStart());
+        for (int s = 0; s < np; s++) {
+            if (s == ctx->peer_self) continue;
+            if (ctx->route_send_n[s]) MESO_NCCL(ncclSend(ctx->route_sbuf[s].p, (size_t)ctx->route_send_n[s] * RECF, ncclDouble, ctx->peer_rank[s], comm, st));
+            if (ctx->route_recv_n[s]) MESO_NCCL(ncclRecv(ctx->route_rbuf[s].p, (size_t)ctx->route_recv_n[s] * RECF, ncclDouble, ctx->peer_rank[s], comm, st));
+        }
+        MESO_NCCL(ncclGroupEnd());
+    }
+    k_route_unpack<<<grid, 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts, rt, ctx->box);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
 __global__ void k_mr_reset_ghosts(Counts *cnt)
 {
     cnt->nghost = 0;
@@ -606,6 +845,7 @@ int launch_borders_multi(meso_ctx *ctx)
 {
     int rc = ensure_comm_buffers(ctx);
     if (rc) return rc;
+    if (!ctx->ghost_origin.reserve(ctx->cap)) { ctx->err = "out of device memory (ghost owners)"; return MESO_ECUDA; }
     const Box &box = ctx->box;
     const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
     int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
@@ -617,16 +857,16 @@ int launch_borders_multi(meso_ctx *ctx)
         k_mr_border_scan<<<1, 1024, 0, st>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, d, ctx->swap_cap);
         k_mr_border_pack<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->veloc4.p,
                                                         ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->sendlist[2 * d].p,
-                                                        ctx->sendlist[2 * d + 1].p, box, d, ntiles, ctx->swap_cap);
+                                                        ctx->sendlist[2 * d + 1].p, box, d, ntiles, ctx->swap_cap, ctx->ghost_origin.p, ctx->rank);
         const double *ra, *rb;
-        rc = swap_messages(ctx, d, (size_t)(ctx->swap_cap + 1) * REC, st, ra, rb);
+        rc = swap_messages(ctx, d, (size_t)(ctx->swap_cap + 1) * RECB, st, ra, rb);
         if (rc) return rc;
         k_mr_border_advance<<<1, 1, 0, st>>>(ctx->d_counts, ra, rb, d, (int)ctx->cap);
         k_mr_border_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->coord4.p,
-                                                          ctx->veloc4.p, ctx->d_counts, ra, rb, box, d);
+                                                          ctx->veloc4.p, ctx->d_counts, ra, rb, box, d, ctx->ghost_origin.p);
     }
     MESO_CUDA(cudaGetLastError());
-    return MESO_OK;
+    return ctx->halo_routes ? build_routes(ctx) : MESO_OK;
 }
 
 int comm_share_errors(meso_ctx *ctx)
@@ -653,8 +893,10 @@ int launch_forward_multi(meso_ctx *ctx, cudaStream_t st)
             return MESO_ECAPACITY;
         }
         for (int s = 0; s < 6; s++) { ctx->fwd_send_n[s] = ctx->h_counts->send_n[s]; ctx->fwd_recv_n[s] = ctx->h_counts->swap_n[s]; }
+        for (int s = 0; s < 27; s++) { ctx->route_send_n[s] = ctx->h_counts->route_send_n[s]; ctx->route_recv_n[s] = ctx->h_counts->route_recv_n[s]; }
         ctx->fwd_counts_valid = true;
     }
+    if (ctx->halo_routes) return forward_routes(ctx, st);
     for (int d = 0; d < 3; d++) {
         if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1] && ctx->procgrid[d] == 1) continue;
         k_mr_forward_pack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, ctx->sendlist[2 * d].p,

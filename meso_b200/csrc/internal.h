@@ -27,6 +27,8 @@ struct Counts {
     int send_n[6];                  // atoms this rank sends in each border swap (== swap_n on a self-partnered swap)
     int exch_n[2];                  // migration: leavers to the lower / upper neighbor in the current dimension
     int err_any;                    // max of `err` over all ranks at the last rebuild (multi-rank: every rank fails together)
+    // direct halo routes (comm.cu): per peer slot, how many refresh records this rank sends / receives every step
+    int route_send_n[27], route_recv_n[27];
 };
 
 struct Box {
@@ -154,6 +156,19 @@ struct meso_ctx {
     bool comm_path = false;                   // use the message-based border/forward path (always when nranks > 1)
     int swap_cap = 0, exch_cap = 0;           // records per halo / migration message
     bool comm_caps_agreed = false;            // capacities were max-reduced over the ranks since the last upload
+    // direct halo routes: every ghost remembers its owner (rank, index, accumulated periodic shift); after the 3-phase ghost
+    // creation the ranks exchange request lists once, and the per-step refresh is ONE message per peer instead of three
+    // dependent swaps (the forwarding of earlier ghosts in later dimensions is resolved at the rebuild, not every step)
+    bool halo_routes = true;                  // MESO_HALO_ROUTES=0: per-step refresh by the 3 forwarding swaps
+    int npeers = 0, peer_self = 0, peer_rank[27] = {0};
+    int route_cap = 0;
+    meso::DevBuf<int> peer_slot;              // rank -> peer slot (or -1)
+    meso::DevBuf<int2> ghost_origin;          // per ghost: {owner rank | shift code << 24, owner's local index}
+    meso::DevBuf<int2> route_req[27], route_send_list[27];   // [0] = {count, 0}, then {index, shift code}
+    meso::DevBuf<int> route_dst[27];          // ghost slot of the k-th record received from the peer
+    meso::DevBuf<double> route_sbuf[27], route_rbuf[27];
+    meso::DevBuf<void *> route_ptrs;          // device copy of the request / slot pointer tables
+    int route_send_n[27] = {0}, route_recv_n[27] = {0};
     size_t nloc_cap = 0;                      // capacity for local atoms
     meso::DevBuf<double> send_buf[2], recv_buf[2], reduce_buf;
     meso::DevBuf<int> sendlist[6];
@@ -219,6 +234,7 @@ int launch_forward(meso_ctx *ctx, bool full);     // per-step ghost refresh
 int launch_exchange_multi(meso_ctx *ctx);
 int launch_borders_multi(meso_ctx *ctx);
 int launch_forward_multi(meso_ctx *ctx, cudaStream_t st);
+int comm_build_peers(meso_ctx *ctx);
 int comm_share_errors(meso_ctx *ctx);   // Counts::err_any = max over ranks of Counts::err (stream-ordered, no host sync)
 // ---- neighbor.cu
 int launch_setup_bins(meso_ctx *ctx);
