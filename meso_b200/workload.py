@@ -155,3 +155,31 @@ def polymer_melt(L, chain_len=8, rho=4, bond_len=0.7, seed=20140902, solvent_fra
                 bond_atom[a, num_bond[a]] = tag[o]
                 num_bond[a] += 1
     return x, typ, tag, num_bond, bond_type, bond_atom
+
+
+def amphiphilic_channel(L, chain_len=8, rho=4, bond_len=0.7, seed=20140903, solvent_frac=0.6, margin=0.3):
+    """BASELINE configs[4] flavour: amphiphilic bead-spring chains (first half of a chain hydrophilic = type 2, second half
+    hydrophobic = type 3) in solvent (type 1) between two walls across z (periodic in x, y).  Chains are random walks
+    folded back at z = margin and z = L - margin, so no bond crosses a wall.  Returns x, type, tag, num_bond, bond_type,
+    bond_atom like polymer_melt (per-atom tables, both partners hold each bond)."""
+    x, typ, tag, num_bond, bond_type, bond_atom = polymer_melt(L, chain_len, rho, bond_len, seed, solvent_frac)
+    rng = np.random.default_rng(seed + 1)
+    n = len(x)
+    nchain = int(n * (1.0 - solvent_frac)) // chain_len
+    nsolv = n - nchain * chain_len
+    start = rng.random((nchain, 3)) * np.array([L, L, L - 2 * margin]) + np.array([0.0, 0.0, margin])
+    steps = rng.normal(size=(nchain, chain_len - 1, 3))
+    steps *= bond_len / np.linalg.norm(steps, axis=2, keepdims=True)
+    walk = np.concatenate([start[:, None, :], start[:, None, :] + np.cumsum(steps, axis=1)], axis=1).reshape(-1, 3)
+    z = walk[:, 2] - margin
+    span = L - 2 * margin
+    z = np.abs(np.mod(z + span, 2 * span) - span)          # triangle wave: fold into [0, span]
+    walk[:, 2] = z + margin
+    walk[:, :2] = np.mod(walk[:, :2], L)
+    x[nsolv:] = walk
+    x[:nsolv, 2] = margin + x[:nsolv, 2] * (span / L)     # solvent: squeeze into the channel
+    x = np.round(x, 9)
+    x[:, :2][x[:, :2] >= L] = 0.0
+    pos = (np.arange(n - nsolv) % chain_len)
+    typ[nsolv:] = np.where(pos < chain_len // 2, 2, 3)
+    return np.ascontiguousarray(x), typ, tag, num_bond, bond_type, bond_atom

@@ -341,3 +341,75 @@ def test_gpu_equilibrium_temperature_pressure_rdf_match_stock_lammps():
     assert s == 200 and np.abs(gr[sel] - g["g"][sel]).max() < 0.03, np.abs(gr[sel] - g["g"][sel]).max()
     assert abs(np.mean(ts) - g["temp"].mean()) < 0.01 and abs(np.mean(ps) - g["press"].mean()) < 0.25, (np.mean(ts), np.mean(ps))
     m.close()
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs[4]
+# amphiphilic bead-spring chains in a driven channel: bonds + 1-2 exclusions + three atom types + walls + body force together
+AMPHI_COEFF = {(1, 1): 25.0, (2, 2): 25.0, (3, 3): 25.0, (1, 2): 27.0, (1, 3): 40.0, (2, 3): 40.0}
+
+
+def amphi_worlds(precision, gpu):
+    Lc = 8
+    x, typ, tag, nb, bt, ba = workload.amphiphilic_channel(Lc)
+    v = workload.maxwell_velocities(len(x), seed=99)
+    coeff = np.zeros((3, 3, 7))
+    for (a, b), a0 in AMPHI_COEFF.items():
+        coeff[a - 1, b - 1] = coeff[b - 1, a - 1] = [1.0, 1.0, 1.0, 1.0, a0, 4.5, 3.0]
+    w = oracle.World((0, 0, 0), (Lc, Lc, Lc), periodic=(1, 1, 0), ntypes=3, mass=[0, 1, 1, 1], coeff=coeff.reshape(-1, 7), precision=precision)
+    w.set_atoms(x, v, tag=tag, type=typ)
+    w.set_bonds(nb, bt, ba, tag=tag, k=[0.0, 50.0], r0=[0.0, 0.5], special_lj12=0.0)
+    w.fix_solid_bound("z"); w.fix_pois(2, 0, 0.2)
+    m = None
+    if gpu:
+        from meso_b200.engine import Meso
+        m = Meso(0)
+        m.box((0.0, 0.0, 0.0), (Lc, Lc, Lc), (1, 1, 0))
+        m.masses([0.0, 1.0, 1.0, 1.0])
+        m.neighbor(0.3, "bin")
+        m.neigh_modify(delay=0, every=5, check=False)
+        m.pair_style("dpd/fast/meso" if precision == 0 else "dpd/meso", 1.0, 419084618)
+        for (a, b), a0 in AMPHI_COEFF.items():
+            m.pair_coeff(a, b, a0, 4.5, 3.0, 1.0, 1.0)
+        m.timestep(0.005)
+        m.upload(x, v, tag=tag, type=typ)
+        m.bond_style("harmonic/meso", 1)
+        m.bond_coeff(1, 50.0, 0.5)
+        m.special_bonds(0.0)
+        m.bonds(nb, bt, ba)
+        m.fix("solid_bound/meso", "z", "rho5rc1s1"); m.fix("pois/meso", "z", "x", 0.2)
+    return m, w, Lc, len(x)
+
+
+def test_oracle_amphiphilic_channel_is_stable():
+    _, w, Lc, n = amphi_worlds(0, gpu=False)
+    w.setup()
+    w.run(60)
+    a = w.atoms()
+    assert a["nlocal"] == n and a["x"][:n, 2].min() > 0 and a["x"][:n, 2].max() < Lc
+    assert 0.7 < w.temperature() < 4.5                   # the random start releases conservative energy; the thermostat needs ~400 steps
+    w.bond_compute(1, 0)
+    assert w.bond_energy() < 50.0 * 0.04 * 714            # relaxing from the stretched start (714 bonds at r - r0 = 0.2)
+
+
+@pytest.mark.gpu
+def test_gpu_amphiphilic_channel_fp64_lockstep_and_fp32_run():
+    m, w, Lc, n = amphi_worlds(1, gpu=True)
+    m.setup(); w.setup()
+    m.run(12); w.run(12)
+    ag, ao = m.download(), w.atoms()
+    assert np.array_equal(ag["tag"], ao["tag"][:n])
+    assert np.abs(ag["x"] - ao["x"][:n]).max() < 1e-9 and np.abs(ag["v"] - ao["v"][:n]).max() < 1e-9
+    assert rel_err(ag["f"], ao["f"][:n]) < 1e-9
+    cg, rg = m.neighbors()
+    co, ro = w.neighbors()
+    msk = np.arange(ro.shape[1])[None, :] < co[:, None]
+    assert np.array_equal(cg, co) and np.array_equal(rg[msk], ro[msk])       # exclusion-filtered rows after two rebuilds
+    m.close()
+    m, _, _, _ = amphi_worlds(0, gpu=True)
+    m.setup()
+    m.run(600)
+    a = m.download(("x", "v"))
+    assert a["x"][:, 2].min() > 0 and a["x"][:, 2].max() < Lc and 0.7 < m.temperature() < 1.5
+    z, vx = a["x"][:, 2], a["v"][:, 0]
+    assert vx[z < 0.5 * Lc].mean() > 0.02 and vx[z >= 0.5 * Lc].mean() < -0.02
+    m.close()

@@ -361,6 +361,31 @@ def test_polymer_deck_dpd_bond_meso_and_harmonic_meso(tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_restart_round_trip_continues_the_trajectory(tmp_path):
+    """SURVEY.md s8f N4 (I/O edges): write_restart after 10 steps hands the device atoms back through transfer_pre_output and
+    stores the pair style's restart records (settings {cut_global, seed, mix_flag} + per-pair {a0, gamma, sigma, expw, cut},
+    UM/pair_dpd_meso.cu:363-445); a second process reads the file, needs no pair_style / pair_coeff lines, and lands on the
+    same step-20 state as the uninterrupted deck (both re-neighbour at step 10: bit-for-bit with the two-sided kernel)."""
+    need_binary()
+    L = 8
+    workload.write_data(str(tmp_path / ("%d.data" % L)), workload.dpd_fluid(L), L)
+    env = dict(os.environ, MESO_PAIR_ONCE="0")
+    head = ("dimension 3\nunits lj\natom_style dpd/atomic/meso\nneighbor 0.3 bin\nneigh_modify delay 0 every 5 check no\n")
+    tail = ("run_style mvv/meso\ncompute mythermo all temp/meso\nfix 3 all nve/meso\nthermo 10\nthermo_modify temp mythermo\ntimestep 0.005\n")
+    dump = "dump d all custom 10 %s id x y z vx vy vz fx fy fz\ndump_modify d format \"%%d %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g %%.17g\"\n"
+    (tmp_path / "in.a").write_text(head + "read_data %d.data\npair_style dpd/meso 1.0 419084618\npair_coeff 1 1 15 4.5 3.0 1.0 1.0\n" % L +
+                                   "velocity all create 1.0 788662042 loop all\n" + tail + "run 10\nwrite_restart r.bin\n" + dump % "a.txt" + "run 10\n")
+    (tmp_path / "in.b").write_text(head + "read_restart r.bin\n" + tail + dump % "b.txt" + "run 10\n")
+    for deck in ("in.a", "in.b"):
+        out = subprocess.run([LMP, "-in", deck, "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True, timeout=600, env=env)
+        assert out.returncode == 0, deck + out.stdout[-2000:] + out.stderr[-2000:]
+    fa, fb = frames(str(tmp_path / "a.txt")), frames(str(tmp_path / "b.txt"))
+    assert 20 in fa and 20 in fb
+    assert np.array_equal(fa[10][:, 1:7], fb[10][:, 1:7])              # the restart file carries x, v exactly
+    assert np.array_equal(fa[20][:, 1:10], fb[20][:, 1:10]), np.abs(fa[20][:, 1:10] - fb[20][:, 1:10]).max()
+
+
+@pytest.mark.gpu
 def test_deck_errors_match_the_reference_strings(tmp_path):
     need_binary()
     workload.write_data(str(tmp_path / "4.data"), workload.dpd_fluid(4), 4)
