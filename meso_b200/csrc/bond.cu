@@ -10,8 +10,8 @@
 // The table is column-major ([slot][atom], coalesced over atoms) and travels with its atom through the
 // reorder gather.  Partners are resolved once per rebuild through a direct tag -> index array (atomicMin: a
 // local atom wins over its periodic images, the minimum image then undoes the wrap -- exactly the
-// reference's rule).  Single rank for now: with a decomposition the table would also have to ride the
-// migration messages (meso_bonds_upload refuses when nranks > 1).
+// reference's rule).  On a decomposition the table rides the migration messages (comm.cu: k_mr_exch_bonds_scatter /
+// k_mr_exch_bonds_unpack) and partners across a brick face are found among the ghosts.
 #include "internal.h"
 #include "device_math.cuh"
 #include <utility>

@@ -231,3 +231,37 @@ def test_polymer_forces_match_stock_lammps_bond_harmonic(lj12):
         assert abs(w.bond_energy() - float(g["ebond_lj%d" % lj12])) < 1e-5 * float(g["ebond_lj%d" % lj12])
         _, e = w.virial()
         assert abs(e.sum() - float(g["evdwl_lj%d" % lj12])) < 1e-5 * float(g["evdwl_lj%d" % lj12])
+
+
+def test_amphiphilic_channel_is_decomposition_independent():
+    """The checker of the multi-GPU polymer runs: bead-spring chains + 1-2 exclusions + walls + body force on 2x2x2 simulated
+    ranks (bonds crossing brick faces, partners among the ghosts, the bond table following migrating atoms, a non-periodic
+    decomposed dimension) against the same system on one rank.  Conservative forces only (gamma = sigma = 0): the random
+    force is keyed on the fp32 velocity BITS, and coordinates are packed relative to each brick's centre, so with the
+    thermostat on a last-bit difference re-draws a pair's random number -- trajectories then agree statistically only."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_fixes import AMPHI_COEFF
+    from meso_b200 import workload
+    Lc = 8
+    x, typ, tag, nb, bt, ba = workload.amphiphilic_channel(Lc)
+    v = workload.maxwell_velocities(len(x), seed=99) * 2.0               # hot: atoms cross brick faces within 17 steps
+    coeff = np.zeros((3, 3, 7))
+    for (a, b), a0 in AMPHI_COEFF.items():
+        coeff[a - 1, b - 1] = coeff[b - 1, a - 1] = [1.0, 1.0, 1.0, 1.0, a0, 0.0, 0.0]
+    out = {}
+    for grid in ((1, 1, 1), (2, 2, 2)):
+        w = oracle.World((0, 0, 0), (Lc, Lc, Lc), periodic=(1, 1, 0), procgrid=grid, ntypes=3, mass=[0, 1, 1, 1],
+                         coeff=coeff.reshape(-1, 7), precision=1)
+        w.set_atoms(x, v, tag=tag, type=typ)
+        w.set_bonds(nb, bt, ba, tag=tag, k=[0.0, 50.0], r0=[0.0, 0.5], special_lj12=0.0)
+        w.fix_solid_bound("z"); w.fix_pois(2, 0, 0.2)
+        w.setup()
+        n0 = [w.counts(r)["nlocal"] for r in range(w.nranks)]
+        w.run(17)
+        n1 = [w.counts(r)["nlocal"] for r in range(w.nranks)]
+        out[grid] = (by_tag(w, "x"), by_tag(w, "v"), n0, n1)
+    (x1, v1, _, _), (x8, v8, n0, n1) = out[(1, 1, 1)], out[(2, 2, 2)]
+    assert sum(n1) == len(x) and n0 != n1, "no atom migrated: the test would not exercise the bond table's migration"
+    # fp32 packing relative to different centres: forces differ by ~1e-6 relative, positions by ~1e-7 after 17 steps
+    assert np.abs(x1 - x8).max() < 1e-5 and np.abs(v1 - v8).max() < 1e-3, (np.abs(x1 - x8).max(), np.abs(v1 - v8).max())
