@@ -118,33 +118,75 @@ def procgrid_for(n):
 
 
 # ---------------------------------------------------------------------------------------- reference arm
+STOCK_DECK = ("dimension 3\nunits lj\natom_style atomic\ncommunicate single vel yes\nneighbor 0.3 bin\n"
+              "neigh_modify delay 0 every 5 check no\nread_data c.data\npair_style dpd 1.0 1.0 419084618\n"
+              "pair_coeff 1 1 15 4.5 1.0\nvelocity all create 1.0 788662042 loop all\nfix 3 all nve\n"
+              "thermo_style custom step temp press cpu spcpu\nthermo 100\ntimestep 0.005\nrun %d\nrun %d\n")
+
+
+def host_copies(L):
+    """How many serial LAMMPS processes the CPU legs run side by side: the image has no MPI, so the closest stand-in for
+    `mpirun -np P` on the box's own cores is P independent copies, each simulating one brick of the P-way decomposition
+    of the L^3 box as its own periodic system (same particles per core, no halo traffic: an upper bound of the MPI run)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    p = 1
+    while p * 2 <= min(cores, 64) and all(L % g == 0 and L // g >= 4 for g in procgrid_for(p * 2)):
+        p *= 2
+    return p
+
+
+def stock_lammps_rate(L, warm, steps):
+    """particle-steps/s of stock pair_style dpd + fix nve on the L^3 box spread over host_copies(L) serial processes
+    (returns rate, copies, description) or None when oracle/_ref/lmp_serial did not travel"""
+    from meso_b200 import workload
+    lmp = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
+    if not os.path.exists(lmp):
+        return None
+    p = host_copies(L)
+    grid = procgrid_for(p)
+    brick = tuple(L // g for g in grid)
+    with tempfile.TemporaryDirectory() as d:
+        procs = []
+        for c in range(p):
+            dc = os.path.join(d, "c%d" % c)
+            os.mkdir(dc)
+            workload.write_data(os.path.join(dc, "c.data"), workload.dpd_fluid(brick if len(set(brick)) > 1 else brick[0], seed=workload.DEFAULT_SEED + c), brick)
+            open(os.path.join(dc, "in.ref"), "w").write(STOCK_DECK % (warm, steps))
+        for c in range(p):
+            dc = os.path.join(d, "c%d" % c)
+            procs.append(subprocess.Popen([lmp, "-meso", "off", "-in", "in.ref", "-log", "none"], cwd=dc, stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True))
+        loops = []
+        for pr in procs:
+            out = pr.communicate()[0]
+            t = [float(s.split()[3]) for s in out.split("\n") if s.startswith("Loop time of")]
+            if pr.returncode != 0 or len(t) < 2:
+                return ("stock LAMMPS run failed: " + out[-200:].replace("\n", " "), 0, "")
+            loops.append(t[-1])
+    n = RHO * L ** 3
+    what = ("stock LAMMPS 30Sep2013 pair_style dpd + fix nve (oracle/_ref/lmp_serial): %d serial processes side by side, each one %s brick "
+            "of the case=%d box as its own periodic system (no MPI in the image: stand-in for mpirun -np %d without halo traffic), "
+            "slowest process counts" % (p, "x".join(str(b) for b in brick), L, p))
+    return (n * steps / max(loops), p, what)
+
+
 def reference_arm(args):
-    """Stock LAMMPS pair_style dpd + fix nve on the box's host cores: 1 core, because the image
-    has no MPI and the 2013 tree has no threading on this path."""
+    """Stock LAMMPS pair_style dpd + fix nve on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from meso_b200 import workload
-    lmp = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
     L = args.case
     n = RHO * L ** 3
     sample_steps = max(1, min(args.steps, args.ref_steps))
     warm = max(1, min(args.warmup, 3))
-    if os.path.exists(lmp):
-        with tempfile.TemporaryDirectory() as d:
-            workload.write_data(os.path.join(d, "c.data"), workload.dpd_fluid(L), L)
-            deck = ("dimension 3\nunits lj\natom_style atomic\ncommunicate single vel yes\nneighbor 0.3 bin\n"
-                    "neigh_modify delay 0 every 5 check no\nread_data c.data\npair_style dpd 1.0 1.0 419084618\n"
-                    "pair_coeff 1 1 15 4.5 1.0\nvelocity all create 1.0 788662042 loop all\nfix 3 all nve\n"
-                    "thermo_style custom step temp press cpu spcpu\nthermo 100\ntimestep 0.005\nrun %d\nrun %d\n" % (warm, sample_steps))
-            open(os.path.join(d, "in.ref"), "w").write(deck)
-            out = subprocess.run([lmp, "-meso", "off", "-in", "in.ref", "-log", "none"], cwd=d, capture_output=True, text=True)
-            loops = [float(s.split()[3]) for s in out.stdout.split("\n") if s.startswith("Loop time of")]
-            if out.returncode != 0 or len(loops) < 2:
-                print(json.dumps({"impl": "reference", "unavailable": "stock LAMMPS run failed: " + (out.stderr or out.stdout)[-200:].replace("\n", " ")}))
-                return
-            t = loops[-1]
-        kind, what = "reference", "stock LAMMPS 30Sep2013 pair_style dpd + fix nve (oracle/_ref/lmp_serial), serial"
+    r = stock_lammps_rate(L, warm, sample_steps)
+    if r is not None and r[1] == 0:
+        print(json.dumps({"impl": "reference", "unavailable": r[0]}))
+        return
+    if r is not None:
+        value, cores, what = r
+        kind = "reference"
     else:
         import oracle
         w = oracle.World((0, 0, 0), (L, L, L))
@@ -153,16 +195,15 @@ def reference_arm(args):
         w.run(warm)
         t0 = time.perf_counter()
         w.run(sample_steps)
-        t = time.perf_counter() - t0
-        kind, what = "port", "oracle/meso_oracle.c (scalar C restatement of the MESO algorithm)"
-    value = n * sample_steps / t
+        value = n * sample_steps / (time.perf_counter() - t0)
+        kind, cores, what = "port", 1, "oracle/meso_oracle.c (scalar C restatement of the MESO algorithm), 1 core"
     line = {"impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / sample_steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "example/simple DPD fluid case=%d (%d particles, rho=4, rc=1, skin 0.3, rebuild every 5)" % (L, n),
                        "what": what},
-            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": kind,
-                             "sample": "%d time steps of the case=%d box after %d warm-up steps (of --steps %d)" % (sample_steps, L, warm, args.steps)},
+            "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind,
+                             "sample": "%d time steps of the case=%d box after %d warm-up steps (of --steps %d); %s" % (sample_steps, L, warm, args.steps, what)},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -170,22 +211,12 @@ def reference_arm(args):
 def cpu_baseline_sample(L, budget_s=20.0):
     """bounded CPU sample for the cpu_baseline key: stock LAMMPS if it travelled, else the oracle port"""
     from meso_b200 import workload
-    lmp = os.path.join(ROOT, "oracle", "_ref", "lmp_serial")
     n = RHO * L ** 3
     steps = 10
-    if os.path.exists(lmp):
-        with tempfile.TemporaryDirectory() as d:
-            workload.write_data(os.path.join(d, "c.data"), workload.dpd_fluid(L), L)
-            deck = ("dimension 3\nunits lj\natom_style atomic\ncommunicate single vel yes\nneighbor 0.3 bin\n"
-                    "neigh_modify delay 0 every 5 check no\nread_data c.data\npair_style dpd 1.0 1.0 419084618\n"
-                    "pair_coeff 1 1 15 4.5 1.0\nvelocity all create 1.0 788662042 loop all\nfix 3 all nve\n"
-                    "thermo 100\ntimestep 0.005\nrun 2\nrun %d\n" % steps)
-            open(os.path.join(d, "in.ref"), "w").write(deck)
-            out = subprocess.run([lmp, "-meso", "off", "-in", "in.ref", "-log", "none"], cwd=d, capture_output=True, text=True)
-            loops = [float(s.split()[3]) for s in out.stdout.split("\n") if s.startswith("Loop time of")]
-        if len(loops) >= 2:
-            return {"value": n * steps / loops[-1], "unit": "particle-steps/s", "cores": 1, "kind": "reference",
-                    "sample": "stock LAMMPS pair_style dpd + fix nve, %d steps of the same case=%d box (after 2 warm-up steps), 1 core (no MPI in the image)" % (steps, L)}
+    r = stock_lammps_rate(L, 2, steps)
+    if r is not None and r[1] > 0:
+        return {"value": r[0], "unit": "particle-steps/s", "cores": r[1], "kind": "reference",
+                "sample": "%d steps of the same case=%d box (after 2 warm-up steps); %s" % (steps, L, r[2])}
     import oracle
     w = oracle.World((0, 0, 0), (L, L, L))
     w.set_atoms(workload.dpd_fluid(L), workload.maxwell_velocities(n))
