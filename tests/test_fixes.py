@@ -339,7 +339,9 @@ def test_gpu_equilibrium_temperature_pressure_rdf_match_stock_lammps():
     gr = g_of_r(hist, s, n, n, float(Lb) ** 3)
     sel = g["r"] > 0.3
     assert s == 200 and np.abs(gr[sel] - g["g"][sel]).max() < 0.03, np.abs(gr[sel] - g["g"][sel]).max()
-    assert abs(np.mean(ts) - g["temp"].mean()) < 0.01 and abs(np.mean(ps) - g["press"].mean()) < 0.25, (np.mean(ts), np.mean(ps))
+    # 40 samples of 4000 atoms: sigma of the means ~0.002 in T and ~0.07 in P (stock: 0.0126 / 0.43 per sample); the fp32 pair-once loop
+    # sums with atomics, so every run is its own realisation -- bounds at ~5 sigma
+    assert abs(np.mean(ts) - g["temp"].mean()) < 0.012 and abs(np.mean(ps) - g["press"].mean()) < 0.35, (np.mean(ts), np.mean(ps))
     m.close()
 
 
