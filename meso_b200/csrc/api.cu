@@ -4,6 +4,7 @@
 // never leaves the device: the reference's transfer_pre_exchange / pre_sort / pre_border /
 // post_border / pre_comm / post_comm PCIe round trips (UM/atom_meso.cu:152-266) have no
 // counterpart here; the host only enqueues kernels.
+#include <nvtx3/nvToolsExt.h>
 #include "internal.h"
 #include "device_math.cuh"
 #include <cuda_profiler_api.h>
@@ -42,14 +43,19 @@ struct PhaseTimer {
         if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
         cudaEvent_t e; cudaEventCreate(&e); return e;
     }
+    // every phase is also an NVTX range (the reference brackets its phases with nvtx_push_range/pop under PROFILE=1,
+    // UM/nvtx_meso.h:9-22, UM/mvv_meso.cu:262-406); without a tool attached the calls return at once
     PhaseTimer(meso_ctx *c, int i) : ctx(c), id(i)
     {
+        static const char *const names[MESO_T_COUNT] = {"integrate", "forward", "pair", "rebuild", "neigh"};
+        nvtxRangePushA(names[i]);
         if (!ctx->timers_on) return;
         a = get(ctx); b = get(ctx);
         cudaEventRecord(a, ctx->stream);
     }
     ~PhaseTimer()
     {
+        nvtxRangePop();
         if (!a) return;
         cudaEventRecord(b, ctx->stream);
         ctx->t_pending.push_back({id, {a, b}});
