@@ -265,3 +265,60 @@ def test_amphiphilic_channel_is_decomposition_independent():
     assert sum(n1) == len(x) and n0 != n1, "no atom migrated: the test would not exercise the bond table's migration"
     # fp32 packing relative to different centres: forces differ by ~1e-6 relative, positions by ~1e-7 after 17 steps
     assert np.abs(x1 - x8).max() < 1e-5 and np.abs(v1 - v8).max() < 1e-3, (np.abs(x1 - x8).max(), np.abs(v1 - v8).max())
+
+
+@pytest.mark.parametrize("case", ["cube", "ragged_2rank", "channel"])
+def test_stencil_cell_skip_criterion_is_conservative(case):
+    """Design invariant for the next step of the neighbor build: a stencil cell may be skipped for atom i when
+    the distance from i to that cell's box exceeds r_n.  Checked on the oracle's own lattice, cells and packed fp32 coordinates
+    (ghosts clamped into the outer layer, non-periodic faces, ragged bricks): evaluated in fp32 with a 1e-3 margin on r_n, the
+    criterion never drops a stored neighbor, and it removes a useful share of the 27-cell candidate set."""
+    if case == "cube":
+        w = world(8)
+        ranks = [0]
+    elif case == "ragged_2rank":
+        w = world((6, 7, 12), procgrid=(1, 1, 2))
+        ranks = [0, 1]
+    else:
+        x = workload.dpd_fluid(8)
+        w = oracle.World((0, 0, 0), (8, 8, 8), periodic=(1, 1, 0))
+        w.set_atoms(x, workload.maxwell_velocities(len(x)))
+        ranks = [0]
+    w.setup()
+    rn = np.float32(1.3)
+    limit = (rn * np.float32(1.001)) ** 2
+    tested = kept = 0
+    for r in ranks:
+        a = w.atoms(r)
+        nl = a["nlocal"]
+        m, binsize, _ = w.bins(r)
+        c4, _ = w.packed(r)
+        cs, ca = w.cells(r)
+        cnt, rows = w.neighbors(r)
+        cell_of = np.empty(len(ca), np.int64)
+        for c in range(len(cs) - 1):
+            cell_of[ca[cs[c]:cs[c + 1]]] = c
+        # sub-box geometry in packed coordinates: centre = middle of this rank's sub-box, cell b spans lo + (b-1) binsize
+        sub = np.array([m[d] - 2 for d in range(3)]) * np.array(binsize)
+        lo = -0.5 * sub
+        rng = np.random.default_rng(1)
+        for i in rng.choice(nl, size=min(nl, 400), replace=False):
+            b = np.array([cell_of[i] % m[0], (cell_of[i] // m[0]) % m[1], cell_of[i] // (m[0] * m[1])])
+            cell_lo = (lo + (b - 1) * np.array(binsize)).astype(np.float32)
+            cell_hi = (lo + b * np.array(binsize)).astype(np.float32)
+            p = c4[i, :3]
+            dlo = np.maximum(p - cell_lo, np.float32(0))          # distance to the -1 neighbor along each axis
+            dhi = np.maximum(cell_hi - p, np.float32(0))          # distance to the +1 neighbor
+            skipped = set()
+            for c in w.stencil(int(cell_of[i]), r):
+                nb = np.array([c % m[0], (c // m[0]) % m[1], c // (m[0] * m[1])])
+                off = nb - b
+                d = np.where(off < 0, dlo, np.where(off > 0, dhi, np.float32(0))).astype(np.float32)
+                tested += 1
+                if np.float32((d * d).sum()) > limit:
+                    skipped.add(int(c))
+                else:
+                    kept += 1
+            stored = rows[i, :cnt[i]]
+            assert not (set(cell_of[stored].tolist()) & skipped), (case, r, int(i))
+    assert kept < 0.85 * tested, (kept, tested)                   # ~25 % of the (atom, cell) pairs go away
