@@ -39,11 +39,19 @@ def test_no_torch_types_and_sm100a_only():
 
 
 def test_product_does_not_import_oracle():
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "meso_b200")):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in txt and "meso_oracle" not in txt, f
+    for top in ("meso_b200", os.path.join("lammps", "USER-MESO-B200"), "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in txt and "meso_oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_every_abi_entry_cites_the_reference_interface_it_replaces():
+    """include/meso_b200.h: each declaration (or the block comment right above its group) names a reference file"""
+    src = open(os.path.join(ROOT, "include", "meso_b200.h")).read()
+    cites = len(re.findall(r"(UM/[a-z_]+\.(?:cu|h)|src/[a-z_]+\.(?:cpp|h))(?::\d+)?", src))
+    assert cites >= 40, cites
 
 
 def test_fails_loudly_without_gpu(have_gpu):
