@@ -1,6 +1,6 @@
 #include "mpi.h"
 #include "string.h"
-#include "compute_pe_meso.h"
+#include "compute_styles_meso.h"
 #include "domain.h"
 #include "error.h"
 #include "force.h"

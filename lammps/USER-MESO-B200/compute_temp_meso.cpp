@@ -1,5 +1,5 @@
 #include "mpi.h"
-#include "compute_temp_meso.h"
+#include "compute_styles_meso.h"
 #include "engine_meso.h"
 #include "atom.h"
 #include "domain.h"

@@ -1,5 +1,5 @@
 #include "stdlib.h"
-#include "fix_addforce_meso.h"
+#include "fix_styles_meso.h"
 #include "error.h"
 
 using namespace LAMMPS_NS;

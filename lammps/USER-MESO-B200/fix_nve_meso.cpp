@@ -1,5 +1,5 @@
 #include "string.h"
-#include "fix_nve_meso.h"
+#include "fix_styles_meso.h"
 #include "error.h"
 #include "update.h"
 

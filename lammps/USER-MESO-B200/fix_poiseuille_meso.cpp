@@ -1,6 +1,6 @@
 #include "ctype.h"
 #include "stdlib.h"
-#include "fix_poiseuille_meso.h"
+#include "fix_styles_meso.h"
 #include "error.h"
 
 using namespace LAMMPS_NS;

@@ -2,7 +2,7 @@
 #include "stdio.h"
 #include "stdlib.h"
 #include "string.h"
-#include "fix_rdf_fast_meso.h"
+#include "fix_styles_meso.h"
 #include "atom.h"
 #include "comm.h"
 #include "domain.h"

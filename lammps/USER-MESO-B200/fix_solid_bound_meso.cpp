@@ -1,5 +1,5 @@
 #include "string.h"
-#include "fix_solid_bound_meso.h"
+#include "fix_styles_meso.h"
 #include "error.h"
 
 using namespace LAMMPS_NS;

@@ -1,6 +1,6 @@
 #include "stdlib.h"
 #include "string.h"
-#include "fix_wall_meso.h"
+#include "fix_styles_meso.h"
 #include "error.h"
 
 using namespace LAMMPS_NS;

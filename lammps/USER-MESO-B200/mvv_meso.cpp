@@ -1,8 +1,7 @@
 #include "string.h"
-#include "mvv_meso.h"
+#include "run_style_meso.h"
 #include "engine_meso.h"
-#include "fix_nve_meso.h"
-#include "fix_resident_meso.h"
+#include "fix_styles_meso.h"
 #include "bond_harmonic_meso.h"
 #include "pair_dpd_meso.h"
 #include "atom.h"

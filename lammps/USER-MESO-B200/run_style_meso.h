@@ -1,4 +1,4 @@
-/* mvv_meso.h -- run_style mvv/meso | verlet/meso   (UM/mvv_meso.h:3-4, UM/mvv_meso.cu:79-435)
+/* run_style_meso.h -- run_style mvv/meso | verlet/meso   (UM/mvv_meso.h:3-4, UM/mvv_meso.cu:79-435)
    Drives one DPD time step in the order of ModifiedVerlet::run:
      initial_integrate -> [rebuild every N steps: wrap, migrate, reorder, ghosts, neighbor table | halo refresh]
      -> force clear -> pair (bulk overlapped with the halo, then border) -> final_integrate -> output.
@@ -11,8 +11,8 @@ IntegrateStyle(verlet/meso,ModifiedVerlet)
 
 #else
 
-#ifndef LMP_MESO_MVV
-#define LMP_MESO_MVV
+#ifndef LMP_MESO_B200_RUN_STYLE_H
+#define LMP_MESO_B200_RUN_STYLE_H
 
 #include "integrate.h"
 #include "meso_bridge.h"
