@@ -120,6 +120,7 @@ extern "C" int meso_create(meso_ctx **out, int device)
     ctx->pair_once = !(po && po[0] == '0');
     if (const char *e = getenv("MESO_PAIR_TEX")) ctx->pair_tex = atoi(e) & 3;
     if (const char *e = getenv("MESO_HALO_ROUTES")) ctx->halo_routes = e[0] != '0';
+    if (const char *e = getenv("MESO_EXCH_ONESHOT")) ctx->exch_oneshot = e[0] == '1';
     if (const char *e = getenv("MESO_NB_PER_ATOM")) ctx->nb_per_atom = e[0] == '1';
     cudaMemsetAsync(ctx->d_counts, 0, sizeof(Counts), ctx->stream);
     memset(ctx->h_counts, 0, sizeof(Counts));
@@ -550,7 +551,7 @@ static int rebuild_impl(meso_ctx *ctx)
         if (ctx->comm_path) {
             // Domain::pbc -> Comm::exchange -> sort_local -> Comm::borders (UM/mvv_meso.cu:283-316), all on device
             TRY(launch_pbc(ctx));
-            TRY(launch_exchange_multi(ctx));
+            TRY(ctx->exch_oneshot ? launch_exchange_oneshot(ctx) : launch_exchange_multi(ctx));
             TRY(launch_reorder(ctx));
             TRY(launch_bonds_gather(ctx));
             TRY(launch_borders_multi(ctx));

@@ -833,6 +833,250 @@ static int forward_routes(meso_ctx *ctx, cudaStream_t st)
     return MESO_OK;
 }
 
+// ------------------------------------------------------------------ one-shot migration (MESO_EXCH_ONESHOT=1, off by default)
+// NOT YET RUN ON HARDWARE (written at the end of round 1, when the GPU budget was spent): the validated path is
+// launch_exchange_multi above.  Instead of one dependent exchange per communicating dimension (an atom that leaves through
+// an edge takes two hops), every leaver is sent straight to the brick that will own it: one selection kernel, ONE NCCL group
+// with a fixed-capacity message per peer, one unpack kernel.  Ownership after the exchange is the same as after the three
+// hops; arrival order differs, which only matters for ties of identical sort keys (already a documented deviation).
+struct OneShot {
+    int np, self, bpa;
+    int slot_of_code[27];       // destination offset code (ox+1) + 3(oy+1) + 9(oz+1) -> peer slot, -1: no such brick (atom lost)
+    int multi[3];               // procgrid[d] > 1
+    double *sbuf[27];           // [0] header {count}, then REC doubles per leaver
+    const double *rbuf[27];
+    int2 *bsend[27];            // bond rows of the leavers, (1 + bpa) int2 per record, same order
+    const int2 *brecv[27];
+};
+
+__device__ __forceinline__ int oneshot_code(const double xi[3], const Box &box, const int multi[3])
+{
+    int code = 0, w = 1;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        int o = 0;
+        if (multi[d]) { const Flags f = leave_flags(xi[d], box, d); o = f.a ? -1 : (f.b ? 1 : 0); }
+        code += (o + 1) * w;
+        w *= 3;
+    }
+    return code;
+}
+
+__global__ void __launch_bounds__(CT) k_os_count(SoA3 x, const Counts *__restrict__ cnt, int2 *__restrict__ tile_counts, Box box, OneShot os,
+                                                 int ntiles)
+{
+    tile_count([&](int i) {
+        const double xi[3] = {x.c[0][i], x.c[1][i], x.c[2][i]};
+        Flags f; f.a = oneshot_code(xi, box, os.multi) != 13; f.b = false; return f; }, 0, cnt->nlocal, tile_counts, ntiles);
+}
+
+__global__ void __launch_bounds__(1024) k_os_scan(int2 *__restrict__ tile_counts, Counts *__restrict__ cnt)
+{
+    const int used = (cnt->nlocal + CTILE - 1) / CTILE;
+    const int2 tot = scan_tiles(tile_counts, used);
+    if (threadIdx.x == 0) { cnt->exch_n[0] = tot.x; cnt->exch_n[1] = 0; }
+    if (threadIdx.x < 27) cnt->route_send_n[threadIdx.x] = 0;      // reused as per-peer leaver counters until the routes are rebuilt
+}
+
+__global__ void __launch_bounds__(CT) k_os_scatter(SoA3 x, SoA3 v, const int *__restrict__ tag, const int *__restrict__ type,
+                                                   const int *__restrict__ mask, const int *__restrict__ image, SoA3 xo, SoA3 vo,
+                                                   int *__restrict__ tago, int *__restrict__ typeo, int *__restrict__ masko,
+                                                   int *__restrict__ imageo, Counts *__restrict__ cnt, const int2 *__restrict__ tile_counts,
+                                                   Box box, OneShot os, int ntiles, int exch_cap, const int *__restrict__ nbond,
+                                                   const int2 *__restrict__ bonds, int *__restrict__ nbond_o, int2 *__restrict__ bonds_o,
+                                                   size_t padding)
+{
+    __shared__ int wsum[CT / 32];
+    const int last = cnt->nlocal;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int base = tile * CTILE;
+        if (base >= last) break;
+        int run = tile_counts[tile].x;
+#pragma unroll
+        for (int r = 0; r < CI; r++) {
+            const int i = base + r * CT + threadIdx.x;
+            int code = 13;
+            double xi[3] = {0, 0, 0};
+            if (i < last) {
+#pragma unroll
+                for (int q = 0; q < 3; q++) xi[q] = x.c[q][i];
+                code = oneshot_code(xi, box, os.multi);
+            }
+            const uint32_t ba = __ballot_sync(0xffffffffu, code != 13);
+            if (lane == 0) wsum[w] = __popc(ba);
+            __syncthreads();
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int ww = 0; ww < CT / 32; ww++) { const int c = wsum[ww]; if (ww < w) pre += c; tot += c; }
+            __syncthreads();
+            if (i < last) {
+                if (code == 13) {
+                    const int p = i - (run + pre + __popc(ba & lt));    // stable: stayers keep their relative order
+#pragma unroll
+                    for (int q = 0; q < 3; q++) { xo.c[q][p] = xi[q]; vo.c[q][p] = v.c[q][i]; }
+                    tago[p] = tag[i]; typeo[p] = type[i]; masko[p] = mask[i]; imageo[p] = image[i];
+                    if (os.bpa) {
+                        const int nb = nbond[i];
+                        nbond_o[p] = nb;
+                        for (int q = 0; q < nb; q++) bonds_o[p + q * padding] = bonds[i + q * padding];
+                    }
+                } else {
+                    const int s = os.slot_of_code[code];
+                    if (s < 0) atomicOr(&cnt->err, 8);               // beyond a non-periodic face of the decomposition: lost
+                    else {
+                        const int k = atomicAdd(&cnt->route_send_n[s], 1);
+                        if (k >= exch_cap) atomicOr(&cnt->err, 8);
+                        else {
+                            double *rec = os.sbuf[s] + (size_t)(k + 1) * REC;
+#pragma unroll
+                            for (int q = 0; q < 3; q++) { rec[q] = xi[q]; rec[3 + q] = v.c[q][i]; }
+                            reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
+                            reinterpret_cast<int2 *>(rec)[7] = make_int2(mask[i], image[i]);
+                            if (os.bpa) {
+                                int2 *br = os.bsend[s] + (size_t)k * (1 + os.bpa);
+                                const int nb = nbond[i];
+                                br[0] = make_int2(nb, 0);
+                                for (int q = 0; q < nb; q++) br[1 + q] = bonds[i + q * padding];
+                            }
+                        }
+                    }
+                }
+            }
+            run += tot;
+        }
+    }
+}
+
+__global__ void k_os_headers(Counts *cnt, OneShot os, int exch_cap)
+{
+    const int s = threadIdx.x;
+    if (s < os.np && s != os.self) reinterpret_cast<int *>(os.sbuf[s])[0] = min(cnt->route_send_n[s], exch_cap);
+    if (s == 0) cnt->nlocal -= cnt->exch_n[0];
+}
+
+// arrivals are appended peer by peer in slot order
+__global__ void __launch_bounds__(256) k_os_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
+                                                   int *__restrict__ image, Counts *__restrict__ cnt, OneShot os, Box box, int nloc_cap,
+                                                   int *__restrict__ nbond, int2 *__restrict__ bonds, size_t padding)
+{
+    const int s = blockIdx.y;
+    if (s == os.self) return;
+    int base = cnt->nlocal, total = 0;
+    for (int q = 0; q < os.np; q++) {
+        if (q == os.self) continue;
+        const int nq = reinterpret_cast<const int *>(os.rbuf[q])[0];
+        if (q < s) base += nq;
+        total += nq;
+    }
+    if (cnt->nlocal + total > nloc_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&cnt->err, 8); return; }
+    const int n = reinterpret_cast<const int *>(os.rbuf[s])[0];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double *rec = os.rbuf[s] + (size_t)(k + 1) * REC;
+        const int p = base + k;
+        bool inside = true;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            x.c[q][p] = rec[q]; v.c[q][p] = rec[3 + q];
+            if (os.multi[q]) inside = inside && rec[q] >= box.sublo[q] && rec[q] < box.subhi[q];
+        }
+        const int2 tt = reinterpret_cast<const int2 *>(rec)[6], mi = reinterpret_cast<const int2 *>(rec)[7];
+        tag[p] = tt.x; type[p] = tt.y; mask[p] = mi.x; image[p] = mi.y;
+        if (!inside) atomicOr(&cnt->err, 8);
+        if (os.bpa) {
+            const int2 *br = os.brecv[s] + (size_t)k * (1 + os.bpa);
+            const int nb = min(max(br[0].x, 0), os.bpa);
+            nbond[p] = nb;
+            for (int q = 0; q < nb; q++) bonds[p + q * padding] = br[1 + q];
+        }
+    }
+}
+
+__global__ void k_os_grow(Counts *cnt, OneShot os)
+{
+    int total = 0;
+    for (int q = 0; q < os.np; q++) if (q != os.self) total += reinterpret_cast<const int *>(os.rbuf[q])[0];
+    cnt->nlocal += total;
+    cnt->nall = cnt->nlocal;
+}
+
+int launch_exchange_oneshot(meso_ctx *ctx)
+{
+    int rc = ensure_comm_buffers(ctx);
+    if (rc) return rc;
+    if (ctx->npeers == 0) { rc = comm_build_peers(ctx); if (rc) return rc; }
+    const Box &box = ctx->box;
+    const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
+    int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
+    cudaStream_t st = ctx->stream;
+    const bool bonded = bonds_active(ctx);
+    OneShot os;
+    os.np = ctx->npeers; os.self = ctx->peer_self; os.bpa = bonded ? ctx->bond_per_atom : 0;
+    bool any = false;
+    for (int d = 0; d < 3; d++) { os.multi[d] = ctx->procgrid[d] > 1; any = any || os.multi[d]; }
+    if (!any) return MESO_OK;                     // the periodic wrap already put every atom back into the brick
+    for (int c = 0; c < 27; c++) {
+        const int off[3] = {c % 3 - 1, (c / 3) % 3 - 1, c / 9 - 1};
+        int loc[3], slot = -1;
+        bool ok = true;
+        for (int d = 0; d < 3; d++) {
+            loc[d] = ctx->myloc[d] + off[d];
+            if (loc[d] < 0 || loc[d] >= ctx->procgrid[d]) {
+                if (!box.periodic[d]) { ok = false; break; }
+                loc[d] = (loc[d] + ctx->procgrid[d]) % ctx->procgrid[d];
+            }
+        }
+        if (ok) {
+            const int r = (loc[0] * ctx->procgrid[1] + loc[1]) * ctx->procgrid[2] + loc[2];
+            for (int s = 0; s < ctx->npeers; s++) if (ctx->peer_rank[s] == r) slot = s;
+        }
+        os.slot_of_code[c] = slot;
+    }
+    const size_t msg = (size_t)(ctx->exch_cap + 1) * REC, bmsg = (size_t)ctx->exch_cap * (size_t)(1 + os.bpa);
+    bool okm = true;
+    for (int s = 0; s < 27; s++) { os.sbuf[s] = nullptr; os.rbuf[s] = nullptr; os.bsend[s] = nullptr; os.brecv[s] = nullptr; }
+    for (int s = 0; s < os.np; s++) {
+        if (s == os.self) continue;
+        okm = okm && ctx->os_sbuf[s].reserve(msg) && ctx->os_rbuf[s].reserve(msg);
+        if (bonded) okm = okm && ctx->os_bsend[s].reserve(bmsg) && ctx->os_brecv[s].reserve(bmsg);
+        os.sbuf[s] = ctx->os_sbuf[s].p; os.rbuf[s] = ctx->os_rbuf[s].p;
+        os.bsend[s] = ctx->os_bsend[s].p; os.brecv[s] = ctx->os_brecv[s].p;
+    }
+    if (!okm) { ctx->err = "out of device memory (one-shot migration buffers)"; return MESO_ECUDA; }
+    k_os_count<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), ctx->d_counts, tc, box, os, ntiles);
+    k_os_scan<<<1, 1024, 0, st>>>(tc, ctx->d_counts);
+    k_os_scatter<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, soa(ctx->xa),
+                                                soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p, ctx->imagea.p, ctx->d_counts, tc, box, os,
+                                                ntiles, ctx->exch_cap, ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p, ctx->cap);
+    for (int q = 0; q < 3; q++) { std::swap(ctx->x[q].p, ctx->xa[q].p); std::swap(ctx->v[q].p, ctx->va[q].p); }
+    std::swap(ctx->tag.p, ctx->taga.p); std::swap(ctx->type.p, ctx->typea.p);
+    std::swap(ctx->mask.p, ctx->maska.p); std::swap(ctx->image.p, ctx->imagea.p);
+    if (bonded) {
+        std::swap(ctx->nbond.p, ctx->nbond_alt.p); std::swap(ctx->nbond.cap, ctx->nbond_alt.cap);
+        std::swap(ctx->bonds.p, ctx->bonds_alt.p); std::swap(ctx->bonds.cap, ctx->bonds_alt.cap);
+    }
+    k_os_headers<<<1, 32, 0, st>>>(ctx->d_counts, os, ctx->exch_cap);
+    ncclComm_t comm = (ncclComm_t)ctx->nccl;
+    MESO_NCCL(ncclGroupStart());
+    for (int s = 0; s < os.np; s++) {
+        if (s == os.self) continue;
+        MESO_NCCL(ncclSend(ctx->os_sbuf[s].p, msg, ncclDouble, ctx->peer_rank[s], comm, st));
+        MESO_NCCL(ncclRecv(ctx->os_rbuf[s].p, msg, ncclDouble, ctx->peer_rank[s], comm, st));
+        if (bonded) {
+            MESO_NCCL(ncclSend(ctx->os_bsend[s].p, bmsg * 2, ncclInt, ctx->peer_rank[s], comm, st));
+            MESO_NCCL(ncclRecv(ctx->os_brecv[s].p, bmsg * 2, ncclInt, ctx->peer_rank[s], comm, st));
+        }
+    }
+    MESO_NCCL(ncclGroupEnd());
+    const dim3 grid(ctx->sm_count, os.np);
+    k_os_unpack<<<grid, 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, ctx->d_counts, os, box,
+                                    (int)ctx->nloc_cap, ctx->nbond.p, ctx->bonds.p, ctx->cap);
+    k_os_grow<<<1, 1, 0, st>>>(ctx->d_counts, os);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
 __global__ void k_mr_reset_ghosts(Counts *cnt)
 {
     cnt->nghost = 0;

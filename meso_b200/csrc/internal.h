@@ -168,6 +168,9 @@ struct meso_ctx {
     meso::DevBuf<int> route_dst[27];          // ghost slot of the k-th record received from the peer
     meso::DevBuf<double> route_sbuf[27], route_rbuf[27];
     meso::DevBuf<void *> route_ptrs;          // device copy of the request / slot pointer tables
+    bool exch_oneshot = false;                // MESO_EXCH_ONESHOT=1: leavers go straight to their final brick (written, not yet run on hardware)
+    meso::DevBuf<double> os_sbuf[27], os_rbuf[27];
+    meso::DevBuf<int2> os_bsend[27], os_brecv[27];
     int route_send_n[27] = {0}, route_recv_n[27] = {0};
     size_t nloc_cap = 0;                      // capacity for local atoms
     meso::DevBuf<double> send_buf[2], recv_buf[2], reduce_buf;
@@ -232,6 +235,7 @@ int launch_borders(meso_ctx *ctx);     // ghost creation (single rank: periodic 
 int launch_forward(meso_ctx *ctx, bool full);     // per-step ghost refresh
 // ---- comm.cu
 int launch_exchange_multi(meso_ctx *ctx);
+int launch_exchange_oneshot(meso_ctx *ctx);
 int launch_borders_multi(meso_ctx *ctx);
 int launch_forward_multi(meso_ctx *ctx, cudaStream_t st);
 int comm_build_peers(meso_ctx *ctx);
