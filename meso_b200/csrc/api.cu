@@ -121,6 +121,7 @@ extern "C" int meso_create(meso_ctx **out, int device)
     if (const char *e = getenv("MESO_PAIR_TEX")) ctx->pair_tex = atoi(e) & 3;
     if (const char *e = getenv("MESO_HALO_ROUTES")) ctx->halo_routes = e[0] != '0';
     if (const char *e = getenv("MESO_EXCH_ONESHOT")) ctx->exch_oneshot = e[0] == '1';
+    if (const char *e = getenv("MESO_NB_SKIP")) ctx->nb_skip = e[0] == '1';
     if (const char *e = getenv("MESO_NB_PER_ATOM")) ctx->nb_per_atom = e[0] == '1';
     cudaMemsetAsync(ctx->d_counts, 0, sizeof(Counts), ctx->stream);
     memset(ctx->h_counts, 0, sizeof(Counts));

@@ -135,6 +135,7 @@ struct meso_ctx {
     meso::DevBuf<float4> facc;                // fp32 per-atom force accumulator of the pair-once kernel (zero between uses)
     cudaTextureObject_t tex_coord = 0, tex_veloc = 0;   // linear float4 textures over coord4 / veloc4 (gather-path experiments)
     int pair_tex = 2;                         // which gathers of the pair-once kernel use the texture data pipe (MESO_PAIR_TEX)
+    bool nb_skip = false;                     // MESO_NB_SKIP=1: the build skips stencil cells beyond r_n of the atom (written, not yet run on hardware)
     bool nb_per_atom = true;                  // thread-per-atom neighbor build (MESO_NB_PER_ATOM=0: warp-per-cell ballot kernel + per-atom fix-up)
     bool pair_once = true;                    // meso_run evaluates each local pair once (MESO_PAIR_ONCE=0: two-sided kernel)
     meso::DevBuf<double> virial, e_pair;      // [6][cap] SoA, [cap]

@@ -129,12 +129,19 @@ constexpr int NB_THREADS = 128;
 // final position (reverse encounter order after the core entries) and the reference's join pass disappears.
 // Rows denser than the queue (> 60 hits, never at rho = 4) take the spill path: core entries are flushed
 // forward, skin entries backward from slot n_col-1 as in the reference, and joined at the end.
-template <int NB_DEPTH, int NB_BATCH>
+// SKIP (MESO_NB_SKIP=1, off by default, NOT YET RUN ON HARDWARE): a stencil cell whose box lies farther than r_n from the
+// atom is not walked at all -- half of the corner cells and a quarter of the edge cells, ~26 % of the candidate tests.  The
+// criterion (fp32, 1e-3 margin on r_n^2) never drops a stored neighbor: tests/test_oracle_world.py::
+// test_stencil_cell_skip_criterion_is_conservative checks it on the oracle's lattice.  SkipGeom: packed coordinate of the
+// lower face of cell index 1 (= sublo - centre), cell size, cells per dimension, the per-cell stencil code rows.
+struct SkipGeom { float lo[3], bs[3]; int m[3]; const unsigned char *stencil; float limit; };
+
+template <int NB_DEPTH, int NB_BATCH, bool SKIP = false>
 __global__ void __launch_bounds__(NB_THREADS) k_build_neighbors(const float4 *__restrict__ coord4, const int *__restrict__ cell_of,
                                                                 const int2 *__restrict__ runs, const float4 *__restrict__ cell_xyzj,
                                                                 int *__restrict__ pair_count, int *__restrict__ pair_table,
                                                                 Counts *__restrict__ cnt, int n_col, float rc2_core, float rc2_tail,
-                                                                const int *__restrict__ fixup)
+                                                                const int *__restrict__ fixup, SkipGeom sg = SkipGeom())
 {
     __shared__ int stage[NB_THREADS / 32][NB_DEPTH][32];
     // fix-up mode: only the rows the warp-per-cell kernel marked (pair_count == -1); nothing to do when no cell was marked
@@ -146,7 +153,33 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_neighbors(const float4 *__
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
         if (fixup && pair_count[i] >= 0) continue;
         const float4 ci = coord4[i];
-        const int2 *my = runs + (size_t)cell_of[i] * 27;
+        const int mycell = cell_of[i];
+        const int2 *my = runs + (size_t)mycell * 27;
+        // SKIP: squared distance from the atom to the -1 / +1 neighbor layer along each axis (0 when the atom sits outside its
+        // clamped cell on that side) and this cell's stencil code row
+        float d2lo[3] = {0.f, 0.f, 0.f}, d2hi[3] = {0.f, 0.f, 0.f};
+        const unsigned char *srow = nullptr;
+        if constexpr (SKIP) {
+            const int b[3] = {mycell % sg.m[0], (mycell / sg.m[0]) % sg.m[1], mycell / (sg.m[0] * sg.m[1])};
+            const float p[3] = {ci.x, ci.y, ci.z};
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const float clo = sg.lo[d] + (float)(b[d] - 1) * sg.bs[d], chi = sg.lo[d] + (float)b[d] * sg.bs[d];
+                const float a = fmaxf(p[d] - clo, 0.f), c = fmaxf(chi - p[d], 0.f);
+                d2lo[d] = a * a; d2hi[d] = c * c;
+            }
+            srow = sg.stencil + (size_t)mycell * 32;
+        }
+        auto run_of = [&](int ss) -> int2 {
+            int2 rr = my[ss];
+            if constexpr (SKIP) {
+                const int code = srow[ss], ox = code % 3, oy = (code / 3) % 3, oz = code / 9;
+                const float d2 = (ox == 0 ? d2lo[0] : (ox == 2 ? d2hi[0] : 0.f)) + (oy == 0 ? d2lo[1] : (oy == 2 ? d2hi[1] : 0.f)) +
+                                 (oz == 0 ? d2lo[2] : (oz == 2 ? d2hi[2] : 0.f));
+                if (d2 > sg.limit) rr.y = 0;
+            }
+            return rr;
+        };
         int *row0 = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
         int ncq = 0, nsq = 0;          // staged core / skin entries
         int ncw = 0, nsw = 0;          // entries already written to the table by the spill path
@@ -157,10 +190,10 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_neighbors(const float4 *__
         // flattened walk over the 27 runs: every lane advances through its own concatenated candidate list, so lanes of
         // different cells do not wait for each other's cell sizes
         int s = 0;
-        int2 run = my[0], nrun = my[1];
+        int2 run = run_of(0), nrun = run_of(1);
         int q = run.x, n = run.y;
         while (true) {
-            while (n == 0 && s < 26) { s++; run = nrun; q = run.x; n = run.y; nrun = my[min(s + 1, 26)]; }
+            while (n == 0 && s < 26) { s++; run = nrun; q = run.x; n = run.y; nrun = run_of(min(s + 1, 26)); }
             if (n == 0) break;
             if (ncq + nsq > NB_DEPTH - NB_BATCH) {                               // spill path (dense rows only)
                 for (int t = 0; t < ncq; t++) put(ncw + t, qq[t][lane]);
@@ -510,6 +543,13 @@ int launch_neighbor_build(meso_ctx *ctx)
                                                                    ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, ctx->nb_fixup.p);
     } else {
 #define MESO_NB_ARGS ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p, ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, nullptr
+        if (ctx->nb_skip) {
+            SkipGeom sg;
+            for (int d = 0; d < 3; d++) { sg.lo[d] = (float)(box.sublo[d] - box.centre[d]); sg.bs[d] = (float)box.binsize[d]; sg.m[d] = box.m[d]; }
+            sg.stencil = ctx->stencil.p;
+            sg.limit = rc2_tail * 1.002f;                           // (1.001 r_n)^2
+            k_build_neighbors<48, 4, true><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS, sg);
+        } else
         k_build_neighbors<48, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS);   // 48 slots: 9 CTAs/SM; 40 spills too often, 56+ loses occupancy (measured)
 #undef MESO_NB_ARGS
     }
