@@ -40,3 +40,28 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 1e4 and "workload" in d["config"]
+
+
+def test_workload_files_round_trip(tmp_path):
+    """the synthetic data files have the layout of example/simple/25.data and survive a write -> read round trip bit for bit
+    (positions are rounded to the %.9e of the file when they are generated)"""
+    import numpy as np
+    from meso_b200 import workload
+    x = workload.dpd_fluid(5)
+    assert x.shape == (500, 3) and x.min() >= 0 and x.max() < 5
+    cells = np.floor(x).astype(int)
+    assert (np.bincount(cells[:, 0] + 5 * (cells[:, 1] + 5 * cells[:, 2]), minlength=125) == 4).all()   # 4 atoms per unit cell, in cell order
+    p = str(tmp_path / "5.data")
+    workload.write_data(p, x, 5)
+    x2, tag, typ, lo, hi, mass = workload.read_data(p)
+    assert np.array_equal(x2, x) and np.array_equal(tag, np.arange(1, 501)) and (typ == 1).all() and hi == [5.0, 5.0, 5.0] and mass == [0.0, 1.0]
+    v = workload.maxwell_velocities(500)
+    assert abs((v * v).sum() / (3 * 500 - 3) - 1.0) < 1e-12 and np.abs(v.sum(0)).max() < 1e-10
+    # bead-spring writer: every bond once, both partners hold it in the per-atom table
+    xp, typ, tag, nb, bt, ba = workload.polymer_melt(4, chain_len=4, seed=1)
+    nbonds = workload.write_data_bond(str(tmp_path / "p.data"), xp, 4, typ, 2, nb, bt, ba)
+    assert 2 * nbonds == nb.sum()
+    txt = open(str(tmp_path / "p.data")).read()
+    assert "%d bonds" % nbonds in txt and "Bonds" in txt and "1 bond types" in txt
+    xa, typa, _, nba, _, baa = workload.amphiphilic_channel(6)
+    assert set(np.unique(typa)) == {1, 2, 3} and xa[:, 2].min() > 0.29 and xa[:, 2].max() < 5.71
