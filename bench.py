@@ -348,8 +348,9 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": b_force, "particles_per_launch": nloc * args.steps / max(pair_calls, 1),
                 "avg_launch_ms": pair_ms / max(pair_calls, 1), "share_of_step": pair_ms / ms,
-                "note": "not HBM-bound: the kernel saturates the L1 data pipe (l1tex__data_pipe_lsu_wavefronts ~78 % of peak, one tag "
-                        "lookup per ~1.7 gathered neighbors) with the issue slots at ~56 %; see DESIGN.md s3 and profiles/"}
+                "note": "not HBM-bound: a list-based gather kernel on the L1/issue ridge (ncu: LSU data-pipe wavefronts 62-78 % depending on "
+                        "how many gathers take the texture pipe, issue slots 56-60 %, DRAM 21 %, 1.2x the algorithmic bytes moved); "
+                        "see DESIGN.md s3.1 and profiles/"}
     phases = {k: {"ms_total": round(v[0], 3), "calls": int(v[1])} for k, v in tm.items()}
 
     # ---- end-to-end leg through the C ABI with HOST buffers: the deck's `run K` with `thermo 100`
