@@ -763,9 +763,11 @@ extern "C" int meso_fix_rdf(meso_ctx *ctx, int groupbit, int j_groupbit, int nbi
     meso::FixOp op{};
     op.kind = meso::FIX_RDF; op.groupbit = groupbit; op.aux = j_groupbit; op.dims = nbin;
     op.p[0] = every; op.p[1] = ctx->cut_global;                  // MesoFixRDFFast::init: rc = force->pair->cutforce
+    if (ctx->fixes.n >= meso::MAX_FIX) FAIL(MESO_EINVAL, "too many device-resident fixes (limit 8)");
+    const int slot = ctx->fixes.n;                                // the handle fix_register is about to hand out
+    if (!ctx->rdf_hist[slot].reserve((size_t)nbin + 2)) FAIL(MESO_ECUDA, "out of device memory (rdf histogram)");
     const int h = fix_register(ctx, op);
     if (h < 0) return h;
-    if (!ctx->rdf_hist[h].reserve((size_t)nbin + 2)) FAIL(MESO_ECUDA, "out of device memory (rdf histogram)");
     MESO_CUDA(cudaMemsetAsync(ctx->rdf_hist[h].p, 0, sizeof(unsigned long long) * ((size_t)nbin + 2), ctx->stream));
     ctx->rdf_samples[h] = 0;
     return h;
