@@ -43,10 +43,13 @@ def main():
                                                                        len([k for k in b if k not in a])))
     for k in changed:
         print("  changed", k)
-    for k in sorted(k for k in a if k not in b):
-        print("  gone   ", k)
-    for k in sorted(k for k in b if k not in a):
-        print("  new    ", k)
+    gone, new = sorted(k for k in a if k not in b), sorted(k for k in b if k not in a)
+    for k in gone:
+        same = [n for n in new if b[n] == a[k]]
+        print("  gone   ", k, ("-> identical code now named " + same[0]) if same else "")
+    for k in new:
+        if not any(a[g] == b[k] for g in gone):
+            print("  new    ", k)
     return 1 if changed else 0
 
 
