@@ -22,13 +22,9 @@ namespace LAMMPS_NS {
 class ModifiedVerlet : public Integrate, protected MesoBridge {
  public:
   ModifiedVerlet(class LAMMPS *, int, char **);
-  virtual ~ModifiedVerlet() {}
-  virtual void init();
-  virtual void setup();
-  virtual void setup_minimal(int);
-  virtual void run(int);
-  virtual void cleanup();
-  virtual void reset_dt();
+  // Integrate interface (src/integrate.h): all of it runs on device-resident atoms
+  void init(); void setup(); void setup_minimal(int);
+  void run(int); void cleanup(); void reset_dt();
 
  protected:
   int fused_groupbit;         // group of the single nve/meso fix, or -1 when the fix list cannot be fused
