@@ -4,9 +4,12 @@
   python bench.py --gpus N --steps K --warmup W            # the CUDA path (through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...   # stock CPU LAMMPS of the reference tree
 
-A "step" is one DPD time step (velocity-Verlet halves + halo refresh + pair force; every 5th step also
-wrap + reorder + ghost rebuild + neighbor-list build) of the example/simple sp.run deck on a synthetic
-rho = 4 fluid.  N = 1: case 64 (1,048,576 particles, BASELINE configs[1]).  Prints ONE JSON line.
+Workload (default): BASELINE configs[3] -- the rho = 4 DPD fluid of example/simple/sp.run in a 200^3 box (32,000,000
+particles), spatially decomposed over the N GPUs ("scaling": "strong"; N = 1 holds the whole box: 20.5 GB of table).
+`--case C` selects the round-1 weak-scaling mode instead (one C^3 brick per GPU; `--case 64` = configs[1],
+`--case 48 --precision dp` = configs[2]).  A "step" is one DPD time step: velocity-Verlet halves + halo refresh + pair
+force; every 5th step also wrap + migration + 2-level reorder + ghost rebuild + neighbor-list build.
+Prints ONE JSON line on stdout.
 """
 import argparse
 import json
@@ -22,9 +25,9 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-CASE = 64                      # box edge of the N = 1 workload
+BOX = 200                      # box edge of the default (north_star) workload
+CASE = 64                      # box edge of the cpu_baseline sample and of `--case` runs
 RHO = 4
-N_BAR_FALLBACK = 35.84         # stored neighbors per particle (measured; stock LAMMPS: 17.92 half-list)
 
 
 def peaks():
@@ -35,11 +38,11 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons sampled through NVML every few ms; only samples that fall inside the timed region
+    """SM clock + throttle reasons sampled through NVML every ms; only samples that fall inside the timed region
     (mark_begin .. mark_end) are reported.  Falls back to one nvidia-smi query if NVML cannot be loaded."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=0.001):
         super().__init__(daemon=True)
         self.index, self.period, self.stop_flag, self.rows = index, period, False, []
         self.t0 = self.t1 = None
@@ -117,6 +120,20 @@ def procgrid_for(n):
     return best
 
 
+def workload_of(args, world):
+    """(box dims, processor grid, brick dims, scaling, description).  Default: the 200^3 box split over the ranks;
+    --case C: one C^3 brick per rank."""
+    grid = procgrid_for(world)
+    if args.case is not None:
+        L = args.case
+        dims = tuple(g * L for g in grid)
+        return dims, grid, (L, L, L), "weak", "example/simple %s.run case=%d per GPU" % (args.precision, L)
+    B = args.box
+    if any(B % g for g in grid):
+        raise SystemExit("--box %d is not divisible by the processor grid %s" % (B, grid))
+    return (B, B, B), grid, tuple(B // g for g in grid), "strong", "DPD fluid %d^3 box (example/simple %s.run deck) decomposed over %d GPU(s)" % (B, args.precision, world)
+
+
 # ---------------------------------------------------------------------------------------- reference arm
 STOCK_DECK = ("dimension 3\nunits lj\natom_style atomic\ncommunicate single vel yes\nneighbor 0.3 bin\n"
               "neigh_modify delay 0 every 5 check no\nread_data c.data\npair_style dpd 1.0 1.0 419084618\n"
@@ -135,6 +152,13 @@ def host_copies(L):
     return p
 
 
+def _write_brick(args):
+    from meso_b200 import workload
+    path, brick, seed = args
+    workload.write_data(path, workload.dpd_fluid(brick if len(set(brick)) > 1 else brick[0], seed=seed), brick)
+    return path
+
+
 def stock_lammps_rate(L, warm, steps):
     """particle-steps/s of stock pair_style dpd + fix nve on the L^3 box spread over host_copies(L) serial processes
     (returns rate, copies, description) or None when oracle/_ref/lmp_serial did not travel"""
@@ -146,12 +170,19 @@ def stock_lammps_rate(L, warm, steps):
     grid = procgrid_for(p)
     brick = tuple(L // g for g in grid)
     with tempfile.TemporaryDirectory() as d:
-        procs = []
+        procs, jobs = [], []
         for c in range(p):
             dc = os.path.join(d, "c%d" % c)
             os.mkdir(dc)
-            workload.write_data(os.path.join(dc, "c.data"), workload.dpd_fluid(brick if len(set(brick)) > 1 else brick[0], seed=workload.DEFAULT_SEED + c), brick)
+            jobs.append((os.path.join(dc, "c.data"), brick, workload.DEFAULT_SEED + c))
             open(os.path.join(dc, "in.ref"), "w").write(STOCK_DECK % (warm, steps))
+        if p > 1 and brick[0] * brick[1] * brick[2] * RHO > 50000:
+            import multiprocessing as mp                    # the data files are written by the same cores that run them afterwards
+            with mp.get_context("fork").Pool(p) as pool:
+                pool.map(_write_brick, jobs)
+        else:
+            for j in jobs:
+                _write_brick(j)
         for c in range(p):
             dc = os.path.join(d, "c%d" % c)
             procs.append(subprocess.Popen([lmp, "-meso", "off", "-in", "in.ref", "-log", "none"], cwd=dc, stdout=subprocess.PIPE,
@@ -165,18 +196,26 @@ def stock_lammps_rate(L, warm, steps):
             loops.append(t[-1])
     n = RHO * L ** 3
     what = ("stock LAMMPS 30Sep2013 pair_style dpd + fix nve (oracle/_ref/lmp_serial): %d serial processes side by side, each one %s brick "
-            "of the case=%d box as its own periodic system (no MPI in the image: stand-in for mpirun -np %d without halo traffic), "
+            "of the %d^3 box as its own periodic system (no MPI in the image: stand-in for mpirun -np %d without halo traffic), "
             "slowest process counts" % (p, "x".join(str(b) for b in brick), L, p))
     return (n * steps / max(loops), p, what)
 
 
 def reference_arm(args):
-    """Stock LAMMPS pair_style dpd + fix nve on the box's host cores."""
+    """Stock LAMMPS pair_style dpd + fix nve on the box's host cores, on this arm's workload:
+    the whole 200^3 box (or the --case brick set) split over the host cores, a bounded number of time steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from meso_b200 import workload
-    L = args.case
+    world = max(1, args.gpus)
+    dims, grid, brick, scaling, wl = workload_of(args, world)
+    if len(set(dims)) != 1:
+        L = round((dims[0] * dims[1] * dims[2]) ** (1.0 / 3.0))           # weak mode on a non-cubic grid: the cube of equal volume
+        while L ** 3 < dims[0] * dims[1] * dims[2]:
+            L += 1
+    else:
+        L = dims[0]
     n = RHO * L ** 3
     sample_steps = max(1, min(args.steps, args.ref_steps))
     warm = max(1, min(args.warmup, 3))
@@ -189,57 +228,121 @@ def reference_arm(args):
         kind = "reference"
     else:
         import oracle
-        w = oracle.World((0, 0, 0), (L, L, L))
-        w.set_atoms(workload.dpd_fluid(L), workload.maxwell_velocities(n))
+        Ls = min(L, 32)                                      # the scalar port: a bounded sub-box of the same fluid
+        n = RHO * Ls ** 3
+        w = oracle.World((0, 0, 0), (Ls, Ls, Ls))
+        w.set_atoms(workload.dpd_fluid(Ls), workload.maxwell_velocities(n))
         w.setup()
         w.run(warm)
         t0 = time.perf_counter()
         w.run(sample_steps)
         value = n * sample_steps / (time.perf_counter() - t0)
-        kind, cores, what = "port", 1, "oracle/meso_oracle.c (scalar C restatement of the MESO algorithm), 1 core"
+        kind, cores, what = "port", 1, "oracle/meso_oracle.c (scalar C restatement of the MESO algorithm) on a %d^3 sub-box, 1 core" % Ls
     line = {"impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "example/simple DPD fluid case=%d (%d particles, rho=4, rc=1, skin 0.3, rebuild every 5)" % (L, n),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * RHO * L ** 3 / value, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %d particles, rho=4, rc=1, skin 0.3, rebuild every 5 steps, dt 0.005" % (wl, RHO * L ** 3),
                        "what": what},
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind,
-                             "sample": "%d time steps of the case=%d box after %d warm-up steps (of --steps %d); %s" % (sample_steps, L, warm, args.steps, what)},
+                             "sample": "%d time steps after %d warm-up steps (of --steps %d); %s" % (sample_steps, warm, args.steps, what)},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def cpu_baseline_sample(L, budget_s=20.0):
-    """bounded CPU sample for the cpu_baseline key: stock LAMMPS if it travelled, else the oracle port"""
+def cpu_baseline_sample(L):
+    """bounded CPU sample for the cpu_baseline key: stock LAMMPS if it travelled, else the oracle port.  Always the
+    case-64 box (particle-steps/s is size-normalised; the 200^3 box is what --impl reference times)."""
     from meso_b200 import workload
     n = RHO * L ** 3
     steps = 10
     r = stock_lammps_rate(L, 2, steps)
     if r is not None and r[1] > 0:
         return {"value": r[0], "unit": "particle-steps/s", "cores": r[1], "kind": "reference",
-                "sample": "%d steps of the same case=%d box (after 2 warm-up steps); %s" % (steps, L, r[2])}
+                "sample": "%d steps of the case=%d box (1,048,576 particles; after 2 warm-up steps); %s" % (steps, L, r[2])}
     import oracle
-    w = oracle.World((0, 0, 0), (L, L, L))
-    w.set_atoms(workload.dpd_fluid(L), workload.maxwell_velocities(n))
+    Ls = min(L, 32)
+    n = RHO * Ls ** 3
+    w = oracle.World((0, 0, 0), (Ls, Ls, Ls))
+    w.set_atoms(workload.dpd_fluid(Ls), workload.maxwell_velocities(n))
     w.setup()
     steps = 5
     t0 = time.perf_counter()
     w.run(steps)
     t = time.perf_counter() - t0
     return {"value": n * steps / t, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-            "sample": "oracle C port, %d steps of the same case=%d box" % (steps, L)}
+            "sample": "oracle C port, %d steps of a %d^3 box of the same fluid" % (steps, Ls)}
+
+
+# ---------------------------------------------------------------------------------------- parity preflight
+def parity_preflight(rank, world, grid, local_rank, dist):
+    """Small-box check of the path that is about to be timed against the CPU oracle (the checker, not the product):
+    one rank = __graft_entry__.smoke()'s comparison; N ranks = tests/mgpu_check.py at L = 12 on the SAME processor grid
+    (fp64 lockstep over 12 steps incl. migration, fp32 forces, ordered ghosts + neighbor lists + TEA signatures)."""
+    t0 = time.perf_counter()
+    out = {"ok": False, "ranks": world, "grid": list(grid)}
+    try:
+        if world == 1:
+            import oracle
+            from meso_b200 import workload
+            from meso_b200.engine import dpd_fluid_deck
+            L = 8
+            x = workload.dpd_fluid(L)
+            v = workload.maxwell_velocities(len(x))
+            errs = {}
+            for precision, tol in (("sp", 1e-5), ("dp", 1e-12)):
+                m = dpd_fluid_deck(L, precision, device=local_rank, x=x, v=v)
+                m.setup()
+                w = oracle.World((0, 0, 0), (L, L, L), precision=0 if precision == "sp" else 1)
+                w.set_atoms(x, v)
+                w.setup()
+                cg, rg = m.neighbors()
+                co, ro = w.neighbors()
+                mask = np.arange(ro.shape[1])[None, :] < co[:, None]
+                assert np.array_equal(cg, co) and np.array_equal(rg[mask], ro[mask]), "neighbor lists differ from the oracle"
+                assert np.array_equal(m.packed()[1].view(np.uint32), w.packed()[1].view(np.uint32)), "TEA signatures differ"
+                fg, fo = m.download(("f",))["f"], w.atoms()["f"]
+                mag = np.linalg.norm(fo, axis=1)
+                errs[precision] = float((np.linalg.norm(fg - fo, axis=1) / np.maximum(mag, mag.mean())).max())
+                assert errs[precision] <= tol, (precision, errs[precision])
+                m.close()
+            out.update(ok=True, box="8^3", force_err_sp=errs["sp"], force_err_dp=errs["dp"], lists="bit-exact", signatures="bit-exact")
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import mgpu_check
+            from meso_b200.engine import Meso
+            dims = (12, 12, 12)
+            inp = mgpu_check.make_inputs(dims)
+            errs = {}
+            for precision in ("dp", "sp"):
+                ids = [Meso.unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                errs[precision] = mgpu_check.check(precision, rank, grid, local_rank, dims, inp, ids[0], steps=12)
+            flags = [None] * world
+            dist.all_gather_object(flags, errs)
+            out.update(ok=True, box="12^3", force_err_sp=max(f["sp"] for f in flags), force_err_dp=max(f["dp"] for f in flags),
+                       lists="bit-exact (ordered, every rank)", ghosts="bit-exact order and values", dp_lockstep_steps=12)
+    except Exception as e:                                   # a failed preflight is reported, and the bench line says so
+        out["error"] = "%s: %s" % (type(e).__name__, str(e)[:300])
+        if world > 1:
+            raise
+    out["seconds"] = round(time.perf_counter() - t0, 2)
+    return out
 
 
 # ---------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="meso_b200", choices=["meso_b200", "reference"])
-    ap.add_argument("--case", type=int, default=CASE, help="box edge per GPU brick (64 = BASELINE configs[1])")
+    ap.add_argument("--box", type=int, default=BOX, help="edge of the periodic box that is decomposed over the GPUs (200 = BASELINE configs[3])")
+    ap.add_argument("--case", type=int, default=None, help="weak-scaling mode: box edge per GPU brick (64 = BASELINE configs[1])")
     ap.add_argument("--precision", default="sp", choices=["sp", "dp"])
     ap.add_argument("--ref-steps", type=int, default=20, help="time steps the reference arm actually runs (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity preflight")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--thermo", type=int, default=100, help="e2e leg: thermo/output interval (deck: 100)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -264,14 +367,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # weak scaling: every rank owns a case^3 brick of a (px*case, py*case, pz*case) periodic box
-    grid = procgrid_for(world)
-    L = args.case
-    dims = tuple(g * L for g in grid)
-    nloc = RHO * L ** 3
+    dims, grid, brick, scaling, wl = workload_of(args, world)
+    parity = None if args.no_parity else parity_preflight(rank, world, grid, local_rank, dist)
+
+    # every rank generates its own brick of the box (4 uniformly random points per unit cell, cells x-fastest: the layout of
+    # example/simple/25.data); tags are consecutive per brick
+    nloc = RHO * brick[0] * brick[1] * brick[2]
     nglob = nloc * world
     loc = (rank // (grid[1] * grid[2]), (rank // grid[2]) % grid[1], rank % grid[2])
-    x = workload.dpd_fluid(L, seed=workload.DEFAULT_SEED + rank) + np.array([loc[0] * L, loc[1] * L, loc[2] * L], dtype=np.float64)
+    x = workload.dpd_fluid(brick if len(set(brick)) > 1 else brick[0], seed=workload.DEFAULT_SEED + rank)
+    x += np.array([loc[d] * brick[d] for d in range(3)], dtype=np.float64)
     v = workload.maxwell_velocities(nloc, seed=788662042 + rank)
     tag = (np.arange(nloc, dtype=np.int64) + 1 + rank * nloc).astype(np.int32)
 
@@ -293,6 +398,7 @@ def main():
     xp = torch.from_numpy(x).pin_memory()
     vp = torch.from_numpy(v).pin_memory()
     tp = torch.from_numpy(tag).pin_memory()
+    del x, v, tag
 
     def barrier():
         if world > 1:
@@ -300,14 +406,16 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident leg: `value`
+    warmup = max(args.warmup, 3)
     m = deck()
     m.upload(xp.numpy(), vp.numpy(), tag=tp.numpy())
     m.setup()
     stream = torch.cuda.ExternalStream(m.stream())
-    m.run(max(args.warmup, 3))
+    m.run(warmup)
     m.sync()
     n_bar = float(m.pair_count().mean())
     m.timers(enable=True, reset=True)
+    m.launch_count(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -319,6 +427,7 @@ def main():
     m.sync()
     sampler.mark_end()
     barrier()
+    launches = m.launch_count()
     ms = e0.elapsed_time(e1)
     clocks = sampler.summary()
     tm = m.timers(enable=False)
@@ -328,8 +437,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = nglob * args.steps / (ms * 1e-3)
-    rebuilds = tm["neigh"][1]
-    launches = tm["integrate"][1] + tm["forward"][1] + tm["pair"][1] + rebuilds * KERNELS_PER_REBUILD(m)
 
     # ---- roofline of the dominant kernel (the pair-force kernel)
     peak, peak_src = peaks()
@@ -338,89 +445,91 @@ def main():
     b_force = 4.0 * n_bar + 32.0 + 24.0                        # algorithmic bytes per particle per force evaluation
     # per rank: every step evaluates the force on all nloc particles (one launch on 1 GPU; bulk + border launches on N > 1)
     achieved = b_force * nloc * args.steps / (pair_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp_path = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
     if os.path.exists(tp_path):
-        traffic = json.load(open(tp_path)).get("dram_bytes_per_launch_%s%s" % (args.precision, "_once" if once else ""))
+        tj = json.load(open(tp_path))
+        key = "%s%s" % (args.precision, "_once" if once else "")
+        if "dram_bytes_per_particle_" + key in tj:
+            # ncu --set full capture of this kernel (profiles/): bytes per particle of that capture x particles per launch here
+            traffic = tj["dram_bytes_per_particle_" + key] * nloc * args.steps / max(pair_calls, 1)
+            traffic_src = tj.get("source_" + key)
     kname = ("k_dpd_once<%s> (each local pair once, REDG scatter)" if once else "k_dpd<%s,0> (two-sided, +fused final_integrate)") % \
         ("float" if args.precision == "sp" else "double")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": b_force, "particles_per_launch": nloc * args.steps / max(pair_calls, 1),
                 "avg_launch_ms": pair_ms / max(pair_calls, 1), "share_of_step": pair_ms / ms,
-                "note": "not HBM-bound: a list-based gather kernel on the L1/issue ridge (ncu: LSU data-pipe wavefronts 62-78 % depending on "
-                        "how many gathers take the texture pipe, issue slots 56-60 %, DRAM 21 %, 1.2x the algorithmic bytes moved); "
-                        "see DESIGN.md s3.1 and profiles/"}
+                "note": "not HBM-bound: a list-based gather kernel on the L1/issue ridge (ncu, profiles/: L1 data-pipe wavefronts and issue "
+                        "slots ~60 %, DRAM ~20 %, ~1.2x the algorithmic bytes moved); see DESIGN.md s3.1"}
     phases = {k: {"ms_total": round(v[0], 3), "calls": int(v[1])} for k, v in tm.items()}
+    m.close()
 
     # ---- end-to-end leg through the C ABI with HOST buffers: the deck's `run K` with `thermo 100`
-    # upload of all atoms (H2D from pinned memory), setup, K steps, temp/meso + transfer_pre_output (D2H x,v,f,tag) every `thermo` steps
-    m.close()
-    m = deck()
-    ncap = nloc if world == 1 else nloc + nloc // 8 + 1024      # atoms migrate between bricks: a rank's count drifts around nloc
-    out = {k: torch.empty((ncap, 3), dtype=torch.float64).pin_memory() for k in ("x", "v", "f")}
-    otag = torch.empty(ncap, dtype=torch.int32).pin_memory()
-    import ctypes as C
-    vp_ = lambda t_: C.c_void_p(t_.data_ptr())
+    # upload of all atoms (H2D from pinned memory), setup, K steps, temp/meso every `thermo` steps, and the positions,
+    # velocities, forces and tags of every atom read back at the end of the run (transfer_pre_output)
+    e2e = None
+    if not args.no_e2e:
+        m = deck()
+        ncap = nloc if world == 1 else nloc + nloc // 8 + 1024      # atoms migrate between bricks: a rank's count drifts around nloc
+        out = {k: torch.empty((ncap, 3), dtype=torch.float64).pin_memory() for k in ("x", "v", "f")}
+        otag = torch.empty(ncap, dtype=torch.int32).pin_memory()
+        import ctypes as C
+        vp_ = lambda t_: C.c_void_p(t_.data_ptr())
 
-    def run_deck(nsteps):
-        m.upload(xp.numpy(), vp.numpy(), tag=tp.numpy())
-        m.ntimestep = 0
-        m.setup()
-        done, d2h, temps = 0, 0, []
-        while done < nsteps:
-            chunk = min(args.thermo, nsteps - done)
-            m.run(chunk)
-            done += chunk
-            temps.append(m.temperature())
+        def run_deck(nsteps):
+            t0 = time.perf_counter()
+            m.upload(xp.numpy(), vp.numpy(), tag=tp.numpy())
+            m.ntimestep = 0
+            m.setup()
+            t_setup = time.perf_counter() - t0                   # meso_setup returns after the device finished (it reads the counts back)
+            done, temps = 0, []
+            while done < nsteps:
+                chunk = min(args.thermo, nsteps - done)
+                m.run(chunk)
+                done += chunk
+                temps.append(m.temperature())
+            t1 = time.perf_counter()
             m._chk(m.L.meso_atoms_download(m.h, ncap, vp_(out["x"]), vp_(out["v"]), vp_(out["f"]), vp_(otag), None, None, None))
-            d2h += m.counts()["nlocal"] * (72 + 4) + 16
-        return d2h, temps
+            t_down = time.perf_counter() - t1
+            d2h = m.counts()["nlocal"] * (72 + 4) + 16 * len(temps)
+            return d2h, temps, t_setup, t_down
 
-    run_deck(min(args.steps, 2 * args.thermo))          # warm-up (allocations, first-touch)
-    barrier()
-    t0 = time.perf_counter()
-    d2h, temps = run_deck(args.steps)
-    barrier()
-    wall = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([wall], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall = float(t.item())
-    h2d = nloc * (48 + 4)
-    e2e = {"value": nglob * args.steps / wall, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / args.steps,
-           "d2h_bytes_per_step": d2h / args.steps,
-           "what": "C-ABI deck run: meso_atoms_upload (pinned host AoS) + meso_setup + %d x meso_run(%d) each followed by temp/meso and "
-                   "meso_atoms_download of x,v,f,tag (transfer_pre_output), wall clock incl. all copies" % (-(-args.steps // args.thermo), args.thermo)}
-    m.close()
+        run_deck(min(args.steps, 10))                        # warm-up (allocations, first-touch)
+        barrier()
+        t0 = time.perf_counter()
+        d2h, temps, t_setup, t_down = run_deck(args.steps)
+        barrier()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([wall, t_setup, t_down], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall, t_setup, t_down = (float(a) for a in t.tolist())
+        h2d = nloc * (48 + 4)
+        e2e = {"value": nglob * args.steps / wall, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "setup_ms": 1e3 * t_setup, "download_ms": 1e3 * t_down,
+               "stepping_ms": 1e3 * (wall - t_setup - t_down), "wall_ms": 1e3 * wall,
+               "what": "C-ABI deck run with pinned HOST buffers: meso_atoms_upload (H2D) + meso_setup (first reorder, ghosts, neighbor table, "
+                       "setup force; = setup_ms) + %d step(s) in chunks of %d each followed by temp/meso (D2H scalar) + one meso_atoms_download "
+                       "of x,v,f,tag (D2H; = download_ms); wall clock over everything, max over ranks" % (args.steps, args.thermo)}
+        m.close()
 
     line = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32" if args.precision == "sp" else "f64", "data": "synthetic",
-            "config": {"workload": "example/simple %s.run case=%d per GPU: DPD fluid rho=4, %d particles/GPU, box %dx%dx%d, rc=1, skin 0.3, "
-                                   "rebuild every 5 steps, dt 0.005" % (args.precision, L, nloc, *dims),
-                       "procgrid": list(grid), "pair_style": "dpd/fast/meso" if args.precision == "sp" else "dpd/meso",
-                       "l2": "per-step working set (~0.8 GB at 1M particles) exceeds the 126 MB L2; no explicit flush",
+            "config": {"workload": "%s: rho=4, %d particles (%d per GPU), box %dx%dx%d, rc=1, skin 0.3, rebuild every 5 steps, dt 0.005"
+                                   % (wl, nglob, nloc, *dims),
+                       "procgrid": list(grid), "brick": list(brick), "pair_style": "dpd/fast/meso" if args.precision == "sp" else "dpd/meso",
+                       "l2": "per-step working set (>= 0.8 GB per million particles) exceeds the 126 MB L2; no explicit flush",
                        "mean_neighbors": n_bar, "temperature_end": T_end},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "phases": phases, "clocks": clocks}
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "phases": phases, "clocks": clocks, "parity_check": parity}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample(L)
+        line["cpu_baseline"] = cpu_baseline_sample(CASE)
     if rank == 0:
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:
         dist.destroy_process_group()
-
-
-def KERNELS_PER_REBUILD(m):
-    # reorder: key + 3/pass sort + gather; borders: 1 + 4/dim; neighbor: cell id + 3/pass sort + bounds + build
-    mm = m.bins()[0]
-    import math
-    l1 = 3 * int(math.floor(math.log2(max(mm) * 2.0)))
-    p1 = -(-(1 + l1 + 12) // 8)
-    ncell = mm[0] * mm[1] * mm[2]
-    p2 = -(-max(1, math.ceil(math.log2(ncell))) // 8)
-    return 2 + 3 * p1 + 1 + 12 + 3 + 3 * p2
 
 
 if __name__ == "__main__":

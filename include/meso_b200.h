@@ -184,6 +184,8 @@ int meso_eval_log2u(meso_ctx *ctx, int n, const uint32_t *a, double *out);
 enum { MESO_T_INTEGRATE = 0, MESO_T_FORWARD, MESO_T_PAIR, MESO_T_REBUILD, MESO_T_NEIGH, MESO_T_COUNT };
 int meso_timers_enable(meso_ctx *ctx, int on);       /* inserts event pairs around phases inside meso_run */
 int meso_timers_read(meso_ctx *ctx, double ms[MESO_T_COUNT], int64_t calls[MESO_T_COUNT], int reset);
+/* number of kernels this library launched on the context's streams since the last reset (NCCL's own kernels not included) */
+int meso_launch_count(meso_ctx *ctx, int64_t *n, int reset);
 
 #ifdef __cplusplus
 }

@@ -288,13 +288,20 @@ static int comm_setup(meso_ctx *ctx)
 }
 
 // ---------------------------------------------------------------- settings
+// Neighbor::init: cutneighmax = largest pair cutoff + skin.  Every setter that touches one of the three inputs goes through
+// here, so the result does not depend on the order of the calls (the global cutoff stands in until the coefficients arrive).
+static void update_cutneighmax(meso_ctx *ctx)
+{
+    ctx->cutneighmax = (ctx->max_pair_cut > 0.0 ? ctx->max_pair_cut : ctx->cut_global) + ctx->skin;
+    ctx->bins_ready = false;
+}
+
 extern "C" int meso_set_neighbor(meso_ctx *ctx, double skin, int every)
 {
     CHECK_CTX();
     if (skin < 0 || every < 1) FAIL(MESO_EINVAL, "meso_set_neighbor: skin >= 0 and every >= 1 required");
     ctx->skin = skin; ctx->every = every;
-    ctx->cutneighmax = ctx->cut_global + skin;
-    ctx->bins_ready = false;
+    update_cutneighmax(ctx);
     return MESO_OK;
 }
 
@@ -317,8 +324,9 @@ extern "C" int meso_pair_dpd_settings(meso_ctx *ctx, int precision, double cut_g
     CHECK_CTX();
     if (precision != MESO_SP && precision != MESO_DP) FAIL(MESO_EINVAL, "Illegal pair_style command");
     ctx->precision = precision; ctx->cut_global = cut_global; ctx->seed = seed;
-    ctx->cutneighmax = cut_global + ctx->skin;
-    ctx->bins_ready = false;
+    ctx->max_pair_cut = 0.0;                                // pair_style resets the coefficients (MesoPairDPD::settings)
+    ctx->coeff_ready = false;
+    update_cutneighmax(ctx);
     return MESO_OK;
 }
 
@@ -332,8 +340,8 @@ extern "C" int meso_pair_dpd_coeff(meso_ctx *ctx, const double *coeff7)
     ctx->coeff.assign(coeff7, coeff7 + n);
     double cmax = 0;
     for (int t = 0; t < ctx->ntypes * ctx->ntypes; t++) cmax = std::max(cmax, coeff7[t * NCOEFF + P_CUT]);
-    // Neighbor::init: cutneighmax = max pair cutoff + skin
-    ctx->cutneighmax = std::max(cmax, 0.0) + ctx->skin;
+    ctx->max_pair_cut = std::max(cmax, 0.0);
+    update_cutneighmax(ctx);
     std::vector<float> sp(n);
     for (int i = 0; i < n; i++) sp[i] = (float)coeff7[i];
     if (!ctx->coeff_sp.reserve(n) || !ctx->coeff_dp.reserve(n)) FAIL(MESO_ECUDA, "out of device memory");
@@ -341,7 +349,6 @@ extern "C" int meso_pair_dpd_coeff(meso_ctx *ctx, const double *coeff7)
     MESO_CUDA(cudaMemcpyAsync(ctx->coeff_dp.p, ctx->coeff.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     MESO_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->coeff_ready = true;
-    ctx->bins_ready = false;
     return MESO_OK;
 }
 
@@ -392,8 +399,14 @@ static int ensure_capacity(meso_ctx *ctx, size_t nlocal)
     size_t nghost = (size_t)((double)nlocal * (vout / vin - 1.0) * 1.25) + 4096;
     size_t nloc_cap = (ctx->nranks > 1) ? nlocal + nlocal / 8 + 1024 : nlocal;
     size_t cap = nloc_cap + nghost;
-    if (cap <= ctx->cap) return MESO_OK;
-    ctx->nloc_cap = nloc_cap;
+    if (cap <= ctx->cap) {
+        // the per-atom arrays are large enough, but the split between locals and ghosts may have moved: the pair table is
+        // reserved from table_rows at the next rebuild (bins_ready is cleared by every upload)
+        ctx->nloc_cap = std::max(ctx->nloc_cap, nloc_cap);
+        ctx->table_rows = std::max(ctx->table_rows, ((ctx->nloc_cap + 31) / 32) * 32);
+        return MESO_OK;
+    }
+    ctx->nloc_cap = std::max(ctx->nloc_cap, nloc_cap);
     bool ok = true;
     for (int d = 0; d < 3; d++)
         ok = ok && ctx->x[d].reserve(cap) && ctx->v[d].reserve(cap) && ctx->f[d].reserve(cap) && ctx->xa[d].reserve(cap) && ctx->va[d].reserve(cap);
@@ -423,7 +436,7 @@ static int ensure_capacity(meso_ctx *ctx, size_t nlocal)
     if (!ctx->facc.reserve(cap)) FAIL(MESO_ECUDA, "out of device memory (force accumulator)");
     MESO_CUDA(cudaMemsetAsync(ctx->facc.p, 0, ctx->facc.bytes(), ctx->stream));
     if (!ctx->virial.reserve(6 * ctx->cap)) FAIL(MESO_ECUDA, "out of device memory (virial)");
-    ctx->table_rows = ((nloc_cap + 31) / 32) * 32;
+    ctx->table_rows = ((ctx->nloc_cap + 31) / 32) * 32;
     return MESO_OK;
 }
 
@@ -541,6 +554,12 @@ extern "C" int meso_neighbor_decide(meso_ctx *ctx)
 
 static int rebuild_impl(meso_ctx *ctx)
 {
+    // a capacity error of an EARLIER rebuild truncates rows / drops ghosts: stop as soon as its Counts mirror has landed
+    // (non-blocking query; the multi-rank path additionally waits once per rebuild in launch_forward_multi)
+    if (ctx->setup_done && ctx->counts_pending && cudaEventQuery(ctx->ev_counts) == cudaSuccess) {
+        ctx->counts_pending = false;
+        TRY(check_device_flags(ctx));
+    }
     if (!ctx->bins_ready) {
         TRY(comm_setup(ctx));
         TRY(launch_setup_bins(ctx));
@@ -571,6 +590,7 @@ static int rebuild_impl(meso_ctx *ctx)
     if (ctx->comm_path) TRY(comm_share_errors(ctx));
     MESO_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(Counts), cudaMemcpyDeviceToHost, ctx->stream));
     MESO_CUDA(cudaEventRecord(ctx->ev_counts, ctx->stream));
+    ctx->counts_pending = true;
     ctx->fwd_counts_valid = false;
     ctx->ago = 0;
     return MESO_OK;
@@ -589,7 +609,13 @@ extern "C" int meso_forward_comm(meso_ctx *ctx)
     TRY(ready(ctx));
     PhaseTimer t(ctx, MESO_T_FORWARD);
     // phase API keeps the reference's order: ghosts' fp64 x,v are refreshed, packing happens in meso_pair_compute
-    if (ctx->comm_path) return launch_forward_multi(ctx, ctx->stream);
+    if (ctx->comm_path) {
+        // the halo records carry the PACKED velocity + signature of the owner (comm.cu: 40-byte records), and in the phase
+        // order initial_integrate -> forward_comm -> pair_compute the locals have not been repacked since the half-kick:
+        // repack them first, so a ghost receives this step's velocity and signature (what its owner's pair kernel uses)
+        TRY(launch_pack(ctx, MESO_LOCAL));
+        return launch_forward_multi(ctx, ctx->stream);
+    }
     return launch_forward(ctx, true);
 }
 
@@ -1127,6 +1153,14 @@ extern "C" int meso_eval_log2u(meso_ctx *ctx, int n, const uint32_t *a, double *
 }
 
 // ---------------------------------------------------------------- timers
+extern "C" int meso_launch_count(meso_ctx *ctx, int64_t *n, int reset)
+{
+    CHECK_CTX();
+    if (n) *n = ctx->n_launch;
+    if (reset) ctx->n_launch = 0;
+    return MESO_OK;
+}
+
 extern "C" int meso_timers_enable(meso_ctx *ctx, int on)
 {
     CHECK_CTX();

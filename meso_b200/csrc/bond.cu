@@ -189,7 +189,7 @@ int bonds_reserve(meso_ctx *ctx)
 int launch_bonds_gather(meso_ctx *ctx)
 {
     if (!bonds_active(ctx)) return MESO_OK;
-    k_gather_bonds<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p, ctx->perm_from.p,
+    k_gather_bonds<<<grid_for(ctx, 4), 256, 0, LS(ctx->stream)>>>(ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p, ctx->perm_from.p,
                                                            ctx->d_counts, ctx->cap, ctx->bond_per_atom);
     std::swap(ctx->nbond.p, ctx->nbond_alt.p); std::swap(ctx->nbond.cap, ctx->nbond_alt.cap);
     std::swap(ctx->bonds.p, ctx->bonds_alt.p); std::swap(ctx->bonds.cap, ctx->bonds_alt.cap);
@@ -204,8 +204,8 @@ int launch_bonds_map(meso_ctx *ctx)
     const int map_size = ctx->map_tag_max + 1;
     if (!ctx->tag_map.reserve((size_t)map_size)) { ctx->err = "out of device memory (tag map)"; return MESO_ECUDA; }
     MESO_CUDA(cudaMemsetAsync(ctx->tag_map.p, 0xff, sizeof(unsigned) * (size_t)map_size, ctx->stream));
-    k_map_set<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->tag.p, ctx->tag_map.p, ctx->d_counts, map_size);
-    k_map_bonds<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->nbond.p, ctx->bonds.p, ctx->bonds_mapped.p, ctx->tag_map.p, ctx->d_counts,
+    k_map_set<<<grid_for(ctx, 4), 256, 0, LS(ctx->stream)>>>(ctx->tag.p, ctx->tag_map.p, ctx->d_counts, map_size);
+    k_map_bonds<<<grid_for(ctx, 4), 256, 0, LS(ctx->stream)>>>(ctx->nbond.p, ctx->bonds.p, ctx->bonds_mapped.p, ctx->tag_map.p, ctx->d_counts,
                                                         ctx->cap, map_size);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -214,7 +214,7 @@ int launch_bonds_map(meso_ctx *ctx)
 int launch_bonds_filter(meso_ctx *ctx)
 {
     if (!bonds_active(ctx) || ctx->special_lj12 != 0.0) return MESO_OK;
-    k_filter_exclusion<<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->tag.p, ctx->nbond.p, ctx->bonds.p, ctx->pair_count.p, ctx->pair_table.p,
+    k_filter_exclusion<<<grid_for(ctx, 8), 128, 0, LS(ctx->stream)>>>(ctx->tag.p, ctx->nbond.p, ctx->bonds.p, ctx->pair_count.p, ctx->pair_table.p,
                                                                ctx->d_counts, ctx->cap, ctx->n_col);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -230,9 +230,9 @@ int launch_bond_force(meso_ctx *ctx, int evflag, bool into_facc)
 #define MESO_BOND_ARGS ctx->coord4.p, ctx->nbond.p, ctx->bonds_mapped.p, f, ctx->facc.p, ctx->virial.p, ctx->e_bond.p, ctx->bond_k_dev.p, \
                        ctx->bond_r0_dev.p, ctx->d_counts, ctx->cap, ctx->cap, period
     const int g = grid_for(ctx, 8);
-    if (evflag) k_bond_harmonic<1, 0><<<g, 256, 0, ctx->stream>>>(MESO_BOND_ARGS);
-    else if (into_facc) k_bond_harmonic<0, 1><<<g, 256, 0, ctx->stream>>>(MESO_BOND_ARGS);
-    else k_bond_harmonic<0, 0><<<g, 256, 0, ctx->stream>>>(MESO_BOND_ARGS);
+    if (evflag) k_bond_harmonic<1, 0><<<g, 256, 0, LS(ctx->stream)>>>(MESO_BOND_ARGS);
+    else if (into_facc) k_bond_harmonic<0, 1><<<g, 256, 0, LS(ctx->stream)>>>(MESO_BOND_ARGS);
+    else k_bond_harmonic<0, 0><<<g, 256, 0, LS(ctx->stream)>>>(MESO_BOND_ARGS);
 #undef MESO_BOND_ARGS
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -244,8 +244,8 @@ int launch_bond_energy_sum(meso_ctx *ctx, double *e)
     if (!bonds_active(ctx)) return MESO_OK;
     const int nb = grid_for(ctx, 2);
     if (!ctx->partial.reserve((size_t)nb + 8)) { ctx->err = "reduce: out of device memory"; return MESO_ECUDA; }
-    k_sum_partial<<<nb, 256, 0, ctx->stream>>>(ctx->e_bond.p, ctx->d_counts, ctx->partial.p);
-    k_sum_final<<<1, 256, 0, ctx->stream>>>(ctx->partial.p, nb, ctx->partial.p + nb);
+    k_sum_partial<<<nb, 256, 0, LS(ctx->stream)>>>(ctx->e_bond.p, ctx->d_counts, ctx->partial.p);
+    k_sum_final<<<1, 256, 0, LS(ctx->stream)>>>(ctx->partial.p, nb, ctx->partial.p + nb);
     MESO_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->partial.p + nb, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MESO_CUDA(cudaStreamSynchronize(ctx->stream));
     *e = ctx->h_result[0];

@@ -565,14 +565,14 @@ int launch_exchange_multi(meso_ctx *ctx)
     }
     for (int d = 0; d < 3; d++) {
         if (ctx->procgrid[d] == 1) continue;        // the periodic wrap already put every atom back into the brick
-        k_mr_exch_count<<<grid_for(ctx, 4), CT, 0, st>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
-        k_mr_exch_scan<<<1, 1024, 0, st>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->exch_cap);
-        k_mr_exch_scatter<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
+        k_mr_exch_count<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
+        k_mr_exch_scan<<<1, 1024, 0, LS(st)>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->exch_cap);
+        k_mr_exch_scatter<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
                                                          soa(ctx->xa), soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p, ctx->imagea.p,
                                                          ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d, ntiles, ctx->exch_cap,
                                                          bonded ? ctx->exch_dest.p : nullptr);
         if (bonded) {
-            k_mr_exch_bonds_scatter<<<grid_for(ctx, 4), 256, 0, st>>>(ctx->exch_dest.p, ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p,
+            k_mr_exch_bonds_scatter<<<grid_for(ctx, 4), 256, 0, LS(st)>>>(ctx->exch_dest.p, ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p,
                                                                    ctx->bond_send[0].p, ctx->bond_send[1].p, ctx->d_counts, ctx->cap, bpa);
             std::swap(ctx->nbond.p, ctx->nbond_alt.p); std::swap(ctx->nbond.cap, ctx->nbond_alt.cap);
             std::swap(ctx->bonds.p, ctx->bonds_alt.p); std::swap(ctx->bonds.cap, ctx->bonds_alt.cap);
@@ -580,11 +580,11 @@ int launch_exchange_multi(meso_ctx *ctx)
         for (int q = 0; q < 3; q++) { std::swap(ctx->x[q].p, ctx->xa[q].p); std::swap(ctx->v[q].p, ctx->va[q].p); }
         std::swap(ctx->tag.p, ctx->taga.p); std::swap(ctx->type.p, ctx->typea.p);
         std::swap(ctx->mask.p, ctx->maska.p); std::swap(ctx->image.p, ctx->imagea.p);
-        k_mr_exch_shrink<<<1, 1, 0, st>>>(ctx->d_counts);
+        k_mr_exch_shrink<<<1, 1, 0, LS(st)>>>(ctx->d_counts);
         const double *ra, *rb;
         rc = swap_messages(ctx, d, (size_t)(ctx->exch_cap + 1) * REC, st, ra, rb);
         if (rc) return rc;
-        k_mr_exch_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
+        k_mr_exch_unpack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
                                                         ctx->d_counts, ra, rb, box, d, (int)ctx->nloc_cap);
         if (bonded) {
             ncclComm_t comm = (ncclComm_t)ctx->nccl;
@@ -595,10 +595,10 @@ int launch_exchange_multi(meso_ctx *ctx)
             MESO_NCCL(ncclSend(ctx->bond_send[1].p, nint, ncclInt, ctx->procneigh[d][1], comm, st));
             MESO_NCCL(ncclRecv(ctx->bond_recv[1].p, nint, ncclInt, ctx->procneigh[d][0], comm, st));
             MESO_NCCL(ncclGroupEnd());
-            k_mr_exch_bonds_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->nbond.p, ctx->bonds.p, ctx->d_counts, ra, rb, ctx->bond_recv[0].p,
+            k_mr_exch_bonds_unpack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(ctx->nbond.p, ctx->bonds.p, ctx->d_counts, ra, rb, ctx->bond_recv[0].p,
                                                                   ctx->bond_recv[1].p, ctx->cap, bpa, (int)ctx->nloc_cap);
         }
-        k_mr_exch_grow<<<1, 1, 0, st>>>(ctx->d_counts, ra, rb);
+        k_mr_exch_grow<<<1, 1, 0, LS(st)>>>(ctx->d_counts, ra, rb);
     }
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -791,9 +791,9 @@ static int build_routes(meso_ctx *ctx)
     route_table(ctx, rt);
     int2 *const *req = reinterpret_cast<int2 *const *>(ctx->route_ptrs.p);
     int *const *dst = reinterpret_cast<int *const *>(ctx->route_ptrs.p + 27);
-    k_route_reset<<<1, 32, 0, st>>>(ctx->d_counts);
-    k_route_build<<<grid_for(ctx, 2), 256, 0, st>>>(ctx->ghost_origin.p, ctx->peer_slot.p, ctx->d_counts, rt, req, dst, ctx->route_cap, ctx->nranks);
-    k_route_headers<<<1, 32, 0, st>>>(ctx->d_counts, req, np, ctx->route_cap);
+    k_route_reset<<<1, 32, 0, LS(st)>>>(ctx->d_counts);
+    k_route_build<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(ctx->ghost_origin.p, ctx->peer_slot.p, ctx->d_counts, rt, req, dst, ctx->route_cap, ctx->nranks);
+    k_route_headers<<<1, 32, 0, LS(st)>>>(ctx->d_counts, req, np, ctx->route_cap);
     if (np > 1) {
         ncclComm_t comm = (ncclComm_t)ctx->nccl;
         const size_t nint = ((size_t)ctx->route_cap + 1) * 2;
@@ -805,7 +805,7 @@ static int build_routes(meso_ctx *ctx)
         }
         MESO_NCCL(ncclGroupEnd());
     }
-    k_route_adopt<<<1, 32, 0, st>>>(ctx->d_counts, rt, ctx->route_cap);
+    k_route_adopt<<<1, 32, 0, LS(st)>>>(ctx->d_counts, rt, ctx->route_cap);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
@@ -817,7 +817,7 @@ static int forward_routes(meso_ctx *ctx, cudaStream_t st)
     RouteTable rt;
     route_table(ctx, rt);
     const dim3 grid(ctx->sm_count, np);
-    k_route_pack<<<grid, 256, 0, st>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, rt, ctx->box);
+    k_route_pack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, rt, ctx->box);
     if (np > 1) {
         ncclComm_t comm = (ncclComm_t)ctx->nccl;
         MESO_NCCL(ncclGroupStart());
@@ -828,7 +828,7 @@ static int forward_routes(meso_ctx *ctx, cudaStream_t st)
         }
         MESO_NCCL(ncclGroupEnd());
     }
-    k_route_unpack<<<grid, 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts, rt, ctx->box);
+    k_route_unpack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts, rt, ctx->box);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
@@ -1044,9 +1044,9 @@ int launch_exchange_oneshot(meso_ctx *ctx)
         os.bsend[s] = ctx->os_bsend[s].p; os.brecv[s] = ctx->os_brecv[s].p;
     }
     if (!okm) { ctx->err = "out of device memory (one-shot migration buffers)"; return MESO_ECUDA; }
-    k_os_count<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), ctx->d_counts, tc, box, os, ntiles);
-    k_os_scan<<<1, 1024, 0, st>>>(tc, ctx->d_counts);
-    k_os_scatter<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, soa(ctx->xa),
+    k_os_count<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), ctx->d_counts, tc, box, os, ntiles);
+    k_os_scan<<<1, 1024, 0, LS(st)>>>(tc, ctx->d_counts);
+    k_os_scatter<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, soa(ctx->xa),
                                                 soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p, ctx->imagea.p, ctx->d_counts, tc, box, os,
                                                 ntiles, ctx->exch_cap, ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p, ctx->cap);
     for (int q = 0; q < 3; q++) { std::swap(ctx->x[q].p, ctx->xa[q].p); std::swap(ctx->v[q].p, ctx->va[q].p); }
@@ -1056,7 +1056,7 @@ int launch_exchange_oneshot(meso_ctx *ctx)
         std::swap(ctx->nbond.p, ctx->nbond_alt.p); std::swap(ctx->nbond.cap, ctx->nbond_alt.cap);
         std::swap(ctx->bonds.p, ctx->bonds_alt.p); std::swap(ctx->bonds.cap, ctx->bonds_alt.cap);
     }
-    k_os_headers<<<1, 32, 0, st>>>(ctx->d_counts, os, ctx->exch_cap);
+    k_os_headers<<<1, 32, 0, LS(st)>>>(ctx->d_counts, os, ctx->exch_cap);
     ncclComm_t comm = (ncclComm_t)ctx->nccl;
     MESO_NCCL(ncclGroupStart());
     for (int s = 0; s < os.np; s++) {
@@ -1070,9 +1070,9 @@ int launch_exchange_oneshot(meso_ctx *ctx)
     }
     MESO_NCCL(ncclGroupEnd());
     const dim3 grid(ctx->sm_count, os.np);
-    k_os_unpack<<<grid, 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, ctx->d_counts, os, box,
+    k_os_unpack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, ctx->d_counts, os, box,
                                     (int)ctx->nloc_cap, ctx->nbond.p, ctx->bonds.p, ctx->cap);
-    k_os_grow<<<1, 1, 0, st>>>(ctx->d_counts, os);
+    k_os_grow<<<1, 1, 0, LS(st)>>>(ctx->d_counts, os);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
@@ -1094,19 +1094,19 @@ int launch_borders_multi(meso_ctx *ctx)
     const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
     int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
     cudaStream_t st = ctx->stream;
-    k_mr_reset_ghosts<<<1, 1, 0, st>>>(ctx->d_counts);
+    k_mr_reset_ghosts<<<1, 1, 0, LS(st)>>>(ctx->d_counts);
     for (int d = 0; d < 3; d++) {
         if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1] && ctx->procgrid[d] == 1) continue;
-        k_mr_border_count<<<grid_for(ctx, 4), CT, 0, st>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
-        k_mr_border_scan<<<1, 1024, 0, st>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, d, ctx->swap_cap);
-        k_mr_border_pack<<<grid_for(ctx, 4), CT, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->veloc4.p,
+        k_mr_border_count<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
+        k_mr_border_scan<<<1, 1024, 0, LS(st)>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, d, ctx->swap_cap);
+        k_mr_border_pack<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->veloc4.p,
                                                         ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->sendlist[2 * d].p,
                                                         ctx->sendlist[2 * d + 1].p, box, d, ntiles, ctx->swap_cap, ctx->ghost_origin.p, ctx->rank);
         const double *ra, *rb;
         rc = swap_messages(ctx, d, (size_t)(ctx->swap_cap + 1) * RECB, st, ra, rb);
         if (rc) return rc;
-        k_mr_border_advance<<<1, 1, 0, st>>>(ctx->d_counts, ra, rb, d, (int)ctx->cap);
-        k_mr_border_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->coord4.p,
+        k_mr_border_advance<<<1, 1, 0, LS(st)>>>(ctx->d_counts, ra, rb, d, (int)ctx->cap);
+        k_mr_border_unpack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->coord4.p,
                                                           ctx->veloc4.p, ctx->d_counts, ra, rb, box, d, ctx->ghost_origin.p);
     }
     MESO_CUDA(cudaGetLastError());
@@ -1143,13 +1143,13 @@ int launch_forward_multi(meso_ctx *ctx, cudaStream_t st)
     if (ctx->halo_routes) return forward_routes(ctx, st);
     for (int d = 0; d < 3; d++) {
         if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1] && ctx->procgrid[d] == 1) continue;
-        k_mr_forward_pack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, ctx->sendlist[2 * d].p,
+        k_mr_forward_pack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, ctx->sendlist[2 * d].p,
                                                          ctx->sendlist[2 * d + 1].p, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d);
         const double *ra, *rb;
         int rc = swap_messages4(ctx, d, (size_t)ctx->fwd_send_n[2 * d] * RECF, (size_t)ctx->fwd_send_n[2 * d + 1] * RECF,
                                 (size_t)ctx->fwd_recv_n[2 * d] * RECF, (size_t)ctx->fwd_recv_n[2 * d + 1] * RECF, st, ra, rb);
         if (rc) return rc;
-        k_mr_forward_unpack<<<grid_for(ctx, 2), 256, 0, st>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
+        k_mr_forward_unpack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
                                                            ra, rb, box, d);
     }
     MESO_CUDA(cudaGetLastError());

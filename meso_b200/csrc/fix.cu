@@ -117,7 +117,7 @@ int launch_fix_rdf(meso_ctx *ctx, int handle)
         const int every = (int)o.p[0], nbin = o.dims;
         if (every > 1 && ctx->ntimestep % every != 0) continue;       // UM/fix_rdf_fast_meso.cu:160
         const float rc = (float)o.p[1];
-        k_rdf<<<grid_for(ctx, 4), 256, sizeof(unsigned) * nbin, ctx->stream>>>(ctx->coord4.p, ctx->mask.p, ctx->pair_count.p, ctx->pair_table.p,
+        k_rdf<<<grid_for(ctx, 4), 256, sizeof(unsigned) * nbin, LS(ctx->stream)>>>(ctx->coord4.p, ctx->mask.p, ctx->pair_count.p, ctx->pair_table.p,
                                                                             ctx->rdf_hist[k].p, ctx->d_counts, ctx->n_col, rc, (float)nbin / rc,
                                                                             nbin, o.groupbit, o.aux);
         ctx->rdf_samples[k]++;
@@ -133,7 +133,7 @@ int fix_rdf_read(meso_ctx *ctx, int handle, int nbin, double *hist, double *ni, 
     std::vector<unsigned long long> h((size_t)nbin + 2, 0ull);
     unsigned long long *cnt2 = ctx->rdf_hist[handle].p + nbin;       // two spare counters behind the bins
     MESO_CUDA(cudaMemsetAsync(cnt2, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    k_group_count<<<grid_for(ctx, 2), 256, 0, ctx->stream>>>(ctx->mask.p, ctx->d_counts, o.groupbit, o.aux, cnt2);
+    k_group_count<<<grid_for(ctx, 2), 256, 0, LS(ctx->stream)>>>(ctx->mask.p, ctx->d_counts, o.groupbit, o.aux, cnt2);
     MESO_CUDA(cudaMemcpyAsync(h.data(), ctx->rdf_hist[handle].p, sizeof(unsigned long long) * (nbin + 2), cudaMemcpyDeviceToHost, ctx->stream));
     MESO_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int b = 0; b < nbin; b++) hist[b] = (double)h[b];
@@ -147,9 +147,9 @@ int launch_fix_post_force(meso_ctx *ctx, int handle, bool into_facc)
     SoA3c x; SoA3 f;
     for (int d = 0; d < 3; d++) { x.c[d] = ctx->x[d].p; f.c[d] = ctx->f[d].p; }
     if (into_facc)
-        k_fix_post_force<1><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(x, f, ctx->facc.p, ctx->mask.p, ctx->d_counts, ctx->box, ctx->fixes, handle);
+        k_fix_post_force<1><<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(x, f, ctx->facc.p, ctx->mask.p, ctx->d_counts, ctx->box, ctx->fixes, handle);
     else
-        k_fix_post_force<0><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(x, f, ctx->facc.p, ctx->mask.p, ctx->d_counts, ctx->box, ctx->fixes, handle);
+        k_fix_post_force<0><<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(x, f, ctx->facc.p, ctx->mask.p, ctx->d_counts, ctx->box, ctx->fixes, handle);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
@@ -159,7 +159,7 @@ int launch_fix_bounce(meso_ctx *ctx, int handle)
     if (ctx->fixes.nbounce == 0) return MESO_OK;
     SoA3 x, v;
     for (int d = 0; d < 3; d++) { x.c[d] = ctx->x[d].p; v.c[d] = ctx->v[d].p; }
-    k_fix_bounce<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(x, v, ctx->mask.p, ctx->d_counts, ctx->box, ctx->fixes, handle);
+    k_fix_bounce<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(x, v, ctx->mask.p, ctx->d_counts, ctx->box, ctx->fixes, handle);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

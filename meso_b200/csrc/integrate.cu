@@ -265,11 +265,11 @@ int launch_initial_integrate(meso_ctx *ctx, int groupbit, bool pack)
 {
     const double dtv = ctx->dt, dtf = 0.5 * ctx->dt * ctx->ftm2v;   // FixNVEMeso::init, UM/fix_nve_meso.cu:42-46
     if (pack)
-        k_initial_integrate<1><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p,
+        k_initial_integrate<1><<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soa(ctx->x), soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p,
                                                                        ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, ctx->veloc4.p,
                                                                        ctx->d_counts, ctx->box, dtf, dtv, groupbit, seed_now(ctx));
     else
-        k_initial_integrate<0><<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p,
+        k_initial_integrate<0><<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soa(ctx->x), soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p,
                                                                        ctx->tag.p, ctx->mass_dev.p, ctx->coord4.p, ctx->veloc4.p,
                                                                        ctx->d_counts, ctx->box, dtf, dtv, groupbit, 0u);
     MESO_CUDA(cudaGetLastError());
@@ -286,10 +286,10 @@ int launch_step_integrate(meso_ctx *ctx, int groupbit, bool do_final, bool do_in
                        ctx->veloc4.p, ctx->d_counts, ctx->box, dtf, dtv, groupbit, pack ? seed_now(ctx) : 0u, do_final, do_initial, src_acc,        \
                        zero_src, write_f, ctx->fixes, bounce_after
     const int g = grid_for(ctx, 8);
-    if (pack && fix) k_step_integrate<1, 1><<<g, 256, 0, ctx->stream>>>(MESO_STEP_ARGS);
-    else if (pack) k_step_integrate<1, 0><<<g, 256, 0, ctx->stream>>>(MESO_STEP_ARGS);
-    else if (fix) k_step_integrate<0, 1><<<g, 256, 0, ctx->stream>>>(MESO_STEP_ARGS);
-    else k_step_integrate<0, 0><<<g, 256, 0, ctx->stream>>>(MESO_STEP_ARGS);
+    if (pack && fix) k_step_integrate<1, 1><<<g, 256, 0, LS(ctx->stream)>>>(MESO_STEP_ARGS);
+    else if (pack) k_step_integrate<1, 0><<<g, 256, 0, LS(ctx->stream)>>>(MESO_STEP_ARGS);
+    else if (fix) k_step_integrate<0, 1><<<g, 256, 0, LS(ctx->stream)>>>(MESO_STEP_ARGS);
+    else k_step_integrate<0, 0><<<g, 256, 0, LS(ctx->stream)>>>(MESO_STEP_ARGS);
 #undef MESO_STEP_ARGS
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -297,7 +297,7 @@ int launch_step_integrate(meso_ctx *ctx, int groupbit, bool do_final, bool do_in
 
 int launch_final_integrate(meso_ctx *ctx, int groupbit)
 {
-    k_final_integrate<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p, ctx->mass_dev.p,
+    k_final_integrate<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soa(ctx->v), soac(ctx->f), ctx->mask.p, ctx->type.p, ctx->mass_dev.p,
                                                               ctx->d_counts, 0.5 * ctx->dt * ctx->ftm2v, groupbit);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -305,7 +305,7 @@ int launch_final_integrate(meso_ctx *ctx, int groupbit)
 
 int launch_clear(meso_ctx *ctx, int range, int vflag)
 {
-    k_clear<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->f), ctx->virial.p, ctx->cap, ctx->d_counts, range, vflag);
+    k_clear<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soa(ctx->f), ctx->virial.p, ctx->cap, ctx->d_counts, range, vflag);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
@@ -314,8 +314,8 @@ int launch_ke(meso_ctx *ctx, int groupbit, double *mv2, double *count)
 {
     const int nb = grid_for(ctx, 4);
     if (!ctx->partial.reserve((size_t)nb * 8)) { ctx->err = "reduce: out of device memory"; return MESO_ECUDA; }
-    k_ke_partial<<<nb, 256, 0, ctx->stream>>>(soac(ctx->v), ctx->mask.p, ctx->type.p, ctx->mass_dev.p, ctx->d_counts, groupbit, ctx->partial.p);
-    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->partial.p, nb, 2, ctx->partial.p + (size_t)nb * 7);
+    k_ke_partial<<<nb, 256, 0, LS(ctx->stream)>>>(soac(ctx->v), ctx->mask.p, ctx->type.p, ctx->mass_dev.p, ctx->d_counts, groupbit, ctx->partial.p);
+    k_reduce_final<<<1, 256, 0, LS(ctx->stream)>>>(ctx->partial.p, nb, 2, ctx->partial.p + (size_t)nb * 7);
     MESO_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->partial.p + (size_t)nb * 7, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MESO_CUDA(cudaStreamSynchronize(ctx->stream));
     *mv2 = ctx->h_result[0];
@@ -327,8 +327,8 @@ int launch_virial_sum(meso_ctx *ctx, double out7[7])
 {
     const int nb = grid_for(ctx, 4);
     if (!ctx->partial.reserve((size_t)nb * 8)) { ctx->err = "reduce: out of device memory"; return MESO_ECUDA; }
-    k_virial_partial<<<nb, 256, 0, ctx->stream>>>(ctx->virial.p, ctx->e_pair.p, ctx->cap, ctx->d_counts, ctx->partial.p);
-    k_reduce_final<<<1, 256, 0, ctx->stream>>>(ctx->partial.p, nb, 7, ctx->partial.p + (size_t)nb * 7);
+    k_virial_partial<<<nb, 256, 0, LS(ctx->stream)>>>(ctx->virial.p, ctx->e_pair.p, ctx->cap, ctx->d_counts, ctx->partial.p);
+    k_reduce_final<<<1, 256, 0, LS(ctx->stream)>>>(ctx->partial.p, nb, 7, ctx->partial.p + (size_t)nb * 7);
     MESO_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->partial.p + (size_t)nb * 7, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MESO_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int q = 0; q < 7; q++) out7[q] = ctx->h_result[q];
@@ -338,25 +338,25 @@ int launch_virial_sum(meso_ctx *ctx, double out7[7])
 // used by api.cu
 int launch_deinterleave3(meso_ctx *ctx, const double *aos, DevBuf<double> *dst, int n)
 {
-    k_deinterleave3<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(aos, soa(dst), n);
+    k_deinterleave3<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(aos, soa(dst), n);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
 int launch_interleave3(meso_ctx *ctx, DevBuf<double> *src, double *aos, int n)
 {
-    k_interleave3<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soac(src), aos, n);
+    k_interleave3<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soac(src), aos, n);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
 int launch_fill_defaults(meso_ctx *ctx, int n, int st, int sy, int sm, int si)
 {
-    k_fill_defaults<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, n, st, sy, sm, si);
+    k_fill_defaults<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, n, st, sy, sm, si);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
 int launch_zero3(meso_ctx *ctx, DevBuf<double> *a, int n)
 {
-    k_zero3<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(a), n);
+    k_zero3<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soa(a), n);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

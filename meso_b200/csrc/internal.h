@@ -104,6 +104,7 @@ struct meso_ctx {
 
     // settings
     double skin = 0.3, cut_global = 1.0, cutneighmax = 1.3, dt = 0.005;
+    double max_pair_cut = 0.0;     // largest per-pair cutoff of the coefficient table (0: not set yet)
     double ftm2v = 1.0;            // force->ftm2v of the host's unit system (1 in lj)
     bool reduce_local = false;     // bead-spring topology (bond.cu): column-major [slot][atom] table of {partner tag, bond type}
     int bond_per_atom = 0, nbondtypes = 0, map_tag_max = 0;
@@ -178,6 +179,7 @@ struct meso_ctx {
     meso::DevBuf<int> sendlist[6];
     cudaEvent_t ev_fwd_begin = nullptr, ev_fwd_end = nullptr;
     cudaEvent_t ev_counts = nullptr;          // the pinned Counts mirror of the last rebuild has landed
+    bool counts_pending = false;              // ev_counts was recorded and its error flags have not been looked at yet
     bool fwd_counts_valid = false;            // fwd_send_n / fwd_recv_n describe the current send lists
     int fwd_send_n[6] = {0}, fwd_recv_n[6] = {0};
     // cells
@@ -204,6 +206,8 @@ struct meso_ctx {
     meso::DevBuf<unsigned long long> rdf_hist[meso::MAX_FIX];   // rdf/fast/meso: pair counts per radial bin, accumulated over samples
     int64_t rdf_samples[meso::MAX_FIX] = {0};
 
+    // every kernel launch of this library passes its stream through LS(): a real count for bench.py's gpu_launches
+    int64_t n_launch = 0;
     // timers
     bool timers_on = false;
     double t_ms[MESO_T_COUNT] = {0};
@@ -213,6 +217,8 @@ struct meso_ctx {
 };
 
 namespace meso {
+
+#define LS(s) (++ctx->n_launch, (s))      // launch-stream wrapper: k<<<grid, block, smem, LS(stream)>>>(...)
 
 #define MESO_CUDA(call)                                                                   \
     do {                                                                                  \

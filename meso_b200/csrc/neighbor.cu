@@ -496,7 +496,7 @@ int launch_setup_bins(meso_ctx *ctx)
         ctx->err = "setup_bins: out of device memory";
         return MESO_ECUDA;
     }
-    k_stencil_codes<<<(box.ncell + 127) / 128, 128, 0, ctx->stream>>>(ctx->stencil.p, box);
+    k_stencil_codes<<<(box.ncell + 127) / 128, 128, 0, LS(ctx->stream)>>>(ctx->stencil.p, box);
     MESO_CUDA(cudaGetLastError());
     ctx->bins_ready = true;
     return MESO_OK;
@@ -506,15 +506,15 @@ int launch_neighbor_build(meso_ctx *ctx)
 {
     const Box &box = ctx->box;
     SoA3c x; for (int d = 0; d < 3; d++) x.c[d] = ctx->x[d].p;
-    k_cell_id<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(x, ctx->cell_key.p, ctx->cell_atoms.p, ctx->cell_of.p, ctx->d_counts, box);
+    k_cell_id<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(x, ctx->cell_key.p, ctx->cell_atoms.p, ctx->cell_of.p, ctx->d_counts, box);
     int bits = 1;
     while ((1 << bits) < box.ncell) bits++;                 // ceil(log2(ncell)), UM/neighbor_meso.cu:541
     int rc = sort_pairs_u64(ctx, ctx->cell_key, ctx->cell_atoms, &ctx->d_counts->nall, ctx->cap, bits);
     if (rc) return rc;
     if (!ctx->cell_xyzj.reserve(ctx->cap + 8) || !ctx->cell_runs.reserve((size_t)box.ncell * 27)) { ctx->err = "neighbor: out of device memory"; return MESO_ECUDA; }
-    k_cell_bounds<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->cell_key.p, ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_start.p, ctx->cell_xyzj.p,
+    k_cell_bounds<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(ctx->cell_key.p, ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_start.p, ctx->cell_xyzj.p,
                                                           ctx->d_counts, box.ncell);
-    k_cell_runs<<<(box.ncell * 27 + 255) / 256, 256, 0, ctx->stream>>>(ctx->stencil.p, ctx->cell_start.p, ctx->cell_runs.p, box);
+    k_cell_runs<<<(box.ncell * 27 + 255) / 256, 256, 0, LS(ctx->stream)>>>(ctx->stencil.p, ctx->cell_start.p, ctx->cell_runs.p, box);
     float rc2_core = (float)pow(ctx->cutneighmax - ctx->skin, 2.0);   // UM/neigh_build_meso.cu:296-297
     float rc2_tail = (float)pow(ctx->cutneighmax, 2.0);
     const bool per_atom = ctx->nb_per_atom;
@@ -536,10 +536,10 @@ int launch_neighbor_build(meso_ctx *ctx)
         if (!ctx->nb_fixup.reserve(1)) { ctx->err = "neighbor: out of device memory"; return MESO_ECUDA; }
         MESO_CUDA(cudaMemsetAsync(ctx->nb_fixup.p, 0, sizeof(int), ctx->stream));
         const int grid = std::max(1, std::min((box.ncell + NC_WARPS - 1) / NC_WARPS, ctx->sm_count * 64));
-        k_build_neighbors_cell<<<grid, NC_WARPS * 32, sh, ctx->stream>>>(ctx->cell_start.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
+        k_build_neighbors_cell<<<grid, NC_WARPS * 32, sh, LS(ctx->stream)>>>(ctx->cell_start.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
                                                                         ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p, box.ncell, ctx->n_col,
                                                                         rc2_core, rc2_tail, t_cap);
-        k_build_neighbors<64, 4><<<grid_atoms, 128, 0, ctx->stream>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
+        k_build_neighbors<64, 4><<<grid_atoms, 128, 0, LS(ctx->stream)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
                                                                    ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, ctx->nb_fixup.p);
     } else {
 #define MESO_NB_ARGS ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p, ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, nullptr
@@ -548,9 +548,9 @@ int launch_neighbor_build(meso_ctx *ctx)
             for (int d = 0; d < 3; d++) { sg.lo[d] = (float)(box.sublo[d] - box.centre[d]); sg.bs[d] = (float)box.binsize[d]; sg.m[d] = box.m[d]; }
             sg.stencil = ctx->stencil.p;
             sg.limit = rc2_tail * 1.002f;                           // (1.001 r_n)^2
-            k_build_neighbors<48, 4, true><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS, sg);
+            k_build_neighbors<48, 4, true><<<grid_atoms, 128, 0, LS(ctx->stream)>>>(MESO_NB_ARGS, sg);
         } else
-        k_build_neighbors<48, 4><<<grid_atoms, 128, 0, ctx->stream>>>(MESO_NB_ARGS);   // 48 slots: 9 CTAs/SM; 40 spills too often, 56+ loses occupancy (measured)
+        k_build_neighbors<48, 4><<<grid_atoms, 128, 0, LS(ctx->stream)>>>(MESO_NB_ARGS);   // 48 slots: 9 CTAs/SM; 40 spills too often, 56+ loses occupancy (measured)
 #undef MESO_NB_ARGS
     }
     MESO_CUDA(cudaGetLastError());

@@ -464,7 +464,7 @@ int launch_pack(meso_ctx *ctx, int range)
 {
     SoA3c x, v;
     for (int d = 0; d < 3; d++) { x.c[d] = ctx->x[d].p; v.c[d] = ctx->v[d].p; }
-    k_pack<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(x, v, ctx->type.p, ctx->tag.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts, ctx->box,
+    k_pack<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(x, v, ctx->type.p, ctx->tag.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts, ctx->box,
                                                    seed_now(ctx), range);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -488,7 +488,7 @@ static int launch_pair_t(meso_ctx *ctx, const REAL *coeff, REAL dtis, int range,
         cudaFuncSetAttribute(k_dpd<REAL, EV>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
         attr_done = true;
     }
-    k_dpd<REAL, EV><<<grid, PAIR_THREADS, sh, ctx->stream>>>(ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, f, v, vir,
+    k_dpd<REAL, EV><<<grid, PAIR_THREADS, sh, LS(ctx->stream)>>>(ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, f, v, vir,
                                                            ctx->e_pair.p, ctx->mask.p, ctx->type.p, ctx->mass_dev.p, coeff, ctx->d_counts,
                                                            ctx->n_col, nt, dtis, range, accumulate, fuse_final, dtf, groupbit);
     MESO_CUDA(cudaGetLastError());
@@ -524,13 +524,13 @@ static int launch_pair_once_t(meso_ctx *ctx, const REAL *coeff, REAL dtis, int r
     const int gmode = ctx->pair_tex;
     if (nt == 1 && pow1) {
         switch (gmode) {
-        case 1: k_dpd_once<REAL, true, true, 1><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS); break;
-        case 2: k_dpd_once<REAL, true, true, 2><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS); break;
-        case 3: k_dpd_once<REAL, true, true, 3><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS); break;
-        default: k_dpd_once<REAL, true, true, 0><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS);
+        case 1: k_dpd_once<REAL, true, true, 1><<<grid, PAIR_THREADS, 0, LS(ctx->stream)>>>(MESO_ONCE_ARGS); break;
+        case 2: k_dpd_once<REAL, true, true, 2><<<grid, PAIR_THREADS, 0, LS(ctx->stream)>>>(MESO_ONCE_ARGS); break;
+        case 3: k_dpd_once<REAL, true, true, 3><<<grid, PAIR_THREADS, 0, LS(ctx->stream)>>>(MESO_ONCE_ARGS); break;
+        default: k_dpd_once<REAL, true, true, 0><<<grid, PAIR_THREADS, 0, LS(ctx->stream)>>>(MESO_ONCE_ARGS);
         }
-    } else if (nt == 1) k_dpd_once<REAL, true, false, 0><<<grid, PAIR_THREADS, 0, ctx->stream>>>(MESO_ONCE_ARGS);
-    else k_dpd_once<REAL, false, false, 0><<<grid, PAIR_THREADS, (size_t)nt * nt * NCOEFF * sizeof(REAL), ctx->stream>>>(MESO_ONCE_ARGS);
+    } else if (nt == 1) k_dpd_once<REAL, true, false, 0><<<grid, PAIR_THREADS, 0, LS(ctx->stream)>>>(MESO_ONCE_ARGS);
+    else k_dpd_once<REAL, false, false, 0><<<grid, PAIR_THREADS, (size_t)nt * nt * NCOEFF * sizeof(REAL), LS(ctx->stream)>>>(MESO_ONCE_ARGS);
 #undef MESO_ONCE_ARGS
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -545,19 +545,19 @@ int launch_pair_once(meso_ctx *ctx, int range)
 
 int eval_gaussian(meso_ctx *ctx, int n, const uint32_t *si, const uint32_t *sj, float *osp, double *odp)
 {
-    k_eval_gaussian<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, si, sj, osp, odp);
+    k_eval_gaussian<<<(n + 255) / 256, 256, 0, LS(ctx->stream)>>>(n, si, sj, osp, odp);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
 int eval_math(meso_ctx *ctx, int fn, int n, const double *a, const double *b, double *out)
 {
-    k_eval_math<<<(n + 255) / 256, 256, 0, ctx->stream>>>(fn, n, a, b, out);
+    k_eval_math<<<(n + 255) / 256, 256, 0, LS(ctx->stream)>>>(fn, n, a, b, out);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
 int eval_log2u(meso_ctx *ctx, int n, const uint32_t *a, double *out)
 {
-    k_eval_log2u<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, a, out);
+    k_eval_log2u<<<(n + 255) / 256, 256, 0, LS(ctx->stream)>>>(n, a, out);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

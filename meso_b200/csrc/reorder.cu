@@ -339,7 +339,7 @@ static inline SoA3c soac(DevBuf<double> *b) { SoA3c s; for (int d = 0; d < 3; d+
 
 int launch_pbc(meso_ctx *ctx)
 {
-    k_pbc<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), ctx->image.p, ctx->d_counts, ctx->box);
+    k_pbc<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soa(ctx->x), ctx->image.p, ctx->d_counts, ctx->box);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
@@ -353,11 +353,11 @@ int launch_reorder(meso_ctx *ctx)
     const int l2_width = 12;
     uint64_t border_mask = 1ULL << (l1_width + l2_width);
     int bits = 1 + l1_width + l2_width;
-    k_reorder_key<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soa(ctx->x), ctx->image.p, ctx->key.p, ctx->perm_from.p, ctx->d_counts,
+    k_reorder_key<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soa(ctx->x), ctx->image.p, ctx->key.p, ctx->perm_from.p, ctx->d_counts,
                                                           box, l2_width, border_mask);
     int rc = sort_pairs_u64(ctx, ctx->key, ctx->perm_from, &ctx->d_counts->nlocal, ctx->cap, bits);
     if (rc) return rc;
-    k_gather<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(soac(ctx->x), soac(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
+    k_gather<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soac(ctx->x), soac(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
                                                      soa(ctx->xa), soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p,
                                                      ctx->imagea.p, ctx->coord4.p, ctx->veloc4.p, ctx->key.p, ctx->perm_from.p,
                                                      ctx->d_counts, box, border_mask, seed_now(ctx));
@@ -374,15 +374,15 @@ int launch_borders(meso_ctx *ctx)
     const int ntiles = (int)((ctx->cap + GH_TILE - 1) / GH_TILE);
     if (!ctx->tile_counts.reserve((size_t)ntiles * 2)) { ctx->err = "borders: out of device memory"; return MESO_ECUDA; }
     int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
-    k_counts_reset_ghosts<<<1, 1, 0, ctx->stream>>>(ctx->d_counts);
+    k_counts_reset_ghosts<<<1, 1, 0, LS(ctx->stream)>>>(ctx->d_counts);
     for (int d = 0; d < 3; d++) {
         if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1]) continue;
-        k_ghost_count<<<grid_for(ctx, 4), GH_THREADS, 0, ctx->stream>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
-        k_ghost_scan<<<1, 1024, 0, ctx->stream>>>(tc, ctx->d_counts, d, ntiles, (int)ctx->cap);
-        k_ghost_scatter<<<grid_for(ctx, 4), GH_THREADS, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p,
+        k_ghost_count<<<grid_for(ctx, 4), GH_THREADS, 0, LS(ctx->stream)>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
+        k_ghost_scan<<<1, 1024, 0, LS(ctx->stream)>>>(tc, ctx->d_counts, d, ntiles, (int)ctx->cap);
+        k_ghost_scatter<<<grid_for(ctx, 4), GH_THREADS, 0, LS(ctx->stream)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p,
                                                                        ctx->coord4.p, ctx->veloc4.p, ctx->ghost_root.p,
                                                                        ctx->ghost_shift.p, ctx->d_counts, tc, box, d, ntiles);
-        k_ghost_advance<<<1, 1, 0, ctx->stream>>>(ctx->d_counts, d);
+        k_ghost_advance<<<1, 1, 0, LS(ctx->stream)>>>(ctx->d_counts, d);
     }
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
@@ -391,10 +391,10 @@ int launch_borders(meso_ctx *ctx)
 int launch_forward(meso_ctx *ctx, bool full)
 {
     if (full)
-        k_forward_self<1><<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), ctx->coord4.p, ctx->veloc4.p, ctx->ghost_root.p,
+        k_forward_self<1><<<grid_for(ctx, 4), 256, 0, LS(ctx->stream)>>>(soa(ctx->x), soa(ctx->v), ctx->coord4.p, ctx->veloc4.p, ctx->ghost_root.p,
                                                                   ctx->ghost_shift.p, ctx->type.p, ctx->d_counts, ctx->box);
     else
-        k_forward_self<0><<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(soa(ctx->x), soa(ctx->v), ctx->coord4.p, ctx->veloc4.p, ctx->ghost_root.p,
+        k_forward_self<0><<<grid_for(ctx, 4), 256, 0, LS(ctx->stream)>>>(soa(ctx->x), soa(ctx->v), ctx->coord4.p, ctx->veloc4.p, ctx->ghost_root.p,
                                                                   ctx->ghost_shift.p, ctx->type.p, ctx->d_counts, ctx->box);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;

@@ -156,10 +156,10 @@ static int sort_impl(meso_ctx *ctx, K *&key, int *&val, K *&key_alt, int *&val_a
     if (!ctx->sort.hist.reserve((size_t)256 * nblk + 256)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
     (void)cap;
     for (int shift = 0; shift < bits; shift += 8) {
-        k_radix_hist<K><<<nblk, SORT_THREADS, 0, ctx->stream>>>(key, d_n, ctx->sort.hist.p, shift);
+        k_radix_hist<K><<<nblk, SORT_THREADS, 0, LS(ctx->stream)>>>(key, d_n, ctx->sort.hist.p, shift);
         uint32_t *totals = ctx->sort.hist.p + (size_t)256 * nblk;
-        k_scan_rows<<<256, 256, 0, ctx->stream>>>(ctx->sort.hist.p, totals, nblk);
-        k_radix_scatter<K><<<nblk, SORT_THREADS, 0, ctx->stream>>>(key, val, key_alt, val_alt, d_n, ctx->sort.hist.p, totals, shift);
+        k_scan_rows<<<256, 256, 0, LS(ctx->stream)>>>(ctx->sort.hist.p, totals, nblk);
+        k_radix_scatter<K><<<nblk, SORT_THREADS, 0, LS(ctx->stream)>>>(key, val, key_alt, val_alt, d_n, ctx->sort.hist.p, totals, shift);
         K *tk = key; key = key_alt; key_alt = tk;
         int *tv = val; val = val_alt; val_alt = tv;
     }

@@ -426,6 +426,11 @@ class Meso:
         self._chk(self.L.meso_timers_read(self.h, ms, calls, int(reset)))
         return {n: (ms[i], calls[i]) for i, n in enumerate(_lib.TIMER_NAMES)}
 
+    def launch_count(self, reset=False):
+        n = C.c_int64()
+        self._chk(self.L.meso_launch_count(self.h, C.byref(n), int(reset)))
+        return n.value
+
     def stream(self):
         return self.L.meso_stream(self.h)
 

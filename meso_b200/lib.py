@@ -78,6 +78,7 @@ SIGNATURES = {
     "meso_eval_log2u": (_i, [_vp, _i, _vp, _vp]),
     "meso_timers_enable": (_i, [_vp, _i]),
     "meso_timers_read": (_i, [_vp, _pd, C.POINTER(_i64), _i]),
+    "meso_launch_count": (_i, [_vp, C.POINTER(_i64), _i]),
 }
 
 MESO_BULK, MESO_BORDER, MESO_LOCAL, MESO_GHOST, MESO_ALL = 1, 2, 3, 4, 7

@@ -18,7 +18,7 @@ def ngpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,L,extra", [(2, (12,), ()), (4, (12,), ()), (8, (12,), ()), (2, (6, 7, 12), ()), (2, (10,), ("--polymer",)),
-                                       (8, (12,), ("--polymer",))])
+                                       (8, (12,), ("--polymer",)), (2, (12,), ("--phases",)), (4, (12,), ("--phases",))])
 def test_multi_gpu_parity(n, L, extra):
     if ngpu() < n:
         pytest.skip("needs %d GPUs" % n)
