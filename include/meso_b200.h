@@ -54,6 +54,15 @@ int meso_set_box(meso_ctx *ctx, const double boxlo[3], const double boxhi[3], co
  * ranks (from meso_comm_unique_id on rank 0), NULL when nranks==1.  Replaces the MPI world of the reference. */
 int meso_comm_unique_id(void *id128);
 int meso_set_decomposition(meso_ctx *ctx, int rank, const int procgrid[3], const void *nccl_id);
+/* Halo bootstrap without NCCL (nccl_id == NULL above): ranks that live in ONE process (one context per GPU) or share ONE GPU.
+ * The halo itself never uses NCCL: every rank owns a receive arena in its HBM and its neighbors store their records there
+ * directly (CUDA IPC between processes, peer pointers inside one; meso_b200/csrc/comm.cu).  After meso_atoms_upload (and
+ * meso_bonds_upload) on every rank: blob[r] = meso_comm_export(rank r) (meso_comm_blob_size() bytes each), then every rank
+ * meso_comm_import(all blobs in rank order), then meso_setup.  Reductions (meso_compute_ke ...) then return the rank's own
+ * part, as with meso_set_reduce_scope(1).  Replaces MPI_Init / the communicator of the reference (src/lammps.cpp:432-452). */
+int meso_comm_blob_size(void);
+int meso_comm_export(meso_ctx *ctx, void *blob);
+int meso_comm_import(meso_ctx *ctx, const void *blobs, int nranks);
 
 /* ---- styles' settings ---- */
 /* neighbor <skin> bin; neigh_modify delay 0 every N check no (src/neighbor.cpp:1216-1231) */
@@ -171,8 +180,13 @@ int meso_export_ghosts(meso_ctx *ctx, int nmax, double *x, double *v, int *tag, 
 int meso_export_cells(meso_ctx *ctx, int ncell_plus1, int *cell_start, int nmax, int *cell_atoms); /* binning_meso */
 int meso_export_stencil(meso_ctx *ctx, int cell, int out27[27]);                                /* gpu_stencil_full_bin_3d */
 int meso_export_pair_count(meso_ctx *ctx, int nmax, int *pair_count);
-/* tile-transposed table, UM/neigh_list_meso.cu:97-102: ceil32(nlocal)*n_col ints */
+/* tile-transposed table, UM/neigh_list_meso.cu:97-102: ceil32(nlocal)*n_col ints, rows in the reference's order
+ * (core entries in stencil order, then skin entries reversed: UM/neigh_build_meso.cu:58-117,166-200) */
 int meso_export_pair_table(meso_ctx *ctx, int64_t nmax, int *pair_table);
+/* the same table as the force kernels read it: rows [owned core][owned skin][other core][other skin] (same sets, same
+ * core/skin split, traversal order inside a segment); owned_count[i] = entries whose pair row i evaluates,
+ * core_split[i] = owned core | other core << 16.  Any pointer may be NULL. */
+int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_table, int *owned_count, int *core_split);
 int meso_export_virial(meso_ctx *ctx, int nmax, double *virial6, double *e_pair);
 /* device-side evaluation of the per-pair Gaussians on n signature pairs (A8) */
 int meso_eval_gaussian(meso_ctx *ctx, int n, const uint32_t *sig_i, const uint32_t *sig_j, float *out_sp, double *out_dp);

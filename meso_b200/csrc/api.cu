@@ -29,6 +29,7 @@ int comm_allreduce_sum(meso_ctx *ctx, double *host_vals, int n);
 }
 
 static std::string g_create_err;
+static int comm_setup_public(meso_ctx *ctx);
 
 #define CHECK_CTX() do { if (!ctx) return MESO_EINVAL; } while (0)
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
@@ -119,10 +120,8 @@ extern "C" int meso_create(meso_ctx **out, int device)
     const char *po = getenv("MESO_PAIR_ONCE");               // 0: two-sided force kernel in meso_run (A/B measurements)
     ctx->pair_once = !(po && po[0] == '0');
     if (const char *e = getenv("MESO_PAIR_TEX")) ctx->pair_tex = atoi(e) & 3;
-    if (const char *e = getenv("MESO_HALO_ROUTES")) ctx->halo_routes = e[0] != '0';
-    if (const char *e = getenv("MESO_EXCH_ONESHOT")) ctx->exch_oneshot = e[0] == '1';
-    if (const char *e = getenv("MESO_NB_SKIP")) ctx->nb_skip = e[0] == '1';
-    if (const char *e = getenv("MESO_NB_PER_ATOM")) ctx->nb_per_atom = e[0] == '1';
+    if (const char *e = getenv("MESO_NB_SLOW")) ctx->nb_slow = e[0] == '1';
+    if (const char *e = getenv("MESO_NB_CLIP")) ctx->nb_clip = atoi(e);
     cudaMemsetAsync(ctx->d_counts, 0, sizeof(Counts), ctx->stream);
     memset(ctx->h_counts, 0, sizeof(Counts));
     *out = ctx;
@@ -159,7 +158,8 @@ static int check_device_flags(meso_ctx *ctx)
     ctx->err = "device-side capacity error:";
     if (e & 1) ctx->err += " ghost capacity exceeded;";
     if (e & 2) ctx->err += " pair table overflow (local density too high for n_col);";
-    if (e & 8) ctx->err += " atom lost in migration;";
+    if (e & 8) ctx->err += " atom lost in migration (migration message capacity, or an atom beyond a non-periodic face);";
+    if (e & 16) ctx->err += " a neighbor rank did not deliver its halo message in time;";
     if (e & 32) ctx->err += " Bond atoms missing (a bond partner is neither local nor ghost);";
     return MESO_ECAPACITY;
 }
@@ -198,8 +198,10 @@ extern "C" int meso_memory_usage(meso_ctx *ctx, uint64_t *bytes)
          ctx->maska.bytes() + ctx->imagea.bytes() + ctx->coord4.bytes() + ctx->veloc4.bytes() + ctx->virial.bytes() + ctx->e_pair.bytes() +
          ctx->staging.bytes() + ctx->istaging.bytes() + ctx->key.bytes() + ctx->perm_from.bytes() + ctx->sort.key_alt.bytes() +
          ctx->sort.val_alt.bytes() + ctx->sort.hist.bytes() + ctx->ghost_root.bytes() + ctx->ghost_shift.bytes() + ctx->tile_counts.bytes() +
-         ctx->cell_key.bytes() + ctx->cell_of.bytes() + ctx->cell_atoms.bytes() + ctx->cell_start.bytes() + ctx->stencil.bytes() +
-         ctx->pair_count.bytes() + ctx->pair_table.bytes() + ctx->partial.bytes();
+         ctx->cell_of.bytes() + ctx->cell_atoms.bytes() + ctx->cell_start.bytes() + ctx->stencil.bytes() + ctx->slotrank.bytes() +
+         ctx->cell_cnt.bytes() + ctx->fine_of.bytes() + ctx->fine_start.bytes() + ctx->fine_rec.bytes() + ctx->scan_sums.bytes() +
+         ctx->pair_count.bytes() + ctx->owned_count.bytes() + ctx->core_split.bytes() + ctx->pair_table.bytes() + ctx->partial.bytes() +
+         ctx->facc.bytes() + ctx->virial.bytes() + ctx->e_pair.bytes();
     *bytes = b;
     return MESO_OK;
 }
@@ -221,7 +223,6 @@ static void update_subbox(meso_ctx *ctx)
 
 extern "C" int meso_set_box(meso_ctx *ctx, const double boxlo[3], const double boxhi[3], const int periodic[3])
 {
-    if (ctx) ctx->npeers = 0;
     CHECK_CTX();
     for (int d = 0; d < 3; d++) {
         if (!(boxhi[d] > boxlo[d])) FAIL(MESO_EINVAL, "meso_set_box: boxhi must exceed boxlo");
@@ -233,9 +234,27 @@ extern "C" int meso_set_box(meso_ctx *ctx, const double boxlo[3], const double b
     return MESO_OK;
 }
 
+// host-driven bootstrap of the halo (include/meso_b200.h)
+extern "C" int meso_comm_blob_size(void) { return 1024; }
+extern "C" int meso_comm_export(meso_ctx *ctx, void *blob)
+{
+    CHECK_CTX();
+    if (!blob) FAIL(MESO_EINVAL, "meso_comm_export: null blob");
+    if (!ctx->box_set) FAIL(MESO_EINVAL, "meso_comm_export: call after meso_set_box / meso_set_decomposition / meso_atoms_upload");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(comm_setup_public(ctx));
+    return comm_export_blob(ctx, blob);
+}
+extern "C" int meso_comm_import(meso_ctx *ctx, const void *blobs, int nranks)
+{
+    CHECK_CTX();
+    if (!blobs) FAIL(MESO_EINVAL, "meso_comm_import: null blobs");
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    return comm_import_blobs(ctx, blobs, nranks);
+}
+
 extern "C" int meso_set_decomposition(meso_ctx *ctx, int rank, const int procgrid[3], const void *nccl_id)
 {
-    if (ctx) ctx->npeers = 0;
     CHECK_CTX();
     int n = procgrid[0] * procgrid[1] * procgrid[2];
     if (n < 1 || rank < 0 || rank >= n) FAIL(MESO_EINVAL, "meso_set_decomposition: bad rank/procgrid");
@@ -253,8 +272,9 @@ extern "C" int meso_set_decomposition(meso_ctx *ctx, int rank, const int procgri
     }
     if (ctx->box_set) update_subbox(ctx);
     if (n > 1) {
-        if (!nccl_id) FAIL(MESO_EINVAL, "meso_set_decomposition: nranks > 1 needs an ncclUniqueId");
-        TRY(comm_init(ctx, nccl_id));
+        // with an ncclUniqueId the library bootstraps itself (NCCL carries the memory handles and the thermo reductions);
+        // without one the host exchanges meso_comm_export blobs (ranks of one process, or of one GPU) and sums reductions itself
+        if (nccl_id) TRY(comm_init(ctx, nccl_id));
         ctx->comm_path = true;
     }
     return MESO_OK;
@@ -286,6 +306,8 @@ static int comm_setup(meso_ctx *ctx)
     }
     return MESO_OK;
 }
+
+static int comm_setup_public(meso_ctx *ctx) { return comm_setup(ctx); }
 
 // ---------------------------------------------------------------- settings
 // Neighbor::init: cutneighmax = largest pair cutoff + skin.  Every setter that touches one of the three inputs goes through
@@ -413,7 +435,7 @@ static int ensure_capacity(meso_ctx *ctx, size_t nlocal)
     ok = ok && ctx->tag.reserve(cap) && ctx->type.reserve(cap) && ctx->mask.reserve(cap) && ctx->image.reserve(cap) &&
          ctx->taga.reserve(cap) && ctx->typea.reserve(cap) && ctx->maska.reserve(cap) && ctx->imagea.reserve(cap) &&
          ctx->coord4.reserve(cap + 1) && ctx->veloc4.reserve(cap + 1) && ctx->key.reserve(cap) && ctx->perm_from.reserve(cap) &&
-         ctx->ghost_root.reserve(cap) && ctx->ghost_shift.reserve(cap) && ctx->cell_key.reserve(cap) && ctx->cell_of.reserve(cap) &&
+         ctx->ghost_root.reserve(cap) && ctx->ghost_shift.reserve(cap) && ctx->cell_of.reserve(cap) &&
          ctx->cell_atoms.reserve(cap) && ctx->e_pair.reserve(cap) && ctx->pair_count.reserve(cap);
     if (!ok) FAIL(MESO_ECUDA, "out of device memory growing the atom store");
     ctx->cap = cap;
@@ -476,7 +498,7 @@ extern "C" int meso_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, con
     ctx->bins_ready = false;
     ctx->setup_done = false;
     ctx->f_cleared = true;
-    ctx->comm_caps_agreed = false;
+    comm_invalidate(ctx);
     ctx->bond_per_atom = 0;                    // a bond table describes the atoms of ONE upload: re-send it with meso_bonds_upload
     return MESO_OK;
 }
@@ -571,7 +593,7 @@ static int rebuild_impl(meso_ctx *ctx)
         if (ctx->comm_path) {
             // Domain::pbc -> Comm::exchange -> sort_local -> Comm::borders (UM/mvv_meso.cu:283-316), all on device
             TRY(launch_pbc(ctx));
-            TRY(ctx->exch_oneshot ? launch_exchange_oneshot(ctx) : launch_exchange_multi(ctx));
+            TRY(launch_exchange_multi(ctx));
             TRY(launch_reorder(ctx));
             TRY(launch_bonds_gather(ctx));
             TRY(launch_borders_multi(ctx));
@@ -587,11 +609,9 @@ static int rebuild_impl(meso_ctx *ctx)
         TRY(launch_neighbor_build(ctx));
         TRY(launch_bonds_filter(ctx));       // filter_exclusion_meso, UM/neigh_build_meso.cu:546-569
     }
-    if (ctx->comm_path) TRY(comm_share_errors(ctx));
     MESO_CUDA(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(Counts), cudaMemcpyDeviceToHost, ctx->stream));
     MESO_CUDA(cudaEventRecord(ctx->ev_counts, ctx->stream));
     ctx->counts_pending = true;
-    ctx->fwd_counts_valid = false;
     ctx->ago = 0;
     return MESO_OK;
 }
@@ -986,6 +1006,13 @@ extern "C" int meso_export_bins(meso_ctx *ctx, int m[3], double binsize[3], doub
 }
 
 template <typename T>
+struct Tmp {
+    T *p = nullptr;
+    ~Tmp() { if (p) cudaFree(p); }
+    bool alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)) == cudaSuccess; }
+};
+
+template <typename T>
 static int d2h(meso_ctx *ctx, T *dst, const T *src, size_t n)
 {
     MESO_CUDA(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1040,6 +1067,7 @@ extern "C" int meso_export_cells(meso_ctx *ctx, int ncell_plus1, int *cell_start
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     int n = ctx->h_counts->nlocal + ctx->h_counts->nghost;
+    TRY(launch_cell_lists(ctx));
     if (cell_start) {
         if (ncell_plus1 < ctx->box.ncell + 1) FAIL(MESO_EINVAL, "buffer too small");
         TRY(d2h(ctx, cell_start, ctx->cell_start.p, ctx->box.ncell + 1));
@@ -1085,7 +1113,29 @@ extern "C" int meso_export_pair_table(meso_ctx *ctx, int64_t nmax, int *pair_tab
     size_t rows = ((size_t)ctx->h_counts->nlocal + 31) / 32 * 32;
     size_t n = rows * (size_t)ctx->n_col;
     if ((size_t)nmax < n) FAIL(MESO_EINVAL, "buffer too small");
-    return d2h(ctx, pair_table, ctx->pair_table.p, n);
+    // rows leave in the reference's order (neighbor.cu:k_canonical_rows); the production layout is meso_export_pair_rows
+    Tmp<int> scratch;
+    if (!scratch.alloc(n)) FAIL(MESO_ECUDA, "out of device memory (canonical table)");
+    MESO_CUDA(cudaMemsetAsync(scratch.p, 0, sizeof(int) * n, ctx->stream));
+    TRY(launch_canonical_rows(ctx, scratch.p));
+    return d2h(ctx, pair_table, scratch.p, n);
+}
+
+// the table as the force kernels read it: rows [owned core][owned skin][other core][other skin], with the two split arrays
+extern "C" int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_table, int *owned_count, int *core_split)
+{
+    CHECK_CTX();
+    MESO_CUDA(cudaSetDevice(ctx->device));
+    TRY(refresh_counts(ctx));
+    const int nl = ctx->h_counts->nlocal;
+    size_t n = ((size_t)nl + 31) / 32 * 32 * (size_t)ctx->n_col;
+    if (pair_table) {
+        if ((size_t)nmax < n) FAIL(MESO_EINVAL, "buffer too small");
+        TRY(d2h(ctx, pair_table, ctx->pair_table.p, n));
+    }
+    if (owned_count) TRY(d2h(ctx, owned_count, ctx->owned_count.p, nl));
+    if (core_split) TRY(d2h(ctx, core_split, ctx->core_split.p, nl));
+    return MESO_OK;
 }
 
 extern "C" int meso_export_virial(meso_ctx *ctx, int nmax, double *virial6, double *e_pair)
@@ -1105,13 +1155,6 @@ extern "C" int meso_export_virial(meso_ctx *ctx, int nmax, double *virial6, doub
     if (e_pair) TRY(d2h(ctx, e_pair, ctx->e_pair.p, n));
     return MESO_OK;
 }
-
-template <typename T>
-struct Tmp {
-    T *p = nullptr;
-    ~Tmp() { if (p) cudaFree(p); }
-    bool alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)) == cudaSuccess; }
-};
 
 extern "C" int meso_eval_gaussian(meso_ctx *ctx, int n, const uint32_t *sig_i, const uint32_t *sig_j, float *out_sp, double *out_dp)
 {

@@ -1,22 +1,33 @@
-// comm.cu -- spatial decomposition across GPUs: migration, ghost creation and the per-step halo
-// refresh, with NCCL send/recv over NVLink.
+// comm.cu -- spatial decomposition across GPUs: migration, ghost creation and the per-step halo refresh as
+// remote stores into peer memory over NVLink / NVSwitch, synchronised by flags.  NCCL only bootstraps (it carries the
+// memory handles) and reduces thermo scalars; no NCCL call sits on the data path.
 //
 // Reference path (host MPI through pinned staging buffers, every step):
-//   MesoComm::exchange                UM/comm_meso.cu:256-420        (migration, per dimension)
-//   MesoComm::borders                 UM/comm_meso.cu:41-186         (ghost creation, 6 swaps)
-//   Comm::forward_comm                src/comm.cpp:686-753           (ghost x,v refresh, 6 swaps)
+//   MesoComm::exchange                UM/comm_meso.cu:256-420        (migration, one dependent hop per dimension)
+//   MesoComm::borders                 UM/comm_meso.cu:41-186         (ghost creation, 6 dependent swaps, later
+//                                                                     dimensions forward the ghosts of earlier ones)
+//   Comm::forward_comm                src/comm.cpp:686-753           (ghost x,v refresh, the same 6 swaps)
 //   pack/unpack_{border,comm}_vel     UM/atom_vec_dpd_atomic_meso.cu:61-243
 //   MPI_Allreduce of thermo scalars   UM/compute_temp_meso.cu:97
-// The swap structure (3 dimensions x {to-lower, to-upper}, later dimensions forwarding earlier
-// ghosts) is kept, because it fixes the ghost ORDER and with it the neighbor-list order.  What
-// changes: selection, packing and unpacking are device kernels (ordered stream compaction, no
-// atomics); messages are fixed-capacity with the record count in a header, so neither side ever
-// needs a host round trip to size a message -- the whole rebuild and every step stay asynchronous;
-// a swap whose partner is this rank itself (procgrid[d] == 1) unpacks straight from its own send
-// buffer; the per-step refresh runs on a side stream so that it overlaps the bulk force kernel.
+//
+// Design.  Every rank owns an ARENA in its HBM with one receive slot per direction code c = (ox+1) + 3(oy+1) + 9(oz+1):
+// slot c of a rank holds what its neighbor at -o sent in direction o.  Arenas are shared between the processes of a node
+// through CUDA IPC handles (or plain peer pointers inside one process), so a sender's pack kernel stores its records
+// straight into the receiver's slot; its last CTA then publishes {count, error bits} and an epoch flag, and the receiver's
+// stream continues behind a one-warp wait kernel.  No host round trip, no message sizing, no dependent hops:
+//   * migration: every leaver goes straight to the brick that will own it (ONE exchange instead of one per dimension);
+//   * ghost creation: an atom inside the send slabs of several dimensions is sent as every image it will have -- face,
+//     edge and corner neighbors at once -- instead of being forwarded swap by swap.  The receiver orders the 26 slots
+//     exactly as the reference's 6-swap sequence would have delivered them (slot_order below) and records inside a
+//     slot keep the owner's index order, so ghost indices -- hence neighbor rows -- are bit-identical to the reference;
+//   * per-step refresh: the send lists of the ghost creation are replayed (ONE pack kernel, one wait, one unpack kernel),
+//     double-buffered by the parity of the epoch, on the side stream under the bulk force kernel.
+// All ordered placements are multi-category stream compactions (27 categories per atom, ballots + a per-tile scan): no
+// atomics decide an order, results are the same in every run.
 #include "internal.h"
 #include "device_math.cuh"
 #include <nccl.h>
+#include <unistd.h>
 #include <algorithm>
 #include <climits>
 #include <cstring>
@@ -36,11 +47,73 @@ namespace meso {
 struct SoA3 { double *c[3]; };
 static inline SoA3 soa(DevBuf<double> *b) { SoA3 s; for (int d = 0; d < 3; d++) s.c[d] = b[d].p; return s; }
 
-constexpr int REC = 8;            // doubles per migration record (64 B); record 0 of every message is the header {count}
-constexpr int RECB = 9;           // doubles per border record: + {owner rank | shift code << 24, owner's local index}
-constexpr int CT = 256;           // threads
-constexpr int CI = 4;             // items per thread
+constexpr int NS = 27;            // direction codes; 13 = the rank itself (no message)
+constexpr int RECM = 8;           // doubles per migration record {x(3), v(3), tag|type, mask|image}
+constexpr int RECB = 8;           // doubles per ghost-creation record {x+shift(3), v(3), tag|type, mask|signature}
+constexpr int RECF = 5;           // doubles per refresh record {x+shift(3), packed velocity + signature}
+constexpr int CT = 256;           // threads of the compaction kernels
+constexpr int CI = 4;             // candidates per thread and tile
 constexpr int CTILE = CT * CI;
+
+// first 4 KB of every arena: written by the senders, indexed by the sender's direction code
+struct ArenaHdr {
+    int flag_mig[32], flag_halo[2][32];   // epoch of the message in the slot (halo: ghost creation and refresh share one sequence,
+                                          // buffer = epoch & 1)
+    int cnt_mig[32], cnt_halo[32];        // record counts of the migration / ghost-creation message
+    int err[32];                          // sender's error bits
+    int ack_mig[32], ack_halo[32];        // written by the RECEIVER of what this rank sent in direction c: last epoch consumed
+};
+constexpr size_t HDR_BYTES = 4096;
+
+// where my messages go: for direction c, the receiver's arena and the layout of MY slot there
+struct Peers {
+    unsigned char *arena[NS];
+    unsigned long long mig_off[NS], bond_off[NS], gho_off[NS];
+    int mcap[NS], gcap[NS];
+    int bpa;
+};
+// my own arena: slot c holds what the neighbor at -o(c) sent
+struct Mine {
+    unsigned char *arena;
+    unsigned long long mig_off[NS], bond_off[NS], gho_off[NS];
+    int mcap[NS], gcap[NS];
+    unsigned recv_mask;           // bit c: a sender exists for slot c
+    int order[26];                // slots in the reference's ghost order
+    int bpa;
+};
+
+struct CommBlob {                 // what a rank tells the others (1 KB, carried by an NCCL all-gather or by the host)
+    unsigned magic;
+    int rank, device, bpa;
+    long long pid;
+    unsigned long long arena_ptr, arena_bytes;
+    cudaIpcMemHandle_t handle;
+    unsigned long long mig_off[NS], bond_off[NS], gho_off[NS];
+    int mcap[NS], gcap[NS];
+};
+static_assert(sizeof(CommBlob) <= 1024, "comm blob grew past its wire size");
+constexpr unsigned BLOB_MAGIC = 0x4d45534fu;
+
+struct CommState {                // host-side bookkeeping, hangs off meso_ctx::comm
+    unsigned char *arena = nullptr;
+    size_t arena_bytes = 0;
+    Mine mine{};
+    Peers peers{};
+    bool ready = false;           // peers' arenas are mapped
+    int epoch_mig = 0, epoch_halo = 0;
+    int peer_rank[NS];
+    std::vector<void *> opened;   // IPC mappings to close
+    DevBuf<int> sendlist[NS];     // local indices of the atoms sent in direction c at the last ghost creation
+    DevBuf<int> tile_counts;      // [ntiles][32]
+    DevBuf<int> sync;             // last-CTA tickets, category totals
+    int bpa = -1;
+};
+
+static CommState *state(meso_ctx *ctx)
+{
+    if (!ctx->comm) ctx->comm = new CommState();
+    return static_cast<CommState *>(ctx->comm);
+}
 
 int comm_init(meso_ctx *ctx, const void *nccl_id)
 {
@@ -55,16 +128,30 @@ int comm_init(meso_ctx *ctx, const void *nccl_id)
     return MESO_OK;
 }
 
+static void close_peers(CommState *cs)
+{
+    for (void *p : cs->opened) cudaIpcCloseMemHandle(p);
+    cs->opened.clear();
+    cs->ready = false;
+}
+
 void comm_destroy(meso_ctx *ctx)
 {
+    if (ctx->comm) {
+        CommState *cs = static_cast<CommState *>(ctx->comm);
+        close_peers(cs);
+        if (cs->arena) cudaFree(cs->arena);
+        delete cs;
+        ctx->comm = nullptr;
+    }
     if (ctx->nccl) { ncclCommDestroy((ncclComm_t)ctx->nccl); ctx->nccl = nullptr; }
 }
 
-// small host-visible reductions (thermo scalars, global atom count)
+// small host-visible reductions (thermo scalars, global atom count).  Without a communicator (the host exchanged the memory
+// handles itself: several ranks of one process, or of one GPU) the values stay this rank's part and the host sums them.
 int comm_allreduce_sum(meso_ctx *ctx, double *host_vals, int n)
 {
-    if (ctx->nranks == 1) return MESO_OK;
-    if (!ctx->nccl) { ctx->err = "communicator not initialised"; return MESO_ENCCL; }
+    if (ctx->nranks == 1 || !ctx->nccl) return MESO_OK;
     if (!ctx->reduce_buf.reserve(std::max(64, n))) { ctx->err = "out of device memory"; return MESO_ECUDA; }
     MESO_CUDA(cudaMemcpyAsync(ctx->reduce_buf.p, host_vals, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     MESO_NCCL(ncclAllReduce(ctx->reduce_buf.p, ctx->reduce_buf.p, n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
@@ -73,196 +160,652 @@ int comm_allreduce_sum(meso_ctx *ctx, double *host_vals, int n)
     return MESO_OK;
 }
 
-// ------------------------------------------------------------------ generic ordered 2-way compaction
-// flags a,b per candidate in [first,last); tile counts -> exclusive scan -> ranks.  Used for (lo,hi) slabs
-// and for (left,right) leavers.
-struct Flags { bool a, b; };
+// ------------------------------------------------------------------ geometry of the 27 directions
+static inline void code_offsets(int c, int o[3]) { o[0] = c % 3 - 1; o[1] = (c / 3) % 3 - 1; o[2] = c / 9 - 1; }
 
-template <typename F>
-__device__ __forceinline__ void tile_count(F flag, int first, int last, int2 *tile_counts, int ntiles)
+// rank of the brick at myloc + o, or -1 beyond a non-periodic face
+static int rank_at(const meso_ctx *ctx, const int o[3])
 {
-    __shared__ int sa[CT / 32], sb[CT / 32];
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int na = 0, nb = 0;
-        const int base = first + tile * CTILE;
-#pragma unroll
-        for (int r = 0; r < CI; r++) {
-            const int i = base + r * CT + threadIdx.x;
-            if (i < last) { Flags f = flag(i); na += f.a; nb += f.b; }
+    int loc[3];
+    for (int d = 0; d < 3; d++) {
+        loc[d] = ctx->myloc[d] + o[d];
+        if (loc[d] < 0 || loc[d] >= ctx->procgrid[d]) {
+            if (!ctx->box.periodic[d]) return -1;
+            loc[d] = (loc[d] + ctx->procgrid[d]) % ctx->procgrid[d];
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
-        if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = na; sb[threadIdx.x >> 5] = nb; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int a = 0, b = 0;
-            for (int w = 0; w < CT / 32; w++) { a += sa[w]; b += sb[w]; }
-            tile_counts[tile] = make_int2(a, b);
-        }
-        __syncthreads();
+    }
+    return (loc[0] * ctx->procgrid[1] + loc[1]) * ctx->procgrid[2] + loc[2];
+}
+
+// The reference creates ghosts by 6 swaps (dimension d: swap 2d sends the lower slab to the lower neighbor, swap 2d+1 the upper
+// slab to the upper one), and the candidates of dimension d are a rank's border atoms followed by the ghosts it received in
+// the dimensions before (UM/comm_meso.cu:60-81).  An image that hopped in dimensions d1 < d2 < d3 therefore sits, in the
+// receiver's ghost array, in the range of the swap of its LAST hop, behind the sender's own atoms and ordered like the
+// sender's ghosts -- recursively.  Key of a direction code = (swap of the last hop, of the one before, of the first),
+// absent hops = -1; ascending lexicographic order is the reference's ghost order.
+static void slot_order(int order[26])
+{
+    struct K { int k[3], c; };
+    K keys[26];
+    int n = 0;
+    for (int c = 0; c < NS; c++) {
+        if (c == 13) continue;
+        int o[3];
+        code_offsets(c, o);
+        K e; e.c = c; e.k[0] = e.k[1] = e.k[2] = -1;
+        int p = 0;
+        for (int d = 2; d >= 0; d--) if (o[d]) e.k[p++] = 2 * d + (o[d] > 0 ? 1 : 0);
+        keys[n++] = e;
+    }
+    std::sort(keys, keys + n, [](const K &a, const K &b) {
+        for (int q = 0; q < 3; q++) if (a.k[q] != b.k[q]) return a.k[q] < b.k[q];
+        return false;
+    });
+    for (int q = 0; q < 26; q++) order[q] = keys[q].c;
+}
+
+// ------------------------------------------------------------------ arena
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// capacities of my receive slots from my own brick (a sender checks them before it writes: no agreement is needed)
+static int ensure_arena(meso_ctx *ctx)
+{
+    CommState *cs = state(ctx);
+    const Box &b = ctx->box;
+    const int bpa = bonds_active(ctx) ? ctx->bond_per_atom : 0;
+    double w[3], vol = 1.0;
+    for (int d = 0; d < 3; d++) { w[d] = b.subhi[d] - b.sublo[d]; vol *= w[d]; }
+    const double dens = std::max(1.0, (double)std::max(ctx->nlocal_host, 1) / vol);
+    const double cut = ctx->cutneighmax;
+    Mine m{};
+    size_t off = HDR_BYTES;
+    m.recv_mask = 0;
+    m.bpa = bpa;
+    for (int c = 0; c < NS; c++) {
+        m.mcap[c] = m.gcap[c] = 0;
+        m.mig_off[c] = m.bond_off[c] = m.gho_off[c] = 0;
+        cs->peer_rank[c] = -1;
+        if (c == 13) continue;
+        int o[3], back[3];
+        code_offsets(c, o);
+        for (int d = 0; d < 3; d++) back[d] = -o[d];
+        const int sender = rank_at(ctx, back);
+        cs->peer_rank[c] = rank_at(ctx, o);
+        if (sender < 0) continue;
+        m.recv_mask |= 1u << c;
+        double gvol = 1.0, face = 1.0;
+        int nz = 0;
+        for (int d = 0; d < 3; d++) { gvol *= o[d] ? cut : w[d]; face *= o[d] ? 1.0 : w[d]; nz += o[d] != 0; }
+        // ghosts: the image region at the brick's density, +30 % and a floor for small / inhomogeneous systems
+        m.gcap[c] = (int)(gvol * dens * 1.3) + 1024;
+        // leavers per rebuild through a face: a layer ~0.05 thick at the deck's temperature; generous floors elsewhere
+        m.mcap[c] = nz == 1 ? std::max(4096, (int)(face * dens * 0.25)) : 1024;
+        m.mig_off[c] = off; off = align_up(off + (size_t)m.mcap[c] * RECM * 8, 256);
+        m.bond_off[c] = off; off = align_up(off + (size_t)m.mcap[c] * (1 + bpa) * 8, 256);
+        m.gho_off[c] = off; off = align_up(off + 2 * (size_t)m.gcap[c] * RECB * 8, 256);
+    }
+    slot_order(m.order);
+    bool fits = cs->arena && off <= cs->arena_bytes && bpa == cs->bpa && m.recv_mask == cs->mine.recv_mask;
+    for (int c = 0; c < NS && fits; c++) fits = m.gcap[c] <= cs->mine.gcap[c] && m.mcap[c] <= cs->mine.mcap[c];
+    if (fits) return MESO_OK;                                  // the mapped arena still serves: nothing to re-publish
+    close_peers(cs);
+    if (cs->arena) { cudaFree(cs->arena); cs->arena = nullptr; }
+    MESO_CUDA(cudaMalloc(&cs->arena, off));
+    MESO_CUDA(cudaMemsetAsync(cs->arena, 0, HDR_BYTES, ctx->stream));
+    cs->arena_bytes = off;
+    m.arena = cs->arena;
+    cs->mine = m;
+    cs->bpa = bpa;
+    // the epoch counters are NOT reset: every rank advances them in step, whatever happens to one rank's arena
+    if (!cs->sync.reserve(128)) { ctx->err = "out of device memory"; return MESO_ECUDA; }
+    MESO_CUDA(cudaMemsetAsync(cs->sync.p, 0, 128 * sizeof(int), ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MESO_OK;
+}
+
+static void fill_blob(meso_ctx *ctx, CommBlob &bl)
+{
+    CommState *cs = state(ctx);
+    memset(&bl, 0, sizeof bl);
+    bl.magic = BLOB_MAGIC; bl.rank = ctx->rank; bl.device = ctx->device; bl.bpa = cs->mine.bpa;
+    bl.pid = (long long)getpid();
+    bl.arena_ptr = (unsigned long long)(uintptr_t)cs->arena; bl.arena_bytes = cs->arena_bytes;
+    if (cudaIpcGetMemHandle(&bl.handle, cs->arena) != cudaSuccess) cudaGetLastError();   // same-process peers use arena_ptr
+    for (int c = 0; c < NS; c++) {
+        bl.mig_off[c] = cs->mine.mig_off[c]; bl.bond_off[c] = cs->mine.bond_off[c]; bl.gho_off[c] = cs->mine.gho_off[c];
+        bl.mcap[c] = cs->mine.mcap[c]; bl.gcap[c] = cs->mine.gcap[c];
     }
 }
 
-// single CTA: exclusive scan of `used` tile counts; totals to tot[0..1]
-__device__ __forceinline__ int2 scan_tiles(int2 *tile_counts, int used)
+// map the arenas of my (at most 26 distinct) neighbors: IPC between processes, plain pointers inside one
+static int import_blobs(meso_ctx *ctx, const unsigned char *blobs, int nranks)
 {
-    __shared__ int2 wsum[32];
-    __shared__ int2 carry_s;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) carry_s = make_int2(0, 0);
-    __syncthreads();
-    for (int base = 0; base < used; base += 1024) {
-        const int i = base + t;
-        int2 v = (i < used) ? tile_counts[i] : make_int2(0, 0), x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int ya = __shfl_up_sync(0xffffffffu, x.x, o), yb = __shfl_up_sync(0xffffffffu, x.y, o);
-            if (lane >= o) { x.x += ya; x.y += yb; }
-        }
-        if (lane == 31) wsum[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            int2 s = wsum[lane], z = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int ya = __shfl_up_sync(0xffffffffu, z.x, o), yb = __shfl_up_sync(0xffffffffu, z.y, o);
-                if (lane >= o) { z.x += ya; z.y += yb; }
+    CommState *cs = state(ctx);
+    close_peers(cs);
+    std::vector<unsigned char *> base((size_t)nranks, nullptr);
+    Peers p{};
+    p.bpa = cs->mine.bpa;
+    for (int c = 0; c < NS; c++) {
+        p.arena[c] = nullptr;
+        p.mig_off[c] = p.bond_off[c] = p.gho_off[c] = 0;
+        p.mcap[c] = p.gcap[c] = 0;
+        if (c == 13) continue;
+        const int r = cs->peer_rank[c];
+        if (r < 0) continue;
+        CommBlob bl;
+        memcpy(&bl, blobs + (size_t)r * 1024, sizeof bl);
+        if (bl.magic != BLOB_MAGIC || bl.rank != r) { ctx->err = "comm import: malformed blob"; return MESO_EINVAL; }
+        if (bl.bpa != cs->mine.bpa) { ctx->err = "comm import: ranks disagree on bond_per_atom"; return MESO_EINVAL; }
+        if (!base[r]) {
+            if (r == ctx->rank) base[r] = cs->arena;
+            else if (bl.pid == (long long)getpid()) {
+                if (bl.device != ctx->device) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(bl.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx->err = "cudaDeviceEnablePeerAccess failed"; return MESO_ECUDA; }
+                    cudaGetLastError();
+                }
+                base[r] = (unsigned char *)(uintptr_t)bl.arena_ptr;
+            } else {
+                void *q = nullptr;
+                MESO_CUDA(cudaIpcOpenMemHandle(&q, bl.handle, cudaIpcMemLazyEnablePeerAccess));
+                cs->opened.push_back(q);
+                base[r] = (unsigned char *)q;
             }
-            wsum[lane] = make_int2(z.x - s.x, z.y - s.y);
         }
-        __syncthreads();
-        const int2 c = carry_s;
-        const int2 e = make_int2(c.x + wsum[w].x + x.x - v.x, c.y + wsum[w].y + x.y - v.y);
-        if (i < used) tile_counts[i] = e;
-        __syncthreads();
-        if (t == 1023) carry_s = make_int2(e.x + v.x, e.y + v.y);
-        __syncthreads();
+        p.arena[c] = base[r];
+        p.mig_off[c] = bl.mig_off[c]; p.bond_off[c] = bl.bond_off[c]; p.gho_off[c] = bl.gho_off[c];
+        p.mcap[c] = bl.mcap[c]; p.gcap[c] = bl.gcap[c];
+        if (!cs->sendlist[c].reserve((size_t)std::max(p.gcap[c], 1))) { ctx->err = "out of device memory (send lists)"; return MESO_ECUDA; }
     }
-    return carry_s;
+    cs->peers = p;
+    cs->ready = true;
+    return MESO_OK;
 }
 
-// rank of candidate i inside its tile for both flags (blocked order: round r covers CT consecutive candidates)
-struct TileRank {
-    int2 run;       // running totals of previous rounds in this tile
-};
-
-// ------------------------------------------------------------------ ghosts (borders)
-__device__ __forceinline__ Flags slab_flags(double xd, const Box &box, int d)
+// called at the first rebuild after an upload: every rank reaches it at the same point
+static int ensure_peers(meso_ctx *ctx)
 {
-    Flags f;
-    f.a = box.sendflag[2 * d] && xd <= box.slab_lo_hi[d];
-    f.b = box.sendflag[2 * d + 1] && xd >= box.slab_hi_lo[d];
-    return f;
+    int rc = ensure_arena(ctx);
+    if (rc) return rc;
+    CommState *cs = state(ctx);
+    if (cs->ready) return MESO_OK;
+    if (ctx->nranks == 1) {
+        CommBlob bl;
+        fill_blob(ctx, bl);
+        unsigned char buf[1024] = {0};
+        memcpy(buf, &bl, sizeof bl);
+        return import_blobs(ctx, buf, 1);
+    }
+    if (!ctx->nccl) { ctx->err = "decomposition without a communicator: exchange meso_comm_export blobs and call meso_comm_import before meso_setup"; return MESO_EINVAL; }
+    // all-gather of the 1 KB blobs through NCCL (bootstrap only)
+    DevBuf<unsigned char> dev;
+    if (!dev.reserve((size_t)1024 * (ctx->nranks + 1))) { ctx->err = "out of device memory"; return MESO_ECUDA; }
+    std::vector<unsigned char> host((size_t)1024 * ctx->nranks, 0);
+    CommBlob bl;
+    fill_blob(ctx, bl);
+    unsigned char mine[1024] = {0};
+    memcpy(mine, &bl, sizeof bl);
+    unsigned char *sendp = dev.p + (size_t)1024 * ctx->nranks;
+    MESO_CUDA(cudaMemcpyAsync(sendp, mine, 1024, cudaMemcpyHostToDevice, ctx->stream));
+    MESO_NCCL(ncclAllGather(sendp, dev.p, 1024, ncclChar, (ncclComm_t)ctx->nccl, ctx->stream));
+    MESO_CUDA(cudaMemcpyAsync(host.data(), dev.p, host.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return import_blobs(ctx, host.data(), ctx->nranks);
 }
 
-__global__ void __launch_bounds__(CT) k_mr_border_count(const double *__restrict__ xd, const Counts *__restrict__ cnt,
-                                                        int2 *__restrict__ tile_counts, Box box, int d, int ntiles)
-{
-    const int first = cnt->n_bulk, last = cnt->nlocal + cnt->nghost;
-    tile_count([&](int i) { return slab_flags(xd[i], box, d); }, first, last, tile_counts, ntiles);
-}
+// ------------------------------------------------------------------ flags
+__device__ __forceinline__ void st_sys(int *p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_sys(const int *p) { int v; asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
-__global__ void __launch_bounds__(1024) k_mr_border_scan(int2 *__restrict__ tile_counts, Counts *__restrict__ cnt, double *__restrict__ send_lo,
-                                                         double *__restrict__ send_hi, int d, int swap_cap)
+// A sender may overwrite a slot only after the receiver has consumed what it held: the receiver acknowledges every epoch in
+// the SENDER's header (ack_*[c]), and a pack kernel starts by waiting for the acknowledgement of the previous use of its
+// target buffer (migration: epoch - 1; halo, double-buffered: epoch - 2).  With double buffering the wait never blocks in
+// practice; it is what makes the protocol safe when ranks drift apart (or time-share one GPU).
+__device__ __forceinline__ void wait_ack(const Mine &mine, Counts *cnt, const Peers &peers, int c, int need, int kind)
 {
-    const int first = cnt->n_bulk, last = cnt->nlocal + cnt->nghost;
-    const int used = (max(last - first, 0) + CTILE - 1) / CTILE;
-    int2 tot = scan_tiles(tile_counts, used);
-    if (threadIdx.x == 0) {
-        if (tot.x > swap_cap || tot.y > swap_cap) { cnt->err |= 1; tot.x = min(tot.x, swap_cap); tot.y = min(tot.y, swap_cap); }
-        cnt->send_n[2 * d] = tot.x; cnt->send_n[2 * d + 1] = tot.y;
-        reinterpret_cast<int *>(send_lo)[0] = tot.x;           // message headers
-        reinterpret_cast<int *>(send_hi)[0] = tot.y;
+    if (need <= 0 || c == 13 || !peers.arena[c]) return;
+    const ArenaHdr *h = reinterpret_cast<const ArenaHdr *>(mine.arena);
+    const int *a = kind == 0 ? &h->ack_mig[c] : &h->ack_halo[c];
+    const long long t0 = clock64();
+    while (ld_sys(a) < need) {
+        if (clock64() - t0 > 40000000000LL) { atomicOr(&cnt->err, 16); break; }
+        __nanosleep(100);
     }
 }
 
-// pack_border_vel (UM/atom_vec_dpd_atomic_meso.cu:61-100): record = {x+shift (3), v (3), tag|type, mask|signature}
-__global__ void __launch_bounds__(CT) k_mr_border_pack(SoA3 x, SoA3 v, const int *__restrict__ tag, const int *__restrict__ type,
-                                                       const int *__restrict__ mask, const float4 *__restrict__ veloc4,
-                                                       const Counts *__restrict__ cnt, const int2 *__restrict__ tile_counts,
-                                                       double *__restrict__ send_lo, double *__restrict__ send_hi,
-                                                       int *__restrict__ list_lo, int *__restrict__ list_hi, Box box, int d, int ntiles,
-                                                       int swap_cap, const int2 *__restrict__ ghost_origin, int my_rank)
+// End of a pack kernel: every CTA has fenced its remote stores; the last one publishes the per-direction record counts and
+// error bits, then the epoch flags.  kind: 0 = migration, 1 = ghost creation, 2 = refresh.
+__device__ __forceinline__ void publish(const Peers &peers, int *ticket, const int *counts, int errbits, int epoch, int kind)
 {
-    __shared__ int2 wsum[CT / 32];
-    const int nlocal = cnt->nlocal;
-    const int first = cnt->n_bulk, last = nlocal + cnt->nghost;
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    const int c = threadIdx.x;
+    if (c < NS && c != 13 && peers.arena[c]) {
+        ArenaHdr *h = reinterpret_cast<ArenaHdr *>(peers.arena[c]);
+        if (kind == 0) { st_sys(&h->cnt_mig[c], counts[c]); st_sys(&h->err[c], errbits); }
+        else if (kind == 1) { st_sys(&h->cnt_halo[c], counts[c]); st_sys(&h->err[c], errbits); }
+        __threadfence_system();
+        st_sys(kind == 0 ? &h->flag_mig[c] : &h->flag_halo[epoch & 1][c], epoch);
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
+// End of an unpack kernel: the last CTA tells every sender that its slot is free again (slot c was filled by the neighbor at
+// -o(c), which sent in direction c: its arena is peers.arena[26 - c])
+__device__ __forceinline__ void acknowledge(const Mine &mine, const Peers &peers, int *ticket, int epoch, int kind)
+{
+    __syncthreads();
+    __shared__ int s_last_ack;
+    if (threadIdx.x == 0) { __threadfence(); s_last_ack = atomicAdd(ticket, 1) == (int)(gridDim.x * gridDim.y) - 1; }
+    __syncthreads();
+    if (!s_last_ack) return;
+    const int c = threadIdx.x;
+    if (c < NS && c != 13 && ((mine.recv_mask >> c) & 1u) && peers.arena[26 - c]) {
+        ArenaHdr *h = reinterpret_cast<ArenaHdr *>(peers.arena[26 - c]);
+        st_sys(kind == 0 ? &h->ack_mig[c] : &h->ack_halo[c], epoch);
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
+// one warp: lane c waits until the neighbor that fills slot c has published `epoch` (bounded: a lost peer sets an error bit
+// instead of hanging the GPU); sender-side errors are adopted.  kind 0: migration, otherwise halo.
+__global__ void k_wait(Mine mine, Counts *cnt, int epoch, int kind)
+{
+    const int c = threadIdx.x;
+    if (c >= NS || !((mine.recv_mask >> c) & 1u)) return;
+    ArenaHdr *h = reinterpret_cast<ArenaHdr *>(mine.arena);
+    const int *f = kind == 0 ? &h->flag_mig[c] : &h->flag_halo[epoch & 1][c];
+    const long long t0 = clock64();
+    while (ld_sys(f) < epoch) {
+        if (clock64() - t0 > 40000000000LL) { atomicOr(&cnt->err, 16); break; }      // ~20 s
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    if (kind < 2) { const int e = ld_sys(&h->err[c]); if (e) atomicOr(&cnt->err, e); }
+}
+
+// ------------------------------------------------------------------ ordered compaction into 27 categories
+// Every candidate belongs to a set of categories (bit mask).  Rank of a candidate inside category c = number of earlier
+// candidates (by index) in c.  Tiles of CTILE candidates in blocked order (round r covers CT consecutive candidates).
+// tile_counts[tile][32]: per-tile totals, exclusive-scanned over the tiles by k_mc_scan.
+template <typename F>
+__device__ __forceinline__ void mc_count(F mask_of, int first, int last, int *tile_counts, int ntiles)
+{
+    __shared__ int wsum[CT / 32][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int base = first + tile * CTILE;
         if (base >= last) break;
-        int2 run = tile_counts[tile];
+        int mine = 0;                                          // lane c: this warp's count of category c
 #pragma unroll
         for (int r = 0; r < CI; r++) {
             const int i = base + r * CT + threadIdx.x;
-            Flags f{false, false};
-            double xi[3] = {0, 0, 0};
-            if (i < last) {
-#pragma unroll
-                for (int q = 0; q < 3; q++) xi[q] = x.c[q][i];
-                f = slab_flags(xi[d], box, d);
+            const unsigned m = i < last ? mask_of(i) : 0u;
+            const unsigned any = __reduce_or_sync(0xffffffffu, m);
+            for (unsigned rest = any; rest; rest &= rest - 1) {
+                const int c = __ffs(rest) - 1;
+                const unsigned b = __ballot_sync(0xffffffffu, (m >> c) & 1u);
+                if (lane == c) mine += __popc(b);
             }
-            const uint32_t ba = __ballot_sync(0xffffffffu, f.a), bb = __ballot_sync(0xffffffffu, f.b);
-            if (lane == 0) wsum[w] = make_int2(__popc(ba), __popc(bb));
-            __syncthreads();
-            int2 pre = make_int2(0, 0), tot = make_int2(0, 0);
-#pragma unroll
-            for (int ww = 0; ww < CT / 32; ww++) {
-                const int2 c = wsum[ww];
-                if (ww < w) { pre.x += c.x; pre.y += c.y; }
-                tot.x += c.x; tot.y += c.y;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                if (!(side ? f.b : f.a)) continue;
-                const int k = side ? run.y + pre.y + __popc(bb & lt) : run.x + pre.x + __popc(ba & lt);
-                if (k >= swap_cap) continue;
-                const int pbc = box.pbc[2 * d + side];
-                double xg[3] = {xi[0], xi[1], xi[2]};
-                if (pbc) xg[d] = pbc > 0 ? xi[d] + box.prd[d] : xi[d] - box.prd[d];   // x + pbc*prd
-                double *rec = (side ? send_hi : send_lo) + (size_t)(k + 1) * RECB;
-                // owner of this image: a local atom is its own, a forwarded ghost keeps the owner it arrived with;
-                // shift code 2 bits per dimension (1 = +prd, 2 = -prd), accumulated over the swaps it went through
-                int2 org = (i < nlocal) ? make_int2(my_rank, i) : ghost_origin[i - nlocal];
-                if (pbc) org.x |= (pbc > 0 ? 1 : 2) << (24 + 2 * d);
-                reinterpret_cast<int2 *>(rec)[8] = org;
-                rec[0] = xg[0]; rec[1] = xg[1]; rec[2] = xg[2];
-                rec[3] = v.c[0][i]; rec[4] = v.c[1][i]; rec[5] = v.c[2][i];
-                reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
-                reinterpret_cast<int2 *>(rec)[7] = make_int2(mask[i], __float_as_int(veloc4[i].w));
-                (side ? list_hi : list_lo)[k] = i;
-            }
-            run.x += tot.x; run.y += tot.y;
         }
+        wsum[w][lane] = mine;
+        __syncthreads();
+        if (w == 0) {
+            int t = 0;
+#pragma unroll
+            for (int ww = 0; ww < CT / 32; ww++) t += wsum[ww][lane];
+            tile_counts[(size_t)tile * 32 + lane] = t;
+        }
+        __syncthreads();
     }
 }
 
-// publishes the ghost ranges of the two swaps of dimension d from the received headers
-__global__ void k_mr_border_advance(Counts *cnt, const double *recv_a, const double *recv_b, int d, int cap)
+// one warp per category: exclusive scan of its column over the used tiles; totals to tot[c]
+// range_kind 0: all locals (migration), 1: the border atoms (ghost creation)
+__global__ void __launch_bounds__(1024) k_mc_scan(int *__restrict__ tile_counts, const Counts *__restrict__ cnt, int range_kind, int *__restrict__ tot)
 {
-    int na = reinterpret_cast<const int *>(recv_a)[0], nb = reinterpret_cast<const int *>(recv_b)[0];
-    const int last = cnt->nlocal + cnt->nghost;
-    if (last + na + nb > cap) { cnt->err |= 1; na = 0; nb = 0; }
-    cnt->swap_first[2 * d] = last;          cnt->swap_n[2 * d] = na;
-    cnt->swap_first[2 * d + 1] = last + na; cnt->swap_n[2 * d + 1] = nb;
-    cnt->nghost += na + nb;
-    cnt->nall = cnt->nlocal + cnt->nghost;
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    if (c >= NS) return;
+    const int first = range_kind == 0 ? 0 : cnt->n_bulk, last = cnt->nlocal;
+    const int used = (max(last - first, 0) + CTILE - 1) / CTILE;
+    int carry = 0;
+    for (int t0 = 0; t0 < used; t0 += 32) {
+        const int t = t0 + lane;
+        const int v = t < used ? tile_counts[(size_t)t * 32 + c] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (t < used) tile_counts[(size_t)t * 32 + c] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) tot[c] = carry;
+}
+
+// ranks of the candidates of one tile: calls emit(i, c, rank) for every (candidate, category) pair
+template <typename F, typename E>
+__device__ __forceinline__ void mc_place(F mask_of, E emit, int first, int last, const int *tile_counts, int ntiles)
+{
+    __shared__ unsigned bal[CI][CT / 32][32];
+    __shared__ int pre[CI][CT / 32][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int base = first + tile * CTILE;
+        if (base >= last) break;
+        unsigned m[CI];
+#pragma unroll
+        for (int r = 0; r < CI; r++) {
+            const int i = base + r * CT + threadIdx.x;
+            m[r] = i < last ? mask_of(i) : 0u;
+            bal[r][w][lane] = 0u;
+            const unsigned any = __reduce_or_sync(0xffffffffu, m[r]);
+            __syncwarp();
+            for (unsigned rest = any; rest; rest &= rest - 1) {
+                const int c = __ffs(rest) - 1;
+                const unsigned b = __ballot_sync(0xffffffffu, (m[r] >> c) & 1u);
+                if (lane == c) bal[r][w][c] = b;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {                                // lane = category: prefix over the (round, warp) chunks of the tile
+            int run = tile_counts[(size_t)tile * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < CI; r++)
+#pragma unroll
+                for (int ww = 0; ww < CT / 32; ww++) { pre[r][ww][lane] = run; run += __popc(bal[r][ww][lane]); }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < CI; r++) {
+            const int i = base + r * CT + threadIdx.x;
+            for (unsigned rest = m[r]; rest; rest &= rest - 1) {
+                const int c = __ffs(rest) - 1;
+                emit(i, c, pre[r][w][c] + __popc(bal[r][w][c] & lt));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ migration
+// destination of a local atom after the periodic wrap: `x >= hi || x < lo`, direction by the minimum image of x - mid
+// (UM/comm_meso.cu:303-330), all communicating dimensions at once
+struct MigGeom { int multi[3]; };
+
+__device__ __forceinline__ int leave_dir(double xd, const Box &box, int d)
+{
+    if (xd >= box.subhi[d] || xd < box.sublo[d]) {
+        double dist = xd - 0.5 * (box.sublo[d] + box.subhi[d]);
+        if (box.periodic[d] && fabs(dist) > 0.5 * box.prd[d]) dist += dist < 0.0 ? box.prd[d] : -box.prd[d];
+        return dist < 0 ? -1 : 1;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ unsigned mig_mask(const SoA3 &x, int i, const Box &box, const MigGeom &g)
+{
+    int code = 0, w = 1;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const int o = g.multi[d] ? leave_dir(x.c[d][i], box, d) : 0;
+        code += (o + 1) * w;
+        w *= 3;
+    }
+    return 1u << code;
+}
+
+__global__ void __launch_bounds__(CT) k_mig_count(SoA3 x, const Counts *__restrict__ cnt, int *__restrict__ tile_counts, Box box, MigGeom g,
+                                                  int ntiles)
+{
+    mc_count([&](int i) { return mig_mask(x, i, box, g); }, 0, cnt->nlocal, tile_counts, ntiles);
+}
+
+// stayers (category 13) are compacted in order into the alternate arrays; leavers become records in the slot of their
+// destination brick.  tot[c] = number of atoms of category c.
+__global__ void __launch_bounds__(CT) k_mig_pack(SoA3 x, SoA3 v, const int *__restrict__ tag, const int *__restrict__ type,
+                                                 const int *__restrict__ mask, const int *__restrict__ image, SoA3 xo, SoA3 vo,
+                                                 int *__restrict__ tago, int *__restrict__ typeo, int *__restrict__ masko,
+                                                 int *__restrict__ imageo, Counts *__restrict__ cnt, const int *__restrict__ tile_counts,
+                                                 const int *__restrict__ tot, Box box, MigGeom g, Peers peers, int ntiles,
+                                                 const int *__restrict__ nbond, const int2 *__restrict__ bonds, int *__restrict__ nbond_o,
+                                                 int2 *__restrict__ bonds_o, size_t padding, int *ticket, int *sendn, int epoch, Mine mine)
+{
+    const int bpa = peers.bpa;
+    if (threadIdx.x < NS) wait_ack(mine, cnt, peers, threadIdx.x, epoch - 1, 0);
+    __syncthreads();
+    mc_place([&](int i) { return mig_mask(x, i, box, g); },
+             [&](int i, int c, int k) {
+                 if (c == 13) {
+#pragma unroll
+                     for (int q = 0; q < 3; q++) { xo.c[q][k] = x.c[q][i]; vo.c[q][k] = v.c[q][i]; }
+                     tago[k] = tag[i]; typeo[k] = type[i]; masko[k] = mask[i]; imageo[k] = image[i];
+                     if (bpa) {
+                         const int nb = nbond[i];
+                         nbond_o[k] = nb;
+                         for (int q = 0; q < nb; q++) bonds_o[k + q * padding] = bonds[i + q * padding];
+                     }
+                 } else if (!peers.arena[c]) atomicOr(&cnt->err, 8);                 // beyond a non-periodic face: lost
+                 else if (k < peers.mcap[c]) {
+                     double *rec = reinterpret_cast<double *>(peers.arena[c] + peers.mig_off[c]) + (size_t)k * RECM;
+#pragma unroll
+                     for (int q = 0; q < 3; q++) { rec[q] = x.c[q][i]; rec[3 + q] = v.c[q][i]; }
+                     reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
+                     reinterpret_cast<int2 *>(rec)[7] = make_int2(mask[i], image[i]);
+                     if (bpa) {
+                         int2 *br = reinterpret_cast<int2 *>(peers.arena[c] + peers.bond_off[c]) + (size_t)k * (1 + bpa);
+                         const int nb = nbond[i];
+                         br[0] = make_int2(nb, 0);
+                         for (int q = 0; q < nb; q++) br[1 + q] = bonds[i + q * padding];
+                     }
+                 }
+             },
+             0, cnt->nlocal, tile_counts, ntiles);
+    // counts for the headers (clamped; an overflow would lose atoms: error bit 8 travels with the message).  Every CTA computes
+    // the same values; the last one publishes them.
+    if (threadIdx.x < NS) {
+        const int c = threadIdx.x;
+        int n = tot[c];
+        if (c != 13 && peers.arena[c] && n > peers.mcap[c]) { n = peers.mcap[c]; atomicOr(&cnt->err, 8); }
+        if (blockIdx.x == 0) sendn[c] = c == 13 ? 0 : n;
+    }
+    __syncthreads();
+    publish(peers, ticket, sendn, cnt->err & 8, epoch, 0);
+}
+
+__global__ void k_mig_shrink(Counts *cnt, const int *tot) { cnt->nlocal = tot[13]; cnt->nall = tot[13]; }
+
+// arrivals are appended slot by slot (ascending direction code), inside a slot in the sender's index order
+__global__ void __launch_bounds__(256) k_mig_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
+                                                    int *__restrict__ image, Counts *__restrict__ cnt, Mine mine, Box box, MigGeom g,
+                                                    int nloc_cap, int *__restrict__ nbond, int2 *__restrict__ bonds, size_t padding,
+                                                    Peers peers, int *ticket, int epoch)
+{
+    const int s = blockIdx.y;
+    const ArenaHdr *h = reinterpret_cast<const ArenaHdr *>(mine.arena);
+    int base = cnt->nlocal, total = 0;
+    for (int q = 0; q < NS; q++) {
+        if (!((mine.recv_mask >> q) & 1u)) continue;
+        const int nq = min(max(h->cnt_mig[q], 0), mine.mcap[q]);
+        if (q < s) base += nq;
+        total += nq;
+    }
+    const bool fits = cnt->nlocal + total <= nloc_cap;
+    if (!fits && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicOr(&cnt->err, 8);
+    const int n = (fits && ((mine.recv_mask >> s) & 1u)) ? min(max(h->cnt_mig[s], 0), mine.mcap[s]) : 0;
+    const double *buf = reinterpret_cast<const double *>(mine.arena + mine.mig_off[s]);
+    const int2 *bbuf = reinterpret_cast<const int2 *>(mine.arena + mine.bond_off[s]);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double *rec = buf + (size_t)k * RECM;
+        const int p = base + k;
+        bool inside = true;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            x.c[q][p] = rec[q]; v.c[q][p] = rec[3 + q];
+            if (g.multi[q]) inside = inside && rec[q] >= box.sublo[q] && rec[q] < box.subhi[q];
+        }
+        const int2 tt = reinterpret_cast<const int2 *>(rec)[6], mi = reinterpret_cast<const int2 *>(rec)[7];
+        tag[p] = tt.x; type[p] = tt.y; mask[p] = mi.x; image[p] = mi.y;
+        if (!inside) atomicOr(&cnt->err, 8);                     // an arrival outside the brick is dropped by the reference too
+        if (mine.bpa) {
+            const int2 *br = bbuf + (size_t)k * (1 + mine.bpa);
+            const int nb = min(max(br[0].x, 0), mine.bpa);
+            nbond[p] = nb;
+            for (int q = 0; q < nb; q++) bonds[p + q * padding] = br[1 + q];
+        }
+    }
+    acknowledge(mine, peers, ticket, epoch, 0);
+}
+
+__global__ void k_mig_grow(Counts *cnt, Mine mine, int nloc_cap)
+{
+    const ArenaHdr *h = reinterpret_cast<const ArenaHdr *>(mine.arena);
+    int total = 0;
+    for (int q = 0; q < NS; q++) if ((mine.recv_mask >> q) & 1u) total += min(max(h->cnt_mig[q], 0), mine.mcap[q]);
+    if (cnt->nlocal + total <= nloc_cap) cnt->nlocal += total;
+    cnt->nall = cnt->nlocal;
+}
+
+static int tiles_for(meso_ctx *ctx) { return (int)((ctx->cap + CTILE - 1) / CTILE); }
+
+int launch_exchange_multi(meso_ctx *ctx)
+{
+    int rc = ensure_peers(ctx);
+    if (rc) return rc;
+    CommState *cs = state(ctx);
+    MigGeom g;
+    bool any = false;
+    for (int d = 0; d < 3; d++) { g.multi[d] = ctx->procgrid[d] > 1; any = any || g.multi[d]; }
+    if (!any) return MESO_OK;                     // the periodic wrap already put every atom back into the brick
+    const Box &box = ctx->box;
+    const int ntiles = tiles_for(ctx);
+    if (!cs->tile_counts.reserve((size_t)ntiles * 32 + 64)) { ctx->err = "out of device memory (tile counts)"; return MESO_ECUDA; }
+    int *tc = cs->tile_counts.p, *tot = cs->sync.p + 8, *sendn = cs->sync.p + 40;
+    cudaStream_t st = ctx->stream;
+    const bool bonded = bonds_active(ctx);
+    const int epoch = ++cs->epoch_mig;
+    k_mig_count<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), ctx->d_counts, tc, box, g, ntiles);
+    k_mc_scan<<<1, 1024, 0, LS(st)>>>(tc, ctx->d_counts, 0, tot);
+    k_mig_pack<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, soa(ctx->xa),
+                                                 soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p, ctx->imagea.p, ctx->d_counts, tc, tot, box,
+                                                 g, cs->peers, ntiles, ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p, ctx->cap,
+                                                 cs->sync.p + 0, sendn, epoch, cs->mine);
+    for (int q = 0; q < 3; q++) { std::swap(ctx->x[q].p, ctx->xa[q].p); std::swap(ctx->v[q].p, ctx->va[q].p); }
+    std::swap(ctx->tag.p, ctx->taga.p); std::swap(ctx->type.p, ctx->typea.p);
+    std::swap(ctx->mask.p, ctx->maska.p); std::swap(ctx->image.p, ctx->imagea.p);
+    if (bonded) {
+        std::swap(ctx->nbond.p, ctx->nbond_alt.p); std::swap(ctx->nbond.cap, ctx->nbond_alt.cap);
+        std::swap(ctx->bonds.p, ctx->bonds_alt.p); std::swap(ctx->bonds.cap, ctx->bonds_alt.cap);
+    }
+    k_mig_shrink<<<1, 1, 0, LS(st)>>>(ctx->d_counts, tot);
+    k_wait<<<1, 32, 0, LS(st)>>>(cs->mine, ctx->d_counts, epoch, 0);
+    const dim3 grid(std::max(1, ctx->sm_count / 4), NS);
+    k_mig_unpack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, ctx->d_counts, cs->mine, box,
+                                        g, (int)ctx->nloc_cap, ctx->nbond.p, ctx->bonds.p, ctx->cap, cs->peers, cs->sync.p + 3, epoch);
+    k_mig_grow<<<1, 1, 0, LS(st)>>>(ctx->d_counts, cs->mine, (int)ctx->nloc_cap);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+// ------------------------------------------------------------------ ghost creation
+// An atom goes in direction o iff, in every dimension with o_d != 0, it lies in the send slab of that side
+// (x <= sublo + cutghost for o_d = -1, x >= subhi - cutghost for o_d = +1; src/comm.cpp:590-625) -- the product of the
+// per-dimension choices {stay, lower?, upper?} the 6 swaps would have made one after the other.
+__device__ __forceinline__ unsigned ghost_mask(const SoA3 &x, int i, const Box &box)
+{
+    unsigned m[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double xd = x.c[d][i];
+        m[d] = 2u | ((box.sendflag[2 * d] && xd <= box.slab_lo_hi[d]) ? 1u : 0u) | ((box.sendflag[2 * d + 1] && xd >= box.slab_hi_lo[d]) ? 4u : 0u);
+    }
+    const unsigned row = m[0];
+    const unsigned plane = ((m[1] & 1u) ? row : 0u) | ((m[1] & 2u) ? row << 3 : 0u) | ((m[1] & 4u) ? row << 6 : 0u);
+    const unsigned all = ((m[2] & 1u) ? plane : 0u) | ((m[2] & 2u) ? plane << 9 : 0u) | ((m[2] & 4u) ? plane << 18 : 0u);
+    return all & ~(1u << 13);
+}
+
+__global__ void __launch_bounds__(CT) k_gho_count(SoA3 x, const Counts *__restrict__ cnt, int *__restrict__ tile_counts, Box box, int ntiles)
+{
+    mc_count([&](int i) { return ghost_mask(x, i, box); }, cnt->n_bulk, cnt->nlocal, tile_counts, ntiles);
+}
+
+// per-direction periodic shift of the images this rank sends (+prd across the lower box face, -prd across the upper one)
+struct Shifts { double s[NS][3]; };
+
+// pack_border_vel (UM/atom_vec_dpd_atomic_meso.cu:61-100): record = {x+shift (3), v (3), tag|type, mask|signature}
+__global__ void __launch_bounds__(CT) k_gho_pack(SoA3 x, SoA3 v, const int *__restrict__ tag, const int *__restrict__ type,
+                                                 const int *__restrict__ mask, const float4 *__restrict__ veloc4, Counts *__restrict__ cnt,
+                                                 const int *__restrict__ tile_counts, const int *__restrict__ tot, Box box, Peers peers,
+                                                 Shifts sh, int *const *sendlist, int ntiles, int *ticket, int epoch, Mine mine)
+{
+    if (threadIdx.x < NS) wait_ack(mine, cnt, peers, threadIdx.x, epoch - 2, 1);
+    __syncthreads();
+    const size_t parity = (size_t)(epoch & 1);
+    mc_place([&](int i) { return ghost_mask(x, i, box); },
+             [&](int i, int c, int k) {
+                 if (!peers.arena[c] || k >= peers.gcap[c]) return;
+                 double *rec = reinterpret_cast<double *>(peers.arena[c] + peers.gho_off[c] + parity * peers.gcap[c] * RECB * 8) + (size_t)k * RECB;
+                 rec[0] = x.c[0][i] + sh.s[c][0]; rec[1] = x.c[1][i] + sh.s[c][1]; rec[2] = x.c[2][i] + sh.s[c][2];
+                 rec[3] = v.c[0][i]; rec[4] = v.c[1][i]; rec[5] = v.c[2][i];
+                 reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
+                 reinterpret_cast<int2 *>(rec)[7] = make_int2(mask[i], __float_as_int(veloc4[i].w));
+                 sendlist[c][k] = i;
+             },
+             cnt->n_bulk, cnt->nlocal, tile_counts, ntiles);
+    if (threadIdx.x < NS) {
+        const int c = threadIdx.x;
+        int n = (c == 13 || !peers.arena[c]) ? 0 : tot[c];
+        if (n > peers.gcap[c]) { n = peers.gcap[c]; atomicOr(&cnt->err, 1); }
+        if (blockIdx.x == 0) cnt->route_send_n[c] = n;
+    }
+    __syncthreads();
+    publish(peers, ticket, cnt->route_send_n, cnt->err & 1, epoch, 1);
+}
+
+// ghost ranges: the 26 slots in the reference's order; also the 6 swap ranges it would have produced
+__global__ void k_gho_bases(Counts *cnt, Mine mine, int cap)
+{
+    const ArenaHdr *h = reinterpret_cast<const ArenaHdr *>(mine.arena);
+    int base = 0;
+    for (int s = 0; s < 6; s++) { cnt->swap_first[s] = cnt->nlocal; cnt->swap_n[s] = 0; }
+    for (int q = 0; q < NS; q++) { cnt->route_recv_n[q] = 0; cnt->slot_base[q] = 0; }
+    int cur_swap = -1;
+    for (int q = 0; q < 26; q++) {
+        const int c = mine.order[q];
+        int n = ((mine.recv_mask >> c) & 1u) ? min(max(h->cnt_halo[c], 0), mine.gcap[c]) : 0;
+        if (cnt->nlocal + base + n > cap) { cnt->err |= 1; n = 0; }
+        // swap of the last hop: highest dimension with a non-zero offset
+        const int o[3] = {c % 3 - 1, (c / 3) % 3 - 1, c / 9 - 1};
+        const int d = o[2] ? 2 : (o[1] ? 1 : 0);
+        const int swap = 2 * d + (o[d] > 0 ? 1 : 0);
+        if (swap != cur_swap) { cnt->swap_first[swap] = cnt->nlocal + base; cur_swap = swap; }
+        cnt->swap_n[swap] += n;
+        cnt->slot_base[c] = base;
+        cnt->route_recv_n[c] = n;
+        base += n;
+    }
+    cnt->nghost = base;
+    cnt->nall = cnt->nlocal + base;
+    cnt->max_pair = 0;
 }
 
 // unpack_border_vel (UM/atom_vec_dpd_atomic_meso.cu:137-163) + packing of the new ghosts
-__global__ void __launch_bounds__(256) k_mr_border_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
-                                                          float4 *__restrict__ coord4, float4 *__restrict__ veloc4,
-                                                          const Counts *__restrict__ cnt, const double *__restrict__ recv_a,
-                                                          const double *__restrict__ recv_b, Box box, int d, int2 *__restrict__ ghost_origin)
+__global__ void __launch_bounds__(256) k_gho_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
+                                                    float4 *__restrict__ coord4, float4 *__restrict__ veloc4,
+                                                    const Counts *__restrict__ cnt, Mine mine, Box box, Peers peers, int *ticket, int epoch)
 {
-    const int na = cnt->swap_n[2 * d], n = na + cnt->swap_n[2 * d + 1], g0 = cnt->swap_first[2 * d];
-    const int nlocal = cnt->nlocal;
+    const int s = blockIdx.y;
+    const int n = cnt->route_recv_n[s];
+    const int g0 = cnt->nlocal + cnt->slot_base[s];
+    const double *buf = reinterpret_cast<const double *>(mine.arena + mine.gho_off[s] + (size_t)(epoch & 1) * mine.gcap[s] * RECB * 8);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const double *rec = (k < na) ? recv_a + (size_t)(k + 1) * RECB : recv_b + (size_t)(k - na + 1) * RECB;
+        const double *rec = buf + (size_t)k * RECB;
         const int g = g0 + k;
-        ghost_origin[g - nlocal] = reinterpret_cast<const int2 *>(rec)[8];
         const double xx = rec[0], yy = rec[1], zz = rec[2], vx = rec[3], vy = rec[4], vz = rec[5];
         const int2 tt = reinterpret_cast<const int2 *>(rec)[6], ms = reinterpret_cast<const int2 *>(rec)[7];
         x.c[0][g] = xx; x.c[1][g] = yy; x.c[2][g] = zz;
@@ -274,42 +817,93 @@ __global__ void __launch_bounds__(256) k_mr_border_unpack(SoA3 x, SoA3 v, int *_
         w.x = (float)vx; w.y = (float)vy; w.z = (float)vz; w.w = __int_as_float(ms.y);
         coord4[g] = c; veloc4[g] = w;
     }
+    acknowledge(mine, peers, ticket, epoch, 1);
 }
 
-// ------------------------------------------------------------------ per-step forward (pack_comm_vel / unpack_comm_vel)
-// Forward records are 40 bytes: {x + shift (3 x fp64), veloc4 = fp32 v + this step's signature}.  The force kernel reads
-// ghosts only through the packed views, and a ghost's packed velocity is what later dimensions forward, so the fp64 ghost
-// velocity is simply the widened fp32 value.  Messages carry exactly the records of the send lists built at the last
-// rebuild (sizes known to both sides from that rebuild's counts): no headers, no padding.
-constexpr int RECF = 5;
-
-__global__ void __launch_bounds__(256) k_mr_forward_pack(SoA3 x, const float4 *__restrict__ veloc4, const Counts *__restrict__ cnt,
-                                                         const int *__restrict__ list_lo, const int *__restrict__ list_hi,
-                                                         double *__restrict__ send_lo, double *__restrict__ send_hi, Box box, int d)
+static void make_shifts(const meso_ctx *ctx, Shifts &sh)
 {
-    const int na = cnt->send_n[2 * d], n = na + cnt->send_n[2 * d + 1];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int side = k >= na;
-        const int kk = side ? k - na : k;
-        const int i = (side ? list_hi : list_lo)[kk];
-        const int pbc = box.pbc[2 * d + side];
-        double *rec = (side ? send_hi : send_lo) + (size_t)kk * RECF;
-        double xg[3] = {x.c[0][i], x.c[1][i], x.c[2][i]};
-        if (pbc) xg[d] = pbc > 0 ? xg[d] + box.prd[d] : xg[d] - box.prd[d];
-        rec[0] = xg[0]; rec[1] = xg[1]; rec[2] = xg[2];
-        const float4 w = veloc4[i];
-        reinterpret_cast<float2 *>(rec)[3] = make_float2(w.x, w.y);
-        reinterpret_cast<float2 *>(rec)[4] = make_float2(w.z, w.w);
+    const Box &b = ctx->box;
+    for (int c = 0; c < NS; c++) {
+        int o[3];
+        code_offsets(c, o);
+        for (int d = 0; d < 3; d++) {
+            // an image sent to the lower neighbor from the lowest brick appears beyond the upper box face: +prd (and vice versa)
+            double s = 0.0;
+            if (o[d] < 0 && b.pbc[2 * d]) s = b.pbc[2 * d] * b.prd[d];
+            if (o[d] > 0 && b.pbc[2 * d + 1]) s = b.pbc[2 * d + 1] * b.prd[d];
+            sh.s[c][d] = s;
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) k_mr_forward_unpack(SoA3 x, SoA3 v, const int *__restrict__ type, float4 *__restrict__ coord4,
-                                                           float4 *__restrict__ veloc4, Counts *__restrict__ cnt,
-                                                           const double *__restrict__ recv_a, const double *__restrict__ recv_b, Box box, int d)
+int launch_borders_multi(meso_ctx *ctx)
 {
-    const int na = cnt->swap_n[2 * d], n = na + cnt->swap_n[2 * d + 1], g0 = cnt->swap_first[2 * d];
+    int rc = ensure_peers(ctx);
+    if (rc) return rc;
+    CommState *cs = state(ctx);
+    const Box &box = ctx->box;
+    const int ntiles = tiles_for(ctx);
+    if (!cs->tile_counts.reserve((size_t)ntiles * 32 + 64) || !ctx->route_ptrs.reserve(64)) { ctx->err = "out of device memory (tile counts)"; return MESO_ECUDA; }
+    int *tc = cs->tile_counts.p, *tot = cs->sync.p + 8;
+    cudaStream_t st = ctx->stream;
+    void *hp[NS];
+    for (int c = 0; c < NS; c++) hp[c] = cs->sendlist[c].p;
+    MESO_CUDA(cudaMemcpyAsync(ctx->route_ptrs.p, hp, sizeof hp, cudaMemcpyHostToDevice, st));
+    Shifts sh;
+    make_shifts(ctx, sh);
+    const int epoch = ++cs->epoch_halo;
+    k_gho_count<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), ctx->d_counts, tc, box, ntiles);
+    k_mc_scan<<<1, 1024, 0, LS(st)>>>(tc, ctx->d_counts, 1, tot);
+    k_gho_pack<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->veloc4.p, ctx->d_counts, tc,
+                                                 tot, box, cs->peers, sh, reinterpret_cast<int *const *>(ctx->route_ptrs.p), ntiles,
+                                                 cs->sync.p + 1, epoch, cs->mine);
+    k_wait<<<1, 32, 0, LS(st)>>>(cs->mine, ctx->d_counts, epoch, 1);
+    k_gho_bases<<<1, 1, 0, LS(st)>>>(ctx->d_counts, cs->mine, (int)ctx->cap);
+    const dim3 grid(std::max(1, ctx->sm_count / 2), NS);
+    k_gho_unpack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->coord4.p, ctx->veloc4.p,
+                                        ctx->d_counts, cs->mine, box, cs->peers, cs->sync.p + 4, epoch);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+// ------------------------------------------------------------------ per-step refresh (pack_comm_vel / unpack_comm_vel)
+// Records are 40 bytes: {x + shift (3 x fp64), veloc4 = fp32 v + this step's signature}.  The force kernel reads ghosts only
+// through the packed views, so the fp64 ghost velocity is simply the widened fp32 value.  The send lists and the slot
+// ranges are those of the last ghost creation; sizes live on the device.
+__global__ void __launch_bounds__(256) k_fwd_pack(SoA3 x, const float4 *__restrict__ veloc4, const Counts *__restrict__ cnt, Peers peers,
+                                                  Shifts sh, int *const *sendlist, int *ticket, int epoch, Mine mine, Counts *cntw)
+{
+    const int c = blockIdx.y;
+    const int parity = epoch & 1;
+    if (threadIdx.x == 0) wait_ack(mine, cntw, peers, c, epoch - 2, 1);
+    __syncthreads();
+    const int n = cnt->route_send_n[c];
+    if (n > 0 && peers.arena[c]) {
+        const int *list = sendlist[c];
+        double *buf = reinterpret_cast<double *>(peers.arena[c] + peers.gho_off[c] + (size_t)parity * peers.gcap[c] * RECB * 8);
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+            const int i = list[k];
+            double *rec = buf + (size_t)k * RECF;
+            rec[0] = x.c[0][i] + sh.s[c][0]; rec[1] = x.c[1][i] + sh.s[c][1]; rec[2] = x.c[2][i] + sh.s[c][2];
+            const float4 w = veloc4[i];
+            reinterpret_cast<float2 *>(rec)[3] = make_float2(w.x, w.y);
+            reinterpret_cast<float2 *>(rec)[4] = make_float2(w.z, w.w);
+        }
+    }
+    publish(peers, ticket, nullptr, 0, epoch, 2);
+}
+
+__global__ void __launch_bounds__(256) k_fwd_unpack(SoA3 x, SoA3 v, const int *__restrict__ type, float4 *__restrict__ coord4,
+                                                    float4 *__restrict__ veloc4, const Counts *__restrict__ cnt, Mine mine, Box box, Peers peers,
+                                                    int *ticket, int epoch)
+{
+    const int s = blockIdx.y;
+    const int parity = epoch & 1;
+    const int n = cnt->route_recv_n[s];
+    const int g0 = cnt->nlocal + cnt->slot_base[s];
+    const double *buf = reinterpret_cast<const double *>(mine.arena + mine.gho_off[s] + (size_t)parity * mine.gcap[s] * RECB * 8);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const double *rec = (k < na) ? recv_a + (size_t)k * RECF : recv_b + (size_t)(k - na) * RECF;
+        const double *rec = buf + (size_t)k * RECF;
         const int g = g0 + k;
         const double xx = rec[0], yy = rec[1], zz = rec[2];
         const float2 w01 = reinterpret_cast<const float2 *>(rec)[3], w23 = reinterpret_cast<const float2 *>(rec)[4];
@@ -320,840 +914,51 @@ __global__ void __launch_bounds__(256) k_mr_forward_unpack(SoA3 x, SoA3 v, const
         c.w = __int_as_float(type[g] - 1);
         coord4[g] = c; veloc4[g] = make_float4(w01.x, w01.y, w23.x, w23.y);
     }
+    acknowledge(mine, peers, ticket, epoch, 1);
 }
 
-// ------------------------------------------------------------------ migration (exchange)
-// leaving test `x >= hi || x < lo`, direction by the minimum image of x - mid (UM/comm_meso.cu:303-330)
-__device__ __forceinline__ Flags leave_flags(double xd, const Box &box, int d)
-{
-    Flags f{false, false};
-    if (xd >= box.subhi[d] || xd < box.sublo[d]) {
-        double dist = xd - 0.5 * (box.sublo[d] + box.subhi[d]);
-        if (box.periodic[d] && fabs(dist) > 0.5 * box.prd[d]) dist += dist < 0.0 ? box.prd[d] : -box.prd[d];
-        f.a = dist < 0;
-        f.b = !f.a;
-    }
-    return f;
-}
-
-__global__ void __launch_bounds__(CT) k_mr_exch_count(const double *__restrict__ xd, const Counts *__restrict__ cnt,
-                                                      int2 *__restrict__ tile_counts, Box box, int d, int ntiles)
-{
-    tile_count([&](int i) { return leave_flags(xd[i], box, d); }, 0, cnt->nlocal, tile_counts, ntiles);
-}
-
-__global__ void __launch_bounds__(1024) k_mr_exch_scan(int2 *__restrict__ tile_counts, Counts *__restrict__ cnt, double *__restrict__ send_l,
-                                                       double *__restrict__ send_r, int exch_cap)
-{
-    const int used = (cnt->nlocal + CTILE - 1) / CTILE;
-    int2 tot = scan_tiles(tile_counts, used);
-    if (threadIdx.x == 0) {
-        if (tot.x > exch_cap || tot.y > exch_cap) cnt->err |= 8;      // would lose atoms
-        cnt->exch_n[0] = min(tot.x, exch_cap); cnt->exch_n[1] = min(tot.y, exch_cap);
-        reinterpret_cast<int *>(send_l)[0] = cnt->exch_n[0];
-        reinterpret_cast<int *>(send_r)[0] = cnt->exch_n[1];
-    }
-}
-
-// stayers are compacted in order into the alternate arrays; leavers become records {x(3), v(3), tag|type, mask|image}
-__global__ void __launch_bounds__(CT) k_mr_exch_scatter(SoA3 x, SoA3 v, const int *__restrict__ tag, const int *__restrict__ type,
-                                                        const int *__restrict__ mask, const int *__restrict__ image, SoA3 xo, SoA3 vo,
-                                                        int *__restrict__ tago, int *__restrict__ typeo, int *__restrict__ masko,
-                                                        int *__restrict__ imageo, const Counts *__restrict__ cnt,
-                                                        const int2 *__restrict__ tile_counts, double *__restrict__ send_l,
-                                                        double *__restrict__ send_r, Box box, int d, int ntiles, int exch_cap,
-                                                        int *__restrict__ dest)
-{
-    __shared__ int2 wsum[CT / 32];
-    const int last = cnt->nlocal;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int base = tile * CTILE;
-        if (base >= last) break;
-        int2 run = tile_counts[tile];
-#pragma unroll
-        for (int r = 0; r < CI; r++) {
-            const int i = base + r * CT + threadIdx.x;
-            Flags f{false, false};
-            if (i < last) f = leave_flags(x.c[d][i], box, d);
-            const uint32_t ba = __ballot_sync(0xffffffffu, f.a), bb = __ballot_sync(0xffffffffu, f.b);
-            if (lane == 0) wsum[w] = make_int2(__popc(ba), __popc(bb));
-            __syncthreads();
-            int2 pre = make_int2(0, 0), tot = make_int2(0, 0);
-#pragma unroll
-            for (int ww = 0; ww < CT / 32; ww++) {
-                const int2 c = wsum[ww];
-                if (ww < w) { pre.x += c.x; pre.y += c.y; }
-                tot.x += c.x; tot.y += c.y;
-            }
-            __syncthreads();
-            if (i < last) {
-                const int ka = run.x + pre.x + __popc(ba & lt), kb = run.y + pre.y + __popc(bb & lt);
-                if (!f.a && !f.b) {
-                    const int p = i - ka - kb;                  // stable: stayers keep their relative order
-#pragma unroll
-                    for (int q = 0; q < 3; q++) { xo.c[q][p] = x.c[q][i]; vo.c[q][p] = v.c[q][i]; }
-                    tago[p] = tag[i]; typeo[p] = type[i]; masko[p] = mask[i]; imageo[p] = image[i];
-                    if (dest) dest[i] = p;
-                } else {
-                    const int k = f.a ? ka : kb;
-                    if (dest) dest[i] = k < exch_cap ? -(2 * k + (f.a ? 0 : 1)) - 1 : INT_MIN;   // record k of the left / right message
-                    if (k < exch_cap) {
-                        double *rec = (f.a ? send_l : send_r) + (size_t)(k + 1) * REC;
-#pragma unroll
-                        for (int q = 0; q < 3; q++) { rec[q] = x.c[q][i]; rec[3 + q] = v.c[q][i]; }
-                        reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
-                        reinterpret_cast<int2 *>(rec)[7] = make_int2(mask[i], image[i]);
-                    }
-                }
-            }
-            run.x += tot.x; run.y += tot.y;
-        }
-    }
-}
-
-__global__ void k_mr_exch_shrink(Counts *cnt) { cnt->nlocal -= cnt->exch_n[0] + cnt->exch_n[1]; }
-
-// arrivals are appended: first the upper neighbor's left-movers, then the lower neighbor's right-movers
-// (UM/comm_meso.cu:385-417); an arrival outside [lo,hi) in this dimension is dropped there too ("rejected")
-__global__ void __launch_bounds__(256) k_mr_exch_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
-                                                        int *__restrict__ image, Counts *__restrict__ cnt, const double *__restrict__ recv_a,
-                                                        const double *__restrict__ recv_b, Box box, int d, int nloc_cap)
-{
-    const int na = reinterpret_cast<const int *>(recv_a)[0], n = na + reinterpret_cast<const int *>(recv_b)[0];
-    const int base = cnt->nlocal;
-    if (base + n > nloc_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&cnt->err, 8); return; }
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const double *rec = (k < na) ? recv_a + (size_t)(k + 1) * REC : recv_b + (size_t)(k - na + 1) * REC;
-        const int p = base + k;
-#pragma unroll
-        for (int q = 0; q < 3; q++) { x.c[q][p] = rec[q]; v.c[q][p] = rec[3 + q]; }
-        const int2 tt = reinterpret_cast<const int2 *>(rec)[6], mi = reinterpret_cast<const int2 *>(rec)[7];
-        tag[p] = tt.x; type[p] = tt.y; mask[p] = mi.x; image[p] = mi.y;
-        if (!(rec[d] >= box.sublo[d] && rec[d] < box.subhi[d])) atomicOr(&cnt->err, 8);
-    }
-}
-
-__global__ void k_mr_exch_grow(Counts *cnt, const double *recv_a, const double *recv_b)
-{
-    cnt->nlocal += reinterpret_cast<const int *>(recv_a)[0] + reinterpret_cast<const int *>(recv_b)[0];
-    cnt->nall = cnt->nlocal;
-}
-
-// bead-spring topology rides the migration (AtomVecDPDBond::pack_exchange / unpack_exchange, UM/atom_vec_dpd_bond_meso.cu):
-// a second message per direction, records of (1 + bond_per_atom) int2 = {nbond, 0}, {partner tag, bond type}..., in the
-// order of the atom records; stayers are compacted with the destination map the atom scatter wrote
-__global__ void __launch_bounds__(256) k_mr_exch_bonds_scatter(const int *__restrict__ dest, const int *__restrict__ nbond,
-                                                               const int2 *__restrict__ bonds, int *__restrict__ nbond_o,
-                                                               int2 *__restrict__ bonds_o, int2 *__restrict__ send_l, int2 *__restrict__ send_r,
-                                                               const Counts *__restrict__ cnt, size_t padding, int bpa)
-{
-    const int n = cnt->nlocal;                                   // still the count before the leavers were removed
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int dd = dest[i], nb = nbond[i];
-        if (dd >= 0) {
-            nbond_o[dd] = nb;
-            for (int q = 0; q < nb; q++) bonds_o[dd + q * padding] = bonds[i + q * padding];
-        } else if (dd != INT_MIN) {
-            const int sidx = -(dd + 1), k = sidx >> 1;
-            int2 *rec = ((sidx & 1) ? send_r : send_l) + (size_t)k * (1 + bpa);
-            rec[0] = make_int2(nb, 0);
-            for (int q = 0; q < nb; q++) rec[1 + q] = bonds[i + q * padding];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_mr_exch_bonds_unpack(int *__restrict__ nbond, int2 *__restrict__ bonds, const Counts *__restrict__ cnt,
-                                                              const double *__restrict__ hdr_a, const double *__restrict__ hdr_b,
-                                                              const int2 *__restrict__ recv_a, const int2 *__restrict__ recv_b, size_t padding,
-                                                              int bpa, int nloc_cap)
-{
-    const int na = reinterpret_cast<const int *>(hdr_a)[0], n = na + reinterpret_cast<const int *>(hdr_b)[0];
-    const int base = cnt->nlocal;                                // arrivals are appended; k_mr_exch_grow runs after this kernel
-    if (base + n > nloc_cap) return;                             // flagged by k_mr_exch_unpack
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int2 *rec = (k < na) ? recv_a + (size_t)k * (1 + bpa) : recv_b + (size_t)(k - na) * (1 + bpa);
-        const int p = base + k, nb = min(max(rec[0].x, 0), bpa);
-        nbond[p] = nb;
-        for (int q = 0; q < nb; q++) bonds[p + q * padding] = rec[1 + q];
-    }
-}
-
-// ------------------------------------------------------------------ host drivers
-static int ensure_comm_buffers(meso_ctx *ctx)
-{
-    // slab of width cutghost over the largest (ghost-extended) face, at the brick's density, with head room
-    const Box &b = ctx->box;
-    double w[3], vol = 1.0;
-    for (int d = 0; d < 3; d++) { w[d] = b.subhi[d] - b.sublo[d]; vol *= w[d]; }
-    const double dens = std::max(1.0, (double)ctx->nlocal_host / vol);
-    double face = 0;
-    for (int d = 0; d < 3; d++) {
-        double a = 1.0;
-        for (int q = 0; q < 3; q++) if (q != d) a *= w[q] + 2.0 * ctx->cutneighmax;
-        face = std::max(face, a);
-    }
-    // ghosts of one swap: slab of width cutghost over the ghost-extended face (+20 %, density fluctuations are ~1 % at this size);
-    // leavers per dimension and rebuild: a layer |v| * every * dt thick, ~0.1 % of the brick -- 1/64 is ample; overflow sets err
-    int swap_cap = (int)(face * ctx->cutneighmax * dens * 1.2) + 4096;
-    int exch_cap = std::max(8192, ctx->nlocal_host / 64);
-    if (ctx->nranks > 1 && !ctx->comm_caps_agreed) {
-        // message sizes are part of the protocol: every rank must use the same capacities (ranks own slightly different
-        // atom counts, so the local estimates can differ).  One max-reduction at the first rebuild after an upload,
-        // which every rank reaches at the same point.
-        double caps[2] = {(double)swap_cap, (double)exch_cap};
-        if (!ctx->reduce_buf.reserve(64)) { ctx->err = "out of device memory"; return MESO_ECUDA; }
-        MESO_CUDA(cudaMemcpyAsync(ctx->reduce_buf.p, caps, sizeof caps, cudaMemcpyHostToDevice, ctx->stream));
-        MESO_NCCL(ncclAllReduce(ctx->reduce_buf.p, ctx->reduce_buf.p, 2, ncclDouble, ncclMax, (ncclComm_t)ctx->nccl, ctx->stream));
-        MESO_CUDA(cudaMemcpyAsync(caps, ctx->reduce_buf.p, sizeof caps, cudaMemcpyDeviceToHost, ctx->stream));
-        MESO_CUDA(cudaStreamSynchronize(ctx->stream));
-        swap_cap = (int)caps[0]; exch_cap = (int)caps[1];
-        ctx->swap_cap = 0; ctx->exch_cap = 0;                 // adopt the agreed sizes exactly
-        ctx->comm_caps_agreed = true;
-    } else if (ctx->nranks > 1) return MESO_OK;               // agreed sizes stay until the next upload
-    if (swap_cap <= ctx->swap_cap && exch_cap <= ctx->exch_cap) return MESO_OK;
-    ctx->swap_cap = std::max(ctx->swap_cap, swap_cap);
-    ctx->exch_cap = std::max(ctx->exch_cap, exch_cap);
-    const size_t msg = (size_t)(std::max(ctx->swap_cap, ctx->exch_cap) + 1) * RECB;
-    bool ok = true;
-    for (int s = 0; s < 2; s++) ok = ok && ctx->send_buf[s].reserve(msg) && ctx->recv_buf[s].reserve(msg);
-    for (int s = 0; s < 6; s++) ok = ok && ctx->sendlist[s].reserve((size_t)ctx->swap_cap);
-    const size_t ntiles = (ctx->cap + CTILE - 1) / CTILE;
-    ok = ok && ctx->tile_counts.reserve(ntiles * 2 + 16) && ctx->ghost_origin.reserve(ctx->cap);
-    if (!ok) { ctx->err = "out of device memory (halo buffers)"; return MESO_ECUDA; }
-    return MESO_OK;
-}
-
-// one dimension's pair of messages: mine to lower/upper neighbor, theirs from upper/lower.  Self-partnered
-// dimensions alias the receive pointers to the send buffers (no copy, no NCCL).
-static int swap_messages4(meso_ctx *ctx, int d, size_t send_lo, size_t send_hi, size_t recv_up, size_t recv_lo, cudaStream_t st,
-                          const double *&recv_a, const double *&recv_b)
-{
-    if (ctx->procgrid[d] == 1) { recv_a = ctx->send_buf[0].p; recv_b = ctx->send_buf[1].p; return MESO_OK; }
-    ncclComm_t comm = (ncclComm_t)ctx->nccl;
-    const int lower = ctx->procneigh[d][0], upper = ctx->procneigh[d][1];
-    MESO_NCCL(ncclGroupStart());
-    if (send_lo) MESO_NCCL(ncclSend(ctx->send_buf[0].p, send_lo, ncclDouble, lower, comm, st));
-    if (recv_up) MESO_NCCL(ncclRecv(ctx->recv_buf[0].p, recv_up, ncclDouble, upper, comm, st));
-    if (send_hi) MESO_NCCL(ncclSend(ctx->send_buf[1].p, send_hi, ncclDouble, upper, comm, st));
-    if (recv_lo) MESO_NCCL(ncclRecv(ctx->recv_buf[1].p, recv_lo, ncclDouble, lower, comm, st));
-    MESO_NCCL(ncclGroupEnd());
-    recv_a = ctx->recv_buf[0].p; recv_b = ctx->recv_buf[1].p;
-    return MESO_OK;
-}
-static int swap_messages(meso_ctx *ctx, int d, size_t ndoubles, cudaStream_t st, const double *&recv_a, const double *&recv_b)
-{
-    return swap_messages4(ctx, d, ndoubles, ndoubles, ndoubles, ndoubles, st, recv_a, recv_b);
-}
-
-int launch_exchange_multi(meso_ctx *ctx)
-{
-    int rc = ensure_comm_buffers(ctx);
-    if (rc) return rc;
-    const Box &box = ctx->box;
-    const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
-    int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
-    cudaStream_t st = ctx->stream;
-    const bool bonded = bonds_active(ctx);
-    const int bpa = ctx->bond_per_atom;
-    const size_t bond_msg = (size_t)ctx->exch_cap * (size_t)(1 + bpa);      // int2 records per bond message
-    if (bonded) {
-        bool ok = ctx->exch_dest.reserve(ctx->cap);
-        for (int q = 0; q < 2; q++) ok = ok && ctx->bond_send[q].reserve(bond_msg) && ctx->bond_recv[q].reserve(bond_msg);
-        if (!ok) { ctx->err = "out of device memory (bond migration buffers)"; return MESO_ECUDA; }
-    }
-    for (int d = 0; d < 3; d++) {
-        if (ctx->procgrid[d] == 1) continue;        // the periodic wrap already put every atom back into the brick
-        k_mr_exch_count<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
-        k_mr_exch_scan<<<1, 1024, 0, LS(st)>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->exch_cap);
-        k_mr_exch_scatter<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
-                                                         soa(ctx->xa), soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p, ctx->imagea.p,
-                                                         ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d, ntiles, ctx->exch_cap,
-                                                         bonded ? ctx->exch_dest.p : nullptr);
-        if (bonded) {
-            k_mr_exch_bonds_scatter<<<grid_for(ctx, 4), 256, 0, LS(st)>>>(ctx->exch_dest.p, ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p,
-                                                                   ctx->bond_send[0].p, ctx->bond_send[1].p, ctx->d_counts, ctx->cap, bpa);
-            std::swap(ctx->nbond.p, ctx->nbond_alt.p); std::swap(ctx->nbond.cap, ctx->nbond_alt.cap);
-            std::swap(ctx->bonds.p, ctx->bonds_alt.p); std::swap(ctx->bonds.cap, ctx->bonds_alt.cap);
-        }
-        for (int q = 0; q < 3; q++) { std::swap(ctx->x[q].p, ctx->xa[q].p); std::swap(ctx->v[q].p, ctx->va[q].p); }
-        std::swap(ctx->tag.p, ctx->taga.p); std::swap(ctx->type.p, ctx->typea.p);
-        std::swap(ctx->mask.p, ctx->maska.p); std::swap(ctx->image.p, ctx->imagea.p);
-        k_mr_exch_shrink<<<1, 1, 0, LS(st)>>>(ctx->d_counts);
-        const double *ra, *rb;
-        rc = swap_messages(ctx, d, (size_t)(ctx->exch_cap + 1) * REC, st, ra, rb);
-        if (rc) return rc;
-        k_mr_exch_unpack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
-                                                        ctx->d_counts, ra, rb, box, d, (int)ctx->nloc_cap);
-        if (bonded) {
-            ncclComm_t comm = (ncclComm_t)ctx->nccl;
-            const size_t nint = bond_msg * 2;
-            MESO_NCCL(ncclGroupStart());
-            MESO_NCCL(ncclSend(ctx->bond_send[0].p, nint, ncclInt, ctx->procneigh[d][0], comm, st));
-            MESO_NCCL(ncclRecv(ctx->bond_recv[0].p, nint, ncclInt, ctx->procneigh[d][1], comm, st));
-            MESO_NCCL(ncclSend(ctx->bond_send[1].p, nint, ncclInt, ctx->procneigh[d][1], comm, st));
-            MESO_NCCL(ncclRecv(ctx->bond_recv[1].p, nint, ncclInt, ctx->procneigh[d][0], comm, st));
-            MESO_NCCL(ncclGroupEnd());
-            k_mr_exch_bonds_unpack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(ctx->nbond.p, ctx->bonds.p, ctx->d_counts, ra, rb, ctx->bond_recv[0].p,
-                                                                  ctx->bond_recv[1].p, ctx->cap, bpa, (int)ctx->nloc_cap);
-        }
-        k_mr_exch_grow<<<1, 1, 0, LS(st)>>>(ctx->d_counts, ra, rb);
-    }
-    MESO_CUDA(cudaGetLastError());
-    return MESO_OK;
-}
-
-// ------------------------------------------------------------------ direct halo routes
-// The 3-phase creation above fixes WHICH images a rank holds and in WHAT order; it also forwards ghosts of earlier
-// dimensions, which makes the per-step refresh of the reference three dependent messages.  Every ghost record carries its
-// owner, so after the creation each rank groups its ghosts by owner rank, sends every owner the list {index, shift} it wants
-// refreshed (one message per peer, once per rebuild), and from then on a step's refresh is ONE pack kernel, ONE NCCL group
-// (a message per peer, exact size) and ONE unpack kernel.  Values are bit-identical to the forwarded ones: each coordinate is
-// shifted by at most one period, and the packed velocity/signature is copied.
-struct RouteTable {
-    int np, self;
-    const int2 *slist[27];      // what peer s asked me to send: [0] = {count, 0}, then {index, shift code}
-    const int *dst[27];         // ghost slot (0-based behind nlocal) of the k-th record peer s sends me
-    double *sbuf[27];           // staging of the records for peer s
-    const double *rbuf[27];     // records received from peer s (self: my own staging buffer)
-};
-
-__global__ void __launch_bounds__(256) k_route_build(const int2 *__restrict__ ghost_origin, const int *__restrict__ peer_slot, Counts *cnt,
-                                                     RouteTable rt, int2 *const *req, int *const *dst, int route_cap, int nranks)
-{
-    const int ng = cnt->nghost;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    // whole warps iterate together; the lanes that want the same peer share ONE atomic (a handful of counters would
-    // otherwise serialise ~10^5 same-address atomics)
-    for (int g0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; g0 < ng; g0 += gridDim.x * blockDim.x) {
-        const int g = g0 + lane;
-        int s = -1;
-        int2 o = make_int2(0, 0);
-        if (g < ng) {
-            o = ghost_origin[g];
-            const int r = o.x & 0xffffff;
-            s = (r >= 0 && r < nranks) ? peer_slot[r] : -1;
-            if (s < 0) atomicOr(&cnt->err, 1);
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, s);
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (lane == leader && s >= 0) base = atomicAdd(&cnt->route_recv_n[s], __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (s < 0) continue;
-        const int k = base + __popc(peers & lt);
-        if (k >= route_cap) { atomicOr(&cnt->err, 1); continue; }
-        req[s][k + 1] = make_int2(o.y, (o.x >> 24) & 63);
-        dst[s][k] = g;
-    }
-}
-
-__global__ void k_route_reset(Counts *cnt)
-{
-    if (threadIdx.x < 27) { cnt->route_recv_n[threadIdx.x] = 0; cnt->route_send_n[threadIdx.x] = 0; }
-}
-
-__global__ void k_route_headers(Counts *cnt, int2 *const *req, int np, int route_cap)
-{
-    const int s = threadIdx.x;
-    if (s < np) {
-        const int n = min(cnt->route_recv_n[s], route_cap);
-        cnt->route_recv_n[s] = n;
-        req[s][0] = make_int2(n, 0);
-    }
-}
-
-__global__ void k_route_adopt(Counts *cnt, RouteTable rt, int route_cap)
-{
-    const int s = threadIdx.x;
-    if (s < rt.np) {
-        int n = rt.slist[s][0].x;
-        if (n < 0 || n > route_cap) { atomicOr(&cnt->err, 1); n = 0; }
-        cnt->route_send_n[s] = n;
-    }
-}
-
-// records: {x + shift (3 x fp64), veloc4 = fp32 v + this step's signature} = 40 bytes, as in the forwarding refresh
-__global__ void __launch_bounds__(256) k_route_pack(SoA3 x, const float4 *__restrict__ veloc4, const Counts *__restrict__ cnt, RouteTable rt,
-                                                    Box box)
-{
-    const int s = blockIdx.y;
-    const int n = cnt->route_send_n[s];
-    const int2 *list = rt.slist[s] + 1;
-    double *buf = rt.sbuf[s];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int2 e = list[k];
-        const int i = e.x;
-        double xg[3] = {x.c[0][i], x.c[1][i], x.c[2][i]};
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const int c = (e.y >> (2 * d)) & 3;
-            if (c) xg[d] = c == 1 ? xg[d] + box.prd[d] : xg[d] - box.prd[d];
-        }
-        double *rec = buf + (size_t)k * RECF;
-        rec[0] = xg[0]; rec[1] = xg[1]; rec[2] = xg[2];
-        const float4 w = veloc4[i];
-        reinterpret_cast<float2 *>(rec)[3] = make_float2(w.x, w.y);
-        reinterpret_cast<float2 *>(rec)[4] = make_float2(w.z, w.w);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_route_unpack(SoA3 x, SoA3 v, const int *__restrict__ type, float4 *__restrict__ coord4,
-                                                      float4 *__restrict__ veloc4, const Counts *__restrict__ cnt, RouteTable rt, Box box)
-{
-    const int s = blockIdx.y;
-    const int n = cnt->route_recv_n[s], nlocal = cnt->nlocal;
-    const int *dst = rt.dst[s];
-    const double *buf = rt.rbuf[s];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const double *rec = buf + (size_t)k * RECF;
-        const int g = nlocal + dst[k];
-        const double xx = rec[0], yy = rec[1], zz = rec[2];
-        const float2 w01 = reinterpret_cast<const float2 *>(rec)[3], w23 = reinterpret_cast<const float2 *>(rec)[4];
-        x.c[0][g] = xx; x.c[1][g] = yy; x.c[2][g] = zz;
-        v.c[0][g] = (double)w01.x; v.c[1][g] = (double)w01.y; v.c[2][g] = (double)w23.x;
-        float4 c;
-        c.x = (float)(xx - box.centre[0]); c.y = (float)(yy - box.centre[1]); c.z = (float)(zz - box.centre[2]);
-        c.w = __int_as_float(type[g] - 1);
-        coord4[g] = c; veloc4[g] = make_float4(w01.x, w01.y, w23.x, w23.y);
-    }
-}
-
-// distinct ranks among this brick's 26 neighbors, plus itself (slot peer_self)
-int comm_build_peers(meso_ctx *ctx)
-{
-    const Box &b = ctx->box;
-    ctx->npeers = 0;
-    std::vector<int> slot((size_t)ctx->nranks, -1);
-    auto add = [&](int r) {
-        if (slot[r] >= 0) return;
-        slot[r] = ctx->npeers;
-        ctx->peer_rank[ctx->npeers++] = r;
-    };
-    add(ctx->rank);
-    ctx->peer_self = 0;
-    for (int dz = -1; dz <= 1; dz++)
-        for (int dy = -1; dy <= 1; dy++)
-            for (int dx = -1; dx <= 1; dx++) {
-                int off[3] = {dx, dy, dz}, loc[3];
-                bool ok = true;
-                for (int d = 0; d < 3; d++) {
-                    loc[d] = ctx->myloc[d] + off[d];
-                    if (loc[d] < 0 || loc[d] >= ctx->procgrid[d]) {
-                        if (!b.periodic[d]) { ok = false; break; }
-                        loc[d] = (loc[d] + ctx->procgrid[d]) % ctx->procgrid[d];
-                    }
-                }
-                if (ok) add((loc[0] * ctx->procgrid[1] + loc[1]) * ctx->procgrid[2] + loc[2]);
-            }
-    if (!ctx->peer_slot.reserve((size_t)ctx->nranks)) { ctx->err = "out of device memory"; return MESO_ECUDA; }
-    MESO_CUDA(cudaMemcpyAsync(ctx->peer_slot.p, slot.data(), sizeof(int) * ctx->nranks, cudaMemcpyHostToDevice, ctx->stream));
-    MESO_CUDA(cudaStreamSynchronize(ctx->stream));
-    return MESO_OK;
-}
-
-static int route_table(meso_ctx *ctx, RouteTable &rt)
-{
-    rt.np = ctx->npeers; rt.self = ctx->peer_self;
-    for (int s = 0; s < 27; s++) { rt.slist[s] = nullptr; rt.dst[s] = nullptr; rt.sbuf[s] = nullptr; rt.rbuf[s] = nullptr; }
-    for (int s = 0; s < ctx->npeers; s++) {
-        const bool self = s == ctx->peer_self;
-        rt.slist[s] = self ? ctx->route_req[s].p : ctx->route_send_list[s].p;     // my own requests are my own send list
-        rt.dst[s] = ctx->route_dst[s].p;
-        rt.sbuf[s] = ctx->route_sbuf[s].p;
-        rt.rbuf[s] = self ? ctx->route_sbuf[s].p : ctx->route_rbuf[s].p;
-    }
-    return MESO_OK;
-}
-
-// after the ghosts exist: group them by owner, exchange the request lists (once per rebuild)
-static int build_routes(meso_ctx *ctx)
-{
-    if (ctx->npeers == 0) { int rc = comm_build_peers(ctx); if (rc) return rc; }
-    const int np = ctx->npeers;
-    ctx->route_cap = 6 * ctx->swap_cap;           // a peer (or this rank itself, through periodic images) can own the ghosts of all six swaps
-    bool ok = true;
-    for (int s = 0; s < np; s++) {
-        ok = ok && ctx->route_req[s].reserve((size_t)ctx->route_cap + 1) && ctx->route_dst[s].reserve((size_t)ctx->route_cap) &&
-             ctx->route_sbuf[s].reserve((size_t)ctx->route_cap * RECF);
-        if (s != ctx->peer_self) ok = ok && ctx->route_send_list[s].reserve((size_t)ctx->route_cap + 1) && ctx->route_rbuf[s].reserve((size_t)ctx->route_cap * RECF);
-    }
-    // device-side pointer tables for the build kernel
-    ok = ok && ctx->route_ptrs.reserve(64);
-    if (!ok) { ctx->err = "out of device memory (halo routes)"; return MESO_ECUDA; }
-    void *hp[54];
-    for (int s = 0; s < 27; s++) { hp[s] = s < np ? (void *)ctx->route_req[s].p : nullptr; hp[27 + s] = s < np ? (void *)ctx->route_dst[s].p : nullptr; }
-    cudaStream_t st = ctx->stream;
-    MESO_CUDA(cudaMemcpyAsync(ctx->route_ptrs.p, hp, sizeof hp, cudaMemcpyHostToDevice, st));
-    RouteTable rt;
-    route_table(ctx, rt);
-    int2 *const *req = reinterpret_cast<int2 *const *>(ctx->route_ptrs.p);
-    int *const *dst = reinterpret_cast<int *const *>(ctx->route_ptrs.p + 27);
-    k_route_reset<<<1, 32, 0, LS(st)>>>(ctx->d_counts);
-    k_route_build<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(ctx->ghost_origin.p, ctx->peer_slot.p, ctx->d_counts, rt, req, dst, ctx->route_cap, ctx->nranks);
-    k_route_headers<<<1, 32, 0, LS(st)>>>(ctx->d_counts, req, np, ctx->route_cap);
-    if (np > 1) {
-        ncclComm_t comm = (ncclComm_t)ctx->nccl;
-        const size_t nint = ((size_t)ctx->route_cap + 1) * 2;
-        MESO_NCCL(ncclGroupStart());
-        for (int s = 0; s < np; s++) {
-            if (s == ctx->peer_self) continue;
-            MESO_NCCL(ncclSend(ctx->route_req[s].p, nint, ncclInt, ctx->peer_rank[s], comm, st));
-            MESO_NCCL(ncclRecv(ctx->route_send_list[s].p, nint, ncclInt, ctx->peer_rank[s], comm, st));
-        }
-        MESO_NCCL(ncclGroupEnd());
-    }
-    k_route_adopt<<<1, 32, 0, LS(st)>>>(ctx->d_counts, rt, ctx->route_cap);
-    MESO_CUDA(cudaGetLastError());
-    return MESO_OK;
-}
-
-// per-step ghost refresh over the routes, on stream `st`
-static int forward_routes(meso_ctx *ctx, cudaStream_t st)
-{
-    const int np = ctx->npeers;
-    RouteTable rt;
-    route_table(ctx, rt);
-    const dim3 grid(ctx->sm_count, np);
-    k_route_pack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, rt, ctx->box);
-    if (np > 1) {
-        ncclComm_t comm = (ncclComm_t)ctx->nccl;
-        MESO_NCCL(ncclGroupStart());
-        for (int s = 0; s < np; s++) {
-            if (s == ctx->peer_self) continue;
-            if (ctx->route_send_n[s]) MESO_NCCL(ncclSend(ctx->route_sbuf[s].p, (size_t)ctx->route_send_n[s] * RECF, ncclDouble, ctx->peer_rank[s], comm, st));
-            if (ctx->route_recv_n[s]) MESO_NCCL(ncclRecv(ctx->route_rbuf[s].p, (size_t)ctx->route_recv_n[s] * RECF, ncclDouble, ctx->peer_rank[s], comm, st));
-        }
-        MESO_NCCL(ncclGroupEnd());
-    }
-    k_route_unpack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts, rt, ctx->box);
-    MESO_CUDA(cudaGetLastError());
-    return MESO_OK;
-}
-
-// ------------------------------------------------------------------ one-shot migration (MESO_EXCH_ONESHOT=1, off by default)
-// NOT YET RUN ON HARDWARE (written at the end of round 1, when the GPU budget was spent): the validated path is
-// launch_exchange_multi above.  Instead of one dependent exchange per communicating dimension (an atom that leaves through
-// an edge takes two hops), every leaver is sent straight to the brick that will own it: one selection kernel, ONE NCCL group
-// with a fixed-capacity message per peer, one unpack kernel.  Ownership after the exchange is the same as after the three
-// hops; arrival order differs, which only matters for ties of identical sort keys (already a documented deviation).
-struct OneShot {
-    int np, self, bpa;
-    int slot_of_code[27];       // destination offset code (ox+1) + 3(oy+1) + 9(oz+1) -> peer slot, -1: no such brick (atom lost)
-    int multi[3];               // procgrid[d] > 1
-    double *sbuf[27];           // [0] header {count}, then REC doubles per leaver
-    const double *rbuf[27];
-    int2 *bsend[27];            // bond rows of the leavers, (1 + bpa) int2 per record, same order
-    const int2 *brecv[27];
-};
-
-__device__ __forceinline__ int oneshot_code(const double xi[3], const Box &box, const int multi[3])
-{
-    int code = 0, w = 1;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        int o = 0;
-        if (multi[d]) { const Flags f = leave_flags(xi[d], box, d); o = f.a ? -1 : (f.b ? 1 : 0); }
-        code += (o + 1) * w;
-        w *= 3;
-    }
-    return code;
-}
-
-__global__ void __launch_bounds__(CT) k_os_count(SoA3 x, const Counts *__restrict__ cnt, int2 *__restrict__ tile_counts, Box box, OneShot os,
-                                                 int ntiles)
-{
-    tile_count([&](int i) {
-        const double xi[3] = {x.c[0][i], x.c[1][i], x.c[2][i]};
-        Flags f; f.a = oneshot_code(xi, box, os.multi) != 13; f.b = false; return f; }, 0, cnt->nlocal, tile_counts, ntiles);
-}
-
-__global__ void __launch_bounds__(1024) k_os_scan(int2 *__restrict__ tile_counts, Counts *__restrict__ cnt)
-{
-    const int used = (cnt->nlocal + CTILE - 1) / CTILE;
-    const int2 tot = scan_tiles(tile_counts, used);
-    if (threadIdx.x == 0) { cnt->exch_n[0] = tot.x; cnt->exch_n[1] = 0; }
-    if (threadIdx.x < 27) cnt->route_send_n[threadIdx.x] = 0;      // reused as per-peer leaver counters until the routes are rebuilt
-}
-
-__global__ void __launch_bounds__(CT) k_os_scatter(SoA3 x, SoA3 v, const int *__restrict__ tag, const int *__restrict__ type,
-                                                   const int *__restrict__ mask, const int *__restrict__ image, SoA3 xo, SoA3 vo,
-                                                   int *__restrict__ tago, int *__restrict__ typeo, int *__restrict__ masko,
-                                                   int *__restrict__ imageo, Counts *__restrict__ cnt, const int2 *__restrict__ tile_counts,
-                                                   Box box, OneShot os, int ntiles, int exch_cap, const int *__restrict__ nbond,
-                                                   const int2 *__restrict__ bonds, int *__restrict__ nbond_o, int2 *__restrict__ bonds_o,
-                                                   size_t padding)
-{
-    __shared__ int wsum[CT / 32];
-    const int last = cnt->nlocal;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int base = tile * CTILE;
-        if (base >= last) break;
-        int run = tile_counts[tile].x;
-#pragma unroll
-        for (int r = 0; r < CI; r++) {
-            const int i = base + r * CT + threadIdx.x;
-            int code = 13;
-            double xi[3] = {0, 0, 0};
-            if (i < last) {
-#pragma unroll
-                for (int q = 0; q < 3; q++) xi[q] = x.c[q][i];
-                code = oneshot_code(xi, box, os.multi);
-            }
-            const uint32_t ba = __ballot_sync(0xffffffffu, code != 13);
-            if (lane == 0) wsum[w] = __popc(ba);
-            __syncthreads();
-            int pre = 0, tot = 0;
-#pragma unroll
-            for (int ww = 0; ww < CT / 32; ww++) { const int c = wsum[ww]; if (ww < w) pre += c; tot += c; }
-            __syncthreads();
-            if (i < last) {
-                if (code == 13) {
-                    const int p = i - (run + pre + __popc(ba & lt));    // stable: stayers keep their relative order
-#pragma unroll
-                    for (int q = 0; q < 3; q++) { xo.c[q][p] = xi[q]; vo.c[q][p] = v.c[q][i]; }
-                    tago[p] = tag[i]; typeo[p] = type[i]; masko[p] = mask[i]; imageo[p] = image[i];
-                    if (os.bpa) {
-                        const int nb = nbond[i];
-                        nbond_o[p] = nb;
-                        for (int q = 0; q < nb; q++) bonds_o[p + q * padding] = bonds[i + q * padding];
-                    }
-                } else {
-                    const int s = os.slot_of_code[code];
-                    if (s < 0) atomicOr(&cnt->err, 8);               // beyond a non-periodic face of the decomposition: lost
-                    else {
-                        const int k = atomicAdd(&cnt->route_send_n[s], 1);
-                        if (k >= exch_cap) atomicOr(&cnt->err, 8);
-                        else {
-                            double *rec = os.sbuf[s] + (size_t)(k + 1) * REC;
-#pragma unroll
-                            for (int q = 0; q < 3; q++) { rec[q] = xi[q]; rec[3 + q] = v.c[q][i]; }
-                            reinterpret_cast<int2 *>(rec)[6] = make_int2(tag[i], type[i]);
-                            reinterpret_cast<int2 *>(rec)[7] = make_int2(mask[i], image[i]);
-                            if (os.bpa) {
-                                int2 *br = os.bsend[s] + (size_t)k * (1 + os.bpa);
-                                const int nb = nbond[i];
-                                br[0] = make_int2(nb, 0);
-                                for (int q = 0; q < nb; q++) br[1 + q] = bonds[i + q * padding];
-                            }
-                        }
-                    }
-                }
-            }
-            run += tot;
-        }
-    }
-}
-
-__global__ void k_os_headers(Counts *cnt, OneShot os, int exch_cap)
-{
-    const int s = threadIdx.x;
-    if (s < os.np && s != os.self) reinterpret_cast<int *>(os.sbuf[s])[0] = min(cnt->route_send_n[s], exch_cap);
-    if (s == 0) cnt->nlocal -= cnt->exch_n[0];
-}
-
-// arrivals are appended peer by peer in slot order
-__global__ void __launch_bounds__(256) k_os_unpack(SoA3 x, SoA3 v, int *__restrict__ tag, int *__restrict__ type, int *__restrict__ mask,
-                                                   int *__restrict__ image, Counts *__restrict__ cnt, OneShot os, Box box, int nloc_cap,
-                                                   int *__restrict__ nbond, int2 *__restrict__ bonds, size_t padding)
-{
-    const int s = blockIdx.y;
-    if (s == os.self) return;
-    int base = cnt->nlocal, total = 0;
-    for (int q = 0; q < os.np; q++) {
-        if (q == os.self) continue;
-        const int nq = reinterpret_cast<const int *>(os.rbuf[q])[0];
-        if (q < s) base += nq;
-        total += nq;
-    }
-    if (cnt->nlocal + total > nloc_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&cnt->err, 8); return; }
-    const int n = reinterpret_cast<const int *>(os.rbuf[s])[0];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const double *rec = os.rbuf[s] + (size_t)(k + 1) * REC;
-        const int p = base + k;
-        bool inside = true;
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            x.c[q][p] = rec[q]; v.c[q][p] = rec[3 + q];
-            if (os.multi[q]) inside = inside && rec[q] >= box.sublo[q] && rec[q] < box.subhi[q];
-        }
-        const int2 tt = reinterpret_cast<const int2 *>(rec)[6], mi = reinterpret_cast<const int2 *>(rec)[7];
-        tag[p] = tt.x; type[p] = tt.y; mask[p] = mi.x; image[p] = mi.y;
-        if (!inside) atomicOr(&cnt->err, 8);
-        if (os.bpa) {
-            const int2 *br = os.brecv[s] + (size_t)k * (1 + os.bpa);
-            const int nb = min(max(br[0].x, 0), os.bpa);
-            nbond[p] = nb;
-            for (int q = 0; q < nb; q++) bonds[p + q * padding] = br[1 + q];
-        }
-    }
-}
-
-__global__ void k_os_grow(Counts *cnt, OneShot os)
-{
-    int total = 0;
-    for (int q = 0; q < os.np; q++) if (q != os.self) total += reinterpret_cast<const int *>(os.rbuf[q])[0];
-    cnt->nlocal += total;
-    cnt->nall = cnt->nlocal;
-}
-
-int launch_exchange_oneshot(meso_ctx *ctx)
-{
-    int rc = ensure_comm_buffers(ctx);
-    if (rc) return rc;
-    if (ctx->npeers == 0) { rc = comm_build_peers(ctx); if (rc) return rc; }
-    const Box &box = ctx->box;
-    const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
-    int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
-    cudaStream_t st = ctx->stream;
-    const bool bonded = bonds_active(ctx);
-    OneShot os;
-    os.np = ctx->npeers; os.self = ctx->peer_self; os.bpa = bonded ? ctx->bond_per_atom : 0;
-    bool any = false;
-    for (int d = 0; d < 3; d++) { os.multi[d] = ctx->procgrid[d] > 1; any = any || os.multi[d]; }
-    if (!any) return MESO_OK;                     // the periodic wrap already put every atom back into the brick
-    for (int c = 0; c < 27; c++) {
-        const int off[3] = {c % 3 - 1, (c / 3) % 3 - 1, c / 9 - 1};
-        int loc[3], slot = -1;
-        bool ok = true;
-        for (int d = 0; d < 3; d++) {
-            loc[d] = ctx->myloc[d] + off[d];
-            if (loc[d] < 0 || loc[d] >= ctx->procgrid[d]) {
-                if (!box.periodic[d]) { ok = false; break; }
-                loc[d] = (loc[d] + ctx->procgrid[d]) % ctx->procgrid[d];
-            }
-        }
-        if (ok) {
-            const int r = (loc[0] * ctx->procgrid[1] + loc[1]) * ctx->procgrid[2] + loc[2];
-            for (int s = 0; s < ctx->npeers; s++) if (ctx->peer_rank[s] == r) slot = s;
-        }
-        os.slot_of_code[c] = slot;
-    }
-    const size_t msg = (size_t)(ctx->exch_cap + 1) * REC, bmsg = (size_t)ctx->exch_cap * (size_t)(1 + os.bpa);
-    bool okm = true;
-    for (int s = 0; s < 27; s++) { os.sbuf[s] = nullptr; os.rbuf[s] = nullptr; os.bsend[s] = nullptr; os.brecv[s] = nullptr; }
-    for (int s = 0; s < os.np; s++) {
-        if (s == os.self) continue;
-        okm = okm && ctx->os_sbuf[s].reserve(msg) && ctx->os_rbuf[s].reserve(msg);
-        if (bonded) okm = okm && ctx->os_bsend[s].reserve(bmsg) && ctx->os_brecv[s].reserve(bmsg);
-        os.sbuf[s] = ctx->os_sbuf[s].p; os.rbuf[s] = ctx->os_rbuf[s].p;
-        os.bsend[s] = ctx->os_bsend[s].p; os.brecv[s] = ctx->os_brecv[s].p;
-    }
-    if (!okm) { ctx->err = "out of device memory (one-shot migration buffers)"; return MESO_ECUDA; }
-    k_os_count<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), ctx->d_counts, tc, box, os, ntiles);
-    k_os_scan<<<1, 1024, 0, LS(st)>>>(tc, ctx->d_counts);
-    k_os_scatter<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, soa(ctx->xa),
-                                                soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p, ctx->imagea.p, ctx->d_counts, tc, box, os,
-                                                ntiles, ctx->exch_cap, ctx->nbond.p, ctx->bonds.p, ctx->nbond_alt.p, ctx->bonds_alt.p, ctx->cap);
-    for (int q = 0; q < 3; q++) { std::swap(ctx->x[q].p, ctx->xa[q].p); std::swap(ctx->v[q].p, ctx->va[q].p); }
-    std::swap(ctx->tag.p, ctx->taga.p); std::swap(ctx->type.p, ctx->typea.p);
-    std::swap(ctx->mask.p, ctx->maska.p); std::swap(ctx->image.p, ctx->imagea.p);
-    if (bonded) {
-        std::swap(ctx->nbond.p, ctx->nbond_alt.p); std::swap(ctx->nbond.cap, ctx->nbond_alt.cap);
-        std::swap(ctx->bonds.p, ctx->bonds_alt.p); std::swap(ctx->bonds.cap, ctx->bonds_alt.cap);
-    }
-    k_os_headers<<<1, 32, 0, LS(st)>>>(ctx->d_counts, os, ctx->exch_cap);
-    ncclComm_t comm = (ncclComm_t)ctx->nccl;
-    MESO_NCCL(ncclGroupStart());
-    for (int s = 0; s < os.np; s++) {
-        if (s == os.self) continue;
-        MESO_NCCL(ncclSend(ctx->os_sbuf[s].p, msg, ncclDouble, ctx->peer_rank[s], comm, st));
-        MESO_NCCL(ncclRecv(ctx->os_rbuf[s].p, msg, ncclDouble, ctx->peer_rank[s], comm, st));
-        if (bonded) {
-            MESO_NCCL(ncclSend(ctx->os_bsend[s].p, bmsg * 2, ncclInt, ctx->peer_rank[s], comm, st));
-            MESO_NCCL(ncclRecv(ctx->os_brecv[s].p, bmsg * 2, ncclInt, ctx->peer_rank[s], comm, st));
-        }
-    }
-    MESO_NCCL(ncclGroupEnd());
-    const dim3 grid(ctx->sm_count, os.np);
-    k_os_unpack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p, ctx->d_counts, os, box,
-                                    (int)ctx->nloc_cap, ctx->nbond.p, ctx->bonds.p, ctx->cap);
-    k_os_grow<<<1, 1, 0, LS(st)>>>(ctx->d_counts, os);
-    MESO_CUDA(cudaGetLastError());
-    return MESO_OK;
-}
-
-__global__ void k_mr_reset_ghosts(Counts *cnt)
-{
-    cnt->nghost = 0;
-    cnt->nall = cnt->nlocal;
-    cnt->max_pair = 0;
-    for (int s = 0; s < 6; s++) { cnt->swap_first[s] = cnt->nlocal; cnt->swap_n[s] = 0; cnt->send_n[s] = 0; }
-}
-
-int launch_borders_multi(meso_ctx *ctx)
-{
-    int rc = ensure_comm_buffers(ctx);
-    if (rc) return rc;
-    if (!ctx->ghost_origin.reserve(ctx->cap)) { ctx->err = "out of device memory (ghost owners)"; return MESO_ECUDA; }
-    const Box &box = ctx->box;
-    const int ntiles = (int)((ctx->cap + CTILE - 1) / CTILE);
-    int2 *tc = reinterpret_cast<int2 *>(ctx->tile_counts.p);
-    cudaStream_t st = ctx->stream;
-    k_mr_reset_ghosts<<<1, 1, 0, LS(st)>>>(ctx->d_counts);
-    for (int d = 0; d < 3; d++) {
-        if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1] && ctx->procgrid[d] == 1) continue;
-        k_mr_border_count<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(ctx->x[d].p, ctx->d_counts, tc, box, d, ntiles);
-        k_mr_border_scan<<<1, 1024, 0, LS(st)>>>(tc, ctx->d_counts, ctx->send_buf[0].p, ctx->send_buf[1].p, d, ctx->swap_cap);
-        k_mr_border_pack<<<grid_for(ctx, 4), CT, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->veloc4.p,
-                                                        ctx->d_counts, tc, ctx->send_buf[0].p, ctx->send_buf[1].p, ctx->sendlist[2 * d].p,
-                                                        ctx->sendlist[2 * d + 1].p, box, d, ntiles, ctx->swap_cap, ctx->ghost_origin.p, ctx->rank);
-        const double *ra, *rb;
-        rc = swap_messages(ctx, d, (size_t)(ctx->swap_cap + 1) * RECB, st, ra, rb);
-        if (rc) return rc;
-        k_mr_border_advance<<<1, 1, 0, LS(st)>>>(ctx->d_counts, ra, rb, d, (int)ctx->cap);
-        k_mr_border_unpack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->coord4.p,
-                                                          ctx->veloc4.p, ctx->d_counts, ra, rb, box, d, ctx->ghost_origin.p);
-    }
-    MESO_CUDA(cudaGetLastError());
-    return ctx->halo_routes ? build_routes(ctx) : MESO_OK;
-}
-
-int comm_share_errors(meso_ctx *ctx)
-{
-    Counts *c = ctx->d_counts;
-    MESO_CUDA(cudaMemcpyAsync(&c->err_any, &c->err, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-    if (ctx->nranks > 1)
-        MESO_NCCL(ncclAllReduce(&c->err_any, &c->err_any, 1, ncclInt, ncclMax, (ncclComm_t)ctx->nccl, ctx->stream));
-    return MESO_OK;
-}
-
-// per-step ghost refresh on stream `st` (the side stream when it overlaps the bulk force kernel).  Message sizes come from
-// the counts of the rebuild that built the send lists: the host waits once per rebuild for that (tiny) copy; the
-// sender's send_n[s] equals the receiver's swap_n[s] by construction (it is the header the receiver unpacked).
+// per-step ghost refresh on stream `st` (the side stream when it overlaps the bulk force kernel)
 int launch_forward_multi(meso_ctx *ctx, cudaStream_t st)
 {
-    const Box &box = ctx->box;
-    if (!ctx->fwd_counts_valid) {
-        MESO_CUDA(cudaEventSynchronize(ctx->ev_counts));
-        if (ctx->h_counts->err_any) {
-            // some rank overflowed a capacity during the rebuild: its ghost counts no longer match its partners' send lists.
-            // Every rank sees the same flag and stops here, before a size-mismatched message could block the others.
-            ctx->err = "device-side capacity error on some rank during the last rebuild (ghost / migration / pair-table capacity)";
-            return MESO_ECAPACITY;
-        }
-        for (int s = 0; s < 6; s++) { ctx->fwd_send_n[s] = ctx->h_counts->send_n[s]; ctx->fwd_recv_n[s] = ctx->h_counts->swap_n[s]; }
-        for (int s = 0; s < 27; s++) { ctx->route_send_n[s] = ctx->h_counts->route_send_n[s]; ctx->route_recv_n[s] = ctx->h_counts->route_recv_n[s]; }
-        ctx->fwd_counts_valid = true;
-    }
-    if (ctx->halo_routes) return forward_routes(ctx, st);
-    for (int d = 0; d < 3; d++) {
-        if (!box.sendflag[2 * d] && !box.sendflag[2 * d + 1] && ctx->procgrid[d] == 1) continue;
-        k_mr_forward_pack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, ctx->sendlist[2 * d].p,
-                                                         ctx->sendlist[2 * d + 1].p, ctx->send_buf[0].p, ctx->send_buf[1].p, box, d);
-        const double *ra, *rb;
-        int rc = swap_messages4(ctx, d, (size_t)ctx->fwd_send_n[2 * d] * RECF, (size_t)ctx->fwd_send_n[2 * d + 1] * RECF,
-                                (size_t)ctx->fwd_recv_n[2 * d] * RECF, (size_t)ctx->fwd_recv_n[2 * d + 1] * RECF, st, ra, rb);
-        if (rc) return rc;
-        k_mr_forward_unpack<<<grid_for(ctx, 2), 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts,
-                                                           ra, rb, box, d);
-    }
+    CommState *cs = state(ctx);
+    if (!cs->ready) { ctx->err = "halo refresh before the first rebuild"; return MESO_EINVAL; }
+    Shifts sh;
+    make_shifts(ctx, sh);
+    const int epoch = ++cs->epoch_halo;
+    const dim3 grid(std::max(1, ctx->sm_count / 4), NS);
+    k_fwd_pack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), ctx->veloc4.p, ctx->d_counts, cs->peers, sh, reinterpret_cast<int *const *>(ctx->route_ptrs.p),
+                                      cs->sync.p + 2, epoch, cs->mine, ctx->d_counts);
+    k_wait<<<1, 32, 0, LS(st)>>>(cs->mine, ctx->d_counts, epoch, 2);
+    k_fwd_unpack<<<grid, 256, 0, LS(st)>>>(soa(ctx->x), soa(ctx->v), ctx->type.p, ctx->coord4.p, ctx->veloc4.p, ctx->d_counts, cs->mine, ctx->box,
+                                        cs->peers, cs->sync.p + 5, epoch);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
+}
+
+// a new set of atoms: every rank maps its neighbors again at the next rebuild (all ranks upload together)
+void comm_invalidate(meso_ctx *ctx)
+{
+    if (ctx->comm && ctx->nccl) static_cast<CommState *>(ctx->comm)->ready = false;
+}
+
+// host-driven bootstrap (several ranks in one process, or on one GPU): see include/meso_b200.h
+int comm_export_blob(meso_ctx *ctx, void *blob1024)
+{
+    int rc = ensure_arena(ctx);
+    if (rc) return rc;
+    CommBlob bl;
+    fill_blob(ctx, bl);
+    memset(blob1024, 0, 1024);
+    memcpy(blob1024, &bl, sizeof bl);
+    return MESO_OK;
+}
+
+int comm_import_blobs(meso_ctx *ctx, const void *blobs, int nranks)
+{
+    if (nranks != ctx->nranks) { ctx->err = "meso_comm_import: one blob per rank of the decomposition"; return MESO_EINVAL; }
+    int rc = ensure_arena(ctx);
+    if (rc) return rc;
+    return import_blobs(ctx, static_cast<const unsigned char *>(blobs), nranks);
 }
 
 }  // namespace meso

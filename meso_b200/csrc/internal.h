@@ -27,8 +27,10 @@ struct Counts {
     int send_n[6];                  // atoms this rank sends in each border swap (== swap_n on a self-partnered swap)
     int exch_n[2];                  // migration: leavers to the lower / upper neighbor in the current dimension
     int err_any;                    // max of `err` over all ranks at the last rebuild (multi-rank: every rank fails together)
-    // direct halo routes (comm.cu): per peer slot, how many refresh records this rank sends / receives every step
+    // halo (comm.cu), per direction code: records this rank sends in / receives from that direction at every ghost creation
+    // and refresh, and where the received block starts in the ghost array
     int route_send_n[27], route_recv_n[27];
+    int slot_base[27];
 };
 
 struct Box {
@@ -112,8 +114,6 @@ struct meso_ctx {
     meso::DevBuf<int> nbond, nbond_alt;
     meso::DevBuf<int2> bonds, bonds_alt, bonds_mapped;
     meso::DevBuf<unsigned> tag_map;
-    meso::DevBuf<int> exch_dest;               // migration: where each local atom went (stayer slot / message record)
-    meso::DevBuf<int2> bond_send[2], bond_recv[2];
     meso::DevBuf<double> bond_k_dev, bond_r0_dev, e_bond;
     // reductions return this rank's part only (an MPI host sums them itself)
     int every = 5, ago = 0;
@@ -136,8 +136,8 @@ struct meso_ctx {
     meso::DevBuf<float4> facc;                // fp32 per-atom force accumulator of the pair-once kernel (zero between uses)
     cudaTextureObject_t tex_coord = 0, tex_veloc = 0;   // linear float4 textures over coord4 / veloc4 (gather-path experiments)
     int pair_tex = 2;                         // which gathers of the pair-once kernel use the texture data pipe (MESO_PAIR_TEX)
-    bool nb_skip = false;                     // MESO_NB_SKIP=1: the build skips stencil cells beyond r_n of the atom (written, not yet run on hardware)
-    bool nb_per_atom = true;                  // thread-per-atom neighbor build (MESO_NB_PER_ATOM=0: warp-per-cell ballot kernel + per-atom fix-up)
+    int nb_clip = 1;                          // MESO_NB_CLIP: 2 = per-atom row clipping, 1 = per-cell union (lockstep), 0 = none
+    bool nb_slow = false;                     // MESO_NB_SLOW=1: every row by the plain 27-cell walk (A/B check of the fine-lattice build)
     bool pair_once = true;                    // meso_run evaluates each local pair once (MESO_PAIR_ONCE=0: two-sided kernel)
     meso::DevBuf<double> virial, e_pair;      // [6][cap] SoA, [cap]
     meso::DevBuf<double> mass_dev;            // [ntypes+1]
@@ -154,43 +154,30 @@ struct meso_ctx {
     meso::DevBuf<int> ghost_root;             // per ghost g: local source index
     meso::DevBuf<int> ghost_shift;            // per ghost g: packed shift code (2 bits per dim)
     meso::DevBuf<int> tile_counts;            // compaction scratch
-    // multi-rank halo
+    // multi-rank halo (comm.cu): arenas in peer memory, flags, send lists -- all behind an opaque state object
     bool comm_path = false;                   // use the message-based border/forward path (always when nranks > 1)
-    int swap_cap = 0, exch_cap = 0;           // records per halo / migration message
-    bool comm_caps_agreed = false;            // capacities were max-reduced over the ranks since the last upload
-    // direct halo routes: every ghost remembers its owner (rank, index, accumulated periodic shift); after the 3-phase ghost
-    // creation the ranks exchange request lists once, and the per-step refresh is ONE message per peer instead of three
-    // dependent swaps (the forwarding of earlier ghosts in later dimensions is resolved at the rebuild, not every step)
-    bool halo_routes = true;                  // MESO_HALO_ROUTES=0: per-step refresh by the 3 forwarding swaps
-    int npeers = 0, peer_self = 0, peer_rank[27] = {0};
-    int route_cap = 0;
-    meso::DevBuf<int> peer_slot;              // rank -> peer slot (or -1)
-    meso::DevBuf<int2> ghost_origin;          // per ghost: {owner rank | shift code << 24, owner's local index}
-    meso::DevBuf<int2> route_req[27], route_send_list[27];   // [0] = {count, 0}, then {index, shift code}
-    meso::DevBuf<int> route_dst[27];          // ghost slot of the k-th record received from the peer
-    meso::DevBuf<double> route_sbuf[27], route_rbuf[27];
-    meso::DevBuf<void *> route_ptrs;          // device copy of the request / slot pointer tables
-    bool exch_oneshot = false;                // MESO_EXCH_ONESHOT=1: leavers go straight to their final brick (written, not yet run on hardware)
-    meso::DevBuf<double> os_sbuf[27], os_rbuf[27];
-    meso::DevBuf<int2> os_bsend[27], os_brecv[27];
-    int route_send_n[27] = {0}, route_recv_n[27] = {0};
+    void *comm = nullptr;                     // meso::CommState
+    meso::DevBuf<void *> route_ptrs;          // device copy of the send-list pointer table
     size_t nloc_cap = 0;                      // capacity for local atoms
-    meso::DevBuf<double> send_buf[2], recv_buf[2], reduce_buf;
-    meso::DevBuf<int> sendlist[6];
+    meso::DevBuf<double> reduce_buf;
     cudaEvent_t ev_fwd_begin = nullptr, ev_fwd_end = nullptr;
     cudaEvent_t ev_counts = nullptr;          // the pinned Counts mirror of the last rebuild has landed
     bool counts_pending = false;              // ev_counts was recorded and its error flags have not been looked at yet
-    bool fwd_counts_valid = false;            // fwd_send_n / fwd_recv_n describe the current send lists
-    int fwd_send_n[6] = {0}, fwd_recv_n[6] = {0};
     // cells
-    meso::DevBuf<uint64_t> cell_key;          // sort key (cell id) per atom
-    meso::DevBuf<int> cell_of, cell_atoms, cell_start;
-    meso::DevBuf<unsigned char> stencil;      // [ncell][32]
-    meso::DevBuf<float4> cell_xyzj;           // cell-ordered {x,y,z,bits(atom index)}
-    meso::DevBuf<int2> cell_runs;             // [ncell][27] {first position, count} per stencil cell
-    // neighbor list
+    meso::DevBuf<int> cell_of;                // per atom: cell coordinates packed 10 bits per dimension (x | y << 10 | z << 20)
+    meso::DevBuf<int> cell_atoms, cell_start; // atoms in (cell, ascending index) order; first position of every cell (+ total)
+    meso::DevBuf<int> cell_cnt;               // histograms of the counting sort: [ncell] reference cells, then [8 ncell] fine cells
+    meso::DevBuf<int> fine_of, fine_start, scan_sums;
+    meso::DevBuf<float4> fine_rec;            // fine-cell-ordered records {x, y, z, bits(atom index)}
+    meso::DevBuf<unsigned char> stencil;      // [ncell][32]: stencil codes in the reference's order, byte 31 = count
+    meso::DevBuf<unsigned char> slotrank;     // [ncell][32]: stencil code -> position in that order
+    // neighbor table: row = [owned core][owned skin][other core][other skin]
     meso::DevBuf<int> pair_count, pair_table;
-    meso::DevBuf<int> nb_fixup;               // != 0: some cell's candidate list exceeded the warp-per-cell window
+    meso::DevBuf<int> owned_count;            // entries of the row whose pair this row evaluates (pair-once force kernel)
+    meso::DevBuf<int> core_split;             // owned core | other core << 16
+    meso::DevBuf<int> nb_fixup;               // != 0: some row was left to the fall-back build kernel
+    meso::DevBuf<uint32_t> nb_scratch;        // per-warp hit queues of the build kernel (global memory, L2-resident)
+    bool cells_valid = false;                 // cell_start / cell_atoms describe the last rebuild (built on demand for exports)
     size_t table_rows = 0;
 
     // reductions
@@ -241,15 +228,17 @@ int launch_reorder(meso_ctx *ctx);     // pbc + key + sort + gather(+pack)
 int launch_borders(meso_ctx *ctx);     // ghost creation (single rank: periodic images)
 int launch_forward(meso_ctx *ctx, bool full);     // per-step ghost refresh
 // ---- comm.cu
-int launch_exchange_multi(meso_ctx *ctx);
-int launch_exchange_oneshot(meso_ctx *ctx);
-int launch_borders_multi(meso_ctx *ctx);
-int launch_forward_multi(meso_ctx *ctx, cudaStream_t st);
-int comm_build_peers(meso_ctx *ctx);
-int comm_share_errors(meso_ctx *ctx);   // Counts::err_any = max over ranks of Counts::err (stream-ordered, no host sync)
+int launch_exchange_multi(meso_ctx *ctx);                   // migration: every leaver straight to its new brick
+int launch_borders_multi(meso_ctx *ctx);                    // ghost creation: all 26 images at once, reference order
+int launch_forward_multi(meso_ctx *ctx, cudaStream_t st);   // per-step ghost refresh
+void comm_invalidate(meso_ctx *ctx);
+int comm_export_blob(meso_ctx *ctx, void *blob1024);
+int comm_import_blobs(meso_ctx *ctx, const void *blobs, int nranks);
 // ---- neighbor.cu
 int launch_setup_bins(meso_ctx *ctx);
 int launch_neighbor_build(meso_ctx *ctx);
+int launch_cell_lists(meso_ctx *ctx);                       // reference cell lists of the last rebuild (exports)
+int launch_canonical_rows(meso_ctx *ctx, int *out_table);   // the table in the reference's row order (exports)
 // ---- pair.cu
 int launch_pack(meso_ctx *ctx, int range);
 int launch_pair(meso_ctx *ctx, int range, int evflag, bool accumulate, bool fuse_final, int groupbit);

@@ -1,5 +1,4 @@
-// neighbor.cu -- cell binning and the atomics-free build of the ordered, tile-transposed
-// full neighbor list.
+// neighbor.cu -- cell binning and the atomics-free build of the tile-transposed full neighbor table.
 //
 // Reference path:
 //   MesoNeighbor::setup_bins          UM/neighbor_meso.cu:858-931   (cell lattice aligned to the sub-domain)
@@ -7,13 +6,26 @@
 //   binning_meso                      UM/neighbor_meso.cu:535-711   (cell id, radix sort, boundaries, expanded stencils)
 //   gpu_build_neighbor_list<32,5>     UM/neigh_build_meso.cu:20-119 (warp per cell, 2 ballots per test, row-major rows)
 //   gpu_join_neigh_list / gpu_transpose_neigh_list  UM/neigh_build_meso.cu:166-240 (two more passes over the table)
-// Blackwell version: no materialised per-cell stencil rows (5 KB/cell in the reference) -- a
-// 32-byte per-cell code row names the <=27 neighbor cells in order and each thread walks
-// their atom runs directly; one thread owns one local atom, so the running core/skin
-// counters live in registers (no ballots, no shared counters, no atomics), entries are
-// written straight into the tile-transposed table (core forward from slot 0, skin backward
-// from slot n_col-1) and the owning thread joins its own row at the end: one pass over the
-// table instead of three, with 64-bit table offsets (the reference overflows int past 13.4 M atoms).
+//
+// Blackwell version (round 2).  The reference tests every atom of the 27 stencil cells: 246 distance tests per atom for
+// 36.8 stored neighbors at rho = 4, because its cells are as wide as the list cutoff r_n.  Here:
+//   * binning is a counting sort (histogram with hardware reductions -> exclusive scan -> claim a slot -> order each
+//     cell's handful of atoms by index) instead of a 3-pass radix sort of (cell id, atom) pairs;
+//   * the same pass files every atom in a HALF-CELL lattice (2 x 2 x 2 fine cells per reference cell, x-fastest), whose
+//     cell-ordered copy holds {x, y, z, atom index} records;
+//   * one thread owns one local atom and walks the 6 x 6 fine rows of its 27 stencil cells; each row is clipped to the
+//     chord of the cutoff sphere, so one run of CONTIGUOUS records replaces up to 6 fine cells and about 72 candidates are
+//     tested instead of 246.  The runs of a warp's 32 atoms are staged in shared memory and walked with a predicated
+//     (divergence-free) advance;
+//   * in-range neighbors are staged in a per-lane queue in shared memory (column layout: bank == lane, no atomics, no
+//     ballots) and written out once, when the row's totals are known.
+// Row layout: [owned core][owned skin][other core][other skin], where "owned" marks the entries whose pair the force
+// kernel evaluates from this row (ghost j, or (i+j) odd ? i<j : i>j) and core/skin is the reference's split at
+// r <= r_n - skin (fp32, at build time).  The SET of every row, its counts and the core/skin split are the reference's;
+// the order inside a segment is the traversal order of the fine lattice (deterministic: records of a fine cell are kept
+// in ascending atom index).  The reference's order (stencil cells by (boundary flag, Morton), ascending atom index inside
+// a cell, skin entries reversed) is a pure function of (cell of j, j), so meso_export_pair_table rebuilds it on demand
+// (k_canonical_rows) for the bit-exact parity checks.  Table offsets are 64-bit (the reference overflows int past 13.4 M atoms).
 #include "internal.h"
 #include "device_math.cuh"
 #include <algorithm>
@@ -22,11 +34,10 @@
 
 namespace meso {
 
-int sort_pairs_u64(meso_ctx *ctx, DevBuf<uint64_t> &key, DevBuf<int> &val, const int *d_n, size_t cap, int bits);
-
 // ------------------------------------------------------------------ per-cell stencil code rows
-// byte s (< 27): offset code (i+1) + 3*(j+1) + 9*(k+1) of the s-th neighbor cell; byte 31: count.
-__global__ void k_stencil_codes(unsigned char *__restrict__ stencil, Box box)
+// stencil[cell][s] (s < 27): offset code (i+1) + 3*(j+1) + 9*(k+1) of the s-th neighbor cell; byte 31: count.
+// slotrank[cell][code]: the inverse (position of the neighbor cell `code` in the stencil order, 0xff = outside the lattice).
+__global__ void k_stencil_codes(unsigned char *__restrict__ stencil, unsigned char *__restrict__ slotrank, Box box)
 {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= box.ncell) return;
@@ -46,429 +57,451 @@ __global__ void k_stencil_codes(unsigned char *__restrict__ stencil, Box box)
                 while (p > 0 && key[p - 1] > kk) { key[p] = key[p - 1]; code[p] = code[p - 1]; p--; }
                 key[p] = kk; code[p] = (unsigned char)((i + 1) + 3 * (j + 1) + 9 * (k + 1));
             }
-    unsigned char *row = stencil + (size_t)cell * 32;
-    for (int s = 0; s < 27; s++) row[s] = s < n ? code[s] : 0;
+    unsigned char *row = stencil + (size_t)cell * 32, *inv = slotrank + (size_t)cell * 32;
+    for (int s = 0; s < 32; s++) inv[s] = 0xff;
+    for (int s = 0; s < 27; s++) { row[s] = s < n ? code[s] : 0; if (s < n) inv[code[s]] = (unsigned char)s; }
     row[31] = (unsigned char)n;
 }
 
-// ------------------------------------------------------------------ cell id of every atom (locals + ghosts)
+// ------------------------------------------------------------------ binning: counting sort into reference cells and fine cells
 struct SoA3c { const double *c[3]; };
 
-__global__ void __launch_bounds__(256) k_cell_id(SoA3c x, uint64_t *__restrict__ cell_key, int *__restrict__ cell_val,
-                                                 int *__restrict__ cell_of, const Counts *__restrict__ cnt, Box box)
+constexpr uint32_t MJ = (1u << 27) - 1u;  // atom indices fit 27 bits in the hit queue (3 class bits above them)
+constexpr uint32_t MQ = (1u << 26) - 1u;  // record positions fit 26 bits in a staged run (6 count bits above them); checked on the host
+
+// cell coordinates of every atom (locals + ghosts) packed 10 bits per dimension, its fine cell, and the fine histogram
+__global__ void __launch_bounds__(256) k_bin_count(SoA3c x, int *__restrict__ cellc, int *__restrict__ fine_of, int *__restrict__ fine_cnt,
+                                                   const Counts *__restrict__ cnt, Box box)
 {
     const int nlocal = cnt->nlocal, nall = nlocal + cnt->nghost;
+    const int fm0 = 2 * box.m[0], fm1 = 2 * box.m[1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nall; i += gridDim.x * blockDim.x) {
-        int b[3];
+        int b[3], h[3];
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            double xd = x.c[d][i];
+            const double xd = x.c[d][i];
             b[d] = clamp_rz(__fma_rn(xd - box.sublo[d], box.bininv[d], 1.0), 0, box.m[d]);   // UM/neighbor_meso.cu:410-412
             if (i >= nlocal) b[d] = (xd >= box.sublo[d]) ? (xd <= box.subhi[d] ? b[d] : box.m[d] - 1) : 0;   // :413-417
+            // which half of its cell (the fine lattice only prunes: any consistent rule will do)
+            h[d] = (xd - (box.sublo[d] + (double)(b[d] - 1) * box.binsize[d])) >= 0.5 * box.binsize[d] ? 1 : 0;
         }
-        int c = b[0] + box.m[0] * (b[1] + b[2] * box.m[1]);
-        cell_key[i] = (uint64_t)c;
-        cell_val[i] = i;
-        cell_of[i] = c;
+        cellc[i] = b[0] | (b[1] << 10) | (b[2] << 20);
+        const int f = (2 * b[0] + h[0]) + fm0 * ((2 * b[1] + h[1]) + fm1 * (2 * b[2] + h[2]));
+        fine_of[i] = f;
+        atomicAdd(fine_cnt + f, 1);
     }
 }
 
-// cell_start[c] = first sorted position whose cell id >= c  (gpu_find_bin_boundary, UM/neighbor_meso.cu:423-460);
-// the same pass writes a cell-ordered copy of the packed coordinates, {x, y, z, bits(atom index)}, so that the
-// build kernel streams candidates with ONE contiguous 16-byte load each instead of index load + float4 gather.
-__global__ void __launch_bounds__(256) k_cell_bounds(const uint64_t *__restrict__ cell_sorted, const int *__restrict__ cell_atoms,
-                                                     const float4 *__restrict__ coord4, int *__restrict__ cell_start,
-                                                     float4 *__restrict__ cell_xyzj, const Counts *__restrict__ cnt, int ncell)
+// histogram of the reference cells from the stored cell coordinates (exports only)
+__global__ void __launch_bounds__(256) k_cell_hist(const int *__restrict__ cellc, int *__restrict__ cell_cnt, const Counts *__restrict__ cnt,
+                                                   int m0, int m1)
 {
     const int nall = cnt->nlocal + cnt->nghost;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p <= nall; p += gridDim.x * blockDim.x) {
-        int cur = p < nall ? (int)cell_sorted[p] : ncell;
-        int prev = p > 0 ? (int)cell_sorted[p - 1] : -1;
-        for (int c = prev + 1; c <= cur; c++) cell_start[c] = p;
-        if (p < nall) {
-            const int j = cell_atoms[p];
-            float4 v = coord4[j];
-            v.w = __int_as_float(j);
-            cell_xyzj[p] = v;
-        }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nall; i += gridDim.x * blockDim.x) {
+        const int cc = cellc[i];
+        atomicAdd(cell_cnt + (cc & 1023) + m0 * (((cc >> 10) & 1023) + m1 * (cc >> 20)), 1);
     }
 }
 
-// runs[c][s] = {first position, count} of the s-th stencil cell of cell c, in stencil order
-__global__ void __launch_bounds__(256) k_cell_runs(const unsigned char *__restrict__ stencil, const int *__restrict__ cell_start,
-                                                   int2 *__restrict__ runs, Box box)
+// exclusive scan of in[0..n) into out[1..n] (out[0] = 0): three launches, 4096 elements per CTA
+constexpr int SCAN_T = 256, SCAN_I = 16, SCAN_TILE = SCAN_T * SCAN_I;
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_sums(const int *__restrict__ in, int *__restrict__ sums, int n)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = t / 27, s = t - c * 27;
-    if (c >= box.ncell) return;
-    const unsigned char *row = stencil + (size_t)c * 32;
-    int2 r = make_int2(0, 0);
-    if (s < row[31]) {
-        const int code = row[s];
-        const int nc = c + (code % 3 - 1) + box.m[0] * ((code / 3) % 3 - 1 + box.m[1] * (code / 9 - 1));
-        const int a = cell_start[nc];
-        r = make_int2(a, cell_start[nc + 1] - a);
+    __shared__ int ws[SCAN_T / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_I;
+    int s = 0;
+#pragma unroll
+    for (int u = 0; u < SCAN_I; u += 4) {
+        if (base + u + 3 < n) { const int4 v = *reinterpret_cast<const int4 *>(in + base + u); s += v.x + v.y + v.z + v.w; }
+        else for (int q = 0; q < 4; q++) if (base + u + q < n) s += in[base + u + q];
     }
-    runs[t] = r;
+    s = __reduce_add_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < SCAN_T / 32; w++) t += ws[w]; sums[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_top(int *__restrict__ sums, int nblk)
+{
+    __shared__ int ws[32];
+    __shared__ int carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nblk; base += 1024) {
+        const int i = base + t;
+        const int v = i < nblk ? sums[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) ws[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            const int s = ws[lane];
+            int z = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+            ws[lane] = z - s;
+        }
+        __syncthreads();
+        const int e = carry_s + ws[w] + x - v;
+        if (i < nblk) sums[i] = e;
+        __syncthreads();
+        if (t == 1023) carry_s = e + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const int *__restrict__ in, int *__restrict__ out, const int *__restrict__ sums, int n)
+{
+    __shared__ int ws[SCAN_T / 32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int base = blockIdx.x * SCAN_TILE + t * SCAN_I;
+    int v[SCAN_I], s = 0;
+#pragma unroll
+    for (int u = 0; u < SCAN_I; u += 4) {
+        if (base + u + 3 < n) { const int4 q = *reinterpret_cast<const int4 *>(in + base + u); v[u] = q.x; v[u + 1] = q.y; v[u + 2] = q.z; v[u + 3] = q.w; }
+        else for (int q = 0; q < 4; q++) v[u + q] = base + u + q < n ? in[base + u + q] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < SCAN_I; u++) s += v[u];
+    int x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    int pre = sums[blockIdx.x] + x - s;
+#pragma unroll
+    for (int ww = 0; ww < SCAN_T / 32; ww++) pre += ww < w ? ws[ww] : 0;
+    if (blockIdx.x == 0 && t == 0) out[0] = 0;
+#pragma unroll
+    for (int u = 0; u < SCAN_I; u++) {
+        if (base + u < n) out[base + u + 1] = pre;          // out[i + 1] = sum of in[0..i): becomes start[i + 1] once cell i is filled
+        pre += v[u];
+    }
+}
+
+// every atom claims a slot of its cell: start1 = cell_start + 1 holds the exclusive prefix before the kernel and the
+// inclusive one (= the final cell_start of the next cell) after it
+__global__ void __launch_bounds__(256) k_bin_fill(const int *__restrict__ cellc, int *__restrict__ start1, int *__restrict__ cell_atoms,
+                                                  const Counts *__restrict__ cnt, int m0, int m1)
+{
+    const int nall = cnt->nlocal + cnt->nghost;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nall; i += gridDim.x * blockDim.x) {
+        const int cc = cellc[i];
+        const int c = (cc & 1023) + m0 * (((cc >> 10) & 1023) + m1 * (cc >> 20));
+        cell_atoms[atomicAdd(start1 + c, 1)] = i;
+    }
+}
+
+// atoms of a cell in ascending index (the order the reference's stable sort of (cell id, atom) leaves, UM/neighbor_meso.cu:588)
+__global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell_start, int *__restrict__ cell_atoms, int ncell)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int a = cell_start[c], n = cell_start[c + 1] - a;
+    int *p = cell_atoms + a;
+    for (int k = 1; k < n; k++) {
+        const int v = p[k];
+        int q = k;
+        while (q > 0 && p[q - 1] > v) { p[q] = p[q - 1]; q--; }
+        p[q] = v;
+    }
+}
+
+// cell-ordered records of the fine lattice: {x, y, z, bits(atom index)}
+__global__ void __launch_bounds__(256) k_fine_fill(const float4 *__restrict__ coord4, const int *__restrict__ fine_of, int *__restrict__ fstart1,
+                                                   float4 *__restrict__ fine_rec, const Counts *__restrict__ cnt)
+{
+    const int nall = cnt->nlocal + cnt->nghost;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nall; i += gridDim.x * blockDim.x) {
+        float4 c = coord4[i];
+        c.w = __int_as_float(i);
+        fine_rec[atomicAdd(fstart1 + fine_of[i], 1)] = c;
+    }
+}
+
+// records of a fine cell in ascending atom index: the traversal order, hence the row order, is the same in every run
+__global__ void __launch_bounds__(128) k_fine_order(const int *__restrict__ fine_start, float4 *__restrict__ fine_rec, int nfine)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nfine) return;
+    const int a = fine_start[c], n = fine_start[c + 1] - a;
+    float4 *p = fine_rec + a;
+    for (int k = 1; k < n; k++) {
+        const float4 v = p[k];
+        int q = k;
+        while (q > 0 && __float_as_int(p[q - 1].w) > __float_as_int(v.w)) { p[q] = p[q - 1]; q--; }
+        p[q] = v;
+    }
 }
 
 // ------------------------------------------------------------------ build
+// geometry of the fine lattice in the packed (sub-box centred, fp32) frame
+struct FineGeom {
+    float lat_lo[3];      // lower face of fine cell 0
+    float w[3], inv_w[3]; // fine cell width and its inverse
+    int m[3];             // reference cells per dimension
+    float R2;             // (r_n + margin)^2: rows and chords are clipped with a margin far above the fp32 rounding of the geometry
+    int clip;             // 2: every atom clips its own rows; 1: atoms of a cell share the union of their runs (lockstep); 0: no clipping
+};
+
+constexpr int NF_THREADS = 128;
+constexpr int NROW = 36;          // 6 x 6 fine rows cover the 3 x 3 reference-cell rows of the stencil
+constexpr int NQ = 64;            // per-lane hit queue depth; denser rows take the fall-back kernel
+
+__device__ __forceinline__ void sts_u32(unsigned addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(unsigned addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void stg_u32_if(bool p, uint32_t *addr, uint32_t v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.global.b32 [%0], %1;\n\t}" ::"l"(addr), "r"(v), "r"((int)p) : "memory");
+}
+
+// the entries of row i that its own lane evaluates in the pair-once force kernel (pair.cu): ghost partners always, local
+// partners by the balanced rule (i+j) odd ? i<j : i>j (the mirror entry in row j is then "other")
+__device__ __forceinline__ bool owns(int i, int j, int nlocal)
+{
+    const unsigned key = (unsigned)(j - i) * 0x80000001u;         // sign bit: d odd ? d > 0 : d < 0
+    return (int)(key | (unsigned)(nlocal - 1 - j)) < 0;
+}
+
 __device__ __forceinline__ size_t slot(int i, int k, int n_col)
 {
     return (size_t)((i & ~31) + (k & 31)) * (size_t)n_col + (size_t)((k >> 5) * 32 + (i & 31));
 }
 
-constexpr int NB_THREADS = 128;
-// NB_BATCH: candidates tested per iteration (independent 16-byte loads in flight);
-// NB_DEPTH: per-lane staging slots (core hits grow from the front, skin hits from the back)
-
-// One thread owns one local atom.  In-range candidates are staged in a per-lane two-ended queue in shared
-// memory (column layout [slot][lane]: bank == lane, no conflicts, no atomics), which costs 3 issue slots per
-// candidate instead of the ~25 of computing a tile-transposed global address for a predicated store; the
-// queue is written out once per atom, when both totals are known, so skin entries go straight to their
-// final position (reverse encounter order after the core entries) and the reference's join pass disappears.
-// Rows denser than the queue (> 60 hits, never at rho = 4) take the spill path: core entries are flushed
-// forward, skin entries backward from slot n_col-1 as in the reference, and joined at the end.
-// SKIP (MESO_NB_SKIP=1, off by default, NOT YET RUN ON HARDWARE): a stencil cell whose box lies farther than r_n from the
-// atom is not walked at all -- half of the corner cells and a quarter of the edge cells, ~26 % of the candidate tests.  The
-// criterion (fp32, 1e-3 margin on r_n^2) never drops a stored neighbor: tests/test_oracle_world.py::
-// test_stencil_cell_skip_criterion_is_conservative checks it on the oracle's lattice.  SkipGeom: packed coordinate of the
-// lower face of cell index 1 (= sublo - centre), cell size, cells per dimension, the per-cell stencil code rows.
-struct SkipGeom { float lo[3], bs[3]; int m[3]; const unsigned char *stencil; float limit; };
-
-template <int NB_DEPTH, int NB_BATCH, bool SKIP = false>
-__global__ void __launch_bounds__(NB_THREADS) k_build_neighbors(const float4 *__restrict__ coord4, const int *__restrict__ cell_of,
-                                                                const int2 *__restrict__ runs, const float4 *__restrict__ cell_xyzj,
-                                                                int *__restrict__ pair_count, int *__restrict__ pair_table,
-                                                                Counts *__restrict__ cnt, int n_col, float rc2_core, float rc2_tail,
-                                                                const int *__restrict__ fixup, SkipGeom sg = SkipGeom())
+// Persistent grid (a few CTAs per SM); every warp owns a [NQ][32] hit queue in `scratch` (global memory: it lives in L2 and
+// costs no shared memory, so the run lists are the only shared-memory tenant and ~40 warps per SM hide the record latency).
+__global__ void __launch_bounds__(NF_THREADS) k_build_rows(const float4 *__restrict__ coord4, const int *__restrict__ cellc,
+                                                           const int *__restrict__ fine_start, const float4 *__restrict__ fine_rec,
+                                                           int *__restrict__ pair_count, int *__restrict__ owned_count,
+                                                           int *__restrict__ core_split, int *__restrict__ pair_table,
+                                                           Counts *__restrict__ cnt, int *__restrict__ fixup, uint32_t *__restrict__ scratch,
+                                                           int n_col, float rc2_core, float rc2_tail, FineGeom g)
 {
-    __shared__ int stage[NB_THREADS / 32][NB_DEPTH][32];
-    // fix-up mode: only the rows the warp-per-cell kernel marked (pair_count == -1); nothing to do when no cell was marked
-    if (fixup && *fixup == 0) return;
-    int(*qq)[32] = stage[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t s_runs[NF_THREADS / 32][NROW][32];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned rbase = (unsigned)__cvta_generic_to_shared(&s_runs[wid][0][lane]);
+    uint32_t *const qbase = scratch + ((size_t)blockIdx.x * (NF_THREADS / 32) + wid) * (NQ * 32) + lane;   // entry t at qbase[t * 32]
     const int nlocal = cnt->nlocal;
+    const int fm0 = 2 * g.m[0], fm1 = 2 * g.m[1], fm2 = 2 * g.m[2];
     int worst = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
-        if (fixup && pair_count[i] >= 0) continue;
-        const float4 ci = coord4[i];
-        const int mycell = cell_of[i];
-        const int2 *my = runs + (size_t)mycell * 27;
-        // SKIP: squared distance from the atom to the -1 / +1 neighbor layer along each axis (0 when the atom sits outside its
-        // clamped cell on that side) and this cell's stencil code row
-        float d2lo[3] = {0.f, 0.f, 0.f}, d2hi[3] = {0.f, 0.f, 0.f};
-        const unsigned char *srow = nullptr;
-        if constexpr (SKIP) {
-            const int b[3] = {mycell % sg.m[0], (mycell / sg.m[0]) % sg.m[1], mycell / (sg.m[0] * sg.m[1])};
-            const float p[3] = {ci.x, ci.y, ci.z};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < nlocal; i += gridDim.x * blockDim.x) {
+        const bool active = i < nlocal;
+        const float4 ci = coord4[active ? i : 0];
+        const int cc = cellc[active ? i : 0];
+        const int cx = cc & 1023, cy = (cc >> 10) & 1023, cz = cc >> 20;
+        // position in fine-cell units, clamped onto the lattice (an atom beyond it keeps valid lower bounds)
+        const float ux = fminf(fmaxf((ci.x - g.lat_lo[0]) * g.inv_w[0], 0.f), (float)fm0);
+        const float uy = fminf(fmaxf((ci.y - g.lat_lo[1]) * g.inv_w[1], 0.f), (float)fm1);
+        const float uz = fminf(fmaxf((ci.z - g.lat_lo[2]) * g.inv_w[2], 0.f), (float)fm2);
+        const int xmin = max(0, 2 * (cx - 1)), xmax = min(fm0 - 1, 2 * cx + 3);
+        bool bad = false;
+        const unsigned peers = __match_any_sync(full, active ? cc : -1);
+        // ---- the 36 fine rows of the stencil, each clipped to the chord of the (margin-enlarged) cutoff sphere; the
+        //      non-empty runs {first record, count} are staged compactly, one column per lane.  The 12 boundary loads of a
+        //      plane are independent (clamped addresses, no branch around them) so they are in flight together.
+        unsigned rp = rbase;
+#pragma unroll 1
+        for (int rz = 0; rz < 6; rz++) {
+            const int fz = 2 * (cz - 1) + rz;
+            const float tz = uz - (float)fz;
+            const float dz = (tz < 0.f ? -tz : fmaxf(tz - 1.f, 0.f)) * g.w[2];
+            const float remz = g.R2 - dz * dz;
+            const bool okz = active && fz >= 0 && fz < fm2 && remz >= 0.f;
+            if (g.clip == 2 && !__any_sync(full, okz)) continue;
+            int q0[6], q1[6];
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                const float clo = sg.lo[d] + (float)(b[d] - 1) * sg.bs[d], chi = sg.lo[d] + (float)b[d] * sg.bs[d];
-                const float a = fmaxf(p[d] - clo, 0.f), c = fmaxf(chi - p[d], 0.f);
-                d2lo[d] = a * a; d2hi[d] = c * c;
+            for (int ry = 0; ry < 6; ry++) {
+                const int fy = 2 * (cy - 1) + ry;
+                const float ty = uy - (float)fy;
+                const float dy = (ty < 0.f ? -ty : fmaxf(ty - 1.f, 0.f)) * g.w[1];
+                const float rem = remz - dy * dy;
+                const bool ok = okz && fy >= 0 && fy < fm1 && rem >= 0.f;
+                const float ch = sqrt_approx(fmaxf(rem, 0.f)) * g.inv_w[0];      // MUFU.SQRT: the margin in R2 dwarfs its 1-ulp error
+                int xlo = max(__float2int_rd(ux - ch), xmin), xhi = min(__float2int_rd(ux + ch), xmax);
+                bool take = ok && xlo <= xhi;
+                if (g.clip == 1) {
+                    // lanes of the same reference cell walk the UNION of their clipped runs: identical runs advance in lockstep,
+                    // so a record load of the warp touches one line per cell instead of one per lane
+                    const unsigned grp = __ballot_sync(peers, take);
+                    if (!take) { xlo = 0x7fffffff; xhi = -1; }
+                    xlo = __reduce_min_sync(peers, xlo); xhi = __reduce_max_sync(peers, xhi);
+                    take = active && grp != 0u;
+                } else if (g.clip == 0) { xlo = xmin; xhi = xmax; take = active && fz >= 0 && fz < fm2 && fy >= 0 && fy < fm1; }
+                const int *fs = fine_start + (take ? (size_t)fm0 * (size_t)(fy + fm1 * fz) : (size_t)0);
+                if (!take) { xlo = 0; xhi = -1; }
+                q0[ry] = fs[xlo];
+                q1[ry] = fs[xhi + 1];
             }
-            srow = sg.stencil + (size_t)mycell * 32;
+#pragma unroll
+            for (int ry = 0; ry < 6; ry++) {
+                const int n = q1[ry] - q0[ry];
+                if (n > 63) bad = true;
+                else if (n > 0) { sts_u32(rp, (uint32_t)q0[ry] | ((uint32_t)n << 26)); rp += 128; }
+            }
         }
-        auto run_of = [&](int ss) -> int2 {
-            int2 rr = my[ss];
-            if constexpr (SKIP) {
-                const int code = srow[ss], ox = code % 3, oy = (code / 3) % 3, oz = code / 9;
-                const float d2 = (ox == 0 ? d2lo[0] : (ox == 2 ? d2hi[0] : 0.f)) + (oy == 0 ? d2lo[1] : (oy == 2 ? d2hi[1] : 0.f)) +
-                                 (oz == 0 ? d2lo[2] : (oz == 2 ? d2hi[2] : 0.f));
-                if (d2 > sg.limit) rr.y = 0;
-            }
-            return rr;
-        };
-        int *row0 = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
-        int ncq = 0, nsq = 0;          // staged core / skin entries
-        int ncw = 0, nsw = 0;          // entries already written to the table by the spill path
-        bool overflow = false;
-        auto put = [&](int k, int j) {
-            if (k < n_col) row0[(k & 31) * n_col + (k >> 5) * 32] = j; else overflow = true;
-        };
-        // flattened walk over the 27 runs: every lane advances through its own concatenated candidate list, so lanes of
-        // different cells do not wait for each other's cell sizes
-        int s = 0;
-        int2 run = run_of(0), nrun = run_of(1);
-        int q = run.x, n = run.y;
+        __syncwarp();
+        // ---- walk the runs: every lane advances through its own runs (predicated, no divergence), two candidates per
+        //      iteration; hits go to the lane's queue as j | skin << 27 (past NQ hits the last slot is overwritten and the
+        //      row is redone by the fall-back kernel)
+        unsigned rq = rbase;                                   // next run to fetch
+        int q = 0, n = 0, qn = 0;
         while (true) {
-            while (n == 0 && s < 26) { s++; run = nrun; q = run.x; n = run.y; nrun = run_of(min(s + 1, 26)); }
-            if (n == 0) break;
-            if (ncq + nsq > NB_DEPTH - NB_BATCH) {                               // spill path (dense rows only)
-                for (int t = 0; t < ncq; t++) put(ncw + t, qq[t][lane]);
-                for (int t = 0; t < nsq; t++) { if (ncw + ncq + nsw + t < n_col) put(n_col - 1 - (nsw + t), qq[NB_DEPTH - 1 - t][lane]); else overflow = true; }
-                ncw += ncq; nsw += nsq; ncq = 0; nsq = 0;
-            }
-            const int take = min(n, NB_BATCH);
-            float4 v[NB_BATCH];
-#pragma unroll
-            for (int u = 0; u < NB_BATCH; u++) v[u] = cell_xyzj[q + u];       // unconditional (array is padded): 4 loads in flight
-#pragma unroll
-            for (int u = 0; u < NB_BATCH; u++) {
-                const int j = __float_as_int(v[u].w);
-                const float dx = ci.x - v[u].x, dy = ci.y - v[u].y, dz = ci.z - v[u].z;
-                const float dr2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // UM/neigh_build_meso.cu:86-89
-                const bool ok = u < take && j != i;
-                const bool is_core = ok && dr2 <= rc2_core;
-                const bool is_skin = ok && !is_core && dr2 <= rc2_tail;
-                if (is_core | is_skin) qq[is_core ? ncq : NB_DEPTH - 1 - nsq][lane] = j;
-                ncq += is_core ? 1 : 0;
-                nsq += is_skin ? 1 : 0;
-            }
-            q += take; n -= take;
+            if (n <= 0 && rq < rp) { const uint32_t e = lds_u32(rq); rq += 128; q = (int)(e & MQ); n = (int)(e >> 26); }
+            if (!__any_sync(full, n > 0)) break;
+            const bool a0 = n > 0, a1 = n > 1;
+            const float4 c0 = fine_rec[a0 ? q : 0], c1 = fine_rec[a1 ? q + 1 : 0];
+            const float dx0 = ci.x - c0.x, dy0 = ci.y - c0.y, dz0 = ci.z - c0.z;
+            const float dx1 = ci.x - c1.x, dy1 = ci.y - c1.y, dz1 = ci.z - c1.z;
+            const float r0 = __fmaf_rn(dz0, dz0, __fmaf_rn(dy0, dy0, __fmul_rn(dx0, dx0)));   // UM/neigh_build_meso.cu:86-89
+            const float r1 = __fmaf_rn(dz1, dz1, __fmaf_rn(dy1, dy1, __fmul_rn(dx1, dx1)));
+            const bool h0 = a0 && r0 <= rc2_tail, h1 = a1 && r1 <= rc2_tail;
+            stg_u32_if(h0, qbase + (min(qn, NQ - 1) << 5), (__float_as_uint(c0.w) & MJ) | (r0 <= rc2_core ? 0u : 1u << 27));
+            qn += h0 ? 1 : 0;
+            stg_u32_if(h1, qbase + (min(qn, NQ - 1) << 5), (__float_as_uint(c1.w) & MJ) | (r1 <= rc2_core ? 0u : 1u << 27));
+            qn += h1 ? 1 : 0;
+            q += 2; n -= 2;
         }
-        int n_core = ncw + ncq, n_skin = nsw + nsq;
-        if (nsw == 0) {
-            // common path: everything is staged; skin entry s (encounter order) lands at n_core + n_skin - 1 - s
-            if (n_core + n_skin > n_col) overflow = true;
-            for (int t = 0; t < ncq; t++) put(ncw + t, qq[t][lane]);
-            for (int t = 0; t < nsq; t++) put(n_core + n_skin - 1 - t, qq[NB_DEPTH - 1 - t][lane]);
-        } else {
-            for (int t = 0; t < ncq; t++) put(ncw + t, qq[t][lane]);
-            for (int t = 0; t < nsq; t++) { if (n_core + nsw + t < n_col) put(n_col - 1 - (nsw + t), qq[NB_DEPTH - 1 - t][lane]); else overflow = true; }
-            // join (UM/neigh_build_meso.cu:166-200): ascending t is safe even when the ranges overlap (dst(t) < src(t))
-            if (!overflow)
-                for (int t = 0; t < n_skin; t++) pair_table[slot(i, n_core + t, n_col)] = pair_table[slot(i, n_col - n_skin + t, n_col)];
+        bad = bad || qn > NQ;
+        if (bad) qn = 0;
+        __syncwarp();
+        // ---- classify: drop the atom itself (it is always a hit), decide ownership, count the four classes
+        const int qmax = __reduce_max_sync(full, qn);
+        uint32_t cls_cnt = 0;                                  // 4 x 8-bit counters: owned core, owned skin, other core, other skin
+        for (int t = 0; t < qmax; t++) {
+            if (t < qn) {
+                const uint32_t en = qbase[t << 5];
+                const int j = (int)(en & MJ);
+                uint32_t cls = 4;
+                if (j != i) { cls = (owns(i, j, nlocal) ? 0u : 2u) | (en >> 27); cls_cnt += 1u << (8 * cls); }
+                qbase[t << 5] = (uint32_t)j | (cls << 27);
+            }
         }
-        if (overflow) { n_core = min(n_core, n_col); n_skin = 0; atomicOr(&cnt->err, 2); }
-        pair_count[i] = n_core + n_skin;
-        worst = max(worst, n_core + n_skin);
+        const int n0 = cls_cnt & 255, n1 = (cls_cnt >> 8) & 255, n2 = (cls_cnt >> 16) & 255, n3 = cls_cnt >> 24;
+        const int ntot = n0 + n1 + n2 + n3;
+        bad = bad || ntot > n_col;
+        if (active) {
+            if (bad) { pair_count[i] = -1; atomicOr(fixup, 1); }
+            else { pair_count[i] = ntot; owned_count[i] = n0 + n1; core_split[i] = n0 | (n2 << 16); }
+        }
+        worst = max(worst, bad ? 0 : ntot);
+        // ---- write-out: the four segments, each in encounter order
+        uint32_t pos = (uint32_t)n0 << 8 | (uint32_t)(n0 + n1) << 16 | (uint32_t)(n0 + n1 + n2) << 24;   // running position of each class
+        int *row0 = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
+        for (int t = 0; t < qmax; t++) {
+            if (t < qn && !bad) {
+                const uint32_t en = qbase[t << 5];
+                const uint32_t cls = en >> 27;
+                if (cls < 4) {
+                    const int sh = cls * 8;
+                    const int k = (pos >> sh) & 255;
+                    pos += 1u << sh;
+                    row0[(k & 31) * n_col + (k >> 5) * 32] = (int)(en & MJ);
+                }
+            }
+        }
+        __syncwarp();
     }
     // diagnostics only
-#pragma unroll
-    for (int o = 16; o; o >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    worst = __reduce_max_sync(full, worst);
     if ((threadIdx.x & 31) == 0 && worst > 0) atomicMax(&cnt->max_pair, worst);
 }
 
-// ------------------------------------------------------------------ build, one warp per cell (default)
-// The thread-per-atom kernel above spends ~38 issue slots and ~10 L1 tag lookups per distance test: every lane
-// walks its own cell's candidate runs, so each float4 load touches ~10 different 128-byte lines and every hit is a
-// predicated shared-memory push.  Here a warp owns one cell and the roles are swapped, as in the reference
-// (UM/neigh_build_meso.cu:58-117), but without its shared counters, sentinel, join and transpose passes:
-//   fetch : lanes = 32 consecutive CANDIDATES of the cell's concatenated stencil list (the non-empty runs in stencil
-//           order).  The run of position t comes from one warp OR-reduction per chunk: bit (start_k - t0) of M marks the
-//           runs starting inside the chunk, so k(t0 + lane) = #runs before t0 + popc(M & lanemask_le) - 1.  One
-//           coalesced 16-byte load per candidate; two chunks are held in registers as packed pairs.
-//   test  : the cell's own atoms (<= 32 per pass) are broadcast one by one from shared memory; the distance test of two
-//           candidates is 6 packed fp32x2 instructions (FADD2/FMUL2/FFMA2: same IEEE operations in the same order as
-//           the scalar chain) and the 32 results of a chunk become two ballots (r <= r_n, r <= r_n - skin), stored by
-//           lane 0: ~0.3 issue slots per test and no per-hit memory traffic.
-//   count : lane m clears its own bit (j != i), prefix-sums its ballots over the chunks and publishes the row totals.
-//   emit  : the (atom, chunk) ballots are spread over all 32 lanes (32/pow2(n) lanes per atom); every entry goes straight
-//           to its final slot of the tile-transposed table: core entries ascending from slot 0, skin entries in reverse
-//           encounter order behind them -- bit-identical rows, counts and layout.
-// Cells whose candidate list exceeds the shared-memory window (local density >~ 1.5x the mean) are marked and rebuilt by
-// the thread-per-atom kernel in fix-up mode, so capacity never changes results.
-constexpr int NC_WARPS = 4;
-
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+// Fall-back for the rows the kernel above marked (a fine row longer than 63 records, more than NQ neighbors): plain walk
+// of all 6 x 6 fine rows of the 27 stencil cells, unclipped, two passes (count the classes, then write).  Also the whole build
+// when MESO_NB_SLOW=1 (A/B checks of the kernel above).
+__global__ void __launch_bounds__(128) k_build_rows_slow(const float4 *__restrict__ coord4, const int *__restrict__ cellc,
+                                                         const int *__restrict__ fine_start, const float4 *__restrict__ fine_rec,
+                                                         int *__restrict__ pair_count, int *__restrict__ owned_count,
+                                                         int *__restrict__ core_split, int *__restrict__ pair_table,
+                                                         Counts *__restrict__ cnt, const int *__restrict__ fixup, int all_rows, int n_col,
+                                                         float rc2_core, float rc2_tail, int m0, int m1, int m2)
 {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
-{
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-
-// shared memory per warp: 1408 B + 16 B x t_cap
-//   mxy[32]  float4 {x, x, y, y}    mz[32] float2 {z, z}    mi[32] int (atom index of member m)
-//   tot[32]  int2 {n_core, n_tot}    cfirst[32], coffs[32] int (non-empty runs)
-//   masks[m][pair] uint4 {within A, core A, within B, core B}      (8 B x t_cap)
-//   pre[m][chunk]  uint {core entries before the chunk | skin entries before the chunk << 16}   (4 B x t_cap)
-//   candj[t] int                                                                               (4 B x t_cap)
-__global__ void __launch_bounds__(NC_WARPS * 32) k_build_neighbors_cell(const int *__restrict__ cell_start, const int2 *__restrict__ runs,
-                                                                        const float4 *__restrict__ cell_xyzj,
-                                                                        int *__restrict__ pair_count, int *__restrict__ pair_table,
-                                                                        Counts *__restrict__ cnt, int *__restrict__ fixup, int ncell,
-                                                                        int n_col, float rc2_core, float rc2_tail, int t_cap)
-{
-    extern __shared__ __align__(16) unsigned char nb_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int npair_cap = t_cap >> 6;                                 // chunk pairs per member row
-    unsigned char *base = nb_smem + ((size_t)1408 + (size_t)16 * t_cap) * wid;
-    float4 *mxy = reinterpret_cast<float4 *>(base);
-    float2 *mz = reinterpret_cast<float2 *>(base + 512);
-    int *mis = reinterpret_cast<int *>(base + 768);
-    int2 *tot = reinterpret_cast<int2 *>(base + 896);
-    int *cfirst = reinterpret_cast<int *>(base + 1152);
-    int *coffs = reinterpret_cast<int *>(base + 1280);
-    uint4 *masks = reinterpret_cast<uint4 *>(base + 1408);
-    unsigned *pre = reinterpret_cast<unsigned *>(base + 1408 + (size_t)8 * t_cap);
-    int *candj = reinterpret_cast<int *>(base + 1408 + (size_t)12 * t_cap);
-    const unsigned full = 0xffffffffu, le = 0xffffffffu >> (31 - lane);
+    if (!all_rows && *fixup == 0) return;
     const int nlocal = cnt->nlocal;
-    int worst = 0;
-    for (int c = blockIdx.x * NC_WARPS + wid; c < ncell; c += gridDim.x * NC_WARPS) {
-        const int cs = cell_start[c], nc = cell_start[c + 1] - cs;
-        if (nc == 0) continue;
-        // atoms of a cell are in ascending index order and locals precede ghosts: a cell whose first atom is a ghost has no rows
-        if (__float_as_int(cell_xyzj[cs].w) >= nlocal) continue;
-        // ---- the cell's stencil runs, compacted to the non-empty ones (stencil order kept)
-        const int2 run = lane < 27 ? runs[(size_t)c * 27 + lane] : make_int2(0, 0);
-        int incl = run.y;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(full, incl, o);
-            if (lane >= o) incl += y;
+    const int fm0 = 2 * m0, fm1 = 2 * m1, fm2 = 2 * m2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+        if (!all_rows && pair_count[i] >= 0) continue;
+        const float4 ci = coord4[i];
+        const int cc = cellc[i];
+        const int cx = cc & 1023, cy = (cc >> 10) & 1023, cz = cc >> 20;
+        const int xlo = max(0, 2 * (cx - 1)), xhi = min(fm0 - 1, 2 * cx + 3);
+        int num[4] = {0, 0, 0, 0}, pos[4] = {0, 0, 0, 0};
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1) { pos[0] = 0; pos[1] = num[0]; pos[2] = num[0] + num[1]; pos[3] = num[0] + num[1] + num[2]; }
+            for (int fz = max(0, 2 * (cz - 1)); fz <= min(fm2 - 1, 2 * cz + 3); fz++)
+                for (int fy = max(0, 2 * (cy - 1)); fy <= min(fm1 - 1, 2 * cy + 3); fy++) {
+                    const int *fs = fine_start + (size_t)fm0 * (size_t)(fy + fm1 * fz);
+                    for (int p = fs[xlo]; p < fs[xhi + 1]; p++) {
+                        const float4 c2 = fine_rec[p];
+                        const int j = __float_as_int(c2.w);
+                        if (j == i) continue;
+                        const float dx = ci.x - c2.x, dy = ci.y - c2.y, dz = ci.z - c2.z;
+                        const float dr2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                        if (!(dr2 <= rc2_tail)) continue;
+                        const int cls = (owns(i, j, nlocal) ? 0 : 2) | (dr2 <= rc2_core ? 0 : 1);
+                        if (pass == 0) num[cls]++;
+                        else { const int k = pos[cls]++; if (k < n_col) pair_table[slot(i, k, n_col)] = j; }
+                    }
+                }
         }
-        const int T = __shfl_sync(full, incl, 31);
-        const unsigned nonempty = __ballot_sync(full, run.y > 0);
-        const int nne = __popc(nonempty);
-        __syncwarp();
-        if (run.y > 0) {
-            const int k = __popc(nonempty & (le >> 1));
-            cfirst[k] = run.x - (incl - run.y);                       // first position minus list offset
-            coffs[k] = incl - run.y;
+        int tot = num[0] + num[1] + num[2] + num[3];
+        if (tot > n_col) {                                   // row wider than the table: flagged, clipped (UM/neigh_build_meso.cu:242-252 only printf's)
+            atomicOr(&cnt->err, 2);
+            tot = n_col; num[0] = min(num[0], n_col); num[1] = min(num[1], n_col - num[0]); num[2] = min(num[2], n_col - num[0] - num[1]);
         }
-        __syncwarp();
-        // lane k keeps the list offset of the k-th non-empty run (strictly increasing); lanes >= nne: never inside a chunk
-        const int coff = lane < nne ? coffs[lane] : 0x3fffffff;
-        const unsigned ownb = __ballot_sync(full, run.y > 0 && run.x == cs);
-        const int own_off = __shfl_sync(full, incl - run.y, (__ffs(ownb) - 1) & 31);
-        const bool too_long = T > t_cap;                              // falls back to the thread-per-atom kernel
-        const int nch = too_long ? 0 : (T + 31) >> 5, ncp = (nch + 1) >> 1;
-        __syncwarp();
-        for (int m0 = 0; m0 < nc; m0 += 32) {
-            const int ng = min(32, nc - m0);
-            float4 me = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
-            if (lane < ng) me = cell_xyzj[cs + m0 + lane];
-            const int mi = __float_as_int(me.w);
-            mxy[lane] = make_float4(me.x, me.x, me.y, me.y);
-            mz[lane] = make_float2(me.z, me.z);
-            mis[lane] = mi;
-            __syncwarp();
-            if (too_long) {
-                if (lane < ng && mi < nlocal) { pair_count[mi] = -1; *fixup = 1; }
-                continue;
-            }
-            // ---- fetch + test, two chunks (A, B) per pass
-            int nb = 0;                                               // runs starting before the current chunk
-            for (int cp = 0; cp < ncp; cp++) {
-                unsigned long long nx, ny, nz;                        // packed negated candidate coordinates {A, B}
-                {
-                    float4 cd[2];
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int t0 = (2 * cp + h) * 32, t = t0 + lane;
-                        const unsigned d = (unsigned)(coff - t0);
-                        const unsigned M = __reduce_or_sync(full, d < 32u ? 1u << d : 0u);
-                        const int k = nb + __popc(M & le) - 1;
-                        nb += __popc(M);
-                        cd[h] = make_float4(3.0e18f, 3.0e18f, 3.0e18f, __int_as_float(-1));
-                        if (t < T) cd[h] = cell_xyzj[cfirst[k] + t];
-                        candj[t] = __float_as_int(cd[h].w);
+        pair_count[i] = tot; owned_count[i] = num[0] + num[1]; core_split[i] = num[0] | (num[2] << 16);
+        atomicMax(&cnt->max_pair, tot);
+    }
+}
+
+// ------------------------------------------------------------------ the reference's row order, on demand (exports)
+// core entries in stencil order (neighbor cells by (boundary flag, Morton), ascending atom index inside a cell), then the
+// skin entries in REVERSE stencil order (UM/neigh_build_meso.cu:58-117,166-200).  key = slot rank of j's cell << 27 | j.
+__global__ void __launch_bounds__(128) k_canonical_rows(const int *__restrict__ cellc, const unsigned char *__restrict__ slotrank,
+                                                        const int *__restrict__ pair_count, const int *__restrict__ owned_count,
+                                                        const int *__restrict__ core_split, const int *__restrict__ pair_table,
+                                                        int *__restrict__ out_table, const Counts *__restrict__ cnt, int n_col, int m0, int m1)
+{
+    const int nlocal = cnt->nlocal;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+        const int np = pair_count[i], nown = owned_count[i], cs = core_split[i];
+        const int n_oc = cs & 0xffff, n_nc = cs >> 16;
+        const int cc = cellc[i];
+        const int cx = cc & 1023, cy = (cc >> 10) & 1023, cz = cc >> 20;
+        const unsigned char *inv = slotrank + (size_t)(cx + m0 * (cy + m1 * cz)) * 32;
+        auto key_of = [&](int j) -> uint32_t {
+            const int cj = cellc[j];
+            const int code = ((cj & 1023) - cx + 1) + 3 * (((cj >> 10) & 1023) - cy + 1) + 9 * ((cj >> 20) - cz + 1);
+            return ((uint32_t)inv[code] << 27) | (uint32_t)j;
+        };
+        // insertion sort of one class straight into the output row: class 0 = core -> [0, ncore) ascending keys,
+        // class 1 = skin -> [ncore, np) descending keys
+        const int ncore = n_oc + n_nc;
+        for (int cls = 0; cls < 2; cls++) {
+            const int dst0 = cls ? ncore : 0;
+            int cntk = 0;
+            for (int seg = 0; seg < 2; seg++) {
+                // the two segments of this class in the production row: owned part, then other part
+                const int a = cls == 0 ? (seg == 0 ? 0 : nown) : (seg == 0 ? n_oc : nown + n_nc);
+                const int b = cls == 0 ? (seg == 0 ? n_oc : nown + n_nc) : (seg == 0 ? nown : np);
+                for (int k = a; k < b; k++) {
+                    const int j = pair_table[slot(i, k, n_col)];
+                    const uint32_t key = key_of(j);
+                    int p = cntk++;
+                    while (p > 0) {
+                        const int jp = out_table[slot(i, dst0 + p - 1, n_col)];
+                        const uint32_t kp = key_of(jp);
+                        if (cls == 0 ? kp > key : kp < key) { out_table[slot(i, dst0 + p, n_col)] = jp; p--; } else break;
                     }
-                    nx = pack2(-cd[0].x, -cd[1].x); ny = pack2(-cd[0].y, -cd[1].y); nz = pack2(-cd[0].z, -cd[1].z);
-                }
-                uint4 *mrow = masks + cp;
-#pragma unroll 4
-                for (int m = 0; m < ng; m++) {
-                    const float4 a = mxy[m];
-                    const float2 zz = mz[m];
-                    const unsigned long long dx = add2(pack2(a.x, a.y), nx), dy = add2(pack2(a.z, a.w), ny), dz = add2(pack2(zz.x, zz.y), nz);
-                    const unsigned long long r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));       // UM/neigh_build_meso.cu:86-89
-                    float rA, rB;
-                    unpack2(r2, rA, rB);
-                    uint4 bb;
-                    bb.x = __ballot_sync(full, rA <= rc2_tail); bb.y = __ballot_sync(full, rA <= rc2_core);
-                    bb.z = __ballot_sync(full, rB <= rc2_tail); bb.w = __ballot_sync(full, rB <= rc2_core);
-                    if (lane == 0) mrow[m * npair_cap] = bb;
+                    out_table[slot(i, dst0 + p, n_col)] = j;
                 }
             }
-            __syncwarp();
-            // ---- count: lane = member; clear my own bit, prefix over chunks, totals
-            if (lane < ng) {
-                const int ts = own_off + m0 + lane;                   // my own position in the candidate list (j != i)
-                int ncore = 0, nskin = 0;
-                for (int cp = 0; cp < ncp; cp++) {
-                    uint4 bb = masks[lane * npair_cap + cp];
-                    if ((ts >> 6) == cp) {
-                        const unsigned bit = ~(1u << (ts & 31));
-                        if (ts & 32) { bb.z &= bit; bb.w &= bit; } else { bb.x &= bit; bb.y &= bit; }
-                        masks[lane * npair_cap + cp] = bb;
-                    }
-                    pre[lane * (2 * npair_cap) + 2 * cp] = (unsigned)ncore | ((unsigned)nskin << 16);
-                    ncore += __popc(bb.y); nskin += __popc(bb.x & ~bb.y);
-                    pre[lane * (2 * npair_cap) + 2 * cp + 1] = (unsigned)ncore | ((unsigned)nskin << 16);
-                    ncore += __popc(bb.w); nskin += __popc(bb.z & ~bb.w);
-                }
-                int n_tot = ncore + nskin;
-                if (mi < nlocal) {
-                    if (n_tot > n_col) { atomicOr(&cnt->err, 2); n_tot = -min(ncore, n_col) - 1; }   // overflow: core entries only (as above)
-                    pair_count[mi] = n_tot < 0 ? -n_tot - 1 : n_tot;
-                    worst = max(worst, n_tot < 0 ? -n_tot - 1 : n_tot);
-                }
-                tot[lane] = make_int2(ncore, n_tot);
-            }
-            __syncwarp();
-            // ---- emit: the ng x nch (member, chunk) ballots are dealt round-robin to the 32 lanes; a lane pops one entry
-            //      per iteration and refills from its next item when its ballot is exhausted, so the warp runs
-            //      max_lane(entries) iterations whatever the distribution of hits over chunks
-            {
-                const int nitems = ng * nch;
-                int item = lane;
-                int ch = (int)((float)lane * (1.0f / (float)ng) + 1.0e-4f), m = lane - ch * ng;   // lane = ch * ng + m (exact for lane < 32)
-                const int dch = 32 / ng, dm = 32 - dch * ng;                                        // advance of (ch, m) per 32 items
-                unsigned hits = 0, corem = 0;
-                int kc = 0, ks = 0;
-                int *row0 = pair_table;
-                const int *cj = candj;
-                while (true) {
-                    if (hits == 0) {
-                        if (item >= nitems) break;
-                        const int am = mis[m];
-                        const int2 tt = tot[m];
-                        const uint2 mk = reinterpret_cast<const uint2 *>(masks + m * npair_cap + (ch >> 1))[ch & 1];
-                        const unsigned pw = pre[m * (2 * npair_cap) + ch];
-                        const bool overflow = tt.y < 0;
-                        const int n_tot = overflow ? -tt.y - 1 : tt.y;
-                        kc = pw & 0xffffu; ks = n_tot - 1 - (int)(pw >> 16);
-                        corem = mk.y;
-                        hits = am < nlocal ? (overflow ? mk.y & ((kc < n_col) ? 0xffffffffu : 0u) : mk.x) : 0u;
-                        if (overflow && hits) {                                   // keep the first n_col core entries only
-                            while (kc + __popc(hits) > n_col) hits &= ~(0x80000000u >> __clz(hits));
-                        }
-                        row0 = pair_table + (size_t)(am & ~31) * (size_t)n_col + (am & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
-                        cj = candj + ch * 32;
-                        item += 32; ch += dch; m += dm;
-                        if (m >= ng) { m -= ng; ch++; }
-                        continue;
-                    }
-                    const int b = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const bool is_core = (corem >> b) & 1u;
-                    const int k = is_core ? kc : ks;
-                    kc += is_core ? 1 : 0; ks -= is_core ? 0 : 1;
-                    row0[(k & 31) * n_col + (k & ~31)] = cj[b];
-                }
-            }
-            __syncwarp();
         }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) worst = max(worst, __shfl_xor_sync(full, worst, o));
-    if (lane == 0 && worst > 0) atomicMax(&cnt->max_pair, worst);
 }
 
 // ------------------------------------------------------------------ host drivers
@@ -490,69 +523,105 @@ int launch_setup_bins(meso_ctx *ctx)
         box.m[d] = std::max((int)(dim[d] * inv), 1) + 2;
         box.binsize[d] = dim[d] / (box.m[d] - 2);
         box.bininv[d] = 1.0 / box.binsize[d];
+        if (box.m[d] > 1023) { ctx->err = "setup_bins: more than 1023 cells per dimension"; return MESO_EINVAL; }
     }
     box.ncell = box.m[0] * box.m[1] * box.m[2];
-    if (!ctx->stencil.reserve((size_t)box.ncell * 32) || !ctx->cell_start.reserve((size_t)box.ncell + 2)) {
+    const size_t nfine = (size_t)box.ncell * 8;
+    if (nfine + 2 > (size_t)0x7fffffff) { ctx->err = "setup_bins: fine lattice too large"; return MESO_EINVAL; }
+    if (!ctx->stencil.reserve((size_t)box.ncell * 32) || !ctx->slotrank.reserve((size_t)box.ncell * 32) ||
+        !ctx->cell_start.reserve((size_t)box.ncell + 2) || !ctx->cell_cnt.reserve(nfine + 8) ||
+        !ctx->fine_start.reserve(nfine + 2) || !ctx->scan_sums.reserve((nfine + SCAN_TILE - 1) / SCAN_TILE + 8)) {
         ctx->err = "setup_bins: out of device memory";
         return MESO_ECUDA;
     }
-    k_stencil_codes<<<(box.ncell + 127) / 128, 128, 0, LS(ctx->stream)>>>(ctx->stencil.p, box);
+    k_stencil_codes<<<(box.ncell + 127) / 128, 128, 0, LS(ctx->stream)>>>(ctx->stencil.p, ctx->slotrank.p, box);
     MESO_CUDA(cudaGetLastError());
     ctx->bins_ready = true;
     return MESO_OK;
 }
 
+static void scan_into(meso_ctx *ctx, const int *in, int *out, int n)
+{
+    const int nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_sums<<<nblk, SCAN_T, 0, LS(ctx->stream)>>>(in, ctx->scan_sums.p, n);
+    k_scan_top<<<1, 1024, 0, LS(ctx->stream)>>>(ctx->scan_sums.p, nblk);
+    k_scan_apply<<<nblk, SCAN_T, 0, LS(ctx->stream)>>>(in, out, ctx->scan_sums.p, n);
+}
+
 int launch_neighbor_build(meso_ctx *ctx)
 {
     const Box &box = ctx->box;
-    SoA3c x; for (int d = 0; d < 3; d++) x.c[d] = ctx->x[d].p;
-    k_cell_id<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(x, ctx->cell_key.p, ctx->cell_atoms.p, ctx->cell_of.p, ctx->d_counts, box);
-    int bits = 1;
-    while ((1 << bits) < box.ncell) bits++;                 // ceil(log2(ncell)), UM/neighbor_meso.cu:541
-    int rc = sort_pairs_u64(ctx, ctx->cell_key, ctx->cell_atoms, &ctx->d_counts->nall, ctx->cap, bits);
-    if (rc) return rc;
-    if (!ctx->cell_xyzj.reserve(ctx->cap + 8) || !ctx->cell_runs.reserve((size_t)box.ncell * 27)) { ctx->err = "neighbor: out of device memory"; return MESO_ECUDA; }
-    k_cell_bounds<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(ctx->cell_key.p, ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_start.p, ctx->cell_xyzj.p,
-                                                          ctx->d_counts, box.ncell);
-    k_cell_runs<<<(box.ncell * 27 + 255) / 256, 256, 0, LS(ctx->stream)>>>(ctx->stencil.p, ctx->cell_start.p, ctx->cell_runs.p, box);
-    float rc2_core = (float)pow(ctx->cutneighmax - ctx->skin, 2.0);   // UM/neigh_build_meso.cu:296-297
-    float rc2_tail = (float)pow(ctx->cutneighmax, 2.0);
-    const bool per_atom = ctx->nb_per_atom;
-    int grid_atoms = std::max(1, std::min((int)((nlocal_bound(ctx) + 127) / 128) + 1, ctx->sm_count * 4096));
-    if (!per_atom) {
-        // candidate window per cell: 1.25x the expected stencil population (+64), whole chunk pairs
-        double cellvol = box.binsize[0] * box.binsize[1] * box.binsize[2], vol = 1.0;
-        for (int d = 0; d < 3; d++) vol *= box.subhi[d] - box.sublo[d];
-        const double t_exp = 27.0 * cellvol * std::max(ctx->nlocal_host / vol, 1.0);
-        int t_cap = ((int)(1.25 * t_exp) + 64 + 63) / 64 * 64;
-        t_cap = std::max(256, std::min(t_cap, 2048));
-        if (const char *e = getenv("MESO_NB_TCAP")) t_cap = std::max(64, atoi(e) / 64 * 64);      // tests: force the fix-up path
-        const size_t sh = (size_t)NC_WARPS * (1408 + (size_t)16 * t_cap);
-        static size_t sh_set = 0;
-        if (sh > sh_set) {
-            MESO_CUDA(cudaFuncSetAttribute(k_build_neighbors_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-            sh_set = sh;
-        }
-        if (!ctx->nb_fixup.reserve(1)) { ctx->err = "neighbor: out of device memory"; return MESO_ECUDA; }
-        MESO_CUDA(cudaMemsetAsync(ctx->nb_fixup.p, 0, sizeof(int), ctx->stream));
-        const int grid = std::max(1, std::min((box.ncell + NC_WARPS - 1) / NC_WARPS, ctx->sm_count * 64));
-        k_build_neighbors_cell<<<grid, NC_WARPS * 32, sh, LS(ctx->stream)>>>(ctx->cell_start.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
-                                                                        ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p, box.ncell, ctx->n_col,
-                                                                        rc2_core, rc2_tail, t_cap);
-        k_build_neighbors<64, 4><<<grid_atoms, 128, 0, LS(ctx->stream)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p,
-                                                                   ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, ctx->nb_fixup.p);
-    } else {
-#define MESO_NB_ARGS ctx->coord4.p, ctx->cell_of.p, ctx->cell_runs.p, ctx->cell_xyzj.p, ctx->pair_count.p, ctx->pair_table.p, ctx->d_counts, ctx->n_col, rc2_core, rc2_tail, nullptr
-        if (ctx->nb_skip) {
-            SkipGeom sg;
-            for (int d = 0; d < 3; d++) { sg.lo[d] = (float)(box.sublo[d] - box.centre[d]); sg.bs[d] = (float)box.binsize[d]; sg.m[d] = box.m[d]; }
-            sg.stencil = ctx->stencil.p;
-            sg.limit = rc2_tail * 1.002f;                           // (1.001 r_n)^2
-            k_build_neighbors<48, 4, true><<<grid_atoms, 128, 0, LS(ctx->stream)>>>(MESO_NB_ARGS, sg);
-        } else
-        k_build_neighbors<48, 4><<<grid_atoms, 128, 0, LS(ctx->stream)>>>(MESO_NB_ARGS);   // 48 slots: 9 CTAs/SM; 40 spills too often, 56+ loses occupancy (measured)
-#undef MESO_NB_ARGS
+    const int ncell = box.ncell, nfine = 8 * ncell;
+    if (ctx->cap + 8 > (size_t)MQ) { ctx->err = "neighbor build: more than 2^26 atoms + ghosts on one GPU"; return MESO_EINVAL; }
+    // persistent grid of the build kernel: the hit queues of its warps live in a global scratch buffer
+    const int build_grid = ctx->sm_count * 9;                 // 56 registers x 128 threads: 9 CTAs per SM, one wave
+    if (!ctx->fine_rec.reserve(ctx->cap + 8) || !ctx->fine_of.reserve(ctx->cap) || !ctx->owned_count.reserve(ctx->cap) ||
+        !ctx->core_split.reserve(ctx->cap) || !ctx->nb_fixup.reserve(1) ||
+        !ctx->nb_scratch.reserve((size_t)build_grid * (NF_THREADS / 32) * NQ * 32)) {
+        ctx->err = "neighbor: out of device memory";
+        return MESO_ECUDA;
     }
+    cudaStream_t st = ctx->stream;
+    int *fine_cnt = ctx->cell_cnt.p;
+    MESO_CUDA(cudaMemsetAsync(fine_cnt, 0, sizeof(int) * (size_t)nfine, st));
+    MESO_CUDA(cudaMemsetAsync(ctx->nb_fixup.p, 0, sizeof(int), st));
+    SoA3c x; for (int d = 0; d < 3; d++) x.c[d] = ctx->x[d].p;
+    k_bin_count<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(x, ctx->cell_of.p, ctx->fine_of.p, fine_cnt, ctx->d_counts, box);
+    scan_into(ctx, fine_cnt, ctx->fine_start.p, nfine);
+    k_fine_fill<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->coord4.p, ctx->fine_of.p, ctx->fine_start.p + 1, ctx->fine_rec.p, ctx->d_counts);
+    k_fine_order<<<(nfine + 127) / 128, 128, 0, LS(st)>>>(ctx->fine_start.p, ctx->fine_rec.p, nfine);
+    ctx->cells_valid = false;                               // the reference cell lists are rebuilt on demand (meso_export_cells)
+    const float rc2_core = (float)pow(ctx->cutneighmax - ctx->skin, 2.0);   // UM/neigh_build_meso.cu:296-297
+    const float rc2_tail = (float)pow(ctx->cutneighmax, 2.0);
+    FineGeom g;
+    double ext = 0;
+    for (int d = 0; d < 3; d++) {
+        g.lat_lo[d] = (float)((box.sublo[d] - box.binsize[d]) - box.centre[d]);
+        g.w[d] = (float)(0.5 * box.binsize[d]);
+        g.inv_w[d] = (float)(2.0 * box.bininv[d]);
+        g.m[d] = box.m[d];
+        ext = std::max(ext, box.subhi[d] - box.sublo[d] + 2.0 * box.binsize[d]);
+    }
+    const double margin = 1.0e-3 + 4.0e-6 * ext;            // fp32 rounding of the fine coordinates is ~1e-7 * extent
+    g.R2 = (float)pow(ctx->cutneighmax + margin, 2.0);
+    g.clip = ctx->nb_clip;
+    const int slow_grid = std::max(1, std::min((int)((nlocal_bound(ctx) + 127) / 128) + 1, ctx->sm_count * 64));
+    if (!ctx->nb_slow)
+        k_build_rows<<<build_grid, NF_THREADS, 0, LS(st)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->fine_start.p, ctx->fine_rec.p, ctx->pair_count.p,
+                                                           ctx->owned_count.p, ctx->core_split.p, ctx->pair_table.p, ctx->d_counts,
+                                                           ctx->nb_fixup.p, ctx->nb_scratch.p, ctx->n_col, rc2_core, rc2_tail, g);
+    k_build_rows_slow<<<slow_grid, 128, 0, LS(st)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->fine_start.p, ctx->fine_rec.p, ctx->pair_count.p,
+                                                     ctx->owned_count.p, ctx->core_split.p, ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p,
+                                                     ctx->nb_slow ? 1 : 0, ctx->n_col, rc2_core, rc2_tail, box.m[0], box.m[1], box.m[2]);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
+// atoms in (cell, ascending index) order and the first position of every cell, as binning_meso leaves them
+// (UM/neighbor_meso.cu:535-711): built from the cell coordinates of the last rebuild, when an export asks for them
+int launch_cell_lists(meso_ctx *ctx)
+{
+    if (ctx->cells_valid) return MESO_OK;
+    const Box &box = ctx->box;
+    const int ncell = box.ncell;
+    cudaStream_t st = ctx->stream;
+    int *cell_cnt = ctx->cell_cnt.p;                         // the fine histogram is dead once the table is built
+    MESO_CUDA(cudaMemsetAsync(cell_cnt, 0, sizeof(int) * (size_t)ncell, st));
+    k_cell_hist<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->cell_of.p, cell_cnt, ctx->d_counts, box.m[0], box.m[1]);
+    scan_into(ctx, cell_cnt, ctx->cell_start.p, ncell);
+    k_bin_fill<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->cell_of.p, ctx->cell_start.p + 1, ctx->cell_atoms.p, ctx->d_counts, box.m[0], box.m[1]);
+    k_cell_order<<<(ncell + 127) / 128, 128, 0, LS(st)>>>(ctx->cell_start.p, ctx->cell_atoms.p, ncell);
+    MESO_CUDA(cudaGetLastError());
+    ctx->cells_valid = true;
+    return MESO_OK;
+}
+
+// the table in the reference's row order, for meso_export_pair_table
+int launch_canonical_rows(meso_ctx *ctx, int *out_table)
+{
+    k_canonical_rows<<<grid_for(ctx, 8), 128, 0, LS(ctx->stream)>>>(ctx->cell_of.p, ctx->slotrank.p, ctx->pair_count.p, ctx->owned_count.p,
+                                                                   ctx->core_split.p, ctx->pair_table.p, out_table, ctx->d_counts, ctx->n_col,
+                                                                   ctx->box.m[0], ctx->box.m[1]);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

@@ -229,10 +229,10 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_dpd(const float4 *__restrict__
 // separate runs of TEA + Box-Muller + force.  Every term of the pair force is antisymmetric bit for bit in
 // (i,j): d = r_i - r_j negates exactly, rsq, rinv, d.dv and the Gaussian (keyed on (max,min) of the two
 // signatures) are identical from both sides -- so F_ji == -F_ij to the last bit and one evaluation serves both
-// atoms.  The full, reference-ordered table stays the only list; a lane owns the pair (i,j), j local, iff
+// atoms.  The full table stays the only list; row i owns the pair (i,j), j local, iff
 //      (i+j) odd ? i < j : i > j          (balanced: every atom owns ~half of its in-range neighbors)
 // and pairs with a ghost j are always evaluated by i (the ghost's owner evaluates the mirror pair itself,
-// exactly as before: no reverse communication).  The j side is updated with ONE 16-byte vector reduction
+// exactly as before: no reverse communication).  The build stores the owned entries as a prefix of the row.  The j side is updated with ONE 16-byte vector reduction
 // (red.global.add.v4.f32 -> REDG.E.ADD.F32x4, resolved in L2) into a float4 accumulator per atom that the
 // integrator consumes and clears; the fp64 style reduces into the fp64 force arrays (REDG.E.ADD.F64).
 // Only the order of the fp32 additions differs from the two-sided kernel (each addend is bit-identical).
@@ -257,7 +257,7 @@ __device__ __forceinline__ int lds32(unsigned addr) { int v; asm volatile("ld.sh
 template <typename REAL, bool ONE_TYPE, bool POW1, int GMODE>
 __global__ void __launch_bounds__(PAIR_THREADS) k_dpd_once(cudaTextureObject_t tex_c, cudaTextureObject_t tex_v,
                                                            const float4 *__restrict__ coord4, const float4 *__restrict__ veloc4,
-                                                           const int *__restrict__ pair_count, const int *__restrict__ pair_table,
+                                                           const int *__restrict__ owned_count, const int *__restrict__ pair_table,
                                                            float4 *__restrict__ facc, SoA3 f, const REAL *__restrict__ coeff,
                                                            const Coef1<REAL> k1, const Counts *__restrict__ cnt, int n_col, int n_type,
                                                            REAL dt_inv_sqrt, int range, int far)
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_dpd_once(cudaTextureObject_t t
         // lanes of a warp read the same 16 bytes (one L1 tag lookup instead of a scattered line each)
         const int self = active ? i : far;
         const float4 c1 = coord4[self], v1 = veloc4[self];
-        const int n_pair = active ? pair_count[i] : 0;
+        const int n_pair = active ? owned_count[i] : 0;      // length of the owned prefix of the row
         const int nmax = __reduce_max_sync(full, n_pair);
         const REAL *cf1 = cf + (ONE_TYPE ? 0 : __float_as_uint(c1.w) * n_type * NCOEFF);
         REAL fx = 0, fy = 0, fz = 0;
@@ -359,20 +359,16 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_dpd_once(cudaTextureObject_t t
         };
 
         // ---- scan: SCAN_CHUNK slots per step; slot(k) = tp[(k&31)*n_col + (k>>5)*32], walked with one running pointer.
-        // Ownership and validity fold into one sign test: d = j - i, key = d + (d << 31) = d * 0x80000001 has the sign bit
-        // (d odd ? d > 0 : d < 0); nlocal-1-j is negative for ghosts; k - n_pair is negative inside the row.
+        // The build (neighbor.cu) puts the entries this row owns -- ghost j, or (i+j) odd ? i<j : i>j -- at the front of
+        // the row, so the scan covers the owned prefix only and needs no ownership test.
         const int *pk = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);
-        const unsigned key_c = 0u - (unsigned)i * 0x80000001u;
-        const int nlm1 = nlocal - 1;
         auto load_chunk = [&](int k0, int (&jj)[SCAN_CHUNK]) {
             if (k0 < nmax) {
                 const int kn = k0 - n_pair;
 #pragma unroll
                 for (int u = 0; u < SCAN_CHUNK; u++) {
                     const int j = __ldcs(pk + (ptrdiff_t)u * n_col);
-                    const unsigned key = (unsigned)j * 0x80000001u + key_c;
-                    const int take = (int)((key | (unsigned)(nlm1 - j)) & (unsigned)(kn + u));
-                    jj[u] = take < 0 ? j : far;
+                    jj[u] = (kn + u) < 0 ? j : far;
                 }
                 pk += step4;
                 if (((k0 + SCAN_CHUNK) & 31) == 0) pk += wrap;
@@ -520,7 +516,7 @@ static int launch_pair_once_t(meso_ctx *ctx, const REAL *coeff, REAL dtis, int r
     grid = std::max(1, std::min(grid, ctx->sm_count * 4096));
     bool pow1 = true;
     for (int t = 0; t < nt * nt; t++) pow1 = pow1 && ctx->coeff[(size_t)t * NCOEFF + P_EXPW] == 1.0;
-#define MESO_ONCE_ARGS ctx->tex_coord, ctx->tex_veloc, ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, ctx->facc.p, f, coeff, k1, ctx->d_counts, ctx->n_col, nt, dtis, range, (int)ctx->cap
+#define MESO_ONCE_ARGS ctx->tex_coord, ctx->tex_veloc, ctx->coord4.p, ctx->veloc4.p, ctx->owned_count.p, ctx->pair_table.p, ctx->facc.p, f, coeff, k1, ctx->d_counts, ctx->n_col, nt, dtis, range, (int)ctx->cap
     const int gmode = ctx->pair_tex;
     if (nt == 1 && pow1) {
         switch (gmode) {

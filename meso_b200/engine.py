@@ -60,6 +60,19 @@ class Meso:
             buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
         self._chk(self.L.meso_set_decomposition(self.h, rank, (C.c_int * 3)(*procgrid), buf))
 
+    def comm_export(self):
+        """this rank's halo blob (host-driven bootstrap: ranks of one process or of one GPU); call after upload()"""
+        self._push_coeff()                      # the ghost cutoff (largest pair cutoff + skin) sizes the arena
+        buf = (C.c_char * self.L.meso_comm_blob_size())()
+        self._chk(self.L.meso_comm_export(self.h, buf))
+        return bytes(buf)
+
+    def comm_import(self, blobs):
+        """blobs: every rank's comm_export() in rank order"""
+        raw = b"".join(blobs)
+        buf = (C.c_char * len(raw)).from_buffer_copy(raw)
+        self._chk(self.L.meso_comm_import(self.h, buf, len(blobs)))
+
     @staticmethod
     def unique_id():
         buf = (C.c_char * 128)()
@@ -391,6 +404,22 @@ class Meso:
             idx = ((i[sel] & ~31) + (k & 31)).astype(np.int64) * n_col + (k >> 5) * 32 + (i[sel] & 31)
             rows[sel, k] = t[idx]
         return cnt, rows
+
+    def pair_rows(self):
+        """production rows (pair_count, owned_count, owned core, other core, rows[nlocal][n_col]): the layout the force kernels read"""
+        cnt = self.pair_count()
+        n = len(cnt)
+        n_col = self.bins()[3]
+        t = np.empty(((n + 31) // 32 * 32) * n_col, np.int32)
+        own, split = np.empty(n, np.int32), np.empty(n, np.int32)
+        self._chk(self.L.meso_export_pair_rows(self.h, t.size, _ptr(t), _ptr(own), _ptr(split)))
+        rows = np.full((n, n_col), -1, np.int32)
+        i = np.arange(n)
+        for k in range(int(cnt.max()) if n else 0):
+            sel = cnt > k
+            idx = ((i[sel] & ~31) + (k & 31)).astype(np.int64) * n_col + (k >> 5) * 32 + (i[sel] & 31)
+            rows[sel, k] = t[idx]
+        return cnt, own, split & 0xffff, split >> 16, rows
 
     def per_atom_virial(self):
         n = self.counts()["nlocal"]

@@ -24,6 +24,9 @@ SIGNATURES = {
     "meso_set_box": (_i, [_vp, _pd, _pd, _pi]),
     "meso_comm_unique_id": (_i, [_vp]),
     "meso_set_decomposition": (_i, [_vp, _i, _pi, _vp]),
+    "meso_comm_blob_size": (_i, []),
+    "meso_comm_export": (_i, [_vp, _vp]),
+    "meso_comm_import": (_i, [_vp, _vp, _i]),
     "meso_set_neighbor": (_i, [_vp, _d, _i]),
     "meso_set_types": (_i, [_vp, _i, _pd]),
     "meso_pair_dpd_settings": (_i, [_vp, _i, _d, _i]),
@@ -72,6 +75,7 @@ SIGNATURES = {
     "meso_export_stencil": (_i, [_vp, _i, _vp]),
     "meso_export_pair_count": (_i, [_vp, _i, _vp]),
     "meso_export_pair_table": (_i, [_vp, _i64, _vp]),
+    "meso_export_pair_rows": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "meso_export_virial": (_i, [_vp, _i, _vp, _vp]),
     "meso_eval_gaussian": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "meso_eval_math": (_i, [_vp, _i, _i, _vp, _vp, _vp]),

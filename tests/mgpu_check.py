@@ -39,9 +39,19 @@ def make_inputs(dims, polymer=False):
     return dict(x=x, v=v, tag=tag, typ=typ, ntypes=ntypes, coeff=coeff, bonds=bonds, polymer=polymer)
 
 
-def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, phases=False, periodic=(1, 1, 1)):
+def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, phases=False, periodic=(1, 1, 1), dist=None):
     """returns the max relative force error at setup; raises AssertionError on any mismatch.  Collective: every rank of the
-    grid calls it with the same arguments (nccl_id shared)."""
+    grid calls it with the same arguments.  nccl_id shared by the ranks (one GPU per rank), or None: the ranks then exchange
+    the library's halo blobs through `dist` (torch.distributed, any backend) and sum reductions themselves -- the mode in
+    which several ranks share ONE GPU (CUDA IPC works between processes on the same device)."""
+    host_boot = nccl_id is None
+
+    def allsum(val):
+        if not host_boot:
+            return val
+        vals = [None] * dist.get_world_size()
+        dist.all_gather_object(vals, float(val))
+        return sum(vals)
     x, v, tag, typ, ntypes, coeff, polymer = inp["x"], inp["v"], inp["tag"], inp["typ"], inp["ntypes"], inp["coeff"], inp["polymer"]
     w = oracle.World((0, 0, 0), dims, periodic=periodic, procgrid=grid, precision=1 if precision == "dp" else 0, ntypes=ntypes, coeff=coeff)
     w.set_atoms(x, v, tag=tag, type=typ)
@@ -73,6 +83,10 @@ def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, pha
         m.bond_coeff(1, 50.0, 0.5)
         m.special_bonds(0.0)
         m.bonds(nbond[mine], btype[mine], batom[mine], tag_max=len(x))
+    if host_boot:
+        blobs = [None] * dist.get_world_size()
+        dist.all_gather_object(blobs, m.comm_export())
+        m.comm_import(blobs)
     m.setup(eflag=1, vflag=1)
     cg, co = m.counts(), w.counts(rank)
     for k in ("nlocal", "nghost", "n_bulk", "n_border"):
@@ -94,10 +108,20 @@ def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, pha
     err = (np.linalg.norm(ag["f"] - ao["f"], axis=1) / np.maximum(mag, mag.mean())).max()
     assert err <= ((2e-5 if polymer else 1e-5) if precision == "sp" else (1e-11 if polymer else 1e-12)), err
     if polymer:
-        eb = m.bond_energy()                         # summed over the ranks by the library (collective call)
+        eb = allsum(m.bond_energy())                 # summed over the ranks by the library (collective call) or by the host
         assert abs(eb - w.bond_energy()) < 1e-10 * abs(w.bond_energy()), (eb, w.bond_energy())
-    assert m.L.meso_natoms_global(m.h) == len(x)
-    t_g, t_o = m.temperature(), w.temperature()
+    if not host_boot:
+        assert m.L.meso_natoms_global(m.h) == len(x)
+
+    def temperature():
+        if not host_boot:
+            return m.temperature()
+        import ctypes as C
+        s_, n_ = C.c_double(), C.c_double()
+        m._chk(m.L.meso_compute_ke(m.h, 1, C.byref(s_), C.byref(n_)))
+        return allsum(s_.value) / (3.0 * allsum(n_.value) - 3.0)
+
+    t_g, t_o = temperature(), w.temperature()
     assert abs(t_g - t_o) < 1e-12, (t_g, t_o)
 
     def step_by_phases(mm):
@@ -139,14 +163,14 @@ def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, pha
         sets_g = {int(ag["tag"][i]): frozenset(tags_g[rowsg[i, :cntg[i]]].tolist()) for i in range(nl)}
         sets_o = {int(ao["tag"][i]): frozenset(ao["tag"][rowso[i, :cnto[i]]].tolist()) for i in range(nl)}
         assert sets_g == sets_o, "neighbor sets differ after migration"
-        assert abs(m.temperature() - w.temperature()) < 1e-10
+        assert abs(temperature() - w.temperature()) < 1e-10
     else:
         if phases:
             for _ in range(steps):
                 step_by_phases(m)
         else:
             m.run(steps)
-        t = m.temperature()
+        t = temperature()
         assert 0.5 < t < (6.0 if polymer else 3.0), t      # the polymer case starts at T = 4 (velocities doubled)
     m.close()
     return float(err)

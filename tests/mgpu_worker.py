@@ -24,8 +24,11 @@ ap.add_argument("--steps", type=int, default=12)
 ap.add_argument("--backend", default="nccl")
 ap.add_argument("--polymer", action="store_true", help="bead-spring chains in solvent (bond table rides the migration, ghost partners)")
 ap.add_argument("--phases", action="store_true", help="drive the run through the phase entry points (meso_forward_comm on a decomposition)")
+ap.add_argument("--share-gpu", action="store_true", help="all ranks on GPU 0: halo through CUDA IPC on one device, bootstrap and reductions through gloo")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+if a.share_gpu:
+    local, a.backend = 0, "gloo"
 torch.cuda.set_device(local)
 dist.init_process_group(a.backend, device_id=torch.device("cuda", local) if a.backend == "nccl" else None)
 
@@ -35,11 +38,13 @@ dims = tuple(a.L) * 3 if len(a.L) == 1 else tuple(a.L)
 inp = mgpu_check.make_inputs(dims, a.polymer)
 
 for precision in ("dp", "sp"):
-    ids = [Meso.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    e = mgpu_check.check(precision, rank, grid, local, dims, inp, ids[0], steps=a.steps, phases=a.phases)
+    ids = [None]
+    if not a.share_gpu:
+        ids = [Meso.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+    e = mgpu_check.check(precision, rank, grid, local, dims, inp, ids[0], steps=a.steps, phases=a.phases, dist=dist)
     dist.barrier()
     if rank == 0:
-        print("mgpu parity OK: %d ranks grid %s box %s %s%s%s (force err %.2e)" % (world, grid, dims, precision, " polymer" if a.polymer else "",
-                                                                                 " phases" if a.phases else "", e), flush=True)
+        print("mgpu parity OK: %d ranks%s grid %s box %s %s%s%s (force err %.2e)" % (world, " on one GPU" if a.share_gpu else "", grid, dims, precision,
+                                                                                   " polymer" if a.polymer else "", " phases" if a.phases else "", e), flush=True)
 dist.destroy_process_group()

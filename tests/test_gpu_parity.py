@@ -237,8 +237,9 @@ def test_non_periodic_dimension_and_tiny_box():
 
 
 def test_dense_fluid_rows_longer_than_the_staging_queue():
-    """rho = 8: ~72 stored neighbors per atom (> 60 staging slots, > 2 table tiles): exercises the spill/join path of the
-    list build, the 32-slot tile wrap of the transposed table and the early-drain path of the force kernel."""
+    """rho = 8: ~72 stored neighbors per atom (> 64 staging slots, > 2 table tiles): the rows of the fine-lattice build that
+    overflow its queue are redone by the fall-back kernel; also the 32-slot tile wrap of the transposed table and the
+    early-drain path of the force kernel."""
     x = workload.dpd_fluid(6, rho=8, seed=13)
     for precision in ("sp", "dp"):
         m, w = make_pair(6, precision, x=x)
@@ -248,35 +249,63 @@ def test_dense_fluid_rows_longer_than_the_staging_queue():
         m.close()
 
 
-@pytest.mark.parametrize("tcap", ["64", "384"])
-def test_neighbor_build_window_overflow_falls_back_per_atom(monkeypatch, tcap):
-    """cells whose candidate list exceeds the warp-per-cell kernel's shared-memory window are rebuilt by the
-    thread-per-atom kernel in fix-up mode: all cells (window 64) or a mix (window 384 at ~364 +- 20 candidates)."""
-    monkeypatch.setenv("MESO_NB_TCAP", tcap)
-    monkeypatch.setenv("MESO_NB_PER_ATOM", "0")
-    m, w = make_pair(9, "dp")
-    m.setup(); w.setup()
-    assert_state_identical(m, w, precision="dp")
-    m.run(6); w.run(6)
-    cntg, rowsg = m.neighbors()
-    cnto, rowso = w.neighbors()
-    mask = np.arange(rowso.shape[1])[None, :] < cnto[:, None]
-    assert np.array_equal(cntg, cnto) and np.array_equal(rowsg[mask], rowso[mask])
-    m.close()
+def test_neighbor_build_plain_walk_gives_the_same_table(monkeypatch):
+    """MESO_NB_SLOW=1 builds every row with the plain walk of the 27 stencil cells (the fall-back kernel of the fine-lattice
+    build): same counts, same canonical rows, same split arrays -- and the same state after a run across a rebuild."""
+    for L, precision in ((9, "dp"), ((7, 9, 12), "dp")):      # fp64: the run stays in lockstep with the oracle
+        out = []
+        for slow in ("0", "1"):
+            monkeypatch.setenv("MESO_NB_SLOW", slow)
+            m, w = make_pair(L, precision)
+            m.setup(); w.setup()
+            assert_state_identical(m, w, precision=precision)
+            cnt, own, n_oc, n_nc, rows = m.pair_rows()
+            out.append((cnt, own, n_oc, n_nc, [frozenset(rows[i, :own[i]].tolist()) for i in range(len(cnt))]))
+            m.run(6); w.run(6)
+            cntg, rowsg = m.neighbors()
+            cnto, rowso = w.neighbors()
+            mask = np.arange(rowso.shape[1])[None, :] < cnto[:, None]
+            assert np.array_equal(cntg, cnto) and np.array_equal(rowsg[mask], rowso[mask])
+            m.close()
+        for a, b in zip(out[0][:4], out[1][:4]):
+            assert np.array_equal(a, b)
+        assert out[0][4] == out[1][4]
 
 
 @pytest.mark.parametrize("L", [10, (7, 9, 12)])
-def test_neighbor_build_warp_per_cell_kernel_matches(monkeypatch, L):
-    """the alternative build (one warp per cell, ballots, packed fp32x2 tests) gives the same table bit for bit"""
-    monkeypatch.setenv("MESO_NB_PER_ATOM", "0")
+def test_production_rows_are_the_canonical_rows_in_four_segments(L):
+    """The table the force kernels read: [owned core][owned skin][other core][other skin].  Every segment is a subset of the
+    reference's core / skin part of the row, the four segments partition the row, and "owned" is exactly the rule of the
+    pair-once kernel (ghost j, or (i+j) odd ? i<j : i>j), so every local pair is owned by exactly one of its two rows."""
     m, w = make_pair(L, "sp")
     m.setup(); w.setup()
-    assert_state_identical(m, w, precision="sp")
-    m.close()
-    x = workload.dpd_fluid(6, rho=8, seed=13)               # dense rows, several chunk pairs, > 32 atoms in some cells
-    m, w = make_pair(6, "dp", x=x)
-    m.setup(); w.setup()
-    assert_state_identical(m, w, precision="dp", tol=1e-11)
+    cnt, own, n_oc, n_nc, rows = m.pair_rows()
+    cnto, rowso = w.neighbors()                              # reference order: core entries, then skin entries reversed
+    nl = len(cnt)
+    assert np.array_equal(cnt, cnto)
+    c4, _ = w.packed()
+    owner = {}
+    for i in range(nl):
+        r = rows[i, :cnt[i]]
+        ref = rowso[i, :cnto[i]]
+        assert sorted(r.tolist()) == sorted(ref.tolist())
+        d = c4[ref, :3] - c4[i, :3]
+        r2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        ncore = int((r2 <= np.float32(1.0)).sum())
+        assert ncore == n_oc[i] + n_nc[i]
+        core_ref, skin_ref = set(ref[:ncore].tolist()), set(ref[ncore:].tolist())
+        seg = [r[:n_oc[i]], r[n_oc[i]:own[i]], r[own[i]:own[i] + n_nc[i]], r[own[i] + n_nc[i]:]]
+        assert set(seg[0].tolist()) | set(seg[2].tolist()) == core_ref and set(seg[1].tolist()) | set(seg[3].tolist()) == skin_ref
+        for k, part in enumerate(seg):
+            for j in part.tolist():
+                mine = j >= nl or ((i < j) if (i + j) % 2 else (i > j))
+                assert mine == (k < 2), (i, j, k)
+                if j < nl and k < 2:
+                    key = (min(i, j), max(i, j))
+                    assert key not in owner
+                    owner[key] = i
+    npairs = sum(int((rowso[i, :cnto[i]] < nl).sum()) for i in range(nl)) // 2
+    assert len(owner) == npairs
     m.close()
 
 
@@ -522,41 +551,24 @@ def test_thermostat_equilibrium_statistics():
     m.close()
 
 
-# ------------------------------------------------------------------ full-size properties (BASELINE configs[1], [2])
+# ------------------------------------------------------------------ the benchmarked sizes against the oracle (BASELINE configs[1], [2])
 @pytest.mark.parametrize("L,precision", [(64, "sp"), (48, "dp")])
-def test_full_size_properties(L, precision):
-    from meso_b200.engine import dpd_fluid_deck
-    m = dpd_fluid_deck(L, precision)
+def test_full_size_setup_parity_against_the_oracle(L, precision):
+    """sp.run case 64 (1,048,576 particles) and dp.run case 48 (442,368): everything the rebuild produces bit for bit
+    against the C oracle -- sort keys, permutation, ghosts, cells, ORDERED neighbor rows, the tile-transposed table,
+    packed coordinates and TEA signatures -- and the setup forces to 1e-5 (fp32) / 1e-12 (fp64); then size-independent
+    properties of a short run (sum F = 0, temperature)."""
+    m, w = make_pair(L, precision)
     m.setup()
+    w.setup()
+    assert_state_identical(m, w, precision=precision)
     c = m.counts()
     assert c["nlocal"] == 4 * L ** 3
-    k, p = m.reorder()
-    assert (np.diff(k.astype(np.int64)) >= 0).all(), "reorder keys not sorted"
-    assert np.array_equal(np.sort(p), np.arange(len(p))), "permutation is not a permutation"
     cnt = m.pair_count()
     # stock LAMMPS on 25.data: 17.92 half-list neighbors per atom at r_n = 1.3 (SURVEY.md s4) -> 35.84 full
     assert abs(cnt.mean() - 35.84) < 0.2, cnt.mean()
-    d = m.download(("f", "tag"))
+    d = m.download(("f",))
     assert np.abs(d["f"].sum(0)).max() < (2e-2 if precision == "sp" else 1e-8) * np.sqrt(len(cnt))   # sum F = 0
-    s, a = m.cells()
-    assert s[-1] == c["nlocal"] + c["nghost"] and (np.diff(s) >= 0).all()
-    assert np.array_equal(np.sort(a), np.arange(len(a)))
-    # neighbor symmetry on a sample: j in N(i) <=> i in N(j) (by tag, ghosts map to their owners)
-    t, n_col = m.pair_table()
-    g = m.ghosts()
-    tags_all = np.concatenate([d["tag"], g["tag"]])
-    tag2loc = np.empty(len(d["tag"]) + 1, np.int64)
-    tag2loc[d["tag"]] = np.arange(len(d["tag"]))
-    rng = np.random.default_rng(1)
-
-    def row(i):
-        ks = np.arange(cnt[i])
-        return t[((i & ~31) + (ks & 31)).astype(np.int64) * n_col + (ks >> 5) * 32 + (i & 31)]
-
-    for i in rng.integers(0, c["nlocal"], 200):
-        for j in row(int(i))[:8]:
-            jl = tag2loc[tags_all[j]]
-            assert d["tag"][i] in tags_all[row(int(jl))]
     m.run(10)
     T = m.temperature()
     assert 0.5 < T < 2.5

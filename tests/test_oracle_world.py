@@ -268,11 +268,12 @@ def test_amphiphilic_channel_is_decomposition_independent():
 
 
 @pytest.mark.parametrize("case", ["cube", "ragged_2rank", "channel"])
-def test_stencil_cell_skip_criterion_is_conservative(case):
-    """Design invariant for the next step of the neighbor build: a stencil cell may be skipped for atom i when
-    the distance from i to that cell's box exceeds r_n.  Checked on the oracle's own lattice, cells and packed fp32 coordinates
-    (ghosts clamped into the outer layer, non-periodic faces, ragged bricks): evaluated in fp32 with a 1e-3 margin on r_n, the
-    criterion never drops a stored neighbor, and it removes a useful share of the 27-cell candidate set."""
+def test_fine_lattice_row_clipping_is_conservative(case):
+    """Design invariant of the neighbor build (meso_b200/csrc/neighbor.cu:k_build_rows): every atom walks the 6 x 6 rows of a
+    half-cell lattice over its 27 stencil cells, each row clipped to the chord of a sphere of radius r_n + margin around the
+    atom.  Evaluated here in fp32 exactly as the kernel does, on the oracle's own cells and packed coordinates (ghosts clamped
+    into the outer layer, non-periodic faces, ragged bricks): the clipped rows contain every stored neighbor, and they hold
+    far fewer candidates than the 27 cells."""
     if case == "cube":
         w = world(8)
         ranks = [0]
@@ -285,9 +286,8 @@ def test_stencil_cell_skip_criterion_is_conservative(case):
         w.set_atoms(x, workload.maxwell_velocities(len(x)))
         ranks = [0]
     w.setup()
-    rn = np.float32(1.3)
-    limit = (rn * np.float32(1.001)) ** 2
-    tested = kept = 0
+    f32 = np.float32
+    tested = full = 0
     for r in ranks:
         a = w.atoms(r)
         nl = a["nlocal"]
@@ -298,27 +298,45 @@ def test_stencil_cell_skip_criterion_is_conservative(case):
         cell_of = np.empty(len(ca), np.int64)
         for c in range(len(cs) - 1):
             cell_of[ca[cs[c]:cs[c + 1]]] = c
-        # sub-box geometry in packed coordinates: centre = middle of this rank's sub-box, cell b spans lo + (b-1) binsize
-        sub = np.array([m[d] - 2 for d in range(3)]) * np.array(binsize)
-        lo = -0.5 * sub
+        b3 = np.stack([cell_of % m[0], (cell_of // m[0]) % m[1], cell_of // (m[0] * m[1])], axis=1)
+        bs = np.array(binsize)
+        sub = np.array([m[d] - 2 for d in range(3)]) * bs
+        lat_lo = (-0.5 * sub - bs).astype(f32)                    # lower face of fine cell 0 in the packed (centred) frame
+        wfine, inv_w = (0.5 * bs).astype(f32), (2.0 / bs).astype(f32)
+        # fine cell of every atom: 2 * cell + half, the half decided on the fp64 coordinate relative to its cell
+        xall = a["x"]
+        sublo = np.array(w.sub_box(r)[0]) if hasattr(w, "sub_box") else None
+        pos = c4[:, :3].astype(np.float64) - (-0.5 * sub)         # fp32-packed position relative to sublo (error ~1e-7)
+        half = ((pos - (b3 - 1) * bs) >= 0.5 * bs).astype(np.int64)
+        fine3 = 2 * b3 + half
+        ext = float(sub.max() + 2 * bs.max())
+        R2 = f32((1.3 + 1.0e-3 + 4.0e-6 * ext) ** 2)
         rng = np.random.default_rng(1)
-        for i in rng.choice(nl, size=min(nl, 400), replace=False):
-            b = np.array([cell_of[i] % m[0], (cell_of[i] // m[0]) % m[1], cell_of[i] // (m[0] * m[1])])
-            cell_lo = (lo + (b - 1) * np.array(binsize)).astype(np.float32)
-            cell_hi = (lo + b * np.array(binsize)).astype(np.float32)
-            p = c4[i, :3]
-            dlo = np.maximum(p - cell_lo, np.float32(0))          # distance to the -1 neighbor along each axis
-            dhi = np.maximum(cell_hi - p, np.float32(0))          # distance to the +1 neighbor
-            skipped = set()
-            for c in w.stencil(int(cell_of[i]), r):
-                nb = np.array([c % m[0], (c // m[0]) % m[1], c // (m[0] * m[1])])
-                off = nb - b
-                d = np.where(off < 0, dlo, np.where(off > 0, dhi, np.float32(0))).astype(np.float32)
-                tested += 1
-                if np.float32((d * d).sum()) > limit:
-                    skipped.add(int(c))
-                else:
-                    kept += 1
+        for i in rng.choice(nl, size=min(nl, 300), replace=False):
+            u = np.minimum(np.maximum((c4[i, :3] - lat_lo) * inv_w, f32(0)), (2 * np.array(m)).astype(f32))
+            cx, cy, cz = b3[i]
+            visited = set()
+            for rz in range(6):
+                fz = 2 * (cz - 1) + rz
+                tz = f32(u[2] - f32(fz))
+                dz = (f32(-tz) if tz < 0 else max(f32(tz - f32(1)), f32(0))) * wfine[2]
+                remz = f32(R2 - f32(dz * dz))
+                for ry in range(6):
+                    fy = 2 * (cy - 1) + ry
+                    ty = f32(u[1] - f32(fy))
+                    dy = (f32(-ty) if ty < 0 else max(f32(ty - f32(1)), f32(0))) * wfine[1]
+                    rem = f32(remz - f32(dy * dy))
+                    if not (0 <= fz < 2 * m[2] and 0 <= fy < 2 * m[1] and rem >= 0):
+                        continue
+                    ch = f32(np.sqrt(rem) * f32(1.0 - 2e-7)) * inv_w[0]      # MUFU.SQRT may be 1 ulp low
+                    xlo = max(int(np.floor(f32(u[0] - ch))), max(0, 2 * (cx - 1)))
+                    xhi = min(int(np.floor(f32(u[0] + ch))), min(2 * m[0] - 1, 2 * cx + 3))
+                    for fx in range(xlo, xhi + 1):
+                        visited.add((fx, fy, fz))
             stored = rows[i, :cnt[i]]
-            assert not (set(cell_of[stored].tolist()) & skipped), (case, r, int(i))
-    assert kept < 0.85 * tested, (kept, tested)                   # ~25 % of the (atom, cell) pairs go away
+            for j in stored.tolist():
+                assert tuple(fine3[j]) in visited, (case, r, int(i), int(j))
+            in_fine = np.array([tuple(f) in visited for f in fine3])
+            tested += int(in_fine.sum())
+            full += sum(int(cs[c + 1] - cs[c]) for c in w.stencil(int(cell_of[i]), r))
+    assert tested < 0.45 * full, (tested, full)                   # ~246 -> ~75 candidates per atom at rho = 4
