@@ -121,7 +121,6 @@ extern "C" int meso_create(meso_ctx **out, int device)
     ctx->pair_once = !(po && po[0] == '0');
     if (const char *e = getenv("MESO_PAIR_TEX")) ctx->pair_tex = atoi(e) & 3;
     if (const char *e = getenv("MESO_NB_SLOW")) ctx->nb_slow = e[0] == '1';
-    if (const char *e = getenv("MESO_NB_CLIP")) ctx->nb_clip = atoi(e);
     cudaMemsetAsync(ctx->d_counts, 0, sizeof(Counts), ctx->stream);
     memset(ctx->h_counts, 0, sizeof(Counts));
     *out = ctx;
@@ -199,7 +198,7 @@ extern "C" int meso_memory_usage(meso_ctx *ctx, uint64_t *bytes)
          ctx->staging.bytes() + ctx->istaging.bytes() + ctx->key.bytes() + ctx->perm_from.bytes() + ctx->sort.key_alt.bytes() +
          ctx->sort.val_alt.bytes() + ctx->sort.hist.bytes() + ctx->ghost_root.bytes() + ctx->ghost_shift.bytes() + ctx->tile_counts.bytes() +
          ctx->cell_of.bytes() + ctx->cell_atoms.bytes() + ctx->cell_start.bytes() + ctx->stencil.bytes() + ctx->slotrank.bytes() +
-         ctx->cell_cnt.bytes() + ctx->fine_of.bytes() + ctx->fine_start.bytes() + ctx->fine_rec.bytes() + ctx->scan_sums.bytes() +
+         ctx->cell_cnt.bytes() + ctx->cell_xyzj.bytes() + ctx->scan_sums.bytes() + ctx->nb_scratch.bytes() +
          ctx->pair_count.bytes() + ctx->owned_count.bytes() + ctx->core_split.bytes() + ctx->pair_table.bytes() + ctx->partial.bytes() +
          ctx->facc.bytes() + ctx->virial.bytes() + ctx->e_pair.bytes();
     *bytes = b;
@@ -1067,7 +1066,6 @@ extern "C" int meso_export_cells(meso_ctx *ctx, int ncell_plus1, int *cell_start
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     int n = ctx->h_counts->nlocal + ctx->h_counts->nghost;
-    TRY(launch_cell_lists(ctx));
     if (cell_start) {
         if (ncell_plus1 < ctx->box.ncell + 1) FAIL(MESO_EINVAL, "buffer too small");
         TRY(d2h(ctx, cell_start, ctx->cell_start.p, ctx->box.ncell + 1));

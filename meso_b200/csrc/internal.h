@@ -136,7 +136,6 @@ struct meso_ctx {
     meso::DevBuf<float4> facc;                // fp32 per-atom force accumulator of the pair-once kernel (zero between uses)
     cudaTextureObject_t tex_coord = 0, tex_veloc = 0;   // linear float4 textures over coord4 / veloc4 (gather-path experiments)
     int pair_tex = 2;                         // which gathers of the pair-once kernel use the texture data pipe (MESO_PAIR_TEX)
-    int nb_clip = 1;                          // MESO_NB_CLIP: 2 = per-atom row clipping, 1 = per-cell union (lockstep), 0 = none
     bool nb_slow = false;                     // MESO_NB_SLOW=1: every row by the plain 27-cell walk (A/B check of the fine-lattice build)
     bool pair_once = true;                    // meso_run evaluates each local pair once (MESO_PAIR_ONCE=0: two-sided kernel)
     meso::DevBuf<double> virial, e_pair;      // [6][cap] SoA, [cap]
@@ -166,9 +165,8 @@ struct meso_ctx {
     // cells
     meso::DevBuf<int> cell_of;                // per atom: cell coordinates packed 10 bits per dimension (x | y << 10 | z << 20)
     meso::DevBuf<int> cell_atoms, cell_start; // atoms in (cell, ascending index) order; first position of every cell (+ total)
-    meso::DevBuf<int> cell_cnt;               // histograms of the counting sort: [ncell] reference cells, then [8 ncell] fine cells
-    meso::DevBuf<int> fine_of, fine_start, scan_sums;
-    meso::DevBuf<float4> fine_rec;            // fine-cell-ordered records {x, y, z, bits(atom index)}
+    meso::DevBuf<int> cell_cnt, scan_sums;    // histogram of the counting sort and the block sums of its scan
+    meso::DevBuf<float4> cell_xyzj;           // cell-ordered records {x, y, z, bits(atom index)} the build streams
     meso::DevBuf<unsigned char> stencil;      // [ncell][32]: stencil codes in the reference's order, byte 31 = count
     meso::DevBuf<unsigned char> slotrank;     // [ncell][32]: stencil code -> position in that order
     // neighbor table: row = [owned core][owned skin][other core][other skin]
@@ -176,8 +174,7 @@ struct meso_ctx {
     meso::DevBuf<int> owned_count;            // entries of the row whose pair this row evaluates (pair-once force kernel)
     meso::DevBuf<int> core_split;             // owned core | other core << 16
     meso::DevBuf<int> nb_fixup;               // != 0: some row was left to the fall-back build kernel
-    meso::DevBuf<uint32_t> nb_scratch;        // per-warp hit queues of the build kernel (global memory, L2-resident)
-    bool cells_valid = false;                 // cell_start / cell_atoms describe the last rebuild (built on demand for exports)
+    meso::DevBuf<uint32_t> nb_scratch;        // per-warp overflow of the build kernel's hit queues (global memory, L2-resident)
     size_t table_rows = 0;
 
     // reductions
@@ -237,7 +234,6 @@ int comm_import_blobs(meso_ctx *ctx, const void *blobs, int nranks);
 // ---- neighbor.cu
 int launch_setup_bins(meso_ctx *ctx);
 int launch_neighbor_build(meso_ctx *ctx);
-int launch_cell_lists(meso_ctx *ctx);                       // reference cell lists of the last rebuild (exports)
 int launch_canonical_rows(meso_ctx *ctx, int *out_table);   // the table in the reference's row order (exports)
 // ---- pair.cu
 int launch_pack(meso_ctx *ctx, int range);
