@@ -183,10 +183,10 @@ int meso_export_pair_count(meso_ctx *ctx, int nmax, int *pair_count);
 /* tile-transposed table, UM/neigh_list_meso.cu:97-102: ceil32(nlocal)*n_col ints, rows in the reference's order
  * (core entries in stencil order, then skin entries reversed: UM/neigh_build_meso.cu:58-117,166-200) */
 int meso_export_pair_table(meso_ctx *ctx, int64_t nmax, int *pair_table);
-/* the same table as the force kernels read it: rows [owned core][owned skin][other core][other skin] (same sets, same
- * core/skin split, traversal order inside a segment); owned_count[i] = entries whose pair row i evaluates,
- * core_split[i] = owned core | other core << 16.  Any pointer may be NULL. */
-int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_table, int *owned_count, int *core_split);
+/* the same table as the force kernels read it: rows [owned][other] (same sets; traversal order inside a part);
+ * owned_count[i] = leading entries whose pair row i evaluates in the pair-once force kernel: ghost partners, and local
+ * partners j with (i+j) odd ? i<j : i>j.  Any pointer may be NULL. */
+int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_table, int *owned_count);
 int meso_export_virial(meso_ctx *ctx, int nmax, double *virial6, double *e_pair);
 /* device-side evaluation of the per-pair Gaussians on n signature pairs (A8) */
 int meso_eval_gaussian(meso_ctx *ctx, int n, const uint32_t *sig_i, const uint32_t *sig_j, float *out_sp, double *out_dp);

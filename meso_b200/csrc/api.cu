@@ -198,8 +198,8 @@ extern "C" int meso_memory_usage(meso_ctx *ctx, uint64_t *bytes)
          ctx->staging.bytes() + ctx->istaging.bytes() + ctx->key.bytes() + ctx->perm_from.bytes() + ctx->sort.key_alt.bytes() +
          ctx->sort.val_alt.bytes() + ctx->sort.hist.bytes() + ctx->ghost_root.bytes() + ctx->ghost_shift.bytes() + ctx->tile_counts.bytes() +
          ctx->cell_of.bytes() + ctx->cell_atoms.bytes() + ctx->cell_start.bytes() + ctx->stencil.bytes() + ctx->slotrank.bytes() +
-         ctx->cell_cnt.bytes() + ctx->cell_xyzj.bytes() + ctx->scan_sums.bytes() + ctx->nb_scratch.bytes() +
-         ctx->pair_count.bytes() + ctx->owned_count.bytes() + ctx->core_split.bytes() + ctx->pair_table.bytes() + ctx->partial.bytes() +
+         ctx->cell_cnt.bytes() + ctx->cell_xyzj.bytes() + ctx->scan_sums.bytes() + ctx->pos_of.bytes() +
+         ctx->pair_count.bytes() + ctx->owned_count.bytes() + ctx->pair_table.bytes() + ctx->partial.bytes() +
          ctx->facc.bytes() + ctx->virial.bytes() + ctx->e_pair.bytes();
     *bytes = b;
     return MESO_OK;
@@ -1119,8 +1119,8 @@ extern "C" int meso_export_pair_table(meso_ctx *ctx, int64_t nmax, int *pair_tab
     return d2h(ctx, pair_table, scratch.p, n);
 }
 
-// the table as the force kernels read it: rows [owned core][owned skin][other core][other skin], with the two split arrays
-extern "C" int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_table, int *owned_count, int *core_split)
+// the table as the force kernels read it: rows [owned][other] and the length of the owned part
+extern "C" int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_table, int *owned_count)
 {
     CHECK_CTX();
     MESO_CUDA(cudaSetDevice(ctx->device));
@@ -1132,7 +1132,6 @@ extern "C" int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_tabl
         TRY(d2h(ctx, pair_table, ctx->pair_table.p, n));
     }
     if (owned_count) TRY(d2h(ctx, owned_count, ctx->owned_count.p, nl));
-    if (core_split) TRY(d2h(ctx, core_split, ctx->core_split.p, nl));
     return MESO_OK;
 }
 

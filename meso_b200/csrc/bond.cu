@@ -115,24 +115,23 @@ __global__ void __launch_bounds__(256) k_bond_harmonic(const float4 *__restrict_
 }
 
 // gpu_filter_exclusion (UM/neigh_build_meso.cu:497-544) for special_bonds lj 0 x x: the bonded partners (by tag) leave
-// the row, the order of the survivors is kept.  One thread per row of the tile-transposed table; the row's four segments
-// [owned core][owned skin][other core][other skin] are compacted in place and the three count arrays follow.
+// the row, the order of the survivors is kept.  One thread per row of the tile-transposed table; the row's two parts
+// [owned][other] are compacted in place and the two count arrays follow.
 __global__ void __launch_bounds__(128) k_filter_exclusion(const int *__restrict__ tag, const int *__restrict__ nbond,
                                                           const int2 *__restrict__ bonds, int *__restrict__ pair_count,
-                                                          int *__restrict__ owned_count, int *__restrict__ core_split,
-                                                          int *__restrict__ pair_table, const Counts *__restrict__ cnt, size_t padding,
-                                                          int n_col)
+                                                          int *__restrict__ owned_count, int *__restrict__ pair_table,
+                                                          const Counts *__restrict__ cnt, size_t padding, int n_col)
 {
     const int n = cnt->nlocal;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int nb = nbond[i];
         if (nb == 0) continue;
         int *row0 = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);
-        const int np = pair_count[i], nown = owned_count[i], cs = core_split[i];
-        const int end[4] = {cs & 0xffff, nown, nown + (cs >> 16), np};     // segment ends in the unfiltered row
-        int kept[4] = {0, 0, 0, 0};
+        const int np = pair_count[i], nown = owned_count[i];
+        const int end[2] = {nown, np};                                     // ends of the two parts in the unfiltered row
+        int kept[2] = {0, 0};
         int keep = 0, k = 0;
-        for (int seg = 0; seg < 4; seg++) {
+        for (int seg = 0; seg < 2; seg++) {
             for (; k < end[seg]; k++) {
                 const int j = row0[(k & 31) * n_col + (k & ~31)];
                 const int t = tag[j];
@@ -142,8 +141,7 @@ __global__ void __launch_bounds__(128) k_filter_exclusion(const int *__restrict_
             }
         }
         pair_count[i] = keep;
-        owned_count[i] = kept[0] + kept[1];
-        core_split[i] = kept[0] | (kept[2] << 16);
+        owned_count[i] = kept[0];
     }
 }
 
@@ -223,7 +221,7 @@ int launch_bonds_filter(meso_ctx *ctx)
 {
     if (!bonds_active(ctx) || ctx->special_lj12 != 0.0) return MESO_OK;
     k_filter_exclusion<<<grid_for(ctx, 8), 128, 0, LS(ctx->stream)>>>(ctx->tag.p, ctx->nbond.p, ctx->bonds.p, ctx->pair_count.p, ctx->owned_count.p,
-                                                               ctx->core_split.p, ctx->pair_table.p, ctx->d_counts, ctx->cap, ctx->n_col);
+                                                               ctx->pair_table.p, ctx->d_counts, ctx->cap, ctx->n_col);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

@@ -169,12 +169,11 @@ struct meso_ctx {
     meso::DevBuf<float4> cell_xyzj;           // cell-ordered records {x, y, z, bits(atom index)} the build streams
     meso::DevBuf<unsigned char> stencil;      // [ncell][32]: stencil codes in the reference's order, byte 31 = count
     meso::DevBuf<unsigned char> slotrank;     // [ncell][32]: stencil code -> position in that order
-    // neighbor table: row = [owned core][owned skin][other core][other skin]
+    meso::DevBuf<int> pos_of;                 // per atom: its position in the cell order (index into cell_xyzj / cell_atoms)
+    // neighbor table: row = [owned][other]
     meso::DevBuf<int> pair_count, pair_table;
     meso::DevBuf<int> owned_count;            // entries of the row whose pair this row evaluates (pair-once force kernel)
-    meso::DevBuf<int> core_split;             // owned core | other core << 16
     meso::DevBuf<int> nb_fixup;               // != 0: some row was left to the fall-back build kernel
-    meso::DevBuf<uint32_t> nb_scratch;        // per-warp overflow of the build kernel's hit queues (global memory, L2-resident)
     size_t table_rows = 0;
 
     // reductions

@@ -10,24 +10,20 @@
 // Blackwell version (round 2).
 //   * binning is a counting sort (histogram with hardware reductions -> exclusive scan -> claim a slot -> order each
 //     cell's handful of atoms by index) instead of a 3-pass radix sort of (cell id, atom) pairs; the ordering pass also
-//     writes the cell-ordered records {x, y, z, atom index} the build streams;
-//   * one thread owns one local atom.  Cells are numbered x-fastest, so the 27 stencil cells are NINE contiguous runs of
-//     records (three x-neighbors each): every lane walks its 9 runs with 4 independent 16-byte loads in flight, and lanes of
-//     the same cell walk the same records in lockstep (one cache line per cell and load, not one per lane);
-//   * in-range neighbors are staged in a per-lane queue in shared memory (column layout: bank == lane, no atomics, no
-//     ballots; the rare entries past its depth go to a per-warp overflow area in global memory) and written out once,
-//     when the row's totals are known.
-// Row layout: [owned core][owned skin][other core][other skin], where "owned" marks the entries whose pair the force
-// kernel evaluates from this row (ghost j, or (i+j) odd ? i<j : i>j) and core/skin is the reference's split at
-// r <= r_n - skin (fp32, at build time).  The SET of every row, its counts and the core/skin split are the reference's;
-// the order inside a segment is the walk order (x-rows of the stencil, ascending atom index inside a cell).  The reference's
-// order (stencil cells by (boundary flag, Morton), ascending atom index inside a cell, skin entries reversed) is a pure
-// function of (cell of j, j), so meso_export_pair_table rebuilds it on demand (k_canonical_rows) for the bit-exact parity
+//     writes the cell-ordered records {x, y, z, atom index} the build reads;
+//   * the build stages cell tiles in shared memory with TMA bulk copies and walks them with one lane per atom (see "build"
+//     below); in-range neighbors are staged in a per-lane queue in shared memory (column layout: bank == lane, no atomics,
+//     no ballots) and written out once, when the row's totals are known.
+// Row layout: [owned][other], where "owned" marks the entries whose pair the pair-once force kernel evaluates from this row
+// (ghost j, or (i+j) odd ? i<j : i>j).  The SET of every row and its count are the reference's; the order inside a
+// part is the walk order (x-rows of the stencil, ascending atom index inside a cell).  The reference's order (core entries by
+// stencil position, skin entries reversed; stencil cells by (boundary flag, Morton)) is a pure function of (cell of j, j) and
+// of the build-time distance, so meso_export_pair_table rebuilds it on demand (k_canonical_rows) for the bit-exact parity
 // checks.  Table offsets are 64-bit (the reference overflows int past 13.4 M atoms).
 //
-// Measured and dropped in this round (profiles/r02_s2_build_fine_lattice_ncu_summary.txt): a half-cell lattice with per-atom
-// chord clipping of its rows tests 72 candidates per atom instead of 246, but every lane then reads its own records (16 cache
-// lines per load instead of ~5) and the 36 row set-ups cost as much as the tests they save: 576 us against ~400 us.
+// Measured and dropped in this round (profiles/): a half-cell lattice with per-atom chord clipping (72 candidates per atom
+// instead of 246, but 16 cache lines per load and 36 row set-ups: 576 us); one lane per atom walking the 9 runs straight from
+// global memory through L1 (487 us, 352 M warp instructions, 43 per candidate: run switching and the four-way split of the row).
 #include "internal.h"
 #include "device_math.cuh"
 #include <algorithm>
@@ -182,7 +178,8 @@ __global__ void __launch_bounds__(256) k_bin_fill(const int *__restrict__ cellc,
 // atoms of a cell in ascending index (the order the reference's stable sort of (cell id, atom) leaves, UM/neighbor_meso.cu:588)
 // and the cell-ordered copy of the packed coordinates, {x, y, z, bits(atom index)}, that the build kernel streams
 __global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell_start, int *__restrict__ cell_atoms,
-                                                    const float4 *__restrict__ coord4, float4 *__restrict__ cell_xyzj, int ncell)
+                                                    const float4 *__restrict__ coord4, float4 *__restrict__ cell_xyzj,
+                                                    int *__restrict__ pos_of, int ncell)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
@@ -199,25 +196,64 @@ __global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell
         float4 v = coord4[j];
         v.w = __int_as_float(j);
         cell_xyzj[a + k] = v;
+        pos_of[j] = a + k;
     }
 }
 
 // ------------------------------------------------------------------ build
-constexpr uint32_t MJ = (1u << 27) - 1u;  // atom indices fit 27 bits in the hit queue (class bits above them); checked on the host
-constexpr int NB_THREADS = 128;
-constexpr int NB_BATCH = 4;       // candidates tested per iteration (independent 16-byte loads in flight)
-constexpr int NQ = 40;            // per-lane queue slots in shared memory (5 KB per warp + 2.3 KB of run lists: 7 CTAs per SM)
-constexpr int NQX = 88;           // per-lane overflow slots in global memory (rows of 41 .. 128 hits: a few entries of ~25 % of the rows at rho = 4)
+// Work decomposition.  Locals are sorted by (border bit, Morton(cell), sub-cell), so the atoms of an aligned block of
+// 2^lbx x 2^lby x 2^lbz cells are ONE run of consecutive indices (two where the block holds bulk and border atoms).  Such a
+// run -- a "segment", found on the fly: a CTA owns the segments that START in its 256 atoms -- is built from one
+// shared-memory tile: the block's cells plus one layer around them, i.e. up to 36 x-rows of up to 6 cells, each row one
+// contiguous piece of the cell-ordered records, brought in by one cp.async.bulk per row (TMA, mbarrier completion).
+// One lane owns one atom (lanes = consecutive atoms: the tile-transposed table is written with coalesced stores) and walks
+// its 9 runs of 3 cells in the tile: 4 LDS.128 in flight, 6 FP32 ops and a predicated push per candidate.
+// Row layout: [owned][other], each part in walk order; see owns().
+constexpr int NB_WARPS = 8, NB_THREADS = NB_WARPS * 32;
+constexpr int NB_BATCH = 4;                 // candidates per iteration (independent 16-byte shared-memory loads in flight)
+constexpr int TILE_ROWS = 36, TILE_NX = 7;  // (4+2) x (4+2) x-rows, (4+2)+1 cell offsets per row
+constexpr int TILE_SLACK = 64;              // bytes a batch may read past the last record
+constexpr int TILE_CAP_MAX = 2560;          // records (40 KB): with the static shared memory in front the tile ends below 64 KB
 
 __device__ __forceinline__ void sts_u32(unsigned addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds_u32(unsigned addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void sts_u16(unsigned addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(unsigned addr) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ float4 lds_f4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}\n"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared::cta, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
+}
 
 // the entries of row i that its own lane evaluates in the pair-once force kernel (pair.cu): ghost partners always, local
-// partners by the balanced rule (i+j) odd ? i<j : i>j (the mirror entry in row j is then "other")
+// partners by the balanced rule (i+j) odd ? i<j : i>j (the mirror entry in row j is then "other"): every row owns half of
+// ITS entries (17.9 +- 2.6 at rho = 4; a geometric half-space rule gives +- 5.9 and a 20 % longer slowest lane per warp)
 __device__ __forceinline__ bool owns(int i, int j, int nlocal)
 {
     const unsigned key = (unsigned)(j - i) * 0x80000001u;         // sign bit: d odd ? d > 0 : d < 0
     return (int)(key | (unsigned)(nlocal - 1 - j)) < 0;
+}
+
+__device__ __forceinline__ int block_of(int cc, int lbx, int lby, int lbz)
+{
+    return ((cc & 1023) >> lbx) | ((((cc >> 10) & 1023) >> lby) << 10) | (((cc >> 20) >> lbz) << 20);
 }
 
 __device__ __forceinline__ size_t slot(int i, int k, int n_col)
@@ -225,120 +261,175 @@ __device__ __forceinline__ size_t slot(int i, int k, int n_col)
     return (size_t)((i & ~31) + (k & 31)) * (size_t)n_col + (size_t)((k >> 5) * 32 + (i & 31));
 }
 
-// Persistent grid (9 CTAs per SM).  Hit t of a lane lives in its shared-memory column for t < NQ, else in the warp's overflow
-// area `scratch` (global memory, L2-resident).  Rows with more than NQ + NQX hits (or wider than the table) are left to the
-// fall-back kernel.
-__global__ void __launch_bounds__(NB_THREADS, 7) k_build_rows(const float4 *__restrict__ coord4, const int *__restrict__ cellc,
-                                                           const int *__restrict__ cell_start, const float4 *__restrict__ cell_xyzj,
-                                                           int *__restrict__ pair_count, int *__restrict__ owned_count,
-                                                           int *__restrict__ core_split, int *__restrict__ pair_table,
-                                                           Counts *__restrict__ cnt, int *__restrict__ fixup, uint32_t *__restrict__ scratch,
-                                                           int n_col, float rc2_core, float rc2_tail, int m0, int m1, int m2)
+struct TileGeom { int lbx, lby, lbz, tile_cap, nq; };
+
+__global__ void __launch_bounds__(NB_THREADS, 3) k_build_tiles(const float4 *__restrict__ coord4, const int *__restrict__ cellc,
+                                                              const int *__restrict__ cell_start, const float4 *__restrict__ cell_xyzj,
+                                                              int *__restrict__ pair_count, int *__restrict__ owned_count,
+                                                              int *__restrict__ pair_table, Counts *__restrict__ cnt, int *__restrict__ fixup,
+                                                              int n_col, float rc2, int m0, int m1, int m2, TileGeom g)
 {
-    __shared__ uint32_t s_q[NB_THREADS / 32][NQ][32];
-    __shared__ int2 s_runs[NB_THREADS / 32][9][32];
+    extern __shared__ __align__(128) unsigned char smem[];      // [tile records][slack][per-warp hit queues: nq x 32 x u16]
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_cell[TILE_ROWS * TILE_NX];                 // record offset of every tile cell (+ row end)
+    __shared__ int s_rowsrc[TILE_ROWS], s_rowlen[TILE_ROWS], s_rowoff[TILE_ROWS + 1];
+    __shared__ int s_heads[NB_THREADS], s_nh, s_red[NB_WARPS];
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned qbase = (unsigned)__cvta_generic_to_shared(&s_q[wid][0][lane]);
-    uint32_t *const xbase = scratch + ((size_t)blockIdx.x * (NB_THREADS / 32) + wid) * (NQX * 32) + lane;   // overflow entry t at xbase[t * 32]
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const unsigned tile_base = (unsigned)__cvta_generic_to_shared(smem);
+    // a hit is queued as the 16-bit shared-memory address of its record (the tile ends below 64 KB: checked on the host)
+    const unsigned qbase = tile_base + (unsigned)g.tile_cap * 16u + TILE_SLACK + (unsigned)(wid * g.nq * 64 + lane * 2);
+    const unsigned qlim = qbase + (unsigned)(g.nq - 1) * 64u;   // the last slot absorbs what does not fit (row goes to the fall-back)
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
     const int nlocal = cnt->nlocal;
+    // ---- segments that start in this CTA's atoms
+    if (t == 0) { s_nh = 0; mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    {
+        const int i = blockIdx.x * NB_THREADS + t;
+        if (i < nlocal && (i == 0 || block_of(cellc[i], g.lbx, g.lby, g.lbz) != block_of(cellc[i - 1], g.lbx, g.lby, g.lbz)))
+            s_heads[atomicAdd(&s_nh, 1)] = i;
+    }
+    __syncthreads();
+    const int nh = s_nh;
+    unsigned phase = 0;
     int worst = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < nlocal; i += gridDim.x * blockDim.x) {
-        const bool active = i < nlocal;
-        const float4 ci = coord4[active ? i : 0];
-        const int cc = cellc[active ? i : 0];
-        const int cx = cc & 1023, cy = (cc >> 10) & 1023, cz = cc >> 20;
-        // ---- the 9 x-rows of the stencil: cells (cx-1 .. cx+1, y, z) are contiguous in the cell-ordered records
-        const int xa = max(cx - 1, 0), xb = min(cx + 1, m0 - 1);
+    for (int hh = 0; hh < nh; hh++) {
+        const int a = s_heads[hh];
+        const int b0 = block_of(cellc[a], g.lbx, g.lby, g.lbz);
+        // ---- end of the segment: first atom behind a that lies in another block
+        int e = nlocal;
+        for (int base = a + 1; base < nlocal; base += NB_THREADS) {
+            const int i = base + t;
+            int c = (i < nlocal && block_of(cellc[i], g.lbx, g.lby, g.lbz) != b0) ? i : 0x7fffffff;
+            c = __reduce_min_sync(full, c);
+            if (lane == 0) s_red[wid] = c;
+            __syncthreads();
+            c = s_red[0];
 #pragma unroll
-        for (int r = 0; r < 9; r++) {
-            const int y = cy + r % 3 - 1, z = cz + r / 3 - 1;
-            const bool ok = active && y >= 0 && y < m1 && z >= 0 && z < m2;
-            const int *cs = cell_start + (ok ? (size_t)m0 * (size_t)(y + m1 * z) : (size_t)0);
-            const int a = cs[ok ? xa : 0], b = cs[ok ? xb + 1 : 0];
-            s_runs[wid][r][lane] = make_int2(a, b - a);
+            for (int w = 1; w < NB_WARPS; w++) c = min(c, s_red[w]);
+            __syncthreads();
+            if (c != 0x7fffffff) { e = c; break; }
         }
-        __syncwarp();
-        // ---- flattened walk: every lane advances through its own concatenated candidate list; lanes of the same cell walk
-        //      the same records in lockstep.  Hits are pushed as j | skin << 27 (the atom itself is dropped at write-out).
-        int qn = 0, r = 0;
-        int2 run = s_runs[wid][0][lane];
-        int q = run.x, n = run.y;
-        while (true) {
-#pragma unroll
-            for (int adv = 0; adv < 2; adv++)
-                if (n <= 0 && r < 8) { r++; run = s_runs[wid][r][lane]; q = run.x; n = run.y; }
-            if (!__any_sync(full, n > 0 || r < 8)) break;       // (three empty runs in a row: a non-periodic face)
-            float4 v[NB_BATCH];
-#pragma unroll
-            for (int u = 0; u < NB_BATCH; u++) v[u] = cell_xyzj[n > u ? q + u : 0];
-#pragma unroll
-            for (int u = 0; u < NB_BATCH; u++) {
-                const float dx = ci.x - v[u].x, dy = ci.y - v[u].y, dz = ci.z - v[u].z;
-                const float dr2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // UM/neigh_build_meso.cu:86-89
-                if (n > u && dr2 <= rc2_tail) {
-                    const uint32_t en = (__float_as_uint(v[u].w) & MJ) | (dr2 <= rc2_core ? 0u : 1u << 27);
-                    if (qn < NQ) sts_u32(qbase + (qn << 7), en);
-                    else if (qn < NQ + NQX) xbase[(qn - NQ) << 5] = en;
-                    qn++;
+        // ---- tile geometry: the block's cells and one layer around them, clipped to the lattice
+        const int X0 = (b0 & 1023) << g.lbx, Y0 = ((b0 >> 10) & 1023) << g.lby, Z0 = (b0 >> 20) << g.lbz;
+        const int xlo = max(X0 - 1, 0), xhi = min(X0 + (1 << g.lbx), m0 - 1);
+        const int ylo = max(Y0 - 1, 0), yhi = min(Y0 + (1 << g.lby), m1 - 1);
+        const int zlo = max(Z0 - 1, 0), zhi = min(Z0 + (1 << g.lbz), m2 - 1);
+        const int nxt = xhi - xlo + 1, nyt = yhi - ylo + 1, nrows = nyt * (zhi - zlo + 1);
+        if (t < nrows) {
+            const int c0 = xlo + m0 * ((ylo + t % nyt) + m1 * (zlo + t / nyt));
+            const int g0 = cell_start[c0];
+            s_rowsrc[t] = g0;
+            s_rowlen[t] = cell_start[c0 + nxt] - g0;
+        }
+        __syncthreads();
+        if (t <= nrows) {
+            int off = 0;
+            for (int r = 0; r < t; r++) off += s_rowlen[r];
+            s_rowoff[t] = off;
+        }
+        __syncthreads();
+        const int total = s_rowoff[nrows];
+        const bool fits = total <= g.tile_cap;
+        if (fits) {
+            for (int u = t; u < nrows * TILE_NX; u += NB_THREADS) {
+                const int r = u / TILE_NX, xi = u % TILE_NX;
+                if (xi <= nxt) {
+                    const int c0 = xlo + m0 * ((ylo + r % nyt) + m1 * (zlo + r / nyt));
+                    s_cell[u] = s_rowoff[r] + cell_start[c0 + xi] - s_rowsrc[r];
                 }
             }
-            q += NB_BATCH; n -= NB_BATCH;
-        }
-        bool bad = qn > NQ + NQX;
-        if (bad) qn = 0;
-        __syncwarp();
-        // ---- classify: drop the atom itself (it is always a hit), decide ownership, count the four classes
-        const int qmax = __reduce_max_sync(full, qn);
-        uint32_t cls_cnt = 0;                                  // 4 x 8-bit counters: owned core, owned skin, other core, other skin
-        for (int t = 0; t < qmax; t++) {
-            if (t < qn) {
-                const uint32_t en = t < NQ ? lds_u32(qbase + (t << 7)) : xbase[(t - NQ) << 5];
-                const int j = (int)(en & MJ);
-                uint32_t cls = 4;
-                if (j != i) { cls = (owns(i, j, nlocal) ? 0u : 2u) | (en >> 27); cls_cnt += 1u << (8 * cls); }
-                const uint32_t out = (uint32_t)j | (cls << 27);
-                if (t < NQ) sts_u32(qbase + (t << 7), out); else xbase[(t - NQ) << 5] = out;
+            if (t == 0) mbar_expect_tx(bar, (unsigned)total * 16u);
+            if (t < nrows && s_rowlen[t] > 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bulk_g2s(tile_base + (unsigned)s_rowoff[t] * 16u, cell_xyzj + s_rowsrc[t], (unsigned)s_rowlen[t] * 16u, bar);
             }
+            __syncthreads();                                    // s_cell complete
+            mbar_wait(bar, phase);
+            phase ^= 1u;
         }
-        const int n0 = cls_cnt & 255, n1 = (cls_cnt >> 8) & 255, n2 = (cls_cnt >> 16) & 255, n3 = cls_cnt >> 24;
-        const int ntot = n0 + n1 + n2 + n3;
-        bad = bad || ntot > n_col;
-        if (active) {
-            if (bad) { pair_count[i] = -1; atomicOr(fixup, 1); }
-            else { pair_count[i] = ntot; owned_count[i] = n0 + n1; core_split[i] = n0 | (n2 << 16); }
-        }
-        worst = max(worst, bad ? 0 : ntot);
-        // ---- write-out: the four segments, each in encounter order
-        uint32_t pos = (uint32_t)n0 << 8 | (uint32_t)(n0 + n1) << 16 | (uint32_t)(n0 + n1 + n2) << 24;   // running position of each class
-        int *row0 = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
-        for (int t = 0; t < qmax; t++) {
-            if (t < qn && !bad) {
-                const uint32_t en = t < NQ ? lds_u32(qbase + (t << 7)) : xbase[(t - NQ) << 5];
-                const uint32_t cls = en >> 27;
-                if (cls < 4) {
-                    const int sh = cls * 8;
-                    const int k = (pos >> sh) & 255;
-                    pos += 1u << sh;
-                    row0[(k & 31) * n_col + (k >> 5) * 32] = (int)(en & MJ);
+        // ---- rows of the segment: one warp per 32-aligned group of atoms
+        for (int T = (a >> 5) + wid; T <= ((e - 1) >> 5); T += NB_WARPS) {
+            const int i = T * 32 + lane;
+            const bool active = i >= a && i < e;
+            if (!fits) {
+                if (active) { pair_count[i] = -1; atomicOr(fixup, 1); }
+                continue;
+            }
+            const float4 ci = coord4[active ? i : a];
+            const int cc = cellc[active ? i : a];
+            const int cx = cc & 1023, cy = (cc >> 10) & 1023, cz = cc >> 20;
+            const int xa = max(cx - 1, 0) - xlo, xb = min(cx + 1, m0 - 1) - xlo + 1;
+            unsigned qp = qbase;
+            for (int r = 0; r < 9; r++) {
+                const int y = cy + r % 3 - 1, z = cz + r / 3 - 1;
+                const bool ok = active && y >= 0 && y < m1 && z >= 0 && z < m2;
+                const int row = ok ? ((z - zlo) * nyt + (y - ylo)) * TILE_NX : 0;
+                const int s0 = s_cell[row + xa], s1 = s_cell[row + xb];
+                unsigned q = tile_base + (unsigned)s0 * 16u;
+                const unsigned qe = ok ? tile_base + (unsigned)s1 * 16u : q;
+                while (true) {
+                    const bool more = q < qe;
+                    if (!__any_sync(full, more)) break;
+                    float4 v[NB_BATCH];
+#pragma unroll
+                    for (int u = 0; u < NB_BATCH; u++) v[u] = lds_f4(q + 16u * u);
+#pragma unroll
+                    for (int u = 0; u < NB_BATCH; u++) {
+                        const float dx = ci.x - v[u].x, dy = ci.y - v[u].y, dz = ci.z - v[u].z;
+                        const float dr2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // UM/neigh_build_meso.cu:86-89
+                        const bool hit = (q + 16u * u < qe) && (dr2 <= rc2);
+                        if (hit) { sts_u16(qp, q + 16u * u); qp = min(qp + 64u, qlim); }
+                    }
+                    if (more) q += 16u * NB_BATCH;
                 }
             }
+            __syncwarp();
+            // ---- write-out: owned entries straight to the front of the row while the others are compacted in the queue,
+            //      then the others behind them (both in walk order; the atom itself, always a hit, is dropped)
+            int qn = (int)((qp - qbase) >> 6);
+            const bool bad = qp >= qlim || qn - 1 > n_col;
+            if (!active || bad) qn = 0;
+            const int qmax = __reduce_max_sync(full, qn);
+            int *row0 = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
+            int own = 0, oth = 0;
+            for (int k = 0; k < qmax; k++)
+                if (k < qn) {
+                    const uint32_t rec = lds_u16(qbase + (unsigned)k * 64u);
+                    const int j = (int)lds_u32(rec + 12u);
+                    if (j != i) {
+                        if (owns(i, j, nlocal)) { row0[(own & 31) * n_col + (own >> 5) * 32] = j; own++; }
+                        else { sts_u16(qbase + (unsigned)oth * 64u, rec); oth++; }
+                    }
+                }
+            const int omax = __reduce_max_sync(full, oth);
+            for (int k = 0; k < omax; k++)
+                if (k < oth) {
+                    const int d = own + k;
+                    row0[(d & 31) * n_col + (d >> 5) * 32] = (int)lds_u32(lds_u16(qbase + (unsigned)k * 64u) + 12u);
+                }
+            if (active) {
+                if (bad) { pair_count[i] = -1; atomicOr(fixup, 1); }
+                else { pair_count[i] = own + oth; owned_count[i] = own; worst = max(worst, own + oth); }
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        __syncthreads();                                        // tile and cell offsets are reused by the next segment
     }
     // diagnostics only
     worst = __reduce_max_sync(full, worst);
-    if ((threadIdx.x & 31) == 0 && worst > 0) atomicMax(&cnt->max_pair, worst);
+    if (lane == 0 && worst > 0) atomicMax(&cnt->max_pair, worst);
 }
 
-// Fall-back for the rows the kernel above marked (more than NQ + NQX hits, or wider than the table): plain walk of the same
-// 9 runs, two passes (count the classes, then write).  Also the whole build when MESO_NB_SLOW=1 (A/B checks of the kernel above).
+// Fall-back for the rows the kernel above left (more hits than queue slots, a tile larger than its shared memory, a row wider
+// than the table): plain walk of the same 9 runs in global memory, two passes (count, then write).  Also the whole build when
+// MESO_NB_SLOW=1 (A/B checks of the kernel above).
 __global__ void __launch_bounds__(128) k_build_rows_slow(const float4 *__restrict__ coord4, const int *__restrict__ cellc,
                                                          const int *__restrict__ cell_start, const float4 *__restrict__ cell_xyzj,
                                                          int *__restrict__ pair_count, int *__restrict__ owned_count,
-                                                         int *__restrict__ core_split, int *__restrict__ pair_table,
-                                                         Counts *__restrict__ cnt, const int *__restrict__ fixup, int all_rows, int n_col,
-                                                         float rc2_core, float rc2_tail, int m0, int m1, int m2)
+                                                         int *__restrict__ pair_table, Counts *__restrict__ cnt,
+                                                         const int *__restrict__ fixup, int all_rows, int n_col, float rc2, int m0, int m1, int m2)
 {
     if (!all_rows && *fixup == 0) return;
     const int nlocal = cnt->nlocal;
@@ -348,9 +439,9 @@ __global__ void __launch_bounds__(128) k_build_rows_slow(const float4 *__restric
         const int cc = cellc[i];
         const int cx = cc & 1023, cy = (cc >> 10) & 1023, cz = cc >> 20;
         const int xa = max(cx - 1, 0), xb = min(cx + 1, m0 - 1);
-        int num[4] = {0, 0, 0, 0}, pos[4] = {0, 0, 0, 0};
+        int n_own = 0, n_oth = 0, k_own = 0, k_oth = 0;
         for (int pass = 0; pass < 2; pass++) {
-            if (pass == 1) { pos[0] = 0; pos[1] = num[0]; pos[2] = num[0] + num[1]; pos[3] = num[0] + num[1] + num[2]; }
+            k_oth = n_own;
             for (int z = max(cz - 1, 0); z <= min(cz + 1, m2 - 1); z++)
                 for (int y = max(cy - 1, 0); y <= min(cy + 1, m1 - 1); y++) {
                     const int *cs = cell_start + (size_t)m0 * (size_t)(y + m1 * z);
@@ -360,65 +451,66 @@ __global__ void __launch_bounds__(128) k_build_rows_slow(const float4 *__restric
                         if (j == i) continue;
                         const float dx = ci.x - c2.x, dy = ci.y - c2.y, dz = ci.z - c2.z;
                         const float dr2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                        if (!(dr2 <= rc2_tail)) continue;
-                        const int cls = (owns(i, j, nlocal) ? 0 : 2) | (dr2 <= rc2_core ? 0 : 1);
-                        if (pass == 0) num[cls]++;
-                        else { const int k = pos[cls]++; if (k < n_col) pair_table[slot(i, k, n_col)] = j; }
+                        if (!(dr2 <= rc2)) continue;
+                        const bool mine = owns(i, j, nlocal);
+                        if (pass == 0) { if (mine) n_own++; else n_oth++; }
+                        else { const int k = mine ? k_own++ : k_oth++; if (k < n_col) pair_table[slot(i, k, n_col)] = j; }
                     }
                 }
         }
-        int tot = num[0] + num[1] + num[2] + num[3];
+        int tot = n_own + n_oth;
         if (tot > n_col) {                                   // row wider than the table: flagged, clipped (UM/neigh_build_meso.cu:242-252 only printf's)
             atomicOr(&cnt->err, 2);
-            tot = n_col; num[0] = min(num[0], n_col); num[1] = min(num[1], n_col - num[0]); num[2] = min(num[2], n_col - num[0] - num[1]);
+            tot = n_col; n_own = min(n_own, n_col);
         }
-        pair_count[i] = tot; owned_count[i] = num[0] + num[1]; core_split[i] = num[0] | (num[2] << 16);
+        pair_count[i] = tot; owned_count[i] = n_own;
         atomicMax(&cnt->max_pair, tot);
     }
 }
 
 // ------------------------------------------------------------------ the reference's row order, on demand (exports)
-// core entries in stencil order (neighbor cells by (boundary flag, Morton), ascending atom index inside a cell), then the
-// skin entries in REVERSE stencil order (UM/neigh_build_meso.cu:58-117,166-200).  key = slot rank of j's cell << 27 | j.
+// core entries (r <= r_n - skin at build time) in stencil order (neighbor cells by (boundary flag, Morton), ascending atom index
+// inside a cell), then the skin entries in REVERSE stencil order (UM/neigh_build_meso.cu:58-117,166-200).  The distances are
+// those of the build: cell_xyzj keeps the coordinates the table was built from.  key = slot rank of j's cell << 27 | j.
 __global__ void __launch_bounds__(128) k_canonical_rows(const int *__restrict__ cellc, const unsigned char *__restrict__ slotrank,
-                                                        const int *__restrict__ pair_count, const int *__restrict__ owned_count,
-                                                        const int *__restrict__ core_split, const int *__restrict__ pair_table,
-                                                        int *__restrict__ out_table, const Counts *__restrict__ cnt, int n_col, int m0, int m1)
+                                                        const int *__restrict__ pos_of, const float4 *__restrict__ cell_xyzj,
+                                                        const int *__restrict__ pair_count, const int *__restrict__ pair_table,
+                                                        int *__restrict__ out_table, const Counts *__restrict__ cnt, int n_col, float rc2_core,
+                                                        int m0, int m1)
 {
     const int nlocal = cnt->nlocal;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
-        const int np = pair_count[i], nown = owned_count[i], cs = core_split[i];
-        const int n_oc = cs & 0xffff, n_nc = cs >> 16;
+        const int np = pair_count[i];
         const int cc = cellc[i];
         const int cx = cc & 1023, cy = (cc >> 10) & 1023, cz = cc >> 20;
         const unsigned char *inv = slotrank + (size_t)(cx + m0 * (cy + m1 * cz)) * 32;
+        const float4 ci = cell_xyzj[pos_of[i]];
         auto key_of = [&](int j) -> uint32_t {
             const int cj = cellc[j];
             const int code = ((cj & 1023) - cx + 1) + 3 * (((cj >> 10) & 1023) - cy + 1) + 9 * ((cj >> 20) - cz + 1);
             return ((uint32_t)inv[code] << 27) | (uint32_t)j;
         };
-        // insertion sort of one class straight into the output row: class 0 = core -> [0, ncore) ascending keys,
-        // class 1 = skin -> [ncore, np) descending keys
-        const int ncore = n_oc + n_nc;
-        for (int cls = 0; cls < 2; cls++) {
+        auto is_core = [&](int j) -> bool {
+            const float4 c2 = cell_xyzj[pos_of[j]];
+            const float dx = ci.x - c2.x, dy = ci.y - c2.y, dz = ci.z - c2.z;
+            return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) <= rc2_core;      // UM/neigh_build_meso.cu:296-297
+        };
+        int ncore = 0;
+        for (int k = 0; k < np; k++) ncore += is_core(pair_table[slot(i, k, n_col)]) ? 1 : 0;
+        // insertion sort of each class straight into the output row: core -> [0, ncore) ascending keys, skin -> [ncore, np) descending
+        int have[2] = {0, 0};
+        for (int k = 0; k < np; k++) {
+            const int j = pair_table[slot(i, k, n_col)];
+            const int cls = is_core(j) ? 0 : 1;
             const int dst0 = cls ? ncore : 0;
-            int cntk = 0;
-            for (int seg = 0; seg < 2; seg++) {
-                // the two segments of this class in the production row: owned part, then other part
-                const int a = cls == 0 ? (seg == 0 ? 0 : nown) : (seg == 0 ? n_oc : nown + n_nc);
-                const int b = cls == 0 ? (seg == 0 ? n_oc : nown + n_nc) : (seg == 0 ? nown : np);
-                for (int k = a; k < b; k++) {
-                    const int j = pair_table[slot(i, k, n_col)];
-                    const uint32_t key = key_of(j);
-                    int p = cntk++;
-                    while (p > 0) {
-                        const int jp = out_table[slot(i, dst0 + p - 1, n_col)];
-                        const uint32_t kp = key_of(jp);
-                        if (cls == 0 ? kp > key : kp < key) { out_table[slot(i, dst0 + p, n_col)] = jp; p--; } else break;
-                    }
-                    out_table[slot(i, dst0 + p, n_col)] = j;
-                }
+            const uint32_t key = key_of(j);
+            int p = have[cls]++;
+            while (p > 0) {
+                const int jp = out_table[slot(i, dst0 + p - 1, n_col)];
+                const uint32_t kp = key_of(jp);
+                if (cls == 0 ? kp > key : kp < key) { out_table[slot(i, dst0 + p, n_col)] = jp; p--; } else break;
             }
+            out_table[slot(i, dst0 + p, n_col)] = j;
         }
     }
 }
@@ -465,14 +557,39 @@ static void scan_into(meso_ctx *ctx, const int *in, int *out, int n)
     k_scan_apply<<<nblk, SCAN_T, 0, LS(ctx->stream)>>>(in, out, ctx->scan_sums.p, n);
 }
 
+// shape of the build for this density: the largest Morton-aligned block of cells whose tile (block + one layer) fits the
+// shared-memory budget with 20 % head room, and a hit queue of 1.4 x the expected row length (three CTAs per SM at rho = 4)
+static TileGeom tile_geometry(const meso_ctx *ctx, int *warps_out, size_t *smem_out)
+{
+    const Box &box = ctx->box;
+    const double inner = (double)std::max(box.m[0] - 2, 1) * std::max(box.m[1] - 2, 1) * std::max(box.m[2] - 2, 1);
+    const double per_cell = std::max((double)nlocal_bound(ctx) / inner, 1.0);
+    static const int shapes[7][3] = {{2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}, {1, 1, 0}, {1, 0, 0}, {0, 0, 0}};
+    TileGeom g{};
+    const double rn = ctx->cutneighmax;
+    double vol = 1.0;
+    for (int d = 0; d < 3; d++) vol *= box.binsize[d];
+    const double expect = per_cell / vol * (4.0 / 3.0 * 3.14159265 * rn * rn * rn) + 1.0;
+    g.nq = std::min(std::max(((int)(1.4 * expect + 4.0) + 7) / 8 * 8, 32), 1024);
+    for (int s = 0; s < 7; s++) {
+        g.lbx = shapes[s][0]; g.lby = shapes[s][1]; g.lbz = shapes[s][2];
+        const int cells = ((1 << g.lbx) + 2) * ((1 << g.lby) + 2) * ((1 << g.lbz) + 2);
+        g.tile_cap = ((int)(cells * per_cell * 1.2) + 64 + 63) / 64 * 64;
+        if (g.tile_cap <= TILE_CAP_MAX) break;
+    }
+    g.tile_cap = std::min(g.tile_cap, TILE_CAP_MAX);
+    *smem_out = (size_t)g.tile_cap * 16 + TILE_SLACK + (size_t)NB_WARPS * g.nq * 64;
+    *warps_out = NB_WARPS;
+    return g;
+}
+
 int launch_neighbor_build(meso_ctx *ctx)
 {
     const Box &box = ctx->box;
     const int ncell = box.ncell;
-    if (ctx->cap + 8 > (size_t)MJ) { ctx->err = "neighbor build: more than 2^27 atoms + ghosts on one GPU"; return MESO_EINVAL; }
-    const int build_grid = ctx->sm_count * 7;               // persistent: 7 CTAs per SM (33 KB of queues + run lists each), one wave
-    if (!ctx->cell_xyzj.reserve(ctx->cap + 8) || !ctx->owned_count.reserve(ctx->cap) || !ctx->core_split.reserve(ctx->cap) ||
-        !ctx->nb_fixup.reserve(1) || !ctx->nb_scratch.reserve((size_t)build_grid * (NB_THREADS / 32) * NQX * 32)) {
+    if (ctx->cap + 8 > ((size_t)1 << 30)) { ctx->err = "neighbor build: more than 2^30 atoms + ghosts on one GPU"; return MESO_EINVAL; }
+    if (!ctx->cell_xyzj.reserve(ctx->cap + 8) || !ctx->pos_of.reserve(ctx->cap + 8) || !ctx->owned_count.reserve(ctx->cap) ||
+        !ctx->nb_fixup.reserve(1)) {
         ctx->err = "neighbor: out of device memory";
         return MESO_ECUDA;
     }
@@ -483,18 +600,27 @@ int launch_neighbor_build(meso_ctx *ctx)
     k_bin_count<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(x, ctx->cell_of.p, ctx->cell_cnt.p, ctx->d_counts, box);
     scan_into(ctx, ctx->cell_cnt.p, ctx->cell_start.p, ncell);
     k_bin_fill<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->cell_of.p, ctx->cell_start.p + 1, ctx->cell_atoms.p, ctx->d_counts, box.m[0], box.m[1]);
-    k_cell_order<<<(ncell + 127) / 128, 128, 0, LS(st)>>>(ctx->cell_start.p, ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_xyzj.p, ncell);
-    const float rc2_core = (float)pow(ctx->cutneighmax - ctx->skin, 2.0);   // UM/neigh_build_meso.cu:296-297
-    const float rc2_tail = (float)pow(ctx->cutneighmax, 2.0);
-    const int slow_grid = std::max(1, std::min((int)((nlocal_bound(ctx) + 127) / 128) + 1, ctx->sm_count * 64));
-    if (!ctx->nb_slow)
-        k_build_rows<<<build_grid, NB_THREADS, 0, LS(st)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_xyzj.p, ctx->pair_count.p,
-                                                           ctx->owned_count.p, ctx->core_split.p, ctx->pair_table.p, ctx->d_counts,
-                                                           ctx->nb_fixup.p, ctx->nb_scratch.p, ctx->n_col, rc2_core, rc2_tail, box.m[0], box.m[1],
-                                                           box.m[2]);
+    k_cell_order<<<(ncell + 127) / 128, 128, 0, LS(st)>>>(ctx->cell_start.p, ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_xyzj.p, ctx->pos_of.p, ncell);
+    const float rc2 = (float)pow(ctx->cutneighmax, 2.0);
+    const size_t nbound = nlocal_bound(ctx);
+    const int slow_grid = std::max(1, std::min((int)((nbound + 127) / 128) + 1, ctx->sm_count * 64));
+    if (!ctx->nb_slow) {
+        int warps; size_t smem;
+        const TileGeom g = tile_geometry(ctx, &warps, &smem);
+        static size_t smem_set = 0;
+        if (smem > smem_set) {
+            MESO_CUDA(cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)200 * 1024)));
+            smem_set = std::max(smem, (size_t)200 * 1024);
+        }
+        if (smem > (size_t)200 * 1024) { ctx->err = "neighbor build: hit queues do not fit shared memory (density too high)"; return MESO_EINVAL; }
+        const int grid = std::max(1, (int)((nbound + NB_THREADS - 1) / NB_THREADS));
+        k_build_tiles<<<grid, NB_THREADS, smem, LS(st)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_xyzj.p, ctx->pair_count.p,
+                                                         ctx->owned_count.p, ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p, ctx->n_col, rc2,
+                                                         box.m[0], box.m[1], box.m[2], g);
+    }
     k_build_rows_slow<<<slow_grid, 128, 0, LS(st)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_xyzj.p, ctx->pair_count.p,
-                                                     ctx->owned_count.p, ctx->core_split.p, ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p,
-                                                     ctx->nb_slow ? 1 : 0, ctx->n_col, rc2_core, rc2_tail, box.m[0], box.m[1], box.m[2]);
+                                                     ctx->owned_count.p, ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p, ctx->nb_slow ? 1 : 0,
+                                                     ctx->n_col, rc2, box.m[0], box.m[1], box.m[2]);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }
@@ -502,9 +628,10 @@ int launch_neighbor_build(meso_ctx *ctx)
 // the table in the reference's row order, for meso_export_pair_table
 int launch_canonical_rows(meso_ctx *ctx, int *out_table)
 {
-    k_canonical_rows<<<grid_for(ctx, 8), 128, 0, LS(ctx->stream)>>>(ctx->cell_of.p, ctx->slotrank.p, ctx->pair_count.p, ctx->owned_count.p,
-                                                                   ctx->core_split.p, ctx->pair_table.p, out_table, ctx->d_counts, ctx->n_col,
-                                                                   ctx->box.m[0], ctx->box.m[1]);
+    const float rc2_core = (float)pow(ctx->cutneighmax - ctx->skin, 2.0);   // UM/neigh_build_meso.cu:296-297
+    k_canonical_rows<<<grid_for(ctx, 8), 128, 0, LS(ctx->stream)>>>(ctx->cell_of.p, ctx->slotrank.p, ctx->pos_of.p, ctx->cell_xyzj.p, ctx->pair_count.p,
+                                                                   ctx->pair_table.p, out_table, ctx->d_counts, ctx->n_col, rc2_core, ctx->box.m[0],
+                                                                   ctx->box.m[1]);
     MESO_CUDA(cudaGetLastError());
     return MESO_OK;
 }

@@ -406,20 +406,20 @@ class Meso:
         return cnt, rows
 
     def pair_rows(self):
-        """production rows (pair_count, owned_count, owned core, other core, rows[nlocal][n_col]): the layout the force kernels read"""
+        """production rows (pair_count, owned_count, rows[nlocal][n_col]): the layout the force kernels read"""
         cnt = self.pair_count()
         n = len(cnt)
         n_col = self.bins()[3]
         t = np.empty(((n + 31) // 32 * 32) * n_col, np.int32)
-        own, split = np.empty(n, np.int32), np.empty(n, np.int32)
-        self._chk(self.L.meso_export_pair_rows(self.h, t.size, _ptr(t), _ptr(own), _ptr(split)))
+        own = np.empty(n, np.int32)
+        self._chk(self.L.meso_export_pair_rows(self.h, t.size, _ptr(t), _ptr(own)))
         rows = np.full((n, n_col), -1, np.int32)
         i = np.arange(n)
         for k in range(int(cnt.max()) if n else 0):
             sel = cnt > k
             idx = ((i[sel] & ~31) + (k & 31)).astype(np.int64) * n_col + (k >> 5) * 32 + (i[sel] & 31)
             rows[sel, k] = t[idx]
-        return cnt, own, split & 0xffff, split >> 16, rows
+        return cnt, own, rows
 
     def per_atom_virial(self):
         n = self.counts()["nlocal"]

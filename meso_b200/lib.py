@@ -75,7 +75,7 @@ SIGNATURES = {
     "meso_export_stencil": (_i, [_vp, _i, _vp]),
     "meso_export_pair_count": (_i, [_vp, _i, _vp]),
     "meso_export_pair_table": (_i, [_vp, _i64, _vp]),
-    "meso_export_pair_rows": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "meso_export_pair_rows": (_i, [_vp, _i64, _vp, _vp]),
     "meso_export_virial": (_i, [_vp, _i, _vp, _vp]),
     "meso_eval_gaussian": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "meso_eval_math": (_i, [_vp, _i, _i, _vp, _vp, _vp]),

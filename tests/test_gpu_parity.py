@@ -237,9 +237,8 @@ def test_non_periodic_dimension_and_tiny_box():
 
 
 def test_dense_fluid_rows_longer_than_the_staging_queue():
-    """rho = 8: ~72 stored neighbors per atom (> 64 staging slots, > 2 table tiles): the rows of the fine-lattice build that
-    overflow its queue are redone by the fall-back kernel; also the 32-slot tile wrap of the transposed table and the
-    early-drain path of the force kernel."""
+    """rho = 8: ~72 stored neighbors per atom (> 2 table tiles): the tile build picks a smaller block of cells and deeper hit
+    queues for this density; also the 32-slot tile wrap of the transposed table and the early-drain path of the force kernel."""
     x = workload.dpd_fluid(6, rho=8, seed=13)
     for precision in ("sp", "dp"):
         m, w = make_pair(6, precision, x=x)
@@ -250,8 +249,9 @@ def test_dense_fluid_rows_longer_than_the_staging_queue():
 
 
 def test_neighbor_build_plain_walk_gives_the_same_table(monkeypatch):
-    """MESO_NB_SLOW=1 builds every row with the plain walk of the 27 stencil cells (the fall-back kernel of the fine-lattice
-    build): same counts, same canonical rows, same split arrays -- and the same state after a run across a rebuild."""
+    """MESO_NB_SLOW=1 builds every row with the plain walk of the 27 stencil cells in global memory (the fall-back kernel of
+    the tile build): same counts, same canonical rows, same production rows entry for entry -- and the same state after a run
+    across a rebuild."""
     for L, precision in ((9, "dp"), ((7, 9, 12), "dp")):      # fp64: the run stays in lockstep with the oracle
         out = []
         for slow in ("0", "1"):
@@ -259,51 +259,45 @@ def test_neighbor_build_plain_walk_gives_the_same_table(monkeypatch):
             m, w = make_pair(L, precision)
             m.setup(); w.setup()
             assert_state_identical(m, w, precision=precision)
-            cnt, own, n_oc, n_nc, rows = m.pair_rows()
-            out.append((cnt, own, n_oc, n_nc, [frozenset(rows[i, :own[i]].tolist()) for i in range(len(cnt))]))
+            cnt, own, rows = m.pair_rows()
+            out.append((cnt, own, rows))
             m.run(6); w.run(6)
             cntg, rowsg = m.neighbors()
             cnto, rowso = w.neighbors()
             mask = np.arange(rowso.shape[1])[None, :] < cnto[:, None]
             assert np.array_equal(cntg, cnto) and np.array_equal(rowsg[mask], rowso[mask])
             m.close()
-        for a, b in zip(out[0][:4], out[1][:4]):
+        for a, b in zip(out[0], out[1]):
             assert np.array_equal(a, b)
-        assert out[0][4] == out[1][4]
 
 
 @pytest.mark.parametrize("L", [10, (7, 9, 12)])
-def test_production_rows_are_the_canonical_rows_in_four_segments(L):
-    """The table the force kernels read: [owned core][owned skin][other core][other skin].  Every segment is a subset of the
-    reference's core / skin part of the row, the four segments partition the row, and "owned" is exactly the rule of the
-    pair-once kernel (ghost j, or (i+j) odd ? i<j : i>j), so every local pair is owned by exactly one of its two rows."""
+def test_production_rows_are_the_canonical_rows_in_two_parts(L):
+    """The table the force kernels read: [owned][other].  A row holds exactly the reference's entries; "owned" is exactly the
+    rule of the pair-once kernel (ghost j, or (i+j) odd ? i<j : i>j), so every local pair is owned by exactly one of its two
+    rows; inside a part the entries follow the walk (ascending position in the cell order)."""
     m, w = make_pair(L, "sp")
     m.setup(); w.setup()
-    cnt, own, n_oc, n_nc, rows = m.pair_rows()
+    cnt, own, rows = m.pair_rows()
     cnto, rowso = w.neighbors()                              # reference order: core entries, then skin entries reversed
     nl = len(cnt)
     assert np.array_equal(cnt, cnto)
-    c4, _ = w.packed()
+    cs, ca = w.cells()
+    pos = np.empty(len(ca), np.int64)
+    pos[ca] = np.arange(len(ca))
     owner = {}
     for i in range(nl):
         r = rows[i, :cnt[i]]
-        ref = rowso[i, :cnto[i]]
-        assert sorted(r.tolist()) == sorted(ref.tolist())
-        d = c4[ref, :3] - c4[i, :3]
-        r2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
-        ncore = int((r2 <= np.float32(1.0)).sum())
-        assert ncore == n_oc[i] + n_nc[i]
-        core_ref, skin_ref = set(ref[:ncore].tolist()), set(ref[ncore:].tolist())
-        seg = [r[:n_oc[i]], r[n_oc[i]:own[i]], r[own[i]:own[i] + n_nc[i]], r[own[i] + n_nc[i]:]]
-        assert set(seg[0].tolist()) | set(seg[2].tolist()) == core_ref and set(seg[1].tolist()) | set(seg[3].tolist()) == skin_ref
-        for k, part in enumerate(seg):
-            for j in part.tolist():
-                mine = j >= nl or ((i < j) if (i + j) % 2 else (i > j))
-                assert mine == (k < 2), (i, j, k)
-                if j < nl and k < 2:
-                    key = (min(i, j), max(i, j))
-                    assert key not in owner
-                    owner[key] = i
+        assert sorted(r.tolist()) == sorted(rowso[i, :cnto[i]].tolist())
+        mine = (r >= nl) | np.where((i + r) % 2 == 1, i < r, i > r)
+        assert mine[:own[i]].all() and not mine[own[i]:].any(), i
+        for part in (r[:own[i]], r[own[i]:]):
+            assert np.all(np.diff(pos[part]) > 0), i
+        for j in r[:own[i]].tolist():
+            if j < nl:
+                key = (min(i, j), max(i, j))
+                assert key not in owner
+                owner[key] = i
     npairs = sum(int((rowso[i, :cnto[i]] < nl).sum()) for i in range(nl)) // 2
     assert len(owner) == npairs
     m.close()
