@@ -41,6 +41,13 @@ enum { MESO_SP = 0, MESO_DP = 1 };
 /* ---- device runtime: MesoDevice, UM/engine_meso.cu:38-119 ---- */
 int  meso_device_count(void);                       /* src/lammps.cpp:432-452 device pick */
 int  meso_create(meso_ctx **out, int device);       /* new MesoDevice(lmp, gpu, profile) */
+/* Several GPUs of one node behind ONE handle (one process, one host thread per GPU): replaces the reference's one MPI rank
+ * per GPU (src/lammps.cpp:432-452 device pick, src/comm.cpp:201-287 processor grid, UM/comm_meso.cu:41-254 exchange/borders
+ * through the host) for a host that is a single process.  meso_set_box splits the box into ndev uniform bricks, uploads are
+ * dealt out by brick, downloads come back brick after brick, reductions are whole-box sums; every other entry point behaves as
+ * on a single device except the meso_export_* parity exports (per-brick data: not available).  ndev == 1: meso_create. */
+int  meso_create_gang(meso_ctx **out, int ndev, const int *devices);
+int  meso_gang_size(meso_ctx *ctx);                 /* bricks behind the handle (1 for meso_create) */
 void meso_destroy(meso_ctx *ctx);                   /* MesoDevice::destroy */
 const char *meso_last_error(meso_ctx *ctx);         /* NULL ctx: last creation error */
 int  meso_sync(meso_ctx *ctx);                      /* MesoDevice::sync_device */

@@ -11,6 +11,7 @@
 #include "force.h"
 #include "neighbor.h"
 #include "timer.h"
+#include "universe.h"
 #include "update.h"
 
 using namespace LAMMPS_NS;
@@ -26,7 +27,32 @@ MesoDevice::MesoDevice(LAMMPS *lmp, int device, std::string profile) :
   if (ndev <= 0)
     error->one(FLERR,"<MESO> no CUDA device found: USER-MESO-B200 has no CPU path (run with -meso off for stock styles)");
   if (device < 0 || device >= ndev) error->one(FLERR,"<MESO> -device index out of range");
-  int rc = meso_create(&ctx,device);
+  // MESO_DEVICES=0-7 | 0,1,2,3 | 0,0 : this ONE process drives several GPUs (the image has no MPI; `-device N` of
+  // src/lammps.cpp:177-188 carries a single integer).  The library splits the box into one brick per listed device
+  // (a device may be listed more than once: several bricks share it) and LAMMPS keeps seeing one rank with all atoms.
+  int devs[64], ngang = 0;
+  const char *list = getenv("MESO_DEVICES");
+  if (list && *list) {
+    // (Comm does not exist yet when src/lammps.cpp:455-465 builds this object: Universe does)
+    if (universe->nprocs > 1) error->all(FLERR,"<MESO> MESO_DEVICES is for single-process runs: with MPI use one rank per GPU");
+    const char *s = list;
+    while (*s && ngang < 64) {
+      char *end;
+      long a = strtol(s,&end,10), b = a;
+      if (end == s) error->one(FLERR,"<MESO> MESO_DEVICES: expected a list such as 0-7 or 0,1,2,3");
+      s = end;
+      if (*s == '-') { b = strtol(s+1,&end,10); if (end == s+1) error->one(FLERR,"<MESO> MESO_DEVICES: bad range"); s = end; }
+      for (long d = a; d <= b && ngang < 64; d++) {
+        if (d < 0 || d >= ndev) error->one(FLERR,"<MESO> MESO_DEVICES: device index out of range");
+        devs[ngang++] = (int) d;
+      }
+      if (*s == ',') s++;
+      else if (*s) error->one(FLERR,"<MESO> MESO_DEVICES: expected a list such as 0-7 or 0,1,2,3");
+    }
+  }
+  int rc = ngang > 1 ? meso_create_gang(&ctx,ngang,devs) : meso_create(&ctx,ngang == 1 ? devs[0] : device);
+  if (rc == MESO_OK && ngang > 1 && universe->me == 0 && screen)
+    fprintf(screen,"<MESO> %d bricks on %d listed device(s), one host thread each\n",meso_gang_size(ctx),ngang);
   if (rc != MESO_OK) {
     char msg[512];
     sprintf(msg,"<MESO> cannot create device context: %s",meso_last_error(NULL));

@@ -6,6 +6,7 @@
 #include "pair_dpd_meso.h"
 #include "atom.h"
 #include "comm.h"
+#include "compute.h"
 #include "domain.h"
 #include "error.h"
 #include "fix.h"
@@ -166,6 +167,25 @@ void ModifiedVerlet::step_by_phases(bigint ntimestep)
   if (modify->n_end_of_step) modify->end_of_step();
 }
 
+/* ----------------------------------------------------------------------
+   true if every compute the previous thermo output evaluated keeps its data on the device (the /meso computes) or
+   only combines host scalars that the device styles tally (stock pressure and pe: Pair::virial, Pair::eng_vdwl)
+------------------------------------------------------------------------- */
+
+bool ModifiedVerlet::thermo_reads_device_only()
+{
+  if (modify->n_end_of_step || output->thermo == NULL) return false;
+  const bigint last = output->last_thermo;
+  for (int i = 0; i < modify->ncompute; i++) {
+    Compute *c = modify->compute[i];
+    if (c->invoked_scalar < last && c->invoked_vector < last && c->invoked_array < last &&
+        c->invoked_peratom < last && c->invoked_local < last) continue;          // not part of the thermo line
+    if (strstr(c->style,"/meso") || strcmp(c->style,"pressure") == 0 || strcmp(c->style,"pe") == 0) continue;
+    return false;
+  }
+  return true;
+}
+
 void ModifiedVerlet::flush(int &pending)
 {
   if (pending == 0) return;
@@ -198,7 +218,11 @@ void ModifiedVerlet::run(int n)
 
     if (ntimestep == output->next) {
       flush(pending);
-      dev->download_atoms();             // transfer_pre_output: thermo, dumps and restarts read host arrays
+      // transfer_pre_output (UM/mvv_meso.cu:411-416) copies every per-atom array back at every output step.  Dumps and
+      // restarts read host arrays; a thermo line whose computes all reduce on the device does not: no PCIe traffic then
+      if (ntimestep == output->next_dump_any || (output->restart_flag && ntimestep == output->next_restart) ||
+          !thermo_reads_device_only())
+        dev->download_atoms();
       timer->stamp();
       output->write(ntimestep);
       timer->stamp(TIME_OUTPUT);

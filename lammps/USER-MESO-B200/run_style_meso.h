@@ -33,6 +33,7 @@ class ModifiedVerlet : public Integrate, protected MesoBridge {
   void device_setup(int outflag);
   void step_by_phases(bigint ntimestep);
   void flush(int &pending);
+  bool thermo_reads_device_only();
   void force_clear();
 };
 

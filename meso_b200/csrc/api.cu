@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <functional>
 
 using namespace meso;
 
@@ -26,14 +27,34 @@ int eval_log2u(meso_ctx *ctx, int n, const uint32_t *a, double *out);
 int comm_init(meso_ctx *ctx, const void *nccl_id);
 void comm_destroy(meso_ctx *ctx);
 int comm_allreduce_sum(meso_ctx *ctx, double *host_vals, int n);
+
+// gang.cu: several GPUs behind one handle
+int gang_each(meso_ctx *ctx, const std::function<int(meso_ctx *, int)> &fn);
+int gang_size(meso_ctx *ctx);
+meso_ctx *gang_member(meso_ctx *ctx, int k);
+int gang_create(meso_ctx **out, int ndev, const int *devices);
+void gang_destroy(meso_ctx *ctx);
+int gang_set_box(meso_ctx *ctx, const double boxlo[3], const double boxhi[3], const int periodic[3]);
+int gang_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, const double *v, const int *tag, const int *type, const int *mask, const int *image);
+int gang_bonds_upload(meso_ctx *ctx, int nlocal, int bond_per_atom, const int *num_bond, const int *bond_type, const int *bond_atom, int tag_max);
+int gang_ensure_peers(meso_ctx *ctx);
+int gang_atoms_download(meso_ctx *ctx, int nmax, double *x, double *v, double *f, int *tag, int *type, int *mask, int *image);
+int gang_counts(meso_ctx *ctx, int *nlocal, int *nghost, int *n_bulk, int *n_border);
+int gang_sum(meso_ctx *ctx, int width, double *out, const std::function<int(meso_ctx *, double *)> &fn);
 }
 
 static std::string g_create_err;
+namespace meso { std::string &create_error() { return g_create_err; } }
 static int comm_setup_public(meso_ctx *ctx);
 
 #define CHECK_CTX() do { if (!ctx) return MESO_EINVAL; } while (0)
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 #define TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+// a gang handle (gang.cu) forwards the call to every member, each on its own host thread (`c` = the member)
+#define GANG_ALL(call) do { if (ctx->gang) return gang_each(ctx, [&](meso_ctx *c, int) -> int { return (call); }); } while (0)
+#define GANG_STEP(call) do { if (ctx->gang) { TRY(gang_ensure_peers(ctx)); return gang_each(ctx, [&](meso_ctx *c, int) -> int { return (call); }); } } while (0)
+#define GANG_FIRST(call) do { if (ctx->gang) { meso_ctx *c = gang_member(ctx, 0); int rc_ = (call); if (rc_ < 0) ctx->err = c->err; return rc_; } } while (0)
+#define GANG_NONE(what) do { if (ctx->gang) FAIL(MESO_EINVAL, what ": not available on a multi-GPU handle (ask a member)"); } while (0)
 
 // ---------------------------------------------------------------- timers
 namespace {
@@ -127,11 +148,23 @@ extern "C" int meso_create(meso_ctx **out, int device)
     return MESO_OK;
 }
 
+extern "C" int meso_create_gang(meso_ctx **out, int ndev, const int *devices)
+{
+    if (!out || ndev < 1 || !devices) return MESO_EINVAL;
+    if (ndev == 1) return meso_create(out, devices[0]);
+    *out = nullptr;
+    return gang_create(out, ndev, devices);
+}
+
+extern "C" int meso_gang_size(meso_ctx *ctx) { return ctx ? gang_size(ctx) : 0; }
+
 extern "C" void meso_destroy(meso_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->gang) { gang_destroy(ctx); delete ctx; return; }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    release_retired_buffers();
     comm_destroy(ctx);
     drain_timers(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -173,17 +206,19 @@ static int refresh_counts(meso_ctx *ctx)
 extern "C" int meso_sync(meso_ctx *ctx)
 {
     CHECK_CTX();
+    GANG_ALL(meso_sync(c));
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     drain_timers(ctx);
     return MESO_OK;
 }
 
-extern "C" void *meso_stream(meso_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" void *meso_stream(meso_ctx *ctx) { return ctx ? (void *)(ctx->gang ? gang_member(ctx, 0)->stream : ctx->stream) : nullptr; }
 
 extern "C" int meso_profiler(meso_ctx *ctx, int start)
 {
     CHECK_CTX();
+    GANG_ALL(meso_profiler(c, start));
     if (start) cudaProfilerStart(); else cudaProfilerStop();
     return MESO_OK;
 }
@@ -191,6 +226,12 @@ extern "C" int meso_profiler(meso_ctx *ctx, int start)
 extern "C" int meso_memory_usage(meso_ctx *ctx, uint64_t *bytes)
 {
     CHECK_CTX();
+    if (ctx->gang) {
+        double o = 0.;
+        TRY(gang_sum(ctx, 1, &o, [&](meso_ctx *c, double *part) -> int { uint64_t b = 0; int rc = meso_memory_usage(c, &b); *part = (double)b; return rc; }));
+        if (bytes) *bytes = (uint64_t)o;
+        return MESO_OK;
+    }
     uint64_t b = 0;
     for (int d = 0; d < 3; d++) b += ctx->x[d].bytes() + ctx->v[d].bytes() + ctx->f[d].bytes() + ctx->xa[d].bytes() + ctx->va[d].bytes();
     b += ctx->tag.bytes() + ctx->type.bytes() + ctx->mask.bytes() + ctx->image.bytes() + ctx->taga.bytes() + ctx->typea.bytes() +
@@ -223,6 +264,7 @@ static void update_subbox(meso_ctx *ctx)
 extern "C" int meso_set_box(meso_ctx *ctx, const double boxlo[3], const double boxhi[3], const int periodic[3])
 {
     CHECK_CTX();
+    if (ctx->gang) return gang_set_box(ctx, boxlo, boxhi, periodic);
     for (int d = 0; d < 3; d++) {
         if (!(boxhi[d] > boxlo[d])) FAIL(MESO_EINVAL, "meso_set_box: boxhi must exceed boxlo");
         ctx->box.boxlo[d] = boxlo[d]; ctx->box.boxhi[d] = boxhi[d]; ctx->box.prd[d] = boxhi[d] - boxlo[d];
@@ -238,6 +280,7 @@ extern "C" int meso_comm_blob_size(void) { return 1024; }
 extern "C" int meso_comm_export(meso_ctx *ctx, void *blob)
 {
     CHECK_CTX();
+    GANG_NONE("meso_comm_export");
     if (!blob) FAIL(MESO_EINVAL, "meso_comm_export: null blob");
     if (!ctx->box_set) FAIL(MESO_EINVAL, "meso_comm_export: call after meso_set_box / meso_set_decomposition / meso_atoms_upload");
     MESO_CUDA(cudaSetDevice(ctx->device));
@@ -247,6 +290,7 @@ extern "C" int meso_comm_export(meso_ctx *ctx, void *blob)
 extern "C" int meso_comm_import(meso_ctx *ctx, const void *blobs, int nranks)
 {
     CHECK_CTX();
+    GANG_NONE("meso_comm_import");
     if (!blobs) FAIL(MESO_EINVAL, "meso_comm_import: null blobs");
     MESO_CUDA(cudaSetDevice(ctx->device));
     return comm_import_blobs(ctx, blobs, nranks);
@@ -255,6 +299,7 @@ extern "C" int meso_comm_import(meso_ctx *ctx, const void *blobs, int nranks)
 extern "C" int meso_set_decomposition(meso_ctx *ctx, int rank, const int procgrid[3], const void *nccl_id)
 {
     CHECK_CTX();
+    if (ctx->gang) FAIL(MESO_EINVAL, "meso_set_decomposition: a multi-GPU handle decomposes the box itself");
     int n = procgrid[0] * procgrid[1] * procgrid[2];
     if (n < 1 || rank < 0 || rank >= n) FAIL(MESO_EINVAL, "meso_set_decomposition: bad rank/procgrid");
     ctx->rank = rank; ctx->nranks = n;
@@ -320,6 +365,7 @@ static void update_cutneighmax(meso_ctx *ctx)
 extern "C" int meso_set_neighbor(meso_ctx *ctx, double skin, int every)
 {
     CHECK_CTX();
+    GANG_ALL(meso_set_neighbor(c, skin, every));
     if (skin < 0 || every < 1) FAIL(MESO_EINVAL, "meso_set_neighbor: skin >= 0 and every >= 1 required");
     ctx->skin = skin; ctx->every = every;
     update_cutneighmax(ctx);
@@ -329,6 +375,7 @@ extern "C" int meso_set_neighbor(meso_ctx *ctx, double skin, int every)
 extern "C" int meso_set_types(meso_ctx *ctx, int ntypes, const double *mass)
 {
     CHECK_CTX();
+    GANG_ALL(meso_set_types(c, ntypes, mass));
     if (ntypes < 1 || !mass) FAIL(MESO_EINVAL, "meso_set_types: ntypes >= 1 and mass[ntypes+1] required");
     MESO_CUDA(cudaSetDevice(ctx->device));
     ctx->ntypes = ntypes;
@@ -343,6 +390,7 @@ extern "C" int meso_set_types(meso_ctx *ctx, int ntypes, const double *mass)
 extern "C" int meso_pair_dpd_settings(meso_ctx *ctx, int precision, double cut_global, int seed)
 {
     CHECK_CTX();
+    GANG_ALL(meso_pair_dpd_settings(c, precision, cut_global, seed));
     if (precision != MESO_SP && precision != MESO_DP) FAIL(MESO_EINVAL, "Illegal pair_style command");
     ctx->precision = precision; ctx->cut_global = cut_global; ctx->seed = seed;
     ctx->max_pair_cut = 0.0;                                // pair_style resets the coefficients (MesoPairDPD::settings)
@@ -354,6 +402,7 @@ extern "C" int meso_pair_dpd_settings(meso_ctx *ctx, int precision, double cut_g
 extern "C" int meso_pair_dpd_coeff(meso_ctx *ctx, const double *coeff7)
 {
     CHECK_CTX();
+    GANG_ALL(meso_pair_dpd_coeff(c, coeff7));
     if (ctx->ntypes < 1) FAIL(MESO_EINVAL, "meso_pair_dpd_coeff: call meso_set_types first");
     if (!coeff7) FAIL(MESO_EINVAL, "All pair coeffs are not set");
     MESO_CUDA(cudaSetDevice(ctx->device));
@@ -376,6 +425,7 @@ extern "C" int meso_pair_dpd_coeff(meso_ctx *ctx, const double *coeff7)
 extern "C" int meso_set_timestep_size(meso_ctx *ctx, double dt)
 {
     CHECK_CTX();
+    GANG_ALL(meso_set_timestep_size(c, dt));
     if (!(dt > 0)) FAIL(MESO_EINVAL, "timestep must be positive");
     ctx->dt = dt;
     return MESO_OK;
@@ -383,15 +433,23 @@ extern "C" int meso_set_timestep_size(meso_ctx *ctx, double dt)
 extern "C" int meso_set_force_units(meso_ctx *ctx, double ftm2v)
 {
     CHECK_CTX();
+    GANG_ALL(meso_set_force_units(c, ftm2v));
     if (!(ftm2v > 0)) FAIL(MESO_EINVAL, "ftm2v must be positive");
     ctx->ftm2v = ftm2v;
     return MESO_OK;
 }
-extern "C" int meso_set_reduce_scope(meso_ctx *ctx, int local_only) { CHECK_CTX(); ctx->reduce_local = local_only != 0; return MESO_OK; }
+extern "C" int meso_set_reduce_scope(meso_ctx *ctx, int local_only)
+{
+    CHECK_CTX();
+    if (ctx->gang) return MESO_OK;                          // the gang always returns whole-box sums
+    ctx->reduce_local = local_only != 0;
+    return MESO_OK;
+}
 // page-lock a host array in place so uploads/downloads run at PCIe rate (Pinned<T>, UM/memory_meso.h:224-243)
 extern "C" int meso_host_register(meso_ctx *ctx, void *ptr, uint64_t bytes)
 {
     CHECK_CTX();
+    if (ctx->gang) return MESO_OK;                          // uploads are dealt out through per-member staging copies
     if (!ptr || !bytes) return MESO_OK;
     MESO_CUDA(cudaSetDevice(ctx->device));
     cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
@@ -402,13 +460,20 @@ extern "C" int meso_host_register(meso_ctx *ctx, void *ptr, uint64_t bytes)
 extern "C" int meso_host_unregister(meso_ctx *ctx, void *ptr)
 {
     CHECK_CTX();
+    if (ctx->gang) return MESO_OK;
     if (!ptr) return MESO_OK;
     cudaError_t e = cudaHostUnregister(ptr);
     if (e != cudaSuccess) cudaGetLastError();      // not registered: nothing to undo
     return MESO_OK;
 }
-extern "C" int meso_set_ntimestep(meso_ctx *ctx, int64_t t) { CHECK_CTX(); ctx->ntimestep = t; return MESO_OK; }
-extern "C" int64_t meso_get_ntimestep(meso_ctx *ctx) { return ctx ? ctx->ntimestep : -1; }
+extern "C" int meso_set_ntimestep(meso_ctx *ctx, int64_t t)
+{
+    CHECK_CTX();
+    GANG_ALL(meso_set_ntimestep(c, t));
+    ctx->ntimestep = t;
+    return MESO_OK;
+}
+extern "C" int64_t meso_get_ntimestep(meso_ctx *ctx) { return ctx ? (ctx->gang ? gang_member(ctx, 0)->ntimestep : ctx->ntimestep) : -1; }
 
 // ---------------------------------------------------------------- atom store
 static int ensure_capacity(meso_ctx *ctx, size_t nlocal)
@@ -465,6 +530,7 @@ extern "C" int meso_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, con
                                  const int *mask, const int *image)
 {
     CHECK_CTX();
+    if (ctx->gang) return gang_atoms_upload(ctx, nlocal, x, v, tag, type, mask, image);
     if (!ctx->box_set) FAIL(MESO_EINVAL, "meso_atoms_upload: call meso_set_box first");
     if (nlocal < 0 || (nlocal > 0 && !x)) FAIL(MESO_EINVAL, "meso_atoms_upload: bad arguments");
     MESO_CUDA(cudaSetDevice(ctx->device));
@@ -505,6 +571,7 @@ extern "C" int meso_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, con
 extern "C" int meso_atoms_download(meso_ctx *ctx, int nmax, double *x, double *v, double *f, int *tag, int *type, int *mask, int *image)
 {
     CHECK_CTX();
+    if (ctx->gang) return gang_atoms_download(ctx, nmax, x, v, f, tag, type, mask, image);
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     const int n = ctx->h_counts->nlocal;
@@ -529,6 +596,7 @@ extern "C" int meso_atoms_download(meso_ctx *ctx, int nmax, double *x, double *v
 extern "C" int meso_counts(meso_ctx *ctx, int *nlocal, int *nghost, int *n_bulk, int *n_border)
 {
     CHECK_CTX();
+    if (ctx->gang) return gang_counts(ctx, nlocal, nghost, n_bulk, n_border);
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     if (nlocal) *nlocal = ctx->h_counts->nlocal;
@@ -538,7 +606,7 @@ extern "C" int meso_counts(meso_ctx *ctx, int *nlocal, int *nghost, int *n_bulk,
     return MESO_OK;
 }
 
-extern "C" int64_t meso_natoms_global(meso_ctx *ctx) { return ctx ? ctx->natoms_global : -1; }
+extern "C" int64_t meso_natoms_global(meso_ctx *ctx) { return ctx ? (ctx->gang ? (int64_t)ctx->nlocal_host : ctx->natoms_global) : -1; }
 
 // ---------------------------------------------------------------- phases
 static int ready(meso_ctx *ctx)
@@ -553,6 +621,7 @@ static int ready(meso_ctx *ctx)
 extern "C" int meso_initial_integrate(meso_ctx *ctx, int groupbit)
 {
     CHECK_CTX();
+    GANG_STEP(meso_initial_integrate(c, groupbit));
     TRY(ready(ctx));
     PhaseTimer t(ctx, MESO_T_INTEGRATE);
     return launch_initial_integrate(ctx, groupbit, false);
@@ -561,6 +630,7 @@ extern "C" int meso_initial_integrate(meso_ctx *ctx, int groupbit)
 extern "C" int meso_final_integrate(meso_ctx *ctx, int groupbit)
 {
     CHECK_CTX();
+    GANG_STEP(meso_final_integrate(c, groupbit));
     TRY(ready(ctx));
     PhaseTimer t(ctx, MESO_T_INTEGRATE);
     return launch_final_integrate(ctx, groupbit);
@@ -569,6 +639,7 @@ extern "C" int meso_final_integrate(meso_ctx *ctx, int groupbit)
 extern "C" int meso_neighbor_decide(meso_ctx *ctx)
 {
     CHECK_CTX();
+    GANG_ALL(meso_neighbor_decide(c));
     ctx->ago++;                                            // Neighbor::decide, src/neighbor.cpp:1216-1231 (delay 0, check no)
     return (ctx->ago % ctx->every == 0) ? 1 : 0;
 }
@@ -618,6 +689,7 @@ static int rebuild_impl(meso_ctx *ctx)
 extern "C" int meso_rebuild(meso_ctx *ctx)
 {
     CHECK_CTX();
+    GANG_STEP(meso_rebuild(c));
     TRY(ready(ctx));
     return rebuild_impl(ctx);
 }
@@ -625,6 +697,7 @@ extern "C" int meso_rebuild(meso_ctx *ctx)
 extern "C" int meso_forward_comm(meso_ctx *ctx)
 {
     CHECK_CTX();
+    GANG_STEP(meso_forward_comm(c));
     TRY(ready(ctx));
     PhaseTimer t(ctx, MESO_T_FORWARD);
     // phase API keeps the reference's order: ghosts' fp64 x,v are refreshed, packing happens in meso_pair_compute
@@ -641,6 +714,7 @@ extern "C" int meso_forward_comm(meso_ctx *ctx)
 extern "C" int meso_force_clear(meso_ctx *ctx, int range, int vflag)
 {
     CHECK_CTX();
+    GANG_STEP(meso_force_clear(c, range, vflag));
     TRY(ready(ctx));
     return launch_clear(ctx, range, vflag);
 }
@@ -648,6 +722,7 @@ extern "C" int meso_force_clear(meso_ctx *ctx, int range, int vflag)
 extern "C" int meso_pair_compute(meso_ctx *ctx, int range, int eflag, int vflag)
 {
     CHECK_CTX();
+    GANG_STEP(meso_pair_compute(c, range, eflag, vflag));
     TRY(ready(ctx));
     PhaseTimer t(ctx, MESO_T_PAIR);
     // compute_bulk packs LOCAL, compute_border packs GHOST, compute packs ALL (UM/pair_dpd_meso.cu:241-266)
@@ -659,6 +734,13 @@ extern "C" int meso_pair_compute(meso_ctx *ctx, int range, int eflag, int vflag)
 extern "C" int meso_compute_ke(meso_ctx *ctx, int groupbit, double *mv2_sum, double *count)
 {
     CHECK_CTX();
+    if (ctx->gang) {
+        double o[2];
+        TRY(gang_sum(ctx, 2, o, [&](meso_ctx *c, double *part) -> int { return meso_compute_ke(c, groupbit, part, part + 1); }));
+        if (mv2_sum) *mv2_sum = o[0];
+        if (count) *count = o[1];
+        return MESO_OK;
+    }
     TRY(ready(ctx));
     double vals[2];
     TRY(launch_ke(ctx, groupbit, &vals[0], &vals[1]));
@@ -671,6 +753,13 @@ extern "C" int meso_compute_ke(meso_ctx *ctx, int groupbit, double *mv2_sum, dou
 extern "C" int meso_compute_virial(meso_ctx *ctx, double virial6[6], double *e_pair)
 {
     CHECK_CTX();
+    if (ctx->gang) {
+        double o[7];
+        TRY(gang_sum(ctx, 7, o, [&](meso_ctx *c, double *part) -> int { return meso_compute_virial(c, part, part + 6); }));
+        if (virial6) memcpy(virial6, o, 6 * sizeof(double));
+        if (e_pair) *e_pair = o[6];
+        return MESO_OK;
+    }
     TRY(ready(ctx));
     double out[7];
     TRY(launch_virial_sum(ctx, out));
@@ -684,6 +773,7 @@ extern "C" int meso_compute_virial(meso_ctx *ctx, double virial6[6], double *e_p
 extern "C" int meso_bond_harmonic_coeff(meso_ctx *ctx, int nbondtypes, const double *k, const double *r0)
 {
     CHECK_CTX();
+    GANG_ALL(meso_bond_harmonic_coeff(c, nbondtypes, k, r0));
     if (nbondtypes < 1 || !k || !r0) FAIL(MESO_EINVAL, "Incorrect args for bond coefficients");
     MESO_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->bond_k_dev.reserve(nbondtypes + 1) || !ctx->bond_r0_dev.reserve(nbondtypes + 1)) FAIL(MESO_ECUDA, "out of device memory");
@@ -697,6 +787,7 @@ extern "C" int meso_bond_harmonic_coeff(meso_ctx *ctx, int nbondtypes, const dou
 extern "C" int meso_set_special_bonds(meso_ctx *ctx, double lj12)
 {
     CHECK_CTX();
+    GANG_ALL(meso_set_special_bonds(c, lj12));
     if (lj12 != 0.0 && lj12 != 1.0) FAIL(MESO_EINVAL, "special_bonds: only lj weights 0 (1-2 pairs excluded) and 1 (kept) are supported");
     ctx->special_lj12 = lj12;
     return MESO_OK;
@@ -706,6 +797,7 @@ extern "C" int meso_bonds_upload(meso_ctx *ctx, int nlocal, int bond_per_atom, c
                                  const int *bond_atom, int tag_max)
 {
     CHECK_CTX();
+    if (ctx->gang) return gang_bonds_upload(ctx, nlocal, bond_per_atom, num_bond, bond_type, bond_atom, tag_max);
     if (nlocal != ctx->nlocal_host) FAIL(MESO_EINVAL, "meso_bonds_upload: call right after meso_atoms_upload with the same atoms");
     if (bond_per_atom < 0 || (bond_per_atom > 0 && (!num_bond || !bond_type || !bond_atom))) FAIL(MESO_EINVAL, "meso_bonds_upload: bad arguments");
     MESO_CUDA(cudaSetDevice(ctx->device));
@@ -731,6 +823,7 @@ extern "C" int meso_bonds_upload(meso_ctx *ctx, int nlocal, int bond_per_atom, c
 extern "C" int meso_bond_compute(meso_ctx *ctx, int eflag, int vflag)
 {
     CHECK_CTX();
+    GANG_STEP(meso_bond_compute(c, eflag, vflag));
     TRY(ready(ctx));
     PhaseTimer t(ctx, MESO_T_PAIR);
     return launch_bond_force(ctx, eflag || vflag, false);
@@ -740,6 +833,12 @@ extern "C" int meso_bond_compute(meso_ctx *ctx, int eflag, int vflag)
 extern "C" int meso_compute_bond_energy(meso_ctx *ctx, double *e_bond)
 {
     CHECK_CTX();
+    if (ctx->gang) {
+        double o = 0.;
+        TRY(gang_sum(ctx, 1, &o, [&](meso_ctx *c, double *part) -> int { return meso_compute_bond_energy(c, part); }));
+        if (e_bond) *e_bond = o;
+        return MESO_OK;
+    }
     TRY(ready(ctx));
     double e = 0.;
     TRY(launch_bond_energy_sum(ctx, &e));
@@ -762,6 +861,7 @@ static int fix_register(meso_ctx *ctx, const meso::FixOp &op)
 extern "C" int meso_fix_wall(meso_ctx *ctx, int groupbit, int dims, double d, double f)
 {
     CHECK_CTX();
+    GANG_ALL(meso_fix_wall(c, groupbit, dims, d, f));
     if ((dims & 7) == 0) FAIL(MESO_EINVAL, "Incomplete fix wall command: insufficient arguments");
     meso::FixOp op{};
     op.kind = meso::FIX_WALL; op.groupbit = groupbit; op.dims = dims & 7;
@@ -772,6 +872,7 @@ extern "C" int meso_fix_wall(meso_ctx *ctx, int groupbit, int dims, double d, do
 extern "C" int meso_fix_solid_bound(meso_ctx *ctx, int groupbit, int dims, int force_kernel)
 {
     CHECK_CTX();
+    GANG_ALL(meso_fix_solid_bound(c, groupbit, dims, force_kernel));
     if ((dims & 7) == 0) FAIL(MESO_EINVAL, "Incomplete fix wall command: dimension unspecified");
     if (force_kernel != 1) FAIL(MESO_EINVAL, "Incomplete fix wall command: force kernel unspecified");
     meso::FixOp op{};
@@ -782,6 +883,7 @@ extern "C" int meso_fix_solid_bound(meso_ctx *ctx, int groupbit, int dims, int f
 extern "C" int meso_fix_addforce(meso_ctx *ctx, int groupbit, double fx, double fy, double fz)
 {
     CHECK_CTX();
+    GANG_ALL(meso_fix_addforce(c, groupbit, fx, fy, fz));
     meso::FixOp op{};
     op.kind = meso::FIX_ADDFORCE; op.groupbit = groupbit;
     op.p[0] = fx; op.p[1] = fy; op.p[2] = fz;
@@ -791,6 +893,7 @@ extern "C" int meso_fix_addforce(meso_ctx *ctx, int groupbit, double fx, double 
 extern "C" int meso_fix_pois(meso_ctx *ctx, int groupbit, int dim_ortho, int dim_force, double strength, double bisect_frac)
 {
     CHECK_CTX();
+    GANG_ALL(meso_fix_pois(c, groupbit, dim_ortho, dim_force, strength, bisect_frac));
     if (dim_ortho < 0 || dim_ortho > 2 || dim_force < 0 || dim_force > 2) FAIL(MESO_EINVAL, "Illegal fix CUDAPoiseuille command");
     meso::FixOp op{};
     op.kind = meso::FIX_POIS; op.groupbit = groupbit; op.dims = dim_ortho | (dim_force << 2);
@@ -802,6 +905,7 @@ extern "C" int meso_fix_pois(meso_ctx *ctx, int groupbit, int dim_ortho, int dim
 extern "C" int meso_fix_rdf(meso_ctx *ctx, int groupbit, int j_groupbit, int nbin, int every)
 {
     CHECK_CTX();
+    GANG_ALL(meso_fix_rdf(c, groupbit, j_groupbit, nbin, every));
     if (nbin <= 0 || nbin > 8192) FAIL(MESO_EINVAL, "Incomplete compute rdf command: insufficient arguments");
     if (every < 1) every = 1;
     MESO_CUDA(cudaSetDevice(ctx->device));
@@ -823,6 +927,17 @@ extern "C" int meso_fix_rdf(meso_ctx *ctx, int groupbit, int j_groupbit, int nbi
 extern "C" int meso_fix_rdf_read(meso_ctx *ctx, int handle, int nbin, double *histogram, double *n_samples, double *ni, double *nj)
 {
     CHECK_CTX();
+    if (ctx->gang) {
+        if (nbin <= 0 || !histogram) FAIL(MESO_EINVAL, "meso_fix_rdf_read: bad arguments");
+        std::vector<double> o((size_t)nbin + 3);
+        TRY(gang_sum(ctx, nbin + 3, o.data(), [&](meso_ctx *c, double *part) -> int {
+            return meso_fix_rdf_read(c, handle, nbin, part, part + nbin, part + nbin + 1, part + nbin + 2); }));
+        memcpy(histogram, o.data(), sizeof(double) * nbin);
+        if (n_samples) *n_samples = o[nbin] / gang_size(ctx);      // every member sampled at the same steps
+        if (ni) *ni = o[nbin + 1];
+        if (nj) *nj = o[nbin + 2];
+        return MESO_OK;
+    }
     if (handle < 0 || handle >= ctx->fixes.n || ctx->fixes.op[handle].kind != meso::FIX_RDF || nbin != ctx->fixes.op[handle].dims || !histogram)
         FAIL(MESO_EINVAL, "meso_fix_rdf_read: not an rdf fix / wrong bin count");
     MESO_CUDA(cudaSetDevice(ctx->device));
@@ -839,6 +954,7 @@ extern "C" int meso_fix_rdf_read(meso_ctx *ctx, int handle, int nbin, double *hi
 extern "C" int meso_fix_clear(meso_ctx *ctx)
 {
     CHECK_CTX();
+    GANG_ALL(meso_fix_clear(c));
     ctx->fixes = meso::FixList{};
     return MESO_OK;
 }
@@ -847,6 +963,7 @@ extern "C" int meso_fix_clear(meso_ctx *ctx)
 extern "C" int meso_fix_post_force(meso_ctx *ctx, int handle)
 {
     CHECK_CTX();
+    GANG_STEP(meso_fix_post_force(c, handle));
     TRY(ready(ctx));
     if (handle >= ctx->fixes.n) FAIL(MESO_EINVAL, "meso_fix_post_force: no such fix");
     PhaseTimer t(ctx, MESO_T_INTEGRATE);
@@ -859,6 +976,7 @@ extern "C" int meso_fix_post_force(meso_ctx *ctx, int handle)
 extern "C" int meso_fix_bounce(meso_ctx *ctx, int handle)
 {
     CHECK_CTX();
+    GANG_STEP(meso_fix_bounce(c, handle));
     TRY(ready(ctx));
     if (handle >= ctx->fixes.n) FAIL(MESO_EINVAL, "meso_fix_bounce: no such fix");
     PhaseTimer t(ctx, MESO_T_INTEGRATE);
@@ -869,6 +987,7 @@ extern "C" int meso_fix_bounce(meso_ctx *ctx, int handle)
 extern "C" int meso_setup(meso_ctx *ctx, int eflag, int vflag)
 {
     CHECK_CTX();
+    GANG_STEP(meso_setup(c, eflag, vflag));
     TRY(ready(ctx));
     ctx->bins_ready = false;
     TRY(rebuild_impl(ctx));                                  // pbc, sort_local, borders, neighbor build (UM/mvv_meso.cu:150-185)
@@ -951,6 +1070,7 @@ static int run_pair_once(meso_ctx *ctx, int nsteps, int groupbit)
 extern "C" int meso_run(meso_ctx *ctx, int nsteps, int groupbit)
 {
     CHECK_CTX();
+    GANG_STEP(meso_run(c, nsteps, groupbit));
     TRY(ready(ctx));
     if (!ctx->setup_done) FAIL(MESO_EINVAL, "meso_run: call meso_setup first");
     // bonded forces and post_force fixes need the unfused second half-kick
@@ -998,6 +1118,7 @@ extern "C" int meso_run(meso_ctx *ctx, int nsteps, int groupbit)
 extern "C" int meso_export_bins(meso_ctx *ctx, int m[3], double binsize[3], double bininv[3], int *n_col)
 {
     CHECK_CTX();
+    GANG_FIRST(meso_export_bins(c, m, binsize, bininv, n_col));
     if (!ctx->bins_ready) FAIL(MESO_EINVAL, "bins not set up");
     for (int d = 0; d < 3; d++) { m[d] = ctx->box.m[d]; binsize[d] = ctx->box.binsize[d]; bininv[d] = ctx->box.bininv[d]; }
     if (n_col) *n_col = ctx->n_col;
@@ -1022,6 +1143,7 @@ static int d2h(meso_ctx *ctx, T *dst, const T *src, size_t n)
 extern "C" int meso_export_reorder(meso_ctx *ctx, int nmax, uint64_t *key_sorted, int *permute_from)
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_reorder");
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     int n = ctx->h_counts->nlocal;
@@ -1034,6 +1156,7 @@ extern "C" int meso_export_reorder(meso_ctx *ctx, int nmax, uint64_t *key_sorted
 extern "C" int meso_export_packed(meso_ctx *ctx, int nmax, float *coord4, float *veloc4)
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_packed");
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     int n = ctx->h_counts->nlocal + ctx->h_counts->nghost;
@@ -1046,6 +1169,7 @@ extern "C" int meso_export_packed(meso_ctx *ctx, int nmax, float *coord4, float 
 extern "C" int meso_export_ghosts(meso_ctx *ctx, int nmax, double *x, double *v, int *tag, int *type)
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_ghosts");
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     const int nl = ctx->h_counts->nlocal, ng = ctx->h_counts->nghost;
@@ -1063,6 +1187,7 @@ extern "C" int meso_export_ghosts(meso_ctx *ctx, int nmax, double *x, double *v,
 extern "C" int meso_export_cells(meso_ctx *ctx, int ncell_plus1, int *cell_start, int nmax, int *cell_atoms)
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_cells");
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     int n = ctx->h_counts->nlocal + ctx->h_counts->nghost;
@@ -1080,6 +1205,7 @@ extern "C" int meso_export_cells(meso_ctx *ctx, int ncell_plus1, int *cell_start
 extern "C" int meso_export_stencil(meso_ctx *ctx, int cell, int out27[27])
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_stencil");
     MESO_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->bins_ready || cell < 0 || cell >= ctx->box.ncell) FAIL(MESO_EINVAL, "bad cell");
     unsigned char row[32];
@@ -1096,6 +1222,7 @@ extern "C" int meso_export_stencil(meso_ctx *ctx, int cell, int out27[27])
 extern "C" int meso_export_pair_count(meso_ctx *ctx, int nmax, int *pair_count)
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_pair_count");
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     int n = ctx->h_counts->nlocal;
@@ -1106,6 +1233,7 @@ extern "C" int meso_export_pair_count(meso_ctx *ctx, int nmax, int *pair_count)
 extern "C" int meso_export_pair_table(meso_ctx *ctx, int64_t nmax, int *pair_table)
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_pair_table");
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     size_t rows = ((size_t)ctx->h_counts->nlocal + 31) / 32 * 32;
@@ -1123,6 +1251,7 @@ extern "C" int meso_export_pair_table(meso_ctx *ctx, int64_t nmax, int *pair_tab
 extern "C" int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_table, int *owned_count)
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_pair_rows");
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     const int nl = ctx->h_counts->nlocal;
@@ -1138,6 +1267,7 @@ extern "C" int meso_export_pair_rows(meso_ctx *ctx, int64_t nmax, int *pair_tabl
 extern "C" int meso_export_virial(meso_ctx *ctx, int nmax, double *virial6, double *e_pair)
 {
     CHECK_CTX();
+    GANG_NONE("meso_export_virial");
     MESO_CUDA(cudaSetDevice(ctx->device));
     TRY(refresh_counts(ctx));
     const int n = ctx->h_counts->nlocal;
@@ -1156,6 +1286,7 @@ extern "C" int meso_export_virial(meso_ctx *ctx, int nmax, double *virial6, doub
 extern "C" int meso_eval_gaussian(meso_ctx *ctx, int n, const uint32_t *sig_i, const uint32_t *sig_j, float *out_sp, double *out_dp)
 {
     CHECK_CTX();
+    GANG_FIRST(meso_eval_gaussian(c, n, sig_i, sig_j, out_sp, out_dp));
     MESO_CUDA(cudaSetDevice(ctx->device));
     Tmp<uint32_t> a, b; Tmp<float> s; Tmp<double> d;
     if (!a.alloc(n) || !b.alloc(n) || !s.alloc(n) || !d.alloc(n)) FAIL(MESO_ECUDA, "out of device memory");
@@ -1171,6 +1302,7 @@ extern "C" int meso_eval_gaussian(meso_ctx *ctx, int n, const uint32_t *sig_i, c
 extern "C" int meso_eval_math(meso_ctx *ctx, int fn, int n, const double *a, const double *b, double *out)
 {
     CHECK_CTX();
+    GANG_FIRST(meso_eval_math(c, fn, n, a, b, out));
     MESO_CUDA(cudaSetDevice(ctx->device));
     if (fn < 0 || fn > 7 || (fn == 7 && !b)) FAIL(MESO_EINVAL, "meso_eval_math: bad function id");
     Tmp<double> da, db, dout;
@@ -1184,6 +1316,7 @@ extern "C" int meso_eval_math(meso_ctx *ctx, int fn, int n, const double *a, con
 extern "C" int meso_eval_log2u(meso_ctx *ctx, int n, const uint32_t *a, double *out)
 {
     CHECK_CTX();
+    GANG_FIRST(meso_eval_log2u(c, n, a, out));
     MESO_CUDA(cudaSetDevice(ctx->device));
     Tmp<uint32_t> da; Tmp<double> dout;
     if (!da.alloc(n) || !dout.alloc(n)) FAIL(MESO_ECUDA, "out of device memory");
@@ -1196,6 +1329,12 @@ extern "C" int meso_eval_log2u(meso_ctx *ctx, int n, const uint32_t *a, double *
 extern "C" int meso_launch_count(meso_ctx *ctx, int64_t *n, int reset)
 {
     CHECK_CTX();
+    if (ctx->gang) {
+        double o = 0.;
+        TRY(gang_sum(ctx, 1, &o, [&](meso_ctx *c, double *part) -> int { int64_t v = 0; int rc = meso_launch_count(c, &v, reset); *part = (double)v; return rc; }));
+        if (n) *n = (int64_t)o;
+        return MESO_OK;
+    }
     if (n) *n = ctx->n_launch;
     if (reset) ctx->n_launch = 0;
     return MESO_OK;
@@ -1204,6 +1343,7 @@ extern "C" int meso_launch_count(meso_ctx *ctx, int64_t *n, int reset)
 extern "C" int meso_timers_enable(meso_ctx *ctx, int on)
 {
     CHECK_CTX();
+    GANG_ALL(meso_timers_enable(c, on));
     ctx->timers_on = on != 0;
     return MESO_OK;
 }
@@ -1211,6 +1351,19 @@ extern "C" int meso_timers_enable(meso_ctx *ctx, int on)
 extern "C" int meso_timers_read(meso_ctx *ctx, double ms[MESO_T_COUNT], int64_t calls[MESO_T_COUNT], int reset)
 {
     CHECK_CTX();
+    if (ctx->gang) {                                          // slowest member per phase; call counts of the first
+        const int nk = gang_size(ctx);
+        std::vector<double> all((size_t)nk * MESO_T_COUNT, 0.0);
+        std::vector<int64_t> cl((size_t)nk * MESO_T_COUNT, 0);
+        TRY(gang_each(ctx, [&](meso_ctx *c, int k) -> int { return meso_timers_read(c, &all[(size_t)k * MESO_T_COUNT], &cl[(size_t)k * MESO_T_COUNT], reset); }));
+        for (int q = 0; q < MESO_T_COUNT; q++) {
+            double mx = 0.0;
+            for (int k = 0; k < nk; k++) mx = std::max(mx, all[(size_t)k * MESO_T_COUNT + q]);
+            if (ms) ms[q] = mx;
+            if (calls) calls[q] = cl[q];
+        }
+        return MESO_OK;
+    }
     MESO_CUDA(cudaSetDevice(ctx->device));
     drain_timers(ctx);
     for (int i = 0; i < MESO_T_COUNT; i++) {

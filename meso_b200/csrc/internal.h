@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <functional>
 #include <string>
 #include <vector>
 #include "../../include/meso_b200.h"
@@ -46,6 +47,13 @@ struct Box {
     int ncell;
 };
 
+// Growing a buffer must not synchronise the device: cudaMalloc / cudaFree wait for every kernel of the context, and with
+// several bricks in one process (gang.cu) one of those kernels may be a neighbor's halo kernel waiting for THIS brick.
+// Allocation is stream-ordered (cudaMallocAsync on the calling thread's stream, completed before it is handed out); a buffer
+// that has been outgrown is parked and released when a context is destroyed (kernels in flight may still read it).
+void retire_device_buffer(void *p);
+void release_retired_buffers();
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -57,9 +65,10 @@ struct DevBuf {
         if (n <= cap) return true;
         size_t ncap = n + n / 4 + 256;
         T *q = nullptr;
-        if (cudaMalloc(&q, ncap * sizeof(T)) != cudaSuccess) return false;
+        if (cudaMallocAsync(&q, ncap * sizeof(T), cudaStreamPerThread) != cudaSuccess ||
+            cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) { cudaGetLastError(); return false; }
         if (keep && p && cap) { cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s); cudaStreamSynchronize(s); }
-        if (p) cudaFree(p);
+        if (p) retire_device_buffer(p);
         p = q; cap = ncap;
         return true;
     }
@@ -93,6 +102,7 @@ enum { NCOEFF = 7, P_CUT = 0, P_CUTSQ, P_CUTINV, P_EXPW, P_A0, P_GAMMA, P_SIGMA 
 
 struct meso_ctx {
     int device = 0;
+    void *gang = nullptr;          // != nullptr: this handle stands for several GPUs (gang.cu) and owns no device state itself
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;
@@ -174,6 +184,7 @@ struct meso_ctx {
     meso::DevBuf<int> pair_count, pair_table;
     meso::DevBuf<int> owned_count;            // entries of the row whose pair this row evaluates (pair-once force kernel)
     meso::DevBuf<int> nb_fixup;               // != 0: some row was left to the fall-back build kernel
+    bool nb_smem_optin = false;               // the build kernel may use more than 48 KB of shared memory on this device
     size_t table_rows = 0;
 
     // reductions

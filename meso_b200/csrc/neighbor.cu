@@ -607,10 +607,9 @@ int launch_neighbor_build(meso_ctx *ctx)
     if (!ctx->nb_slow) {
         int warps; size_t smem;
         const TileGeom g = tile_geometry(ctx, &warps, &smem);
-        static size_t smem_set = 0;
-        if (smem > smem_set) {
-            MESO_CUDA(cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)200 * 1024)));
-            smem_set = std::max(smem, (size_t)200 * 1024);
+        if (!ctx->nb_smem_optin) {                          // per device (a gang holds one context per device in this process)
+            MESO_CUDA(cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ctx->nb_smem_optin = true;
         }
         if (smem > (size_t)200 * 1024) { ctx->err = "neighbor build: hit queues do not fit shared memory (density too high)"; return MESO_EINVAL; }
         const int grid = std::max(1, (int)((nbound + NB_THREADS - 1) / NB_THREADS));

@@ -479,11 +479,7 @@ static int launch_pair_t(meso_ctx *ctx, const REAL *coeff, REAL dtis, int range,
     // one CTA per 128 particles (host-side upper bound of the range); the grid-stride loop covers any excess
     int grid = (int)((nlocal_bound(ctx) + PAIR_THREADS - 1) / PAIR_THREADS) + 1;
     grid = std::max(1, std::min(grid, ctx->sm_count * 4096));
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_dpd<REAL, EV>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-        attr_done = true;
-    }
+    cudaFuncSetAttribute(k_dpd<REAL, EV>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);   // per device; a hint, cheap to repeat
     k_dpd<REAL, EV><<<grid, PAIR_THREADS, sh, LS(ctx->stream)>>>(ctx->coord4.p, ctx->veloc4.p, ctx->pair_count.p, ctx->pair_table.p, f, v, vir,
                                                            ctx->e_pair.p, ctx->mask.p, ctx->type.p, ctx->mass_dev.p, coeff, ctx->d_counts,
                                                            ctx->n_col, nt, dtis, range, accumulate, fuse_final, dtf, groupbit);

@@ -26,9 +26,13 @@ def _ptr(a):
 
 class Meso:
     def __init__(self, device=0):
+        """device: one GPU index, or a sequence of them -- several GPUs (or several bricks on one GPU) behind one handle"""
         self.L = _lib.load()
         h = C.c_void_p()
-        rc = self.L.meso_create(C.byref(h), device)
+        if isinstance(device, (list, tuple)):
+            rc = self.L.meso_create_gang(C.byref(h), len(device), (C.c_int * len(device))(*device))
+        else:
+            rc = self.L.meso_create(C.byref(h), device)
         if rc:
             raise MesoError("meso_create failed (%d): %s" % (rc, self.L.meso_last_error(None).decode()))
         self.h = h

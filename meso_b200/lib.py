@@ -15,6 +15,8 @@ _pi, _pd = C.POINTER(C.c_int), C.POINTER(C.c_double)
 SIGNATURES = {
     "meso_device_count": (_i, []),
     "meso_create": (_i, [C.POINTER(_vp), _i]),
+    "meso_create_gang": (_i, [C.POINTER(_vp), _i, _pi]),
+    "meso_gang_size": (_i, [_vp]),
     "meso_destroy": (None, [_vp]),
     "meso_last_error": (C.c_char_p, [_vp]),
     "meso_sync": (_i, [_vp]),

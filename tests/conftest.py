@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# bricks of a gang that share a device (experimental, tests/test_gang.py creates one without running it) need every stream on
+# its own hardware queue and every kernel loaded up front; both are read at CUDA start-up
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -416,3 +416,64 @@ def test_binary_keeps_stock_styles_with_meso_off(tmp_path):
         (tmp_path / "in.meso").write_text("units lj\natom_style dpd/atomic/meso\n")
         out = subprocess.run([LMP, "-in", "in.meso", "-log", "none"], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
         assert "no CUDA device found" in out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndev,extra", [("0,1", ""), ("0-3", "pe press"), ("0-7", "")])
+def test_deck_on_several_gpus_in_one_process(tmp_path, ndev, extra):
+    """MESO_DEVICES lists the GPUs this ONE LAMMPS process drives (the image has no MPI): the library splits the box into a brick
+    per listed device and LAMMPS keeps seeing one rank (skipped on boxes with fewer GPUs).  Same deck and the same setup forces as
+    on a single context, to the tolerance of re-centring the fp32-packed coordinates on each brick.  With the thermostat on, a
+    last-bit difference in a velocity re-draws that atom's pair random numbers (the RNG is keyed on fp32 velocity bits), so
+    the trajectories agree statistically: same atoms, same momentum, thermo trace within a few per cent (the bit-level check of
+    the decomposed path is tests/test_gang.py against the oracle's simulated ranks).  With `pe press` the thermo steps go
+    through the phase entry points and the gang's whole-box sums."""
+    need_binary()
+    from meso_b200 import lib
+    nbrick = int(ndev[-1]) + 1
+    if lib.load().meso_device_count() < nbrick:
+        pytest.skip("needs %d GPUs" % nbrick)
+    L, steps = 12, 20
+    ncol = 4 + len(extra.split())
+    one = tmp_path / "one"
+    one.mkdir()
+    out1 = run_deck(one, L, "dp", steps, thermo=10, extra=extra, env={"MESO_PAIR_ONCE": "0"})
+    assert out1.returncode == 0, out1.stdout[-2000:] + out1.stderr[-2000:]
+    many = tmp_path / "many"
+    many.mkdir()
+    out2 = run_deck(many, L, "dp", steps, thermo=10, extra=extra, env={"MESO_PAIR_ONCE": "0", "MESO_DEVICES": ndev, "CUDA_DEVICE_MAX_CONNECTIONS": "32",
+                                                                              "CUDA_MODULE_LOADING": "EAGER"})
+    assert out2.returncode == 0, out2.stdout[-2000:] + out2.stderr[-2000:]
+    assert "%d bricks on" % nbrick in out2.stdout
+    th1, th2 = thermo_rows(out1.stdout, ncol), thermo_rows(out2.stdout, ncol)
+    assert th1.shape == th2.shape == (3, ncol)
+    assert np.abs(th1[0, 1:ncol - 2] - th2[0, 1:ncol - 2]).max() < 2e-6 * np.abs(th1[0, 1:ncol - 2]).max(), (th1, th2)   # setup: same state
+    assert np.abs(th1[:, 1:ncol - 2] / th2[:, 1:ncol - 2] - 1.0).max() < 5e-2, (th1, th2)
+    f1, f2 = frames(str(one / "traj.txt")), frames(str(many / "traj.txt"))
+    assert np.array_equal(f1[0][:, :7], f2[0][:, :7])                    # same atoms in, by id
+    assert np.abs(f1[0][:, 7:10] - f2[0][:, 7:10]).max() < 1e-5 * np.abs(f1[0][:, 7:10]).max()
+    assert np.array_equal(f1[steps][:, 0], f2[steps][:, 0])              # nobody lost across 4 rebuilds with migration
+    assert np.abs(f2[steps][:, 4:7].sum(axis=0) - f2[0][:, 4:7].sum(axis=0)).max() < 1e-9      # pair forces cancel across brick faces too
+    assert np.abs(f1[steps][:, 1:4] - f2[steps][:, 1:4]).max() < 0.5     # same fluid 0.1 time units later
+
+
+@pytest.mark.gpu
+def test_thermo_only_output_steps_skip_the_download(tmp_path):
+    """A thermo line made of temp/meso, pe and press reduces on the device: mvv/meso then leaves the per-atom arrays where they
+    are (the reference copies everything back at every output step, UM/mvv_meso.cu:411-416).  Same numbers as a run whose dump
+    forces the download at the same steps."""
+    need_binary()
+    L, steps = 10, 30
+    a, b = tmp_path / "thermo_only", tmp_path / "with_dump"
+    a.mkdir(); b.mkdir()
+    env = {"MESO_PAIR_ONCE": "0"}
+    out_a = run_deck(a, L, "dp", steps, thermo=10, extra="pe press", dump=False, env=env)
+    deck_dump = DUMP.format(steps=10)
+    workload.write_data(str(b / ("%d.data" % L)), workload.dpd_fluid(L), L)
+    (b / "in.run").write_text(DECK.format(prec="dp", pair="dpd/meso", extra="pe press", thermo=10, steps=steps, dump=deck_dump))
+    out_b = subprocess.run([LMP, "-in", "in.run", "-var", "case", str(L), "-log", "none"], cwd=str(b), capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, **env))
+    assert out_a.returncode == 0 and out_b.returncode == 0, out_a.stdout[-1500:] + out_b.stdout[-1500:]
+    ta, tb = thermo_rows(out_a.stdout, 6), thermo_rows(out_b.stdout, 6)
+    assert ta.shape == tb.shape == (4, 6)
+    assert np.array_equal(ta[:, :4], tb[:, :4]), (ta, tb)
