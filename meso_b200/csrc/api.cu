@@ -239,7 +239,7 @@ extern "C" int meso_memory_usage(meso_ctx *ctx, uint64_t *bytes)
          ctx->staging.bytes() + ctx->istaging.bytes() + ctx->key.bytes() + ctx->perm_from.bytes() + ctx->sort.key_alt.bytes() +
          ctx->sort.val_alt.bytes() + ctx->sort.hist.bytes() + ctx->ghost_root.bytes() + ctx->ghost_shift.bytes() + ctx->tile_counts.bytes() +
          ctx->cell_of.bytes() + ctx->cell_atoms.bytes() + ctx->cell_start.bytes() + ctx->stencil.bytes() + ctx->slotrank.bytes() +
-         ctx->cell_cnt.bytes() + ctx->cell_xyzj.bytes() + ctx->scan_sums.bytes() + ctx->pos_of.bytes() +
+         ctx->cell_cnt.bytes() + ctx->cell_xyzj.bytes() + ctx->cell_soa.bytes() + ctx->scan_sums.bytes() + ctx->pos_of.bytes() +
          ctx->pair_count.bytes() + ctx->owned_count.bytes() + ctx->pair_table.bytes() + ctx->partial.bytes() +
          ctx->facc.bytes() + ctx->virial.bytes() + ctx->e_pair.bytes();
     *bytes = b;

@@ -176,7 +176,8 @@ struct meso_ctx {
     meso::DevBuf<int> cell_of;                // per atom: cell coordinates packed 10 bits per dimension (x | y << 10 | z << 20)
     meso::DevBuf<int> cell_atoms, cell_start; // atoms in (cell, ascending index) order; first position of every cell (+ total)
     meso::DevBuf<int> cell_cnt, scan_sums;    // histogram of the counting sort and the block sums of its scan
-    meso::DevBuf<float4> cell_xyzj;           // cell-ordered records {x, y, z, bits(atom index)} the build streams
+    meso::DevBuf<float4> cell_xyzj;           // cell-ordered records {x, y, z, bits(atom index)}: fall-back build, exports
+    meso::DevBuf<float> cell_soa;             // the same as four arrays x | y | z | index: what the tile build copies (TMA)
     meso::DevBuf<unsigned char> stencil;      // [ncell][32]: stencil codes in the reference's order, byte 31 = count
     meso::DevBuf<unsigned char> slotrank;     // [ncell][32]: stencil code -> position in that order
     meso::DevBuf<int> pos_of;                 // per atom: its position in the cell order (index into cell_xyzj / cell_atoms)

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_apply(const int *__restrict__ i
         if (base + u + 3 < n) { const int4 q = *reinterpret_cast<const int4 *>(in + base + u); v[u] = q.x; v[u + 1] = q.y; v[u + 2] = q.z; v[u + 3] = q.w; }
         else for (int q = 0; q < 4; q++) v[u + q] = base + u + q < n ? in[base + u + q] : 0;
     }
+
 #pragma unroll
     for (int u = 0; u < SCAN_I; u++) s += v[u];
     int x = s;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) k_bin_fill(const int *__restrict__ cellc,
 // and the cell-ordered copy of the packed coordinates, {x, y, z, bits(atom index)}, that the build kernel streams
 __global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell_start, int *__restrict__ cell_atoms,
                                                     const float4 *__restrict__ coord4, float4 *__restrict__ cell_xyzj,
-                                                    int *__restrict__ pos_of, int ncell)
+                                                    int *__restrict__ pos_of, float *__restrict__ cell_soa, size_t soa_stride, int ncell)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell
         float4 v = coord4[j];
         v.w = __int_as_float(j);
         cell_xyzj[a + k] = v;
+        cell_soa[a + k] = v.x; cell_soa[soa_stride + a + k] = v.y; cell_soa[2 * soa_stride + a + k] = v.z; cell_soa[3 * soa_stride + a + k] = v.w;
         pos_of[j] = a + k;
     }
 }
@@ -212,7 +214,6 @@ __global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell
 constexpr int NB_WARPS = 8, NB_THREADS = NB_WARPS * 32;
 constexpr int NB_BATCH = 4;                 // candidates per iteration (independent 16-byte shared-memory loads in flight)
 constexpr int TILE_ROWS = 36, TILE_NX = 7;  // (4+2) x (4+2) x-rows, (4+2)+1 cell offsets per row
-constexpr int TILE_SLACK = 64;              // bytes a batch may read past the last record
 constexpr int TILE_CAP_MAX = 2560;          // records (40 KB): with the static shared memory in front the tile ends below 64 KB
 
 __device__ __forceinline__ void sts_u32(unsigned addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
@@ -263,22 +264,43 @@ __device__ __forceinline__ size_t slot(int i, int k, int n_col)
 
 struct TileGeom { int lbx, lby, lbz, tile_cap, nq; };
 
-__global__ void __launch_bounds__(NB_THREADS, 3) k_build_tiles(const float4 *__restrict__ coord4, const int *__restrict__ cellc,
-                                                              const int *__restrict__ cell_start, const float4 *__restrict__ cell_xyzj,
-                                                              int *__restrict__ pair_count, int *__restrict__ owned_count,
-                                                              int *__restrict__ pair_table, Counts *__restrict__ cnt, int *__restrict__ fixup,
-                                                              int n_col, float rc2, int m0, int m1, int m2, TileGeom g)
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two candidates per instruction, each half rounded like the scalar operation)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ void lds_2x64(unsigned addr, unsigned long long &a, unsigned long long &b)
 {
-    extern __shared__ __align__(128) unsigned char smem[];      // [tile records][slack][per-warp hit queues: nq x 32 x u16]
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+}
+
+// The tile is four arrays (x, y, z, atom index) of TILE_CAP_MAX words at fixed strides, so one address register serves all
+// three coordinate loads and four candidates cost three LDS.128 (12 shared-memory wavefronts, not 16) and twelve packed
+// floating-point instructions.  Rows are copied in whole 16-byte groups: a run starts at the group that holds its first record
+// and masks what lies outside [first, last).  (Padding every cell to whole groups removes the masks -- 30 instead of 48
+// instructions per four candidates -- but adds 17 % candidates and doubles the cell-ordering pass: 377 + 68 us against
+// 361 + 39 us in a first measurement whose rows were still incomplete (parity red), so the variant was dropped there:
+// profiles/r02_s3_build_tiles_padded_ncu_summary.txt.)
+constexpr unsigned TILE_STRIDE = TILE_CAP_MAX * 4;          // bytes between the arrays of the tile
+
+__global__ void __launch_bounds__(NB_THREADS, 3) k_build_tiles(const float4 *__restrict__ coord4, const int *__restrict__ cellc,
+                                                              const int *__restrict__ cell_start, const float *__restrict__ cell_soa,
+                                                              size_t soa_stride, int *__restrict__ pair_count,
+                                                              int *__restrict__ owned_count, int *__restrict__ pair_table,
+                                                              Counts *__restrict__ cnt, int *__restrict__ fixup, int n_col, float rc2, int m0,
+                                                              int m1, int m2, TileGeom g)
+{
+    extern __shared__ __align__(128) unsigned char smem[];      // [x | y | z | j : TILE_CAP_MAX words each][per-warp hit queues: nq x 32 x u16]
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ int s_cell[TILE_ROWS * TILE_NX];                 // record offset of every tile cell (+ row end)
-    __shared__ int s_rowsrc[TILE_ROWS], s_rowlen[TILE_ROWS], s_rowoff[TILE_ROWS + 1];
+    __shared__ int s_cell[TILE_ROWS * TILE_NX];                 // tile index of the first record of every tile cell (+ row end)
+    __shared__ int s_rowsrc[TILE_ROWS], s_rowlen[TILE_ROWS], s_rowoff[TILE_ROWS + 1];   // per row: first global group, words copied, tile offset
     __shared__ int s_heads[NB_THREADS], s_nh, s_red[NB_WARPS];
     const unsigned full = 0xffffffffu;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const unsigned tile_base = (unsigned)__cvta_generic_to_shared(smem);
-    // a hit is queued as the 16-bit shared-memory address of its record (the tile ends below 64 KB: checked on the host)
-    const unsigned qbase = tile_base + (unsigned)g.tile_cap * 16u + TILE_SLACK + (unsigned)(wid * g.nq * 64 + lane * 2);
+    // a hit is queued as the 16-bit byte offset of its record inside an array of the tile
+    const unsigned qbase = tile_base + 4u * TILE_STRIDE + (unsigned)(wid * g.nq * 64 + lane * 2);
     const unsigned qlim = qbase + (unsigned)(g.nq - 1) * 64u;   // the last slot absorbs what does not fit (row goes to the fall-back)
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
     const int nlocal = cnt->nlocal;
@@ -319,9 +341,9 @@ __global__ void __launch_bounds__(NB_THREADS, 3) k_build_tiles(const float4 *__r
         const int nxt = xhi - xlo + 1, nyt = yhi - ylo + 1, nrows = nyt * (zhi - zlo + 1);
         if (t < nrows) {
             const int c0 = xlo + m0 * ((ylo + t % nyt) + m1 * (zlo + t / nyt));
-            const int g0 = cell_start[c0];
+            const int g0 = cell_start[c0] & ~3, g1 = (cell_start[c0 + nxt] + 3) & ~3;      // whole 16-byte groups
             s_rowsrc[t] = g0;
-            s_rowlen[t] = cell_start[c0 + nxt] - g0;
+            s_rowlen[t] = g1 - g0;
         }
         __syncthreads();
         if (t <= nrows) {
@@ -341,9 +363,11 @@ __global__ void __launch_bounds__(NB_THREADS, 3) k_build_tiles(const float4 *__r
                 }
             }
             if (t == 0) mbar_expect_tx(bar, (unsigned)total * 16u);
-            if (t < nrows && s_rowlen[t] > 0) {
+            if (t < 4 * nrows && s_rowlen[t >> 2] > 0) {
+                const int r = t >> 2, arr = t & 3;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                bulk_g2s(tile_base + (unsigned)s_rowoff[t] * 16u, cell_xyzj + s_rowsrc[t], (unsigned)s_rowlen[t] * 16u, bar);
+                bulk_g2s(tile_base + (unsigned)arr * TILE_STRIDE + (unsigned)s_rowoff[r] * 4u, cell_soa + (size_t)arr * soa_stride + s_rowsrc[r],
+                         (unsigned)s_rowlen[r] * 4u, bar);
             }
             __syncthreads();                                    // s_cell complete
             mbar_wait(bar, phase);
@@ -361,28 +385,38 @@ __global__ void __launch_bounds__(NB_THREADS, 3) k_build_tiles(const float4 *__r
             const int cc = cellc[active ? i : a];
             const int cx = cc & 1023, cy = (cc >> 10) & 1023, cz = cc >> 20;
             const int xa = max(cx - 1, 0) - xlo, xb = min(cx + 1, m0 - 1) - xlo + 1;
+            // x - x_i instead of x_i - x: the squares, hence the distance, are bit-identical (UM/neigh_build_meso.cu:86-89)
+            const unsigned long long nx2 = pack2(-ci.x, -ci.x), ny2 = pack2(-ci.y, -ci.y), nz2 = pack2(-ci.z, -ci.z);
             unsigned qp = qbase;
             for (int r = 0; r < 9; r++) {
                 const int y = cy + r % 3 - 1, z = cz + r / 3 - 1;
                 const bool ok = active && y >= 0 && y < m1 && z >= 0 && z < m2;
                 const int row = ok ? ((z - zlo) * nyt + (y - ylo)) * TILE_NX : 0;
-                const int s0 = s_cell[row + xa], s1 = s_cell[row + xb];
-                unsigned q = tile_base + (unsigned)s0 * 16u;
-                const unsigned qe = ok ? tile_base + (unsigned)s1 * 16u : q;
+                const unsigned s0 = 4u * (unsigned)s_cell[row + xa];                 // byte offsets inside an array of the tile
+                const unsigned s1 = ok ? 4u * (unsigned)s_cell[row + xb] : s0;
+                unsigned q = s0 & ~15u;
                 while (true) {
-                    const bool more = q < qe;
+                    const bool more = q < s1;
                     if (!__any_sync(full, more)) break;
-                    float4 v[NB_BATCH];
-#pragma unroll
-                    for (int u = 0; u < NB_BATCH; u++) v[u] = lds_f4(q + 16u * u);
+                    unsigned long long x01, x23, y01, y23, z01, z23;
+                    lds_2x64(tile_base + q, x01, x23);
+                    lds_2x64(tile_base + TILE_STRIDE + q, y01, y23);
+                    lds_2x64(tile_base + 2u * TILE_STRIDE + q, z01, z23);
+                    x01 = add2(x01, nx2); x23 = add2(x23, nx2);
+                    y01 = add2(y01, ny2); y23 = add2(y23, ny2);
+                    z01 = add2(z01, nz2); z23 = add2(z23, nz2);
+                    const unsigned long long d01 = fma2(z01, z01, fma2(y01, y01, mul2(x01, x01)));
+                    const unsigned long long d23 = fma2(z23, z23, fma2(y23, y23, mul2(x23, x23)));
+                    float dr2[4];
+                    unpack2(d01, dr2[0], dr2[1]);
+                    unpack2(d23, dr2[2], dr2[3]);
 #pragma unroll
                     for (int u = 0; u < NB_BATCH; u++) {
-                        const float dx = ci.x - v[u].x, dy = ci.y - v[u].y, dz = ci.z - v[u].z;
-                        const float dr2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // UM/neigh_build_meso.cu:86-89
-                        const bool hit = (q + 16u * u < qe) && (dr2 <= rc2);
-                        if (hit) { sts_u16(qp, q + 16u * u); qp = min(qp + 64u, qlim); }
+                        const unsigned c = q + 4u * u;
+                        const bool hit = c >= s0 && c < s1 && dr2[u] <= rc2;
+                        if (hit) { sts_u16(qp, c); qp = min(qp + 64u, qlim); }
                     }
-                    if (more) q += 16u * NB_BATCH;
+                    if (more) q += 4u * NB_BATCH;
                 }
             }
             __syncwarp();
@@ -393,22 +427,32 @@ __global__ void __launch_bounds__(NB_THREADS, 3) k_build_tiles(const float4 *__r
             if (!active || bad) qn = 0;
             const int qmax = __reduce_max_sync(full, qn);
             int *row0 = pair_table + (size_t)(i & ~31) * (size_t)n_col + (i & 31);   // slot(i,k) = row0[(k&31)*n_col + (k>>5)*32]
-            int own = 0, oth = 0;
-            for (int k = 0; k < qmax; k++)
-                if (k < qn) {
-                    const uint32_t rec = lds_u16(qbase + (unsigned)k * 64u);
-                    const int j = (int)lds_u32(rec + 12u);
-                    if (j != i) {
-                        if (owns(i, j, nlocal)) { row0[(own & 31) * n_col + (own >> 5) * 32] = j; own++; }
-                        else { sts_u16(qbase + (unsigned)oth * 64u, rec); oth++; }
-                    }
+            const unsigned jbase = tile_base + 3u * TILE_STRIDE;
+            int own = 0;
+            int po = 0;                                          // element offset of slot `own` from row0
+            unsigned qo = qbase;                                 // where the next "other" entry is parked
+            const int wrap = 32 - 31 * n_col;
+            for (int k = 0; k < qmax; k++) {
+                const uint32_t rec = k < qn ? lds_u16(qbase + (unsigned)k * 64u) : 0u;     // (stale slots may hold anything)
+                const int j = (int)lds_u32(jbase + rec);
+                const bool in = k < qn && j != i;
+                const bool mine = in && owns(i, j, nlocal);
+                if (mine) {
+                    row0[po] = j;
+                    po += ((own & 31) == 31) ? wrap : n_col;
+                    own++;
                 }
+                if (in && !mine) { sts_u16(qo, rec); qo += 64u; }
+            }
+            const int oth = (int)((qo - qbase) >> 6);
             const int omax = __reduce_max_sync(full, oth);
-            for (int k = 0; k < omax; k++)
-                if (k < oth) {
-                    const int d = own + k;
-                    row0[(d & 31) * n_col + (d >> 5) * 32] = (int)lds_u32(lds_u16(qbase + (unsigned)k * 64u) + 12u);
-                }
+            int d = own;
+            for (int k = 0; k < omax; k++) {
+                const int j = (int)lds_u32(jbase + (k < oth ? lds_u16(qbase + (unsigned)k * 64u) : 0u));
+                if (k < oth) row0[po] = j;
+                po += ((d & 31) == 31) ? wrap : n_col;
+                d++;
+            }
             if (active) {
                 if (bad) { pair_count[i] = -1; atomicOr(fixup, 1); }
                 else { pair_count[i] = own + oth; owned_count[i] = own; worst = max(worst, own + oth); }
@@ -558,7 +602,7 @@ static void scan_into(meso_ctx *ctx, const int *in, int *out, int n)
 }
 
 // shape of the build for this density: the largest Morton-aligned block of cells whose tile (block + one layer) fits the
-// shared-memory budget with 20 % head room, and a hit queue of 1.4 x the expected row length (three CTAs per SM at rho = 4)
+// shared-memory budget with 15 % head room, and a hit queue of 1.4 x the expected row length (three CTAs per SM at rho = 4)
 static TileGeom tile_geometry(const meso_ctx *ctx, int *warps_out, size_t *smem_out)
 {
     const Box &box = ctx->box;
@@ -574,11 +618,12 @@ static TileGeom tile_geometry(const meso_ctx *ctx, int *warps_out, size_t *smem_
     for (int s = 0; s < 7; s++) {
         g.lbx = shapes[s][0]; g.lby = shapes[s][1]; g.lbz = shapes[s][2];
         const int cells = ((1 << g.lbx) + 2) * ((1 << g.lby) + 2) * ((1 << g.lbz) + 2);
-        g.tile_cap = ((int)(cells * per_cell * 1.2) + 64 + 63) / 64 * 64;
+        const int rows = ((1 << g.lby) + 2) * ((1 << g.lbz) + 2);
+        g.tile_cap = ((int)(cells * per_cell * 1.15) + 4 * rows + 32 + 63) / 64 * 64;     // rows are copied in whole 16-byte groups
         if (g.tile_cap <= TILE_CAP_MAX) break;
     }
     g.tile_cap = std::min(g.tile_cap, TILE_CAP_MAX);
-    *smem_out = (size_t)g.tile_cap * 16 + TILE_SLACK + (size_t)NB_WARPS * g.nq * 64;
+    *smem_out = (size_t)4 * TILE_STRIDE + (size_t)NB_WARPS * g.nq * 64;
     *warps_out = NB_WARPS;
     return g;
 }
@@ -588,7 +633,8 @@ int launch_neighbor_build(meso_ctx *ctx)
     const Box &box = ctx->box;
     const int ncell = box.ncell;
     if (ctx->cap + 8 > ((size_t)1 << 30)) { ctx->err = "neighbor build: more than 2^30 atoms + ghosts on one GPU"; return MESO_EINVAL; }
-    if (!ctx->cell_xyzj.reserve(ctx->cap + 8) || !ctx->pos_of.reserve(ctx->cap + 8) || !ctx->owned_count.reserve(ctx->cap) ||
+    const size_t soa_stride = (ctx->cap + 8 + 63) & ~(size_t)63;     // words per array of the cell-ordered x | y | z | index copy
+    if (!ctx->cell_xyzj.reserve(ctx->cap + 8) || !ctx->pos_of.reserve(ctx->cap + 8) || !ctx->cell_soa.reserve(4 * soa_stride + 64) || !ctx->owned_count.reserve(ctx->cap) ||
         !ctx->nb_fixup.reserve(1)) {
         ctx->err = "neighbor: out of device memory";
         return MESO_ECUDA;
@@ -600,7 +646,7 @@ int launch_neighbor_build(meso_ctx *ctx)
     k_bin_count<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(x, ctx->cell_of.p, ctx->cell_cnt.p, ctx->d_counts, box);
     scan_into(ctx, ctx->cell_cnt.p, ctx->cell_start.p, ncell);
     k_bin_fill<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->cell_of.p, ctx->cell_start.p + 1, ctx->cell_atoms.p, ctx->d_counts, box.m[0], box.m[1]);
-    k_cell_order<<<(ncell + 127) / 128, 128, 0, LS(st)>>>(ctx->cell_start.p, ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_xyzj.p, ctx->pos_of.p, ncell);
+    k_cell_order<<<(ncell + 127) / 128, 128, 0, LS(st)>>>(ctx->cell_start.p, ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_xyzj.p, ctx->pos_of.p, ctx->cell_soa.p, soa_stride, ncell);
     const float rc2 = (float)pow(ctx->cutneighmax, 2.0);
     const size_t nbound = nlocal_bound(ctx);
     const int slow_grid = std::max(1, std::min((int)((nbound + 127) / 128) + 1, ctx->sm_count * 64));
@@ -613,8 +659,8 @@ int launch_neighbor_build(meso_ctx *ctx)
         }
         if (smem > (size_t)200 * 1024) { ctx->err = "neighbor build: hit queues do not fit shared memory (density too high)"; return MESO_EINVAL; }
         const int grid = std::max(1, (int)((nbound + NB_THREADS - 1) / NB_THREADS));
-        k_build_tiles<<<grid, NB_THREADS, smem, LS(st)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_xyzj.p, ctx->pair_count.p,
-                                                         ctx->owned_count.p, ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p, ctx->n_col, rc2,
+        k_build_tiles<<<grid, NB_THREADS, smem, LS(st)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_soa.p, soa_stride,
+                                                         ctx->pair_count.p, ctx->owned_count.p, ctx->pair_table.p, ctx->d_counts, ctx->nb_fixup.p, ctx->n_col, rc2,
                                                          box.m[0], box.m[1], box.m[2], g);
     }
     k_build_rows_slow<<<slow_grid, 128, 0, LS(st)>>>(ctx->coord4.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_xyzj.p, ctx->pair_count.p,
