@@ -281,7 +281,11 @@ __device__ __forceinline__ void lds_2x64(unsigned addr, unsigned long long &a, u
 // and masks what lies outside [first, last).  (Padding every cell to whole groups removes the masks -- 30 instead of 48
 // instructions per four candidates -- but adds 17 % candidates and doubles the cell-ordering pass: 377 + 68 us against
 // 361 + 39 us in a first measurement whose rows were still incomplete (parity red), so the variant was dropped there:
-// profiles/r02_s3_build_tiles_padded_ncu_summary.txt.)
+// profiles/r02_s3_build_tiles_padded_ncu_summary.txt.  Groups of four records [x0..x3][y0..y3][z0..z3][j0..j3], which
+// need one bulk copy per row instead of four (the warps spend 22 % of their time waiting for the 144 small copies of a
+// tile), put the quads of different cells on two bank groups instead of eight: 437 + 68 us, parity green,
+// profiles/r02_s3_build_tiles_grouped_ncu_summary.txt.  Warps per CTA (MESO_NB_WARPS experiment, binning + build per
+// rebuild): 5: 0.522 ms, 6: 0.505, 7: 0.508, 8: 0.506, 9: 0.515, 10: 0.540, 12: 0.547.)
 constexpr unsigned TILE_STRIDE = TILE_CAP_MAX * 4;          // bytes between the arrays of the tile
 
 __global__ void __launch_bounds__(NB_THREADS, 3) k_build_tiles(const float4 *__restrict__ coord4, const int *__restrict__ cellc,

@@ -1,6 +1,6 @@
 #!/bin/bash
-# round 2, pass M (1 GPU): tile-staged neighbor build (TMA bulk copies of cell rows into shared memory)
-O=gpurun_out/r2m; mkdir -p $O
+# round 2, pass O (1 GPU): tile-staged neighbor build (TMA bulk copies of cell rows into shared memory)
+O=gpurun_out/r2o; mkdir -p $O
 timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_fixes.py -m gpu -x -q > $O/pytest.log 2>&1; echo "exit $?" >> $O/pytest.log
 tail -15 $O/pytest.log
 timeout 300 python bench.py --case 64 --no-cpu-baseline --steps 300 --warmup 50 > $O/bench_case64.json 2> $O/bench_case64.err
