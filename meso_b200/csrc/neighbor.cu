@@ -177,10 +177,7 @@ __global__ void __launch_bounds__(256) k_bin_fill(const int *__restrict__ cellc,
 }
 
 // atoms of a cell in ascending index (the order the reference's stable sort of (cell id, atom) leaves, UM/neighbor_meso.cu:588)
-// and the cell-ordered copy of the packed coordinates, {x, y, z, bits(atom index)}, that the build kernel streams
-__global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell_start, int *__restrict__ cell_atoms,
-                                                    const float4 *__restrict__ coord4, float4 *__restrict__ cell_xyzj,
-                                                    int *__restrict__ pos_of, float *__restrict__ cell_soa, size_t soa_stride, int ncell)
+__global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell_start, int *__restrict__ cell_atoms, int ncell)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
@@ -192,13 +189,23 @@ __global__ void __launch_bounds__(128) k_cell_order(const int *__restrict__ cell
         while (q > 0 && p[q - 1] > v) { p[q] = p[q - 1]; q--; }
         p[q] = v;
     }
-    for (int k = 0; k < n; k++) {
-        const int j = p[k];
+}
+
+// the cell-ordered copies of the packed coordinates: records {x, y, z, bits(atom index)} for the fall-back build and the
+// exports, the same as four arrays x | y | z | index for the tile build, and every atom's position in that order.
+// One thread per record: coalesced writes, one 16-byte gather.
+__global__ void __launch_bounds__(256) k_cell_records(const int *__restrict__ cell_atoms, const float4 *__restrict__ coord4,
+                                                      float4 *__restrict__ cell_xyzj, int *__restrict__ pos_of, float *__restrict__ cell_soa,
+                                                      size_t soa_stride, const Counts *__restrict__ cnt)
+{
+    const int nall = cnt->nlocal + cnt->nghost;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nall; p += gridDim.x * blockDim.x) {
+        const int j = cell_atoms[p];
         float4 v = coord4[j];
         v.w = __int_as_float(j);
-        cell_xyzj[a + k] = v;
-        cell_soa[a + k] = v.x; cell_soa[soa_stride + a + k] = v.y; cell_soa[2 * soa_stride + a + k] = v.z; cell_soa[3 * soa_stride + a + k] = v.w;
-        pos_of[j] = a + k;
+        cell_xyzj[p] = v;
+        cell_soa[p] = v.x; cell_soa[soa_stride + p] = v.y; cell_soa[2 * soa_stride + p] = v.z; cell_soa[3 * soa_stride + p] = v.w;
+        pos_of[j] = p;
     }
 }
 
@@ -650,7 +657,9 @@ int launch_neighbor_build(meso_ctx *ctx)
     k_bin_count<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(x, ctx->cell_of.p, ctx->cell_cnt.p, ctx->d_counts, box);
     scan_into(ctx, ctx->cell_cnt.p, ctx->cell_start.p, ncell);
     k_bin_fill<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->cell_of.p, ctx->cell_start.p + 1, ctx->cell_atoms.p, ctx->d_counts, box.m[0], box.m[1]);
-    k_cell_order<<<(ncell + 127) / 128, 128, 0, LS(st)>>>(ctx->cell_start.p, ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_xyzj.p, ctx->pos_of.p, ctx->cell_soa.p, soa_stride, ncell);
+    k_cell_order<<<(ncell + 127) / 128, 128, 0, LS(st)>>>(ctx->cell_start.p, ctx->cell_atoms.p, ncell);
+    k_cell_records<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_xyzj.p, ctx->pos_of.p, ctx->cell_soa.p, soa_stride,
+                                                        ctx->d_counts);
     const float rc2 = (float)pow(ctx->cutneighmax, 2.0);
     const size_t nbound = nlocal_bound(ctx);
     const int slow_grid = std::max(1, std::min((int)((nbound + 127) / 128) + 1, ctx->sm_count * 64));
