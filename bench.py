@@ -338,6 +338,9 @@ def main():
     ap.add_argument("--impl", default="meso_b200", choices=["meso_b200", "reference"])
     ap.add_argument("--box", type=int, default=BOX, help="edge of the periodic box that is decomposed over the GPUs (200 = BASELINE configs[3])")
     ap.add_argument("--case", type=int, default=None, help="weak-scaling mode: box edge per GPU brick (64 = BASELINE configs[1])")
+    ap.add_argument("--workload", default="fluid", choices=["fluid", "polymer_channel"],
+                    help="polymer_channel = BASELINE configs[4]: amphiphilic bead-spring chains (bond_style harmonic, 1-2 exclusions, three atom "
+                         "types) in solvent between walls across z, driven by pois/meso; a cubic --box (default 64) decomposed over the GPUs")
     ap.add_argument("--precision", default="sp", choices=["sp", "dp"])
     ap.add_argument("--ref-steps", type=int, default=20, help="time steps the reference arm actually runs (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -367,7 +370,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    channel = args.workload == "polymer_channel"
+    if channel:
+        if args.case is not None:
+            raise SystemExit("--workload polymer_channel takes --box (a cubic box decomposed over the GPUs), not --case")
+        if args.box == BOX:
+            args.box = 64
     dims, grid, brick, scaling, wl = workload_of(args, world)
+    if channel:
+        wl = "amphiphilic bead-spring chains in a driven channel, %d^3 box (walls across z) decomposed over %d GPU(s)" % (args.box, world)
     parity = None if args.no_parity else parity_preflight(rank, world, grid, local_rank, dist)
 
     # every rank generates its own brick of the box (4 uniformly random points per unit cell, cells x-fastest: the layout of
@@ -375,25 +386,54 @@ def main():
     nloc = RHO * brick[0] * brick[1] * brick[2]
     nglob = nloc * world
     loc = (rank // (grid[1] * grid[2]), (rank // grid[2]) % grid[1], rank % grid[2])
-    x = workload.dpd_fluid(brick if len(set(brick)) > 1 else brick[0], seed=workload.DEFAULT_SEED + rank)
-    x += np.array([loc[d] * brick[d] for d in range(3)], dtype=np.float64)
-    v = workload.maxwell_velocities(nloc, seed=788662042 + rank)
-    tag = (np.arange(nloc, dtype=np.int64) + 1 + rank * nloc).astype(np.int32)
+    typ = bonds = None
+    if channel:
+        # every rank builds the whole channel from the same seed and keeps the beads of its brick (chains cross brick faces)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from mgpu_check import AMPHI_COEFF
+        xa, ta, ga, nb, bt, ba = workload.amphiphilic_channel(args.box)
+        va = workload.maxwell_velocities(len(xa), seed=99)
+        lo = np.array([loc[d] * brick[d] for d in range(3)], dtype=np.float64)
+        mine = np.all((xa >= lo) & (xa < lo + np.array(brick, dtype=np.float64)), axis=1)
+        x, v, tag, typ = np.ascontiguousarray(xa[mine]), np.ascontiguousarray(va[mine]), ga[mine].astype(np.int32), ta[mine].astype(np.int32)
+        bonds = (np.ascontiguousarray(nb[mine]), np.ascontiguousarray(bt[mine]), np.ascontiguousarray(ba[mine]), len(xa))
+        nglob, nloc = len(xa), int(mine.sum())
+        del xa, va, ta, ga, nb, bt, ba
+    else:
+        x = workload.dpd_fluid(brick if len(set(brick)) > 1 else brick[0], seed=workload.DEFAULT_SEED + rank)
+        x += np.array([loc[d] * brick[d] for d in range(3)], dtype=np.float64)
+        v = workload.maxwell_velocities(nloc, seed=788662042 + rank)
+        tag = (np.arange(nloc, dtype=np.int64) + 1 + rank * nloc).astype(np.int32)
 
     def deck():
         m = Meso(local_rank)
-        m.box((0.0, 0.0, 0.0), dims)
+        m.box((0.0, 0.0, 0.0), dims, (1, 1, 0) if channel else (1, 1, 1))
         if world > 1:
             ids = [Meso.unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
             m.decomposition(rank, grid, ids[0])
-        m.masses([0.0, 1.0])
+        m.masses([0.0, 1.0, 1.0, 1.0] if channel else [0.0, 1.0])
         m.neighbor(0.3, "bin")
         m.neigh_modify(delay=0, every=5, check=False)
         m.pair_style("dpd/fast/meso" if args.precision == "sp" else "dpd/meso", 1.0, 419084618)
-        m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
+        if channel:
+            for (a, b), a0 in AMPHI_COEFF.items():
+                m.pair_coeff(a, b, a0, 4.5, 3.0, 1.0, 1.0)
+        else:
+            m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
         m.timestep(0.005)
         return m
+
+    def load(m):
+        """the deck's read_data: atoms (pinned host buffers -> device), and for the channel the bond table and the fixes"""
+        m.upload(xp.numpy(), vp.numpy(), tag=tp.numpy(), type=typ)
+        if channel:
+            m.bond_style("harmonic/meso", 1)
+            m.bond_coeff(1, 50.0, 0.5)
+            m.special_bonds(0.0)
+            m.bonds(bonds[0], bonds[1], bonds[2], tag_max=bonds[3])
+            m.unfix_all()
+            m.fix("solid_bound/meso", "z", "rho5rc1s1"); m.fix("pois/meso", "z", "x", 0.2)
 
     xp = torch.from_numpy(x).pin_memory()
     vp = torch.from_numpy(v).pin_memory()
@@ -408,7 +448,7 @@ def main():
     # ---- device-resident leg: `value`
     warmup = max(args.warmup, 3)
     m = deck()
-    m.upload(xp.numpy(), vp.numpy(), tag=tp.numpy())
+    load(m)
     m.setup()
     stream = torch.cuda.ExternalStream(m.stream())
     m.run(warmup)
@@ -479,7 +519,7 @@ def main():
 
         def run_deck(nsteps):
             t0 = time.perf_counter()
-            m.upload(xp.numpy(), vp.numpy(), tag=tp.numpy())
+            load(m)
             m.ntimestep = 0
             m.setup()
             t_setup = time.perf_counter() - t0                   # meso_setup returns after the device finished (it reads the counts back)
@@ -505,7 +545,7 @@ def main():
             t = torch.tensor([wall, t_setup, t_down], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall, t_setup, t_down = (float(a) for a in t.tolist())
-        h2d = nloc * (48 + 4)
+        h2d = nloc * (48 + 4) + (nloc * (4 + 4 + 4 * int(bonds[1].size // max(len(bonds[0]), 1)) * 2) if channel else 0)
         e2e = {"value": nglob * args.steps / wall, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps, "setup_ms": 1e3 * t_setup, "download_ms": 1e3 * t_down,
                "stepping_ms": 1e3 * (wall - t_setup - t_down), "wall_ms": 1e3 * wall,
@@ -520,6 +560,8 @@ def main():
             "config": {"workload": "%s: rho=4, %d particles (%d per GPU), box %dx%dx%d, rc=1, skin 0.3, rebuild every 5 steps, dt 0.005"
                                    % (wl, nglob, nloc, *dims),
                        "procgrid": list(grid), "brick": list(brick), "pair_style": "dpd/fast/meso" if args.precision == "sp" else "dpd/meso",
+                       **({"bond_style": "harmonic/meso", "special_bonds": "lj 0 1 1", "atom_types": 3,
+                           "fixes": ["solid_bound/meso z rho5rc1s1", "pois/meso z x 0.2", "nve/meso"]} if channel else {}),
                        "l2": "per-step working set (>= 0.8 GB per million particles) exceeds the 126 MB L2; no explicit flush",
                        "mean_neighbors": n_bar, "temperature_end": T_end},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "phases": phases, "clocks": clocks, "parity_check": parity}

@@ -618,7 +618,9 @@ static TileGeom tile_geometry(const meso_ctx *ctx, int *warps_out, size_t *smem_
 {
     const Box &box = ctx->box;
     const double inner = (double)std::max(box.m[0] - 2, 1) * std::max(box.m[1] - 2, 1) * std::max(box.m[2] - 2, 1);
-    const double per_cell = std::max((double)nlocal_bound(ctx) / inner, 1.0);
+    // atoms per cell from what the rank holds now (the capacity bound of a decomposed run carries 50-100 % head room, which
+    // would halve the block and double the tiles)
+    const double per_cell = std::max((double)(ctx->nlocal_host > 0 ? (size_t)ctx->nlocal_host : nlocal_bound(ctx)) / inner, 1.0);
     static const int shapes[7][3] = {{2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}, {1, 1, 0}, {1, 0, 0}, {0, 0, 0}};
     TileGeom g{};
     const double rn = ctx->cutneighmax;

@@ -24,7 +24,21 @@ def brick_of(rank, grid):
     return (rank // (grid[1] * grid[2]), (rank // grid[2]) % grid[1], rank % grid[2])
 
 
-def make_inputs(dims, polymer=False):
+AMPHI_COEFF = {(1, 1): 25.0, (2, 2): 25.0, (3, 3): 25.0, (1, 2): 27.0, (1, 3): 40.0, (2, 3): 40.0}
+
+
+def make_inputs(dims, polymer=False, channel=False):
+    """channel: BASELINE configs[4] -- amphiphilic bead-spring chains in solvent between two walls across z (solid_bound/meso),
+    driven by pois/meso; three atom types, 1-2 exclusions; periodic in x and y only, so a grid that splits z puts the walls on a
+    decomposed non-periodic dimension and chains across brick faces"""
+    if channel:
+        assert len(set(dims)) == 1
+        x, typ, tag, nbond, btype, batom = workload.amphiphilic_channel(dims[0])
+        coeff = np.zeros((3, 3, 7))
+        for (a, b), a0 in AMPHI_COEFF.items():
+            coeff[a - 1, b - 1] = coeff[b - 1, a - 1] = [1.0, 1.0, 1.0, 1.0, a0, 4.5, 3.0]
+        v = workload.maxwell_velocities(len(x), seed=99) * 2.0
+        return dict(x=x, v=v, tag=tag, typ=typ, ntypes=3, coeff=coeff.reshape(-1, 7), bonds=(nbond, btype, batom), polymer=True, channel=True)
     if polymer:
         assert len(set(dims)) == 1
         x, typ, tag, nbond, btype, batom = workload.polymer_melt(dims[0], chain_len=8, seed=5)
@@ -36,7 +50,7 @@ def make_inputs(dims, polymer=False):
         tag = np.arange(1, len(x) + 1, dtype=np.int32)
         typ, ntypes, coeff, bonds = np.ones(len(x), np.int32), 1, None, None
     v = workload.maxwell_velocities(len(x)) * (2.0 if polymer else 1.0)      # hotter chains: more migration within the run
-    return dict(x=x, v=v, tag=tag, typ=typ, ntypes=ntypes, coeff=coeff, bonds=bonds, polymer=polymer)
+    return dict(x=x, v=v, tag=tag, typ=typ, ntypes=ntypes, coeff=coeff, bonds=bonds, polymer=polymer, channel=False)
 
 
 def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, phases=False, periodic=(1, 1, 1), dist=None):
@@ -53,11 +67,17 @@ def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, pha
         dist.all_gather_object(vals, float(val))
         return sum(vals)
     x, v, tag, typ, ntypes, coeff, polymer = inp["x"], inp["v"], inp["tag"], inp["typ"], inp["ntypes"], inp["coeff"], inp["polymer"]
-    w = oracle.World((0, 0, 0), dims, periodic=periodic, procgrid=grid, precision=1 if precision == "dp" else 0, ntypes=ntypes, coeff=coeff)
+    channel = inp.get("channel", False)
+    if channel:
+        periodic = (1, 1, 0)
+    w = oracle.World((0, 0, 0), dims, periodic=periodic, procgrid=grid, precision=1 if precision == "dp" else 0, ntypes=ntypes, coeff=coeff,
+                     **({"mass": [0.0] + [1.0] * ntypes} if channel else {}))
     w.set_atoms(x, v, tag=tag, type=typ)
     if polymer:
         nbond, btype, batom = inp["bonds"]
         w.set_bonds(nbond, btype, batom, tag=tag, k=[0.0, 50.0], r0=[0.0, 0.5], special_lj12=0.0)
+    if channel:
+        w.fix_solid_bound("z"); w.fix_pois(2, 0, 0.2)
     w.setup(eflag=1, vflag=1)
     ao = w.atoms(rank)
     nl = ao["nlocal"]
@@ -72,7 +92,10 @@ def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, pha
     m.neighbor(0.3, "bin")
     m.neigh_modify(delay=0, every=5, check=False)
     m.pair_style("dpd/fast/meso" if precision == "sp" else "dpd/meso", 1.0, 419084618)
-    if polymer:
+    if channel:
+        for (a, b), a0 in AMPHI_COEFF.items():
+            m.pair_coeff(a, b, a0, 4.5, 3.0, 1.0, 1.0)
+    elif polymer:
         m.pair_coeff(1, 1, 25, 4.5, 3.0, 1.0, 1.0); m.pair_coeff(1, 2, 40, 4.5, 3.0, 1.0, 1.0); m.pair_coeff(2, 2, 25, 4.5, 3.0, 1.0, 1.0)
     else:
         m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
@@ -83,6 +106,8 @@ def check(precision, rank, grid, local_device, dims, inp, nccl_id, steps=12, pha
         m.bond_coeff(1, 50.0, 0.5)
         m.special_bonds(0.0)
         m.bonds(nbond[mine], btype[mine], batom[mine], tag_max=len(x))
+    if channel:
+        m.fix("solid_bound/meso", "z", "rho5rc1s1"); m.fix("pois/meso", "z", "x", 0.2)
     if host_boot:
         blobs = [None] * dist.get_world_size()
         dist.all_gather_object(blobs, m.comm_export())

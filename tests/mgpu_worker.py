@@ -23,6 +23,7 @@ ap.add_argument("--grid", type=int, nargs=3, default=None)
 ap.add_argument("--steps", type=int, default=12)
 ap.add_argument("--backend", default="nccl")
 ap.add_argument("--polymer", action="store_true", help="bead-spring chains in solvent (bond table rides the migration, ghost partners)")
+ap.add_argument("--channel", action="store_true", help="BASELINE configs[4]: amphiphilic chains between walls across z, body force; periodic in x, y only")
 ap.add_argument("--phases", action="store_true", help="drive the run through the phase entry points (meso_forward_comm on a decomposition)")
 ap.add_argument("--share-gpu", action="store_true", help="all ranks on GPU 0: halo through CUDA IPC on one device, bootstrap and reductions through gloo")
 a = ap.parse_args()
@@ -35,7 +36,7 @@ dist.init_process_group(a.backend, device_id=torch.device("cuda", local) if a.ba
 grid = tuple(a.grid) if a.grid else procgrid_for(world)
 assert grid[0] * grid[1] * grid[2] == world
 dims = tuple(a.L) * 3 if len(a.L) == 1 else tuple(a.L)
-inp = mgpu_check.make_inputs(dims, a.polymer)
+inp = mgpu_check.make_inputs(dims, a.polymer, a.channel)
 
 for precision in ("dp", "sp"):
     ids = [None]
@@ -46,5 +47,5 @@ for precision in ("dp", "sp"):
     dist.barrier()
     if rank == 0:
         print("mgpu parity OK: %d ranks%s grid %s box %s %s%s%s (force err %.2e)" % (world, " on one GPU" if a.share_gpu else "", grid, dims, precision,
-                                                                                   " polymer" if a.polymer else "", " phases" if a.phases else "", e), flush=True)
+                                                                                   " channel" if a.channel else " polymer" if a.polymer else "", " phases" if a.phases else "", e), flush=True)
 dist.destroy_process_group()

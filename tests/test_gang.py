@@ -29,13 +29,16 @@ def devices_for(nbrick):
     return list(range(nbrick))
 
 
-def deck(m, dims, ntypes, polymer, precision):
-    m.box((0.0, 0.0, 0.0), dims, (1, 1, 1))
+def deck(m, dims, ntypes, polymer, precision, channel=False):
+    m.box((0.0, 0.0, 0.0), dims, (1, 1, 0) if channel else (1, 1, 1))
     m.masses([0.0] + [1.0] * ntypes)
     m.neighbor(0.3, "bin")
     m.neigh_modify(delay=0, every=5, check=False)
     m.pair_style("dpd/fast/meso" if precision == "sp" else "dpd/meso", 1.0, 419084618)
-    if polymer:
+    if channel:
+        for (a, b), a0 in mgpu_check.AMPHI_COEFF.items():
+            m.pair_coeff(a, b, a0, 4.5, 3.0, 1.0, 1.0)
+    elif polymer:
         m.pair_coeff(1, 1, 25, 4.5, 3.0, 1.0, 1.0); m.pair_coeff(1, 2, 40, 4.5, 3.0, 1.0, 1.0); m.pair_coeff(2, 2, 25, 4.5, 3.0, 1.0, 1.0)
     else:
         m.pair_coeff(1, 1, 15, 4.5, 3.0, 1.0, 1.0)
@@ -43,12 +46,15 @@ def deck(m, dims, ntypes, polymer, precision):
 
 
 def oracle_world(dims, grid, inp, precision):
-    w = oracle.World((0, 0, 0), dims, periodic=(1, 1, 1), procgrid=grid, precision=1 if precision == "dp" else 0, ntypes=inp["ntypes"],
-                     coeff=inp["coeff"])
+    channel = inp["channel"]
+    w = oracle.World((0, 0, 0), dims, periodic=(1, 1, 0) if channel else (1, 1, 1), procgrid=grid, precision=1 if precision == "dp" else 0,
+                     ntypes=inp["ntypes"], coeff=inp["coeff"], **({"mass": [0.0, 1.0, 1.0, 1.0]} if channel else {}))
     w.set_atoms(inp["x"], inp["v"], tag=inp["tag"], type=inp["typ"])
     if inp["polymer"]:
         nbond, btype, batom = inp["bonds"]
         w.set_bonds(nbond, btype, batom, tag=inp["tag"], k=[0.0, 50.0], r0=[0.0, 0.5], special_lj12=0.0)
+    if channel:
+        w.fix_solid_bound("z"); w.fix_pois(2, 0, 0.2)
     return w
 
 
@@ -72,16 +78,20 @@ def step_by_phases(m, polymer):
 
 
 @pytest.mark.parametrize("nbrick,L,polymer,phases", [(2, 12, False, False), (4, 12, False, False), (2, 10, True, False), (2, 12, False, True),
-                                                     (4, 12, True, False), (8, 12, False, False)])
+                                                     (4, 12, True, False), (8, 12, False, False), (4, 8, "channel", False),
+                                                     (8, 8, "channel", False)])
 def test_gang_equals_the_oracle_world_brick_after_brick(nbrick, L, polymer, phases):
+    """polymer == "channel": BASELINE configs[4] -- amphiphilic chains between walls on a decomposed non-periodic dimension"""
     dims, grid = (L, L, L), GRIDS[nbrick]
-    inp = mgpu_check.make_inputs(dims, polymer)
+    channel = polymer == "channel"
+    polymer = bool(polymer)
+    inp = mgpu_check.make_inputs(dims, polymer, channel)
     for precision in ("dp", "sp"):
         w = oracle_world(dims, grid, inp, precision)
         w.setup(eflag=1, vflag=1)
         m = Meso(devices_for(nbrick))
         assert m.L.meso_gang_size(m.h) == nbrick
-        deck(m, dims, inp["ntypes"], polymer, precision)
+        deck(m, dims, inp["ntypes"], polymer, precision, channel)
         m.upload(inp["x"], inp["v"], tag=inp["tag"], type=inp["typ"])
         if polymer:
             nbond, btype, batom = inp["bonds"]
@@ -89,6 +99,8 @@ def test_gang_equals_the_oracle_world_brick_after_brick(nbrick, L, polymer, phas
             m.bond_coeff(1, 50.0, 0.5)
             m.special_bonds(0.0)
             m.bonds(nbond, btype, batom, tag_max=len(inp["x"]))
+        if channel:
+            m.fix("solid_bound/meso", "z", "rho5rc1s1"); m.fix("pois/meso", "z", "x", 0.2)
         m.setup(eflag=1, vflag=1)
         parts = [w.atoms(r) for r in range(nbrick)]
         cat = lambda key: np.concatenate([a[key][:a["nlocal"]] for a in parts])

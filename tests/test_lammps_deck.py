@@ -454,7 +454,8 @@ def test_deck_on_several_gpus_in_one_process(tmp_path, ndev, extra):
     assert np.abs(f1[0][:, 7:10] - f2[0][:, 7:10]).max() < 1e-5 * np.abs(f1[0][:, 7:10]).max()
     assert np.array_equal(f1[steps][:, 0], f2[steps][:, 0])              # nobody lost across 4 rebuilds with migration
     assert np.abs(f2[steps][:, 4:7].sum(axis=0) - f2[0][:, 4:7].sum(axis=0)).max() < 1e-9      # pair forces cancel across brick faces too
-    assert np.abs(f1[steps][:, 1:4] - f2[steps][:, 1:4]).max() < 0.5     # same fluid 0.1 time units later
+    dx = np.abs(f1[steps][:, 1:4] - f2[steps][:, 1:4])
+    assert np.minimum(dx, L - dx).max() < 0.5                            # same fluid 0.1 time units later (minimum image)
 
 
 @pytest.mark.gpu

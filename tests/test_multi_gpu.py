@@ -18,7 +18,11 @@ def ngpu():
 
 
 CASES = [(2, (12,), ()), (4, (12,), ()), (8, (12,), ()), (2, (6, 7, 12), ()), (2, (10,), ("--polymer",)), (8, (12,), ("--polymer",)),
-         (2, (12,), ("--phases",)), (4, (12,), ("--phases",))]
+         (2, (12,), ("--phases",)), (4, (12,), ("--phases",)), (2, (8,), ("--channel",)), (4, (8,), ("--channel",)), (8, (8,), ("--channel",))]
+
+
+def case_id(c):
+    return "%d-L%s%s" % (c[0], "x".join(str(v) for v in c[1]), "".join(e.replace("--", "-") for e in c[2]))
 
 
 def run_worker(n, L, extra, port):
@@ -30,7 +34,7 @@ def run_worker(n, L, extra, port):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,L,extra", CASES)
+@pytest.mark.parametrize("n,L,extra", CASES, ids=[case_id(c) for c in CASES])
 def test_multi_gpu_parity(n, L, extra):
     """one rank per GPU (NCCL bootstrap)"""
     if ngpu() < n:
@@ -38,8 +42,11 @@ def test_multi_gpu_parity(n, L, extra):
     run_worker(n, L, extra, 29500 + n)
 
 
+ONE_GPU_CASES = [c for c in CASES if c[0] <= 4] + [(8, (12,), ())]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,L,extra", [c for c in CASES if c[0] <= 4] + [(8, (12,), ())])
+@pytest.mark.parametrize("n,L,extra", ONE_GPU_CASES, ids=[case_id(c) for c in ONE_GPU_CASES])
 def test_multi_rank_parity_on_one_gpu(n, L, extra):
     """the same decompositions with every rank on GPU 0: runs on a single-GPU box (the driver's), exercises the complete
     multi-rank path -- migration, ghost creation in the reference's order, per-step refresh, bond migration, phase API"""
