@@ -273,6 +273,34 @@ def cpu_baseline_sample(L):
             "sample": "oracle C port, %d steps of a %d^3 box of the same fluid" % (steps, Ls)}
 
 
+# ---------------------------------------------------------------------------------------- the real plugin path
+LMP_DECK = ("dimension 3\nunits lj\natom_style dpd/atomic/meso\nneighbor 0.3 bin\nneigh_modify delay 0 every 5 check no\n"
+            "read_data ${case}.data\nrun_style mvv/meso\npair_style %s 1.0 419084618\npair_coeff 1 1 15 4.5 3.0 1.0 1.0\n"
+            "compute mythermo all temp/meso\nvelocity all create 1.0 788662042 loop all\nfix 3 all nve/meso\n"
+            "thermo_style custom step temp cpu spcpu\nthermo 100\nthermo_modify temp mythermo\ntimestep 0.005\nrun %d\n")
+
+
+def lammps_deck_rate(L, precision, steps):
+    """example/simple/{sp,dp}.run (case L) through lammps/_build/lmp_meso_b200 -- the reference's own LAMMPS core with this
+    repository's package -- on GPU 0: particle-steps/s from LAMMPS' own `Loop time` line (host arrays in, thermo every 100 steps).
+    None when the binary did not travel."""
+    from meso_b200 import workload
+    lmp = os.path.join(ROOT, "lammps", "_build", "lmp_meso_b200")
+    if not os.path.exists(lmp):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        workload.write_data(os.path.join(d, "%d.data" % L), workload.dpd_fluid(L), L)
+        open(os.path.join(d, "in.run"), "w").write(LMP_DECK % ("dpd/fast/meso" if precision == "sp" else "dpd/meso", steps))
+        out = subprocess.run([lmp, "-in", "in.run", "-var", "case", str(L), "-log", "none"], cwd=d, capture_output=True, text=True, timeout=900)
+    t = [float(l.split()[3]) for l in out.stdout.split("\n") if l.startswith("Loop time of")]
+    if out.returncode != 0 or not t:
+        return {"error": (out.stdout[-200:] + out.stderr[-200:]).replace("\n", " ")}
+    n = RHO * L ** 3
+    return {"value": n * steps / t[-1], "unit": "particle-steps/s", "loop_time_s": t[-1], "steps": steps,
+            "what": "lmp_meso_b200 -in %s.run -var case %d (%d particles): LAMMPS' own Loop time for `run %d` with thermo 100 "
+                    "(temp/meso reduces on the device: no per-atom download at thermo steps)" % (precision, L, n, steps)}
+
+
 # ---------------------------------------------------------------------------------------- parity preflight
 def parity_preflight(rank, world, grid, local_rank, dist):
     """Small-box check of the path that is about to be timed against the CPU oracle (the checker, not the product):
@@ -565,6 +593,8 @@ def main():
                        "l2": "per-step working set (>= 0.8 GB per million particles) exceeds the 126 MB L2; no explicit flush",
                        "mean_neighbors": n_bar, "temperature_end": T_end},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "phases": phases, "clocks": clocks, "parity_check": parity}
+    if rank == 0 and world == 1 and not args.no_e2e and not channel:
+        line["e2e_lmp"] = lammps_deck_rate(CASE, args.precision, 1000)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(CASE)
     if rank == 0:

@@ -195,6 +195,15 @@ void MesoDevice::upload_topology(int n)
     for (int p = 0; p < 3; p++) topo_nspecial[(size_t)t*3+p] = atom->nspecial[i][p];
     for (int p = 0; p < atom->nspecial[i][2] && p < ms; p++) topo_special[(size_t)t*ms+p] = atom->special[i][p];
   }
+  // the device migrates atoms between ranks: every rank keeps the host-only topology of EVERY tag (each tag is filled by
+  // exactly one rank, the others hold zeros), so atoms that arrive from elsewhere get their bonds back at download time
+  if (comm->nprocs > 1) {
+    std::vector<int> *tabs[6] = {&topo_molecule,&topo_num_bond,&topo_bond_type,&topo_bond_atom,&topo_nspecial,&topo_special};
+    for (int k = 0; k < 6; k++) {
+      std::vector<int> part(*tabs[k]);
+      MPI_Allreduce(&part[0],&(*tabs[k])[0],(int) part.size(),MPI_INT,MPI_SUM,world);
+    }
+  }
   check(meso_bonds_upload(ctx,n,bpa,atom->num_bond,n ? atom->bond_type[0] : NULL,n ? atom->bond_atom[0] : NULL,tmax_all),FLERR);
 }
 
