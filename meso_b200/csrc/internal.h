@@ -79,6 +79,7 @@ struct SortScratch {
     DevBuf<uint64_t> key_alt;
     DevBuf<int> val_alt;
     DevBuf<uint32_t> hist;     // [256][ntiles]
+    DevBuf<int> bucket_cnt, bucket_start, slot_idx;   // bucket sort of the reorder keys (sort.cu)
 };
 
 // device-resident fixes of the channel decks: wall/meso, solid_bound/meso, addforce/meso, pois/meso.
@@ -243,6 +244,7 @@ void comm_invalidate(meso_ctx *ctx);
 int comm_export_blob(meso_ctx *ctx, void *blob1024);
 int comm_import_blobs(meso_ctx *ctx, const void *blobs, int nranks);
 // ---- neighbor.cu
+int scan_into(meso_ctx *ctx, const int *in, int *out, int n);   // exclusive scan: out[0] = 0, out[i + 1] = sum of in[0..i]
 int launch_setup_bins(meso_ctx *ctx);
 int launch_neighbor_build(meso_ctx *ctx);
 int launch_canonical_rows(meso_ctx *ctx, int *out_table);   // the table in the reference's row order (exports)

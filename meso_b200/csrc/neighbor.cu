@@ -604,12 +604,15 @@ int launch_setup_bins(meso_ctx *ctx)
     return MESO_OK;
 }
 
-static void scan_into(meso_ctx *ctx, const int *in, int *out, int n)
+// out[0] = 0, out[i + 1] = in[0] + ... + in[i - 1] ... see k_scan_apply; three launches on the context's stream
+int scan_into(meso_ctx *ctx, const int *in, int *out, int n)
 {
     const int nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (!ctx->scan_sums.reserve((size_t)nblk + 8)) { ctx->err = "scan: out of device memory"; return MESO_ECUDA; }
     k_scan_sums<<<nblk, SCAN_T, 0, LS(ctx->stream)>>>(in, ctx->scan_sums.p, n);
     k_scan_top<<<1, 1024, 0, LS(ctx->stream)>>>(ctx->scan_sums.p, nblk);
     k_scan_apply<<<nblk, SCAN_T, 0, LS(ctx->stream)>>>(in, out, ctx->scan_sums.p, n);
+    return MESO_OK;
 }
 
 // shape of the build for this density: the largest Morton-aligned block of cells whose tile (block + one layer) fits the
@@ -657,7 +660,7 @@ int launch_neighbor_build(meso_ctx *ctx)
     MESO_CUDA(cudaMemsetAsync(ctx->nb_fixup.p, 0, sizeof(int), st));
     SoA3c x; for (int d = 0; d < 3; d++) x.c[d] = ctx->x[d].p;
     k_bin_count<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(x, ctx->cell_of.p, ctx->cell_cnt.p, ctx->d_counts, box);
-    scan_into(ctx, ctx->cell_cnt.p, ctx->cell_start.p, ncell);
+    if (int rc = scan_into(ctx, ctx->cell_cnt.p, ctx->cell_start.p, ncell)) return rc;
     k_bin_fill<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->cell_of.p, ctx->cell_start.p + 1, ctx->cell_atoms.p, ctx->d_counts, box.m[0], box.m[1]);
     k_cell_order<<<(ncell + 127) / 128, 128, 0, LS(st)>>>(ctx->cell_start.p, ctx->cell_atoms.p, ncell);
     k_cell_records<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(ctx->cell_atoms.p, ctx->coord4.p, ctx->cell_xyzj.p, ctx->pos_of.p, ctx->cell_soa.p, soa_stride,

@@ -18,7 +18,7 @@
 
 namespace meso {
 
-int sort_pairs_u64(meso_ctx *ctx, DevBuf<uint64_t> &key, DevBuf<int> &val, const int *d_n, size_t cap, int bits);
+int sort_pairs_u64(meso_ctx *ctx, DevBuf<uint64_t> &key, DevBuf<int> &val, const int *d_n, size_t cap, int bits, int low_bits);
 
 struct SoA3 { double *c[3]; };
 struct SoA3c { const double *c[3]; };
@@ -355,7 +355,7 @@ int launch_reorder(meso_ctx *ctx)
     int bits = 1 + l1_width + l2_width;
     k_reorder_key<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soa(ctx->x), ctx->image.p, ctx->key.p, ctx->perm_from.p, ctx->d_counts,
                                                           box, l2_width, border_mask);
-    int rc = sort_pairs_u64(ctx, ctx->key, ctx->perm_from, &ctx->d_counts->nlocal, ctx->cap, bits);
+    int rc = sort_pairs_u64(ctx, ctx->key, ctx->perm_from, &ctx->d_counts->nlocal, ctx->cap, bits, l2_width);
     if (rc) return rc;
     k_gather<<<grid_for(ctx, 8), 256, 0, LS(ctx->stream)>>>(soac(ctx->x), soac(ctx->v), ctx->tag.p, ctx->type.p, ctx->mask.p, ctx->image.p,
                                                      soa(ctx->xa), soa(ctx->va), ctx->taga.p, ctx->typea.p, ctx->maska.p,

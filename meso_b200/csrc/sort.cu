@@ -8,6 +8,8 @@
 // Stability (needed for "ascending atom index inside a cell", UM/neighbor_meso.cu:588, and
 // for tie order in MesoAtom::sort_local) comes from the warp-blocked element order.
 #include "internal.h"
+#include <cstdlib>
+#include <utility>
 
 namespace meso {
 
@@ -167,15 +169,91 @@ static int sort_impl(meso_ctx *ctx, K *&key, int *&val, K *&key_alt, int *&val_a
     return MESO_OK;
 }
 
+// ------------------------------------------------------------------ bucket sort of the reorder keys
+// The reorder key is border bit | Morton(cell) | 12-bit sub-cell code (UM/atom_meso.cu:345-360): everything above the low
+// `low_bits` bits names one of ~2 x ncell populated buckets of ~9 atoms.  Histogram, exclusive scan, slot claim and a small
+// insertion sort per bucket on (key, original position) give exactly the permutation of the stable LSD radix sort -- one pass
+// over the pairs instead of four or five (31-bit keys at 64^3, 37-bit keys at 200^3).
+__global__ void __launch_bounds__(256) k_bucket_count(const uint64_t *__restrict__ key, const int *__restrict__ d_n, int *__restrict__ cnt, int low_bits)
+{
+    const int n = *d_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(cnt + (size_t)(key[i] >> low_bits), 1);
+}
+
+__global__ void __launch_bounds__(256) k_bucket_fill(const uint64_t *__restrict__ key, const int *__restrict__ d_n, int *__restrict__ start1,
+                                                     int *__restrict__ slot_idx, int low_bits)
+{
+    const int n = *d_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        slot_idx[atomicAdd(start1 + (size_t)(key[i] >> low_bits), 1)] = i;
+}
+
+__global__ void __launch_bounds__(128) k_bucket_order(const int *__restrict__ start, int nbucket, int *__restrict__ slot_idx,
+                                                      const uint64_t *__restrict__ key_in, const int *__restrict__ val_in,
+                                                      uint64_t *__restrict__ key_out, int *__restrict__ val_out)
+{
+    constexpr int LOCAL = 24;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbucket; b += gridDim.x * blockDim.x) {
+        const int a = start[b], n = start[b + 1] - a;
+        if (n == 0) continue;
+        if (n <= LOCAL) {
+            uint64_t k[LOCAL];
+            int p[LOCAL];
+            for (int q = 0; q < n; q++) {
+                const int pi = slot_idx[a + q];
+                const uint64_t ki = key_in[pi];
+                int r = q;
+                while (r > 0 && (k[r - 1] > ki || (k[r - 1] == ki && p[r - 1] > pi))) { k[r] = k[r - 1]; p[r] = p[r - 1]; r--; }
+                k[r] = ki; p[r] = pi;
+            }
+            for (int q = 0; q < n; q++) { key_out[a + q] = k[q]; val_out[a + q] = val_in[p[q]]; }
+        } else {                                            // a crowded bucket: the same insertion sort in place in global memory
+            int *p = slot_idx + a;
+            for (int q = 1; q < n; q++) {
+                const int pi = p[q];
+                const uint64_t ki = key_in[pi];
+                int r = q;
+                while (r > 0 && (key_in[p[r - 1]] > ki || (key_in[p[r - 1]] == ki && p[r - 1] > pi))) { p[r] = p[r - 1]; r--; }
+                p[r] = pi;
+            }
+            for (int q = 0; q < n; q++) { key_out[a + q] = key_in[p[q]]; val_out[a + q] = val_in[p[q]]; }
+        }
+    }
+}
+
+// one pass; the result lands in the alternate buffers (the caller swaps)
+static int bucket_sort(meso_ctx *ctx, const uint64_t *key, const int *val, uint64_t *key_out, int *val_out, const int *d_n, size_t cap, int bits,
+                       int low_bits)
+{
+    const size_t nb = (size_t)1 << (bits - low_bits);
+    SortScratch &s = ctx->sort;
+    if (!s.bucket_cnt.reserve(nb + 8) || !s.bucket_start.reserve(nb + 8) || !s.slot_idx.reserve(cap + 8)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
+    cudaStream_t st = ctx->stream;
+    MESO_CUDA(cudaMemsetAsync(s.bucket_cnt.p, 0, sizeof(int) * nb, st));
+    k_bucket_count<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(key, d_n, s.bucket_cnt.p, low_bits);
+    if (int rc = scan_into(ctx, s.bucket_cnt.p, s.bucket_start.p, (int)nb)) return rc;
+    k_bucket_fill<<<grid_for(ctx, 8), 256, 0, LS(st)>>>(key, d_n, s.bucket_start.p + 1, s.slot_idx.p, low_bits);
+    k_bucket_order<<<grid_for(ctx, 16), 128, 0, LS(st)>>>(s.bucket_start.p, (int)nb, s.slot_idx.p, key, val, key_out, val_out);
+    MESO_CUDA(cudaGetLastError());
+    return MESO_OK;
+}
+
 // Sorts in place from the caller's point of view: on return `key`/`val` hold the sorted
 // pairs (the DevBuf pointers are swapped with the scratch buffers when the pass count is odd).
-int sort_pairs_u64(meso_ctx *ctx, DevBuf<uint64_t> &key, DevBuf<int> &val, const int *d_n, size_t cap, int bits)
+int sort_pairs_u64(meso_ctx *ctx, DevBuf<uint64_t> &key, DevBuf<int> &val, const int *d_n, size_t cap, int bits, int low_bits)
 {
     // size the scratch by the LOGICAL capacity: buffers are swapped below, so sizing by key.cap would ratchet up
     if (!ctx->sort.key_alt.reserve(cap) || !ctx->sort.val_alt.reserve(cap)) { ctx->err = "sort: out of device memory"; return MESO_ECUDA; }
     uint64_t *k = key.p, *ka = ctx->sort.key_alt.p;
     int *v = val.p, *va = ctx->sort.val_alt.p;
-    int rc = sort_impl<uint64_t>(ctx, k, v, ka, va, d_n, cap, bits);
+    int rc;
+    // reorder keys (12 low bits of sub-cell code under a cell code): one bucket pass; MESO_SORT_RADIX=1 keeps the radix passes (A/B)
+    static const bool force_radix = getenv("MESO_SORT_RADIX") && getenv("MESO_SORT_RADIX")[0] == '1';
+    if (low_bits > 0 && bits > low_bits && bits - low_bits <= 26 && !force_radix) {
+        rc = bucket_sort(ctx, k, v, ka, va, d_n, cap, bits, low_bits);
+        std::swap(k, ka); std::swap(v, va);
+    } else
+        rc = sort_impl<uint64_t>(ctx, k, v, ka, va, d_n, cap, bits);
     if (k != key.p) {   // odd number of passes: swap buffer ownership (capacities are compatible by construction)
         std::swap(key.p, ctx->sort.key_alt.p); std::swap(key.cap, ctx->sort.key_alt.cap);
         std::swap(val.p, ctx->sort.val_alt.p); std::swap(val.cap, ctx->sort.val_alt.cap);
