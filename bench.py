@@ -9,6 +9,10 @@ particles), spatially decomposed over the N GPUs ("scaling": "strong"; N = 1 hol
 `--case C` selects the round-1 weak-scaling mode instead (one C^3 brick per GPU; `--case 64` = configs[1],
 `--case 48 --precision dp` = configs[2]).  A "step" is one DPD time step: velocity-Verlet halves + halo refresh + pair
 force; every 5th step also wrap + migration + 2-level reorder + ghost rebuild + neighbor-list build.
+`--workload polymer_channel` times BASELINE configs[4] instead (amphiphilic bead-spring chains in a driven channel, cubic --box,
+default 64).  Besides the contract's keys the line carries `e2e_lmp` (N = 1: sp.run case 64 through the LAMMPS binary
+lmp_meso_b200, LAMMPS' own loop time), `phases` (event-timed phases of the library), `parity_check` (small-box comparison with
+the oracle on the same processor grid, run before anything is timed) and `gpu_launches` (the library's own launch count).
 Prints ONE JSON line on stdout.
 """
 import argparse
@@ -528,8 +532,8 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": b_force, "particles_per_launch": nloc * args.steps / max(pair_calls, 1),
                 "avg_launch_ms": pair_ms / max(pair_calls, 1), "share_of_step": pair_ms / ms,
-                "note": "not HBM-bound: a list-based gather kernel on the L1/issue ridge (ncu, profiles/: L1 data-pipe wavefronts and issue "
-                        "slots ~60 %, DRAM ~20 %, ~1.2x the algorithmic bytes moved); see DESIGN.md s3.1"}
+                "note": "not HBM-bound: a list-based gather kernel that waits for gather latency (ncu, profiles/r02_s3_force_*: issue slots "
+                        "52 %, L1 data pipe 55 %, DRAM 16 %, 0.8x the algorithmic bytes moved: the owned prefix is half a row); see DESIGN.md s3.1"}
     phases = {k: {"ms_total": round(v[0], 3), "calls": int(v[1])} for k, v in tm.items()}
     m.close()
 
