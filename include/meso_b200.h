@@ -176,7 +176,12 @@ int meso_fix_bounce(meso_ctx *ctx, int handle);
 /* ---- whole-run drivers (same results as the phase calls above, fewer launches) ---- */
 /* ModifiedVerlet::setup UM/mvv_meso.cu:139-219 */
 int meso_setup(meso_ctx *ctx, int eflag, int vflag);
-/* ModifiedVerlet::run(n) for the deck's fix list {nve/meso on group `groupbit`} */
+/* ModifiedVerlet::run(n) for the deck's fix list {nve/meso on group `groupbit`}.
+ * Evaluates each local pair once and adds both halves with atomic reductions (fp32 style: fp32 atomics into a per-atom
+ * accumulator; fp64 style: fp64 atomics): every addend is bit-identical to the two-sided evaluation, the ORDER of the additions
+ * is not fixed, so results differ in the last bits from run to run (the reference adds per-atom sums in a fixed order).
+ * MESO_PAIR_ONCE=0 in the environment selects the deterministic two-sided kernel (bit-reproducible; what the bit-for-bit
+ * tests use). */
 int meso_run(meso_ctx *ctx, int nsteps, int groupbit);
 
 /* ---- exports for parity tests (device -> host, synchronous) ---- */
