@@ -48,6 +48,10 @@ int  meso_create(meso_ctx **out, int device);       /* new MesoDevice(lmp, gpu, 
  * on a single device except the meso_export_* parity exports (per-brick data: not available).  ndev == 1: meso_create. */
 int  meso_create_gang(meso_ctx **out, int ndev, const int *devices);
 int  meso_gang_size(meso_ctx *ctx);                 /* bricks behind the handle (1 for meso_create) */
+/* the gang's host-side rules without a device: processor grid for ndev bricks (Comm::set_procs' surface rule,
+ * src/comm.cpp:201-287) and the brick (x-major rank) every position x[3n] is dealt to (Domain::set_local_box's uniform split) */
+int  meso_gang_layout(int ndev, const double boxlo[3], const double boxhi[3], const int periodic[3], int grid[3], int n,
+                      const double *x, int *owner);
 void meso_destroy(meso_ctx *ctx);                   /* MesoDevice::destroy */
 const char *meso_last_error(meso_ctx *ctx);         /* NULL ctx: last creation error */
 int  meso_sync(meso_ctx *ctx);                      /* MesoDevice::sync_device */

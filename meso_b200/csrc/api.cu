@@ -41,6 +41,8 @@ int gang_ensure_peers(meso_ctx *ctx);
 int gang_atoms_download(meso_ctx *ctx, int nmax, double *x, double *v, double *f, int *tag, int *type, int *mask, int *image);
 int gang_counts(meso_ctx *ctx, int *nlocal, int *nghost, int *n_bulk, int *n_border);
 int gang_sum(meso_ctx *ctx, int width, double *out, const std::function<int(meso_ctx *, double *)> &fn);
+void gang_choose_grid(int n, const double prd[3], int grid[3]);
+void gang_deal(const double boxlo[3], const double boxhi[3], const int periodic[3], const int grid[3], int n, const double *x, int *owner);
 }
 
 static std::string g_create_err;
@@ -157,6 +159,19 @@ extern "C" int meso_create_gang(meso_ctx **out, int ndev, const int *devices)
 }
 
 extern "C" int meso_gang_size(meso_ctx *ctx) { return ctx ? gang_size(ctx) : 0; }
+
+// host-side rules of the gang, callable without a GPU (tests): the processor grid for ndev bricks of a box, and the brick
+// (x-major rank) each position is dealt to
+extern "C" int meso_gang_layout(int ndev, const double boxlo[3], const double boxhi[3], const int periodic[3], int grid[3], int n,
+                                const double *x, int *owner)
+{
+    if (ndev < 1 || !boxlo || !boxhi || !periodic || !grid || n < 0 || (n > 0 && (!x || !owner))) return MESO_EINVAL;
+    double prd[3];
+    for (int d = 0; d < 3; d++) { prd[d] = boxhi[d] - boxlo[d]; if (!(prd[d] > 0)) return MESO_EINVAL; }
+    gang_choose_grid(ndev, prd, grid);
+    gang_deal(boxlo, boxhi, periodic, grid, n, x, owner);
+    return MESO_OK;
+}
 
 extern "C" void meso_destroy(meso_ctx *ctx)
 {

@@ -109,6 +109,11 @@ static void choose_grid(int n, const double prd[3], int grid[3])
     }
 }
 
+void gang_choose_grid(int n, const double prd[3], int grid[3]) { choose_grid(n, prd, grid); }
+
+// brick (x-major rank) of a position for a given box and grid: what gang_atoms_upload deals by
+static int brick_of_box(const double boxlo[3], const double boxhi[3], const int periodic[3], const int grid[3], const double *x);
+
 extern std::string &create_error();
 
 int gang_create(meso_ctx **out, int ndev, const int *devices)
@@ -195,23 +200,30 @@ int gang_set_box(meso_ctx *ctx, const double boxlo[3], const double boxhi[3], co
 
 // brick of a position: Domain::set_local_box's uniform split, the position wrapped into a periodic box first (the member
 // wraps and migrates for real at its first rebuild) and clamped into the outer bricks of a non-periodic dimension
-static int brick_of(const Gang *g, const double *x)
+static int brick_of_box(const double boxlo[3], const double boxhi[3], const int periodic[3], const int grid[3], const double *x)
 {
     int loc[3];
     for (int d = 0; d < 3; d++) {
-        const double prd = g->boxhi[d] - g->boxlo[d];
-        double u = (x[d] - g->boxlo[d]) / prd;
-        if (g->periodic[d]) u -= floor(u);
-        int l = (int)(u * g->procgrid[d]);
+        const double prd = boxhi[d] - boxlo[d];
+        double u = (x[d] - boxlo[d]) / prd;
+        if (periodic[d]) u -= floor(u);
+        int l = (int)(u * grid[d]);
         // the member's own test is sublo <= x < subhi with sublo = boxlo + prd * (l / p): settle rounding on that definition
-        const int p = g->procgrid[d];
+        const int p = grid[d];
         l = std::min(std::max(l, 0), p - 1);
-        const double xw = g->periodic[d] ? g->boxlo[d] + u * prd : x[d];
-        while (l > 0 && xw < g->boxlo[d] + prd * (l * (1.0 / p))) l--;
-        while (l < p - 1 && xw >= g->boxlo[d] + prd * ((l + 1) * (1.0 / p))) l++;
+        const double xw = periodic[d] ? boxlo[d] + u * prd : x[d];
+        while (l > 0 && xw < boxlo[d] + prd * (l * (1.0 / p))) l--;
+        while (l < p - 1 && xw >= boxlo[d] + prd * ((l + 1) * (1.0 / p))) l++;
         loc[d] = l;
     }
-    return (loc[0] * g->procgrid[1] + loc[1]) * g->procgrid[2] + loc[2];
+    return (loc[0] * grid[1] + loc[1]) * grid[2] + loc[2];
+}
+
+static int brick_of(const Gang *g, const double *x) { return brick_of_box(g->boxlo, g->boxhi, g->periodic, g->procgrid, x); }
+
+void gang_deal(const double boxlo[3], const double boxhi[3], const int periodic[3], const int grid[3], int n, const double *x, int *owner)
+{
+    for (int i = 0; i < n; i++) owner[i] = brick_of_box(boxlo, boxhi, periodic, grid, x + 3 * (size_t)i);
 }
 
 int gang_atoms_upload(meso_ctx *ctx, int nlocal, const double *x, const double *v, const int *tag, const int *type, const int *mask,

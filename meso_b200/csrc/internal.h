@@ -147,7 +147,7 @@ struct meso_ctx {
     meso::DevBuf<float4> facc;                // fp32 per-atom force accumulator of the pair-once kernel (zero between uses)
     cudaTextureObject_t tex_coord = 0, tex_veloc = 0;   // linear float4 textures over coord4 / veloc4 (gather-path experiments)
     int pair_tex = 2;                         // which gathers of the pair-once kernel use the texture data pipe (MESO_PAIR_TEX)
-    bool nb_slow = false;                     // MESO_NB_SLOW=1: every row by the plain 27-cell walk (A/B check of the fine-lattice build)
+    bool nb_slow = false;                     // MESO_NB_SLOW=1: every row by the plain 27-cell walk (A/B check of the tile build)
     bool pair_once = true;                    // meso_run evaluates each local pair once (MESO_PAIR_ONCE=0: two-sided kernel)
     meso::DevBuf<double> virial, e_pair;      // [6][cap] SoA, [cap]
     meso::DevBuf<double> mass_dev;            // [ntypes+1]

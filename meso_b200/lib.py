@@ -17,6 +17,7 @@ SIGNATURES = {
     "meso_create": (_i, [C.POINTER(_vp), _i]),
     "meso_create_gang": (_i, [C.POINTER(_vp), _i, _pi]),
     "meso_gang_size": (_i, [_vp]),
+    "meso_gang_layout": (_i, [_i, _pd, _pd, _pi, _pi, _i, _vp, _vp]),
     "meso_destroy": (None, [_vp]),
     "meso_last_error": (C.c_char_p, [_vp]),
     "meso_sync": (_i, [_vp]),
