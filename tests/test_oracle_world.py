@@ -265,3 +265,60 @@ def test_amphiphilic_channel_is_decomposition_independent():
     assert sum(n1) == len(x) and n0 != n1, "no atom migrated: the test would not exercise the bond table's migration"
     # fp32 packing relative to different centres: forces differ by ~1e-6 relative, positions by ~1e-7 after 17 steps
     assert np.abs(x1 - x8).max() < 1e-5 and np.abs(v1 - v8).max() < 1e-3, (np.abs(x1 - x8).max(), np.abs(v1 - v8).max())
+
+
+@pytest.mark.parametrize("case", ["cube", "brick_of_8", "channel"])
+def test_block_segments_and_tile_sizes_of_the_tile_build(case):
+    """Design invariants of the neighbor build (meso_b200/csrc/neighbor.cu:k_build_tiles), checked on the oracle's own sorted atoms
+    and cells: (1) the local atoms of an aligned 4 x 4 x 4 block of cells are ONE run of consecutive indices per class (bulk /
+    border), so a box has about as many segments as (block, class) pairs -- never one per cell; (2) the tile of a block (its
+    cells plus one layer, every x-row rounded out to whole 16-byte groups) stays inside the shared-memory budget the host-side
+    geometry reserves for this density; (3) the candidates of every atom's 27 stencil cells lie in its block's tile."""
+    if case == "cube":
+        w, r = world(16), 0
+    elif case == "brick_of_8":
+        w, r = world(24, procgrid=(2, 2, 2)), 5
+    else:
+        x = workload.dpd_fluid(16)
+        w = oracle.World((0, 0, 0), (16, 16, 16), periodic=(1, 1, 0))
+        w.set_atoms(x, workload.maxwell_velocities(len(x)))
+        r = 0
+    w.setup()
+    a = w.atoms(r)
+    nl = a["nlocal"]
+    m, _, _ = w.bins(r)
+    cs, ca = w.cells(r)
+    cell_of = np.empty(len(ca), np.int64)
+    for c in range(len(cs) - 1):
+        cell_of[ca[cs[c]:cs[c + 1]]] = c
+    cx, cy, cz = cell_of % m[0], (cell_of // m[0]) % m[1], cell_of // (m[0] * m[1])
+    block = (cx >> 2) | ((cy >> 2) << 10) | ((cz >> 2) << 20)
+    # (1) segments = maximal runs of equal block id among the locals, in index order
+    heads = np.flatnonzero(np.r_[True, block[1:nl] != block[:nl - 1]])
+    n_bulk = w.counts(r)["n_bulk"]
+    pairs = len(set(block[:n_bulk].tolist())) + len(set(block[n_bulk:nl].tolist()))
+    assert len(heads) == pairs, (len(heads), pairs)
+    assert len(heads) < 0.2 * len(set(cell_of[:nl].tolist()))             # far fewer segments than occupied cells
+    # (2) tile records of every block, rows rounded out to groups of four records
+    inner = max(m[0] - 2, 1) * max(m[1] - 2, 1) * max(m[2] - 2, 1)
+    per_cell = nl / inner
+    cap = (int(216 * per_cell * 1.15) + 4 * 36 + 32 + 63) // 64 * 64       # tile_geometry() of neighbor.cu for 4 x 4 x 4 blocks
+    assert cap <= 2560
+    worst = 0
+    for b in set(block[:nl].tolist()):
+        X0, Y0, Z0 = (b & 1023) << 2, ((b >> 10) & 1023) << 2, (b >> 20) << 2
+        xlo, xhi = max(X0 - 1, 0), min(X0 + 4, m[0] - 1)
+        total = 0
+        for z in range(max(Z0 - 1, 0), min(Z0 + 4, m[2] - 1) + 1):
+            for y in range(max(Y0 - 1, 0), min(Y0 + 4, m[1] - 1) + 1):
+                c0 = xlo + m[0] * (y + m[1] * z)
+                g0, g1 = cs[c0] & ~3, (cs[c0 + xhi - xlo + 1] + 3) & ~3
+                total += g1 - g0
+        worst = max(worst, total)
+    assert worst <= cap, (worst, cap)
+    # (3) every stencil cell of every local atom lies inside its block's tile (block +- one cell, clipped to the lattice)
+    for i in np.random.default_rng(3).choice(nl, size=200, replace=False):
+        for c in w.stencil(int(cell_of[i]), r):
+            sx, sy, sz = c % m[0], (c // m[0]) % m[1], c // (m[0] * m[1])
+            for s, c0 in ((sx, cx[i]), (sy, cy[i]), (sz, cz[i])):
+                assert ((c0 >> 2) << 2) - 1 <= s <= ((c0 >> 2) << 2) + 4
