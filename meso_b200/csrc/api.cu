@@ -101,6 +101,11 @@ void drain_timers(meso_ctx *ctx)
 // ---------------------------------------------------------------- device runtime
 extern "C" int meso_device_count(void)
 {
+    // A process that is about to drive several GPUs (MESO_DEVICES, lammps/USER-MESO-B200/engine_meso.cpp) gets its kernels
+    // loaded up front: with lazy loading the first launch of a kernel waits for the kernels already running in that context,
+    // and a brick's halo kernel may be one of them, waiting for a neighbor.  This is the first CUDA call of such a process
+    // (src/lammps.cpp:439-441 asks for the device count before it builds MesoDevice), so the setting still takes effect.
+    if (getenv("MESO_DEVICES") && !getenv("CUDA_MODULE_LOADING")) setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
